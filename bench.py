@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- EVP substep cell-updates/s (Float64) of the B200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one `time_step_momentum!` (reset + initialize_rheology + `substeps` EVP substeps +
+finalize) over one synthetic batch.  N = 1: BASELINE config 2, the anticyclone case scaled to
+4096 x 4096 (Bounded x Bounded).  N > 1: BASELINE config 3, doubly periodic, y-slabs of
+16384 x 2048 per GPU (16384^2 at N = 8), NCCL halo exchange every K substeps; weak scaling.
+`value`  : cell-updates/s with inputs resident in HBM, CUDA events, max over ranks.
+`e2e`    : the same metric through the host-buffer C-ABI call (pinned host arrays, H2D + D2H inside).
+`roofline`: dominant kernel, algorithmic bytes (144 B per cell-update fused / see DESIGN.md) over
+            its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline`: the CPU oracle (C restatement of the reference's KernelAbstractions-CPU path; the
+            Julia original cannot run in this image) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "EVP substep cell-updates/s (Float64)"
+UNIT = "cell-updates/s"
+SUBSTEPS = 150
+DT_STAGE = 120.0
+BYTES_PER_CELL_FUSED = 144      # r/w u,v,s11,s22,s12 + read h,aice,un,vn,tau_x,tau_y,ue,ve
+BYTES_PER_CELL_STRESS = 120     # unfused stress kernel: read u,v,P,h,aice,s11,s22,s12; write s11,s22,s12,zeta_c,zeta_f,Delta,alpha
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(n, steps, warmup, threads=None):
+    """Times the oracle's time_step_momentum! (150 substeps) on an n x n anticyclone sample."""
+    from climaseaice_b200.synthetic import anticyclone_case
+    from oracle import oracle as O
+    from tests.helpers import oracle_from_case
+    cores = O.set_threads(threads or (os.cpu_count() or 1))
+    case = anticyclone_case(n, substeps=SUBSTEPS)
+    o = oracle_from_case(case)
+    o.update_state()
+    for _ in range(warmup):
+        o.time_step_momentum(DT_STAGE, SUBSTEPS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.time_step_momentum(DT_STAGE, SUBSTEPS)
+    dt = time.perf_counter() - t0
+    return n * n * SUBSTEPS * steps / dt, cores, dt / steps
+
+
+def reference_sample_size(steps, warmup):
+    budget_cells = 1.0e7 * 150.0 / max(1, steps + warmup) / SUBSTEPS  # ~150 s of CPU work at ~1e7 cell-updates/s
+    n = 128
+    while (2 * n) ** 2 <= budget_cells and 2 * n <= 2048:
+        n *= 2
+    return n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = reference_sample_size(args.steps, args.warmup)
+    rate, cores, per_step = cpu_reference_rate(n, args.steps, args.warmup)
+    sample = f"anticyclone {n}x{n}, {SUBSTEPS} substeps per step (bounded sample of the 4096x4096 workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference's KernelAbstractions-CPU path (OpenMP); the Julia original is not runnable in this image"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(ngpus):
+    if ngpus == 1:
+        return {"workload": "anticyclone EVP benchmark scaled to 4096x4096 (BASELINE config 2): Bounded x Bounded, H=7, dx=4 km, "
+                            "FPlane f=1e-4, wind-stress arrays + SemiImplicitStress ocean drag, 150 substeps per step",
+                "grid": [4096, 4096], "substeps": SUBSTEPS, "l2_policy": "inputs larger than L2 (2.4 GB working set vs 126 MB)"}
+    return {"workload": f"doubly periodic EVP on 16384x{2048 * ngpus} (BASELINE config 3 at 8 GPUs = 16384^2), y-slabs of 16384x2048 per GPU, "
+                        "NCCL halo exchange every 4 substeps, 150 substeps per step",
+            "grid": [16384, 2048 * ngpus], "per_gpu": [16384, 2048], "substeps": SUBSTEPS, "exchange_every": 4,
+            "l2_policy": "inputs larger than L2 (4.9 GB working set per GPU vs 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.load_package()
+    from climaseaice_b200 import _lib as L, nccl_unique_id
+    from climaseaice_b200.driver import HostStepper, model_from_case
+    from climaseaice_b200.synthetic import anticyclone_case, periodic_case, slab_of
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    ngpus = world
+
+    nx, ny = (args.nx or 4096, args.ny or 4096) if ngpus == 1 else (args.nx or 16384, args.ny or 2048)
+    K = 4
+    if ngpus == 1:
+        case = anticyclone_case(nx) if not args.periodic else periodic_case(nx, Ny=ny)
+        model = model_from_case(case, solver_impl=args.solver, device=dev)
+    else:
+        # each rank builds only its own slab of the global periodic case (same seed => consistent fields)
+        Hy = 2 * K + 3
+        case = periodic_slab_case(nx, ny, rank, ngpus, Hy)
+        model = model_from_case(case, solver_impl=args.solver, partition=(rank, ngpus, K), device=dev)
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        model.comm_init(ids[0])
+    cells = case.Nx * case.Ny
+    model.update_state()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        model.time_step_momentum(DT_STAGE, SUBSTEPS)
+    barrier()
+    launches0 = model.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            model.time_step_momentum(DT_STAGE, SUBSTEPS)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = model.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = cells * ngpus * SUBSTEPS / (ms_per_step * 1e-3)
+
+    # dominant kernel, timed alone with CUDA events on its stream
+    kern_ms, kern_name, kern_bytes = time_dominant_kernel(model, cells)
+    peak, peak_src = peaks()
+    achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": traffic_from_profile(kern_name), "launch_ms": kern_ms,
+                "algorithmic_bytes_per_launch": kern_bytes,
+                "whole_substep_GBps_at_144B": BYTES_PER_CELL_FUSED * cells * SUBSTEPS / (ms_per_step * 1e-3) / 1e9}
+
+    # full model step (3 RK stages incl. advection), reported beside the headline
+    barrier()
+    ev0.record()
+    model.time_step(case.dt)
+    ev1.record()
+    barrier()
+    full_ms = ev0.elapsed_time(ev1)
+
+    # end to end through the host-buffer entry point
+    e2e = None
+    if ngpus == 1 and not args.no_e2e:
+        model.close()
+        del model
+        torch.cuda.empty_cache()
+        hs = HostStepper(case, solver_impl=args.solver, device_index=local)
+        hs.evp_substeps(DT_STAGE, SUBSTEPS)  # warm-up (allocates the device mirrors)
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            hs.evp_substeps(DT_STAGE, SUBSTEPS)
+        wall = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": cells * SUBSTEPS / wall, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes_momentum,
+               "ms_per_step": wall * 1e3, "call": "csi_evp_substeps_host (pinned host arrays)"}
+        hs.model.close()
+
+    if rank == 0:
+        cpu = None
+        if ngpus == 1 and not args.no_cpu:
+            n = args.cpu_n
+            rate, cores, per_step = cpu_reference_rate(n, 1, 0)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"anticyclone {n}x{n}, one time_step_momentum! of {SUBSTEPS} substeps ({per_step:.1f} s)",
+                   "note": "C restatement of the reference's KernelAbstractions-CPU path; Julia original not runnable here"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(ngpus) if not (args.nx or args.periodic) else {"workload": f"custom {case.name} {case.Nx}x{case.Ny} per GPU"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "solver": args.solver,
+            "full_time_step": {"ms": full_ms, "cell_updates_per_s": cells * ngpus * 3 * SUBSTEPS / (full_ms * 1e-3),
+                               "note": "one time_step! = 3 RK stages x (WENO7 tendencies + 150 substeps + h/aice update)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def periodic_slab_case(nx, ny_local, rank, nranks, Hy):
+    """Rank-local slab of the global doubly periodic case, generated without materialising the global arrays."""
+    import numpy as np
+    from climaseaice_b200.synthetic import Case, LOC
+    Ny = ny_local * nranks
+    c = Case(f"periodic-slab{rank}", nx, ny_local, 7, Hy, ("Periodic", "Periodic"), nx * 4000.0, ny_local * 4000.0)
+    tp = 2 * np.pi
+    Lx, Ly = nx * 4000.0, Ny * 4000.0
+    rng = np.random.default_rng(20260417 + rank)
+
+    def nodes(loc):
+        sy, sx = c.parent_shape(loc)
+        i = np.arange(sx) - c.Hx + 1
+        j = np.arange(sy) - c.Hy + 1 + rank * ny_local
+        x = ((i - 1) if loc[0] else (i - 0.5)) * 4000.0
+        y = ((j - 1) if loc[1] else (j - 0.5)) * 4000.0
+        return x[None, :], y[:, None]
+
+    x, y = nodes(LOC["h"])
+    h = 0.3 + 0.005 * (np.sin(3 * tp * x / Lx) + np.sin(2 * tp * y / Ly)) + 0 * x
+    h = h + 1e-3 * rng.uniform(-1, 1, h.shape)
+    a = 0.9 + 0.1 * rng.uniform(0, 1, h.shape)
+    xu, yu = nodes(LOC["u"])
+    xv, yv = nodes(LOC["v"])
+    f = dict(h=h, a=a, u=0.05 * np.sin(tp * yu / Ly) * np.cos(tp * xu / Lx), v=-0.05 * np.sin(tp * xv / Lx) * np.cos(tp * yv / Ly),
+             ue=0.01 * np.sin(tp * yu / Ly) + 0 * xu, ve=0.01 * np.sin(tp * xv / Lx) + 0 * yv,
+             top_x=0.1 * np.sin(tp * yu / Ly) + 0 * xu, top_y=0.1 * np.cos(tp * xv / Lx) + 0 * yv)
+    c.fields = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
+    # the random parts of h, aice differ between ranks in the overlapping halos; the first exchange
+    # (update_state!) makes them consistent before anything is timed
+    return c
+
+
+def time_dominant_kernel(model, cells, reps=20):
+    """Average duration of the dominant kernel launched alone between two CUDA events."""
+    import ctypes as C
+    from climaseaice_b200 import _lib as L
+    lib = L.lib()
+    if not hasattr(lib, "csi_time_dominant_kernel"):
+        return float("nan"), "n/a", 0
+    f = model.csi_fields()
+    ms = C.c_double()
+    name = C.create_string_buffer(64)
+    bpc = C.c_int32()
+    lib.csi_time_dominant_kernel.argtypes = [C.c_void_p, C.POINTER(L.csi_fields), C.c_double, C.c_int32, C.POINTER(C.c_double), C.c_char_p,
+                                             C.POINTER(C.c_int32), C.c_void_p]
+    L.check(lib.csi_time_dominant_kernel(model._handle, C.byref(f), DT_STAGE, reps, C.byref(ms), name, C.byref(bpc), model._stream()), model._handle)
+    return ms.value, name.value.decode(), bpc.value * cells
+
+
+def traffic_from_profile(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = ROOT / "profiles" / "dominant_kernel_traffic.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get(kernel_name, {}).get("dram_bytes_per_launch")
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--solver", default="auto", choices=["auto", "unfused", "fused"])
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--periodic", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=1024)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

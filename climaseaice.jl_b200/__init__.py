@@ -1,0 +1,12 @@
+"""climaseaice_b200 -- B200-native drop-in for ClimaSeaIce.jl's EVP-substep + h/aice advection hot path.
+
+The product is csrc/ -> libclimaseaice_b200.so (C ABI in include/climaseaice_b200.h).  The Python
+modules here are the host-side mirror of the reference's user interface for that path.
+"""
+from . import _lib
+from ._lib import CsiError, lib
+from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid,
+                    SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress, SplitExplicitSolver, UpwindBiased,
+                    ValueBoundaryCondition, WENO, nccl_unique_id, time_step_b)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

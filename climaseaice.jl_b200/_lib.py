@@ -1,0 +1,133 @@
+"""ctypes binding of libclimaseaice_b200.so (include/climaseaice_b200.h).
+
+The shared library is the product; this module only loads it and mirrors its structs.  There is
+no fallback: if the library is missing, import of the compute entry points raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libclimaseaice_b200.so"
+
+ABI_VERSION = 1
+PERIODIC, BOUNDED = 0, 1
+STRESS_NONE, STRESS_CONST, STRESS_FIELD, STRESS_SEMI_IMPLICIT = 0, 1, 2, 3
+REPLACEMENT_PRESSURE, ICE_STRENGTH = 0, 1
+CORIOLIS_NONE, CORIOLIS_FPLANE = 0, 1
+BC_DEFAULT, BC_VALUE = 0, 1
+RK3, FE = 0, 1
+SOLVER_AUTO, SOLVER_UNFUSED, SOLVER_FUSED = 0, 1, 2
+
+ERRORS = {-1: "CSI_ERR_ARG", -2: "CSI_ERR_SHAPE", -3: "CSI_ERR_UNSUPPORTED", -4: "CSI_ERR_NO_DEVICE", -5: "CSI_ERR_NCCL_MISSING"}
+
+
+class CsiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libclimaseaice_b200: {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class csi_array(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("nx_tot", C.c_int32), ("ny_tot", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32)]
+
+
+class csi_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("Nx", C.c_int32), ("Ny", C.c_int32), ("Hx", C.c_int32), ("Hy", C.c_int32),
+        ("topo_x", C.c_int32), ("topo_y", C.c_int32),
+        ("dx", C.c_double), ("dy", C.c_double),
+        ("immersed_mask", C.c_void_p),
+        ("ice_compressive_strength", C.c_double), ("ice_compaction_hardening", C.c_double),
+        ("yield_curve_eccentricity", C.c_double), ("minimum_plastic_stress", C.c_double),
+        ("min_relaxation_parameter", C.c_double), ("max_relaxation_parameter", C.c_double),
+        ("relaxation_strength", C.c_double),
+        ("pressure_formulation", C.c_int32), ("substeps", C.c_int32),
+        ("minimum_mass", C.c_double), ("minimum_concentration", C.c_double), ("ice_density", C.c_double),
+        ("coriolis_kind", C.c_int32), ("top_stress_kind", C.c_int32),
+        ("coriolis_f", C.c_double), ("top_tau_x", C.c_double), ("top_tau_y", C.c_double),
+        ("bottom_stress_kind", C.c_int32), ("u_south_north_bc", C.c_int32),
+        ("rho_e", C.c_double), ("Cd", C.c_double), ("ue_const", C.c_double), ("ve_const", C.c_double),
+        ("u_south_north_value", C.c_double),
+        ("v_west_east_bc", C.c_int32), ("advection_order", C.c_int32),
+        ("v_west_east_value", C.c_double),
+        ("timestepper", C.c_int32), ("solver_impl", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("exchange_every", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+
+FIELD_NAMES = ("u", "v", "h", "a", "s11", "s22", "s12", "zeta_f", "zeta_c", "delta", "alpha", "un", "vn", "P",
+               "top_x", "top_y", "ue", "ve", "Gh", "Ga", "hm", "am", "um", "vm")
+# (face_x, face_y) of every field, same order
+FIELD_LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), s11=(0, 0), s22=(0, 0), s12=(1, 1), zeta_f=(1, 1),
+                 zeta_c=(0, 0), delta=(0, 0), alpha=(0, 0), un=(1, 0), vn=(0, 1), P=(0, 0), top_x=(1, 0),
+                 top_y=(0, 1), ue=(1, 0), ve=(0, 1), Gh=(0, 0), Ga=(0, 0), hm=(0, 0), am=(0, 0), um=(1, 0), vm=(0, 1))
+
+
+class csi_fields(C.Structure):
+    _fields_ = [(n, csi_array) for n in FIELD_NAMES]
+
+
+# every symbol include/climaseaice_b200.h declares
+EXPORTS = (
+    "csi_version", "csi_last_error", "csi_create", "csi_destroy", "csi_evp_substeps",
+    "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
+    "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
+    "csi_evp_substeps_host", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count",
+    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
+)
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(libclimaseaice_b200 has no Python/CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    H = C.c_void_p
+    L.csi_version.restype = C.c_int
+    L.csi_last_error.restype = C.c_char_p
+    L.csi_last_error.argtypes = [H]
+    L.csi_create.argtypes = [C.POINTER(csi_config), C.POINTER(H)]
+    L.csi_destroy.argtypes = [H]
+    L.csi_evp_substeps.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.c_void_p]
+    L.csi_compute_tracer_tendencies.argtypes = [H, C.POINTER(csi_fields), C.c_void_p]
+    L.csi_dynamic_time_step.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_void_p]
+    L.csi_cache_current_fields.argtypes = [H, C.POINTER(csi_fields), C.c_void_p]
+    L.csi_update_state.argtypes = [H, C.POINTER(csi_fields), C.c_void_p]
+    L.csi_fill_halos.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.csi_time_step.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.c_void_p]
+    L.csi_cell_advection_timescale.argtypes = [H, C.POINTER(csi_fields), C.POINTER(C.c_double), C.c_void_p]
+    L.csi_diagnostics.argtypes = [H, C.POINTER(csi_fields), C.POINTER(C.c_double), C.c_void_p]
+    L.csi_time_step_host.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.c_int32]
+    L.csi_evp_substeps_host.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32]
+    L.csi_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.csi_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
+    L.csi_exchange_halos.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_void_p]
+    L.csi_launch_count.restype = C.c_int64
+    L.csi_launch_count.argtypes = [H]
+    L.csi_last_elapsed_ms.restype = C.c_double
+    L.csi_last_elapsed_ms.argtypes = [H]
+    L.csi_time_dominant_kernel.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.POINTER(C.c_double), C.c_char_p,
+                                           C.POINTER(C.c_int32), C.c_void_p]
+    L.csi_host_exp.restype = C.c_double
+    L.csi_host_exp.argtypes = [C.c_double]
+    L.csi_host_div_by_const.restype = C.c_double
+    L.csi_host_div_by_const.argtypes = [C.c_double, C.c_double]
+    L.csi_host_halo_width.argtypes = [C.c_int32]
+    _lib = L
+    return L
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = lib().csi_last_error(handle)
+        raise CsiError(rc, msg.decode() if msg else "")

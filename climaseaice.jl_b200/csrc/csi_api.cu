@@ -1,0 +1,767 @@
+// csi_api.cu -- the C ABI of libclimaseaice_b200.so (include/climaseaice_b200.h): handle,
+// argument checking, and the host-side orchestration of the hot path, i.e. the bodies of
+//   time_step_momentum!   src/SeaIceDynamics/split_explicit_momentum_equations.jl:103-195
+//   rk_substep!/time_step! src/sea_ice_rk_substep.jl:29-94, src/sea_ice_fe_step.jl:13-50
+//   update_state!         src/sea_ice_model.jl:379-394
+// as sequences of asynchronous kernel launches on the caller's stream.  No CPU fallback exists:
+// every compute entry point needs a CUDA device of compute capability 10.x.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "csi_internal.h"
+#include "csi_math.cuh"
+
+using namespace csi;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: single-GPU users never need the library ------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_uid *) = nullptr;
+    int (*CommInitRank)(void **, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+#define CSI_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+            CSI_SYM(GetUniqueId, "ncclGetUniqueId");
+            CSI_SYM(CommInitRank, "ncclCommInitRank");
+            CSI_SYM(CommDestroy, "ncclCommDestroy");
+            CSI_SYM(Send, "ncclSend");
+            CSI_SYM(Recv, "ncclRecv");
+            CSI_SYM(GroupStart, "ncclGroupStart");
+            CSI_SYM(GroupEnd, "ncclGroupEnd");
+            CSI_SYM(GetErrorString, "ncclGetErrorString");
+#undef CSI_SYM
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+        }
+    }
+    return api;
+}
+const int NCCL_FLOAT64 = 8;
+
+}  // namespace
+
+struct csi_handle {
+    csi_config cfg;
+    DGrid g;
+    DParams p;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    std::string err;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    double *scratch = nullptr;
+    int nscratch = 0;
+    double *out_dev = nullptr;
+    uint8_t *mask_dev = nullptr;
+    FusedPlan *fused = nullptr;
+    bool fused_failed = false;
+    // device mirrors for the *_host entry points, in csi_fields member order
+    std::vector<double *> mirror;
+    std::vector<size_t> mirror_n;
+    cudaStream_t own_stream = nullptr;
+    // slab partition
+    void *comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaStream_t comm_stream = nullptr;
+};
+
+namespace {
+
+int fail(csi_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+int cuda_fail(csi_handle *h, cudaError_t e, const char *where)
+{
+    return fail(h, (int)e > 0 ? (int)e : 1, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CSI_CUDA(h, call)                                      \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__, #call); \
+    } while (0)
+
+constexpr int NFIELDS = sizeof(csi_fields) / sizeof(csi_array);
+struct FieldInfo {
+    const char *name;
+    int lx, ly;
+};
+// locations in csi_fields member order
+const FieldInfo FIELD_INFO[NFIELDS] = {
+    {"u", 1, 0},     {"v", 0, 1},     {"h", 0, 0},      {"a", 0, 0},      {"s11", 0, 0},   {"s22", 0, 0},
+    {"s12", 1, 1},   {"zeta_f", 1, 1}, {"zeta_c", 0, 0}, {"delta", 0, 0},  {"alpha", 0, 0}, {"un", 1, 0},
+    {"vn", 0, 1},    {"P", 0, 0},     {"top_x", 1, 0},  {"top_y", 0, 1},  {"ue", 1, 0},    {"ve", 0, 1},
+    {"Gh", 0, 0},    {"Ga", 0, 0},    {"hm", 0, 0},     {"am", 0, 0},     {"um", 1, 0},    {"vm", 0, 1}};
+
+const csi_array &field_at(const csi_fields &f, int k) { return reinterpret_cast<const csi_array *>(&f)[k]; }
+csi_array &field_at(csi_fields &f, int k) { return reinterpret_cast<csi_array *>(&f)[k]; }
+
+int check_array(csi_handle *h, const csi_array &a, const FieldInfo &fi, bool required)
+{
+    if (!a.ptr) return required ? fail(h, CSI_ERR_ARG, std::string("field '") + fi.name + "' is required but NULL") : CSI_OK;
+    const csi_config &c = h->cfg;
+    const int ex = c.Nx + 2 * c.Hx + ((fi.lx && c.topo_x == CSI_BOUNDED) ? 1 : 0);
+    const int ey = c.Ny + 2 * c.Hy + ((fi.ly && c.topo_y == CSI_BOUNDED && h->nranks == 1) ? 1 : 0);
+    if (a.nx_tot != ex || a.ny_tot != ey || a.off_x != c.Hx || a.off_y != c.Hy) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "field '%s': parent %dx%d offsets (%d,%d), expected %dx%d offsets (%d,%d)", fi.name, a.nx_tot,
+                 a.ny_tot, a.off_x, a.off_y, ex, ey, c.Hx, c.Hy);
+        return fail(h, CSI_ERR_SHAPE, buf);
+    }
+    return CSI_OK;
+}
+
+DArr to_darr(const csi_array &a)
+{
+    DArr d;
+    d.p = a.ptr;
+    d.sx = a.nx_tot;
+    d.sy = a.ny_tot;
+    d.ox = a.off_x;
+    d.oy = a.off_y;
+    return d;
+}
+
+// which fields each entry point needs
+enum Need { NEED_MOMENTUM = 1, NEED_TRACERS = 2, NEED_RK = 4 };
+
+int convert_fields(csi_handle *h, const csi_fields *f, int need, DFields *out)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!f) return fail(h, CSI_ERR_ARG, "csi_fields pointer is NULL");
+    const csi_config &c = h->cfg;
+    for (int k = 0; k < NFIELDS; k++) {
+        bool req = false;
+        const std::string n = FIELD_INFO[k].name;
+        if (need & NEED_MOMENTUM) {
+            req |= (n == "u" || n == "v" || n == "h" || n == "a" || n == "s11" || n == "s22" || n == "s12" || n == "zeta_f" ||
+                    n == "zeta_c" || n == "delta" || n == "alpha" || n == "un" || n == "vn" || n == "P");
+            if (c.top_stress_kind == CSI_STRESS_FIELD) req |= (n == "top_x" || n == "top_y");
+        }
+        if (need & NEED_TRACERS) req |= (n == "u" || n == "v" || n == "h" || n == "a" || n == "Gh" || n == "Ga");
+        if ((need & NEED_RK) && c.timestepper == CSI_RK3) req |= (n == "hm" || n == "am" || n == "um" || n == "vm");
+        int rc = check_array(h, field_at(*f, k), FIELD_INFO[k], req);
+        if (rc) return rc;
+        reinterpret_cast<DArr *>(out)[k] = to_darr(field_at(*f, k));
+    }
+    if ((field_at(*f, 16).ptr == nullptr) != (field_at(*f, 17).ptr == nullptr))
+        return fail(h, CSI_ERR_ARG, "ue and ve must both be arrays or both be constants");
+    return CSI_OK;
+}
+
+struct Timed {
+    csi_handle *h;
+    cudaStream_t s;
+    Timed(csi_handle *h_, cudaStream_t s_) : h(h_), s(s_) { cudaEventRecord(h->ev0, s); }
+    ~Timed()
+    {
+        cudaEventRecord(h->ev1, s);
+        h->timed = true;
+    }
+};
+
+int copy_parent(csi_handle *h, const DArr &dst, const DArr &src, cudaStream_t s)
+{
+    CSI_CUDA(h, cudaMemcpyAsync(dst.p, src.p, sizeof(double) * (size_t)src.sx * src.sy, cudaMemcpyDeviceToDevice, s));
+    return CSI_OK;
+}
+
+Range2 velocity_range(const DGrid &g)
+{
+    // `:xy` on serial grids (se.jl:31); widened into the halo on connected sides (se.jl:40-46)
+    Range2 r{1, g.Nx, 1, g.Ny};
+    if (g.conn_s) r.j0 = -g.Hy + 2;
+    if (g.conn_n) r.j1 = g.Ny + g.Hy - 1;
+    return r;
+}
+
+int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaStream_t s);
+
+// time_step_momentum!  (se.jl:103-195)
+int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStream_t s)
+{
+    LaunchCtx c{s, &h->launches};
+    const DGrid &g = h->g;
+    const DParams &p = h->p;
+    if (h->cfg.timestepper == CSI_RK3 && f.um.p && f.vm.p) {  // reset_velocities!  se.jl:87-93
+        int rc = copy_parent(h, f.u, f.um, s);
+        if (rc) return rc;
+        rc = copy_parent(h, f.v, f.vm, s);
+        if (rc) return rc;
+    }
+    launch_initialize_rheology(c, g, p, f);  // evp.jl:192-216
+    // update_external_stress!  ext.jl:72-78,148-152
+    if (p.top_kind == CSI_STRESS_FIELD) {
+        launch_fill_halo(c, g, p, f.top_x, 1, 0, 0);
+        launch_fill_halo(c, g, p, f.top_y, 0, 1, 0);
+    }
+    if (p.bot_kind == CSI_STRESS_SEMI_IMPLICIT) {
+        launch_fill_halo(c, g, p, f.ue, 1, 0, 0);
+        launch_fill_halo(c, g, p, f.ve, 0, 1, 0);
+    }
+    launch_fill_halo(c, g, p, f.u, 1, 0, 1);  // se.jl:170-171
+    launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+
+    bool use_fused = false;
+    if (h->cfg.solver_impl != CSI_SOLVER_UNFUSED && !h->fused_failed) {
+        char why[256] = {0};
+        use_fused = fused_supported(g, p, f, why, sizeof why) != 0;
+        if (!use_fused && h->cfg.solver_impl == CSI_SOLVER_FUSED) return fail(h, CSI_ERR_UNSUPPORTED, std::string("fused solver: ") + why);
+    }
+    if (use_fused) {
+        char err[256] = {0};
+        if (!h->fused) {
+            h->fused = fused_create(g, p, err, sizeof err);
+            if (!h->fused) {
+                h->fused_failed = true;
+                return fail(h, 1, std::string("fused_create: ") + err);
+            }
+        }
+        int rc = fused_run(h->fused, c, g, p, f, dt, 1, nsub, err, sizeof err);
+        if (rc) return fail(h, rc, std::string("fused_run: ") + err);
+    } else {
+        const Range2 r = velocity_range(g);
+        const int K = h->cfg.exchange_every > 0 ? h->cfg.exchange_every : nsub;
+        for (int sub = 1; sub <= nsub; sub++) {  // se.jl:173-189
+            if (h->nranks > 1 && sub > 1 && (sub - 1) % K == 0) {
+                const DArr arrs[5] = {f.u, f.v, f.s11, f.s22, f.s12};
+                int rc = exchange_slab_halos(h, arrs, 5, g.Hy, s);
+                if (rc) return rc;
+            }
+            launch_evp_stress(c, g, p, f, dt);
+            if (sub % 2 == 0) {
+                launch_u_step(c, g, p, f, dt, r);
+                launch_fill_halo(c, g, p, f.u, 1, 0, 1);
+                launch_v_step(c, g, p, f, dt, r);
+                launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+            } else {
+                launch_v_step(c, g, p, f, dt, r);
+                launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+                launch_u_step(c, g, p, f, dt, r);
+                launch_fill_halo(c, g, p, f.u, 1, 0, 1);
+            }
+        }
+    }
+    // finalize_rheology!  evp.jl:275-280
+    launch_fill_halo(c, g, p, f.s11, 0, 0, 0);
+    launch_fill_halo(c, g, p, f.s12, 1, 1, 0);
+    launch_fill_halo(c, g, p, f.s22, 0, 0, 0);
+    if (h->nranks > 1) {
+        const DArr arrs[3] = {f.s11, f.s12, f.s22};
+        int rc = exchange_slab_halos(h, arrs, 3, g.Hy, s);
+        if (rc) return rc;
+    }
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+// update_state!  (sea_ice_model.jl:379-394): prognostic order h, aice, u, v
+int update_state_impl(csi_handle *h, const DFields &f, cudaStream_t s)
+{
+    LaunchCtx c{s, &h->launches};
+    const DGrid &g = h->g;
+    const DParams &p = h->p;
+    launch_mask_immersed(c, g, f.h, 0, 0);
+    launch_fill_halo(c, g, p, f.h, 0, 0, 0);
+    launch_mask_immersed(c, g, f.a, 0, 0);
+    launch_fill_halo(c, g, p, f.a, 0, 0, 0);
+    launch_mask_immersed(c, g, f.u, 1, 0);
+    launch_fill_halo(c, g, p, f.u, 1, 0, 1);
+    launch_mask_immersed(c, g, f.v, 0, 1);
+    launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+    if (h->nranks > 1) {
+        const DArr arrs[4] = {f.h, f.a, f.u, f.v};
+        int rc = exchange_slab_halos(h, arrs, 4, g.Hy, s);
+        if (rc) return rc;
+    }
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaStream_t s)
+{
+    LaunchCtx c{s, &h->launches};
+    const DGrid &g = h->g;
+    const DParams &p = h->p;
+    int rc;
+    if (first && (rc = update_state_impl(h, f, s))) return rc;
+    const int nsub = h->cfg.substeps;
+    if (h->cfg.timestepper == CSI_FE) {  // fe.jl:13-34
+        launch_tracer_tendencies(c, g, p, f);
+        if ((rc = momentum_impl(h, f, dt, nsub, s))) return rc;
+        launch_dynamic_step(c, g, f, f.h, f.a, dt);
+        return update_state_impl(h, f, s);
+    }
+    // cache_current_fields!  rk.jl:29-42
+    if ((rc = copy_parent(h, f.hm, f.h, s))) return rc;
+    if ((rc = copy_parent(h, f.am, f.a, s))) return rc;
+    if ((rc = copy_parent(h, f.um, f.u, s))) return rc;
+    if ((rc = copy_parent(h, f.vm, f.v, s))) return rc;
+    for (int beta = 3; beta >= 1; beta--) {  // SplitRungeKutta3: dtau = dt / beta
+        const double dtau = dt / beta;
+        launch_tracer_tendencies(c, g, p, f);                      // rk.jl:84
+        if ((rc = momentum_impl(h, f, dtau, nsub, s))) return rc;  // rk.jl:87
+        launch_dynamic_step(c, g, f, f.hm, f.am, dtau);            // rk.jl:89
+        if ((rc = update_state_impl(h, f, s))) return rc;
+    }
+    return CSI_OK;
+}
+
+// Slab neighbours along y: send my first/last `width` interior rows, receive into the halos.
+int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaStream_t s)
+{
+    if (h->nranks <= 1) return CSI_OK;
+    if (!h->comm) return fail(h, CSI_ERR_ARG, "csi_comm_init has not been called on this handle");
+    NcclApi &api = nccl();
+    const DGrid &g = h->g;
+    const int south = g.conn_s ? (h->rank + h->nranks - 1) % h->nranks : -1;
+    const int north = g.conn_n ? (h->rank + 1) % h->nranks : -1;
+    if (width > g.Hy) width = g.Hy;
+    api.GroupStart();
+    for (int k = 0; k < n; k++) {
+        const DArr &a = arrs[k];
+        if (!a.p) continue;
+        const size_t row = (size_t)a.sx, cnt = row * width;
+        // rows are contiguous in the i-fastest layout: zero-copy sends
+        double *send_s = a.p + (size_t)a.oy * row;                       // interior rows 1..width
+        double *recv_s = a.p + (size_t)(a.oy - width) * row;             // halo rows 1-width..0
+        double *send_n = a.p + (size_t)(a.oy + g.Ny - width) * row;      // interior rows Ny-width+1..Ny
+        double *recv_n = a.p + (size_t)(a.oy + g.Ny) * row;              // halo rows Ny+1..Ny+width
+        if (south >= 0) {
+            api.Send(send_s, cnt, NCCL_FLOAT64, south, h->comm, s);
+            api.Recv(recv_s, cnt, NCCL_FLOAT64, south, h->comm, s);
+        }
+        if (north >= 0) {
+            api.Send(send_n, cnt, NCCL_FLOAT64, north, h->comm, s);
+            api.Recv(recv_n, cnt, NCCL_FLOAT64, north, h->comm, s);
+        }
+    }
+    int rc = api.GroupEnd();
+    if (rc != 0) return fail(h, 1000 + rc, std::string("ncclGroupEnd: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+    return CSI_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int csi_version(void) { return CSI_ABI_VERSION; }
+
+const char *csi_last_error(const csi_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int csi_create(const csi_config *cfg, csi_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, CSI_ERR_ARG, "csi_create: NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != CSI_ABI_VERSION) return fail(nullptr, CSI_ERR_ARG, "csi_create: abi_version mismatch");
+    if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Hx < 1 || cfg->Hy < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: sizes and halos must be positive");
+    if (cfg->Hx < 3 || cfg->Hy < 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: halos must be at least 3 (the EVP stencils reach 2 cells)");
+    const int B = cfg->advection_order <= 1 ? 1 : (cfg->advection_order + 1) / 2;
+    if (cfg->advection_order != 0 && cfg->advection_order != 1 && cfg->advection_order != 3 && cfg->advection_order != 5 && cfg->advection_order != 7)
+        return fail(nullptr, CSI_ERR_ARG, "csi_create: advection_order must be 0, 1, 3, 5 or 7");
+    if (cfg->Hx < B || cfg->Hy < B) return fail(nullptr, CSI_ERR_ARG, "csi_create: halo smaller than the advection stencil");
+    if ((cfg->topo_x != CSI_PERIODIC && cfg->topo_x != CSI_BOUNDED) || (cfg->topo_y != CSI_PERIODIC && cfg->topo_y != CSI_BOUNDED))
+        return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED");
+    if (!(cfg->dx > 0) || !(cfg->dy > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: dx, dy must be positive");
+    if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
+    if (cfg->nranks > 1 && cfg->topo_y != CSI_PERIODIC)
+        return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: slab partitions need a Periodic y axis in this version");
+    if (cfg->nranks > 1) {
+        const int K = cfg->exchange_every > 0 ? cfg->exchange_every : cfg->substeps;
+        if (cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: slab partitions need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CSI_ERR_NO_DEVICE, "csi_create: no CUDA device (libclimaseaice_b200 has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, CSI_ERR_NO_DEVICE, "csi_create: cannot query device");
+    if (prop.major != 10) return fail(nullptr, CSI_ERR_NO_DEVICE, "csi_create: kernels are built for sm_100a only");
+
+    csi_handle *h = new csi_handle();
+    h->cfg = *cfg;
+    h->rank = cfg->nranks > 1 ? cfg->rank : 0;
+    h->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
+    cudaSetDevice(cfg->device);
+    DGrid &g = h->g;
+    g.Nx = cfg->Nx; g.Ny = cfg->Ny; g.Hx = cfg->Hx; g.Hy = cfg->Hy;
+    g.topo_x = cfg->topo_x; g.topo_y = cfg->topo_y;
+    g.conn_s = g.conn_n = h->nranks > 1 ? 1 : 0;
+    g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
+    g.mask = nullptr;
+    DParams &p = h->p;
+    p.Pstar = cfg->ice_compressive_strength;
+    p.C = cfg->ice_compaction_hardening;
+    p.em2 = (1 / cfg->yield_curve_eccentricity) * (1 / cfg->yield_curve_eccentricity);  // e^(-2) = inv(e)^2
+    p.Dmin = cfg->minimum_plastic_stress;
+    p.amin = cfg->min_relaxation_parameter;
+    p.amax = cfg->max_relaxation_parameter;
+    p.ca = cfg->relaxation_strength;
+    p.pform = cfg->pressure_formulation;
+    p.cor = cfg->coriolis_kind;
+    p.min_mass = cfg->minimum_mass;
+    p.min_conc = cfg->minimum_concentration;
+    p.rho_i = cfg->ice_density;
+    p.f = cfg->coriolis_f;
+    p.top_kind = cfg->top_stress_kind;
+    p.bot_kind = cfg->bottom_stress_kind;
+    p.ttx = cfg->top_tau_x; p.tty = cfg->top_tau_y;
+    p.rho_e = cfg->rho_e; p.Cd = cfg->Cd; p.ue_c = cfg->ue_const; p.ve_c = cfg->ve_const;
+    p.u_sn_bc = cfg->u_south_north_bc; p.v_we_bc = cfg->v_west_east_bc;
+    p.u_sn_val = cfg->u_south_north_value; p.v_we_val = cfg->v_west_east_value;
+    p.adv_order = cfg->advection_order;
+    p.pad_ = 0;
+    cudaError_t e;
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+        delete h;
+        return cuda_fail(nullptr, e, "cudaEventCreate");
+    }
+    h->nscratch = 592 * 8;
+    if ((e = cudaMalloc(&h->scratch, sizeof(double) * h->nscratch)) != cudaSuccess || (e = cudaMalloc(&h->out_dev, sizeof(double) * 8)) != cudaSuccess) {
+        delete h;
+        return cuda_fail(nullptr, e, "cudaMalloc(scratch)");
+    }
+    if (cfg->immersed_mask) {
+        const size_t n = (size_t)(cfg->Nx + 2 * cfg->Hx) * (cfg->Ny + 2 * cfg->Hy);
+        if ((e = cudaMalloc(&h->mask_dev, n)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(mask)"); }
+        cudaMemcpy(h->mask_dev, cfg->immersed_mask, n, cudaMemcpyDefault);
+        g.mask = h->mask_dev;
+    }
+    h->mirror.assign(NFIELDS, nullptr);
+    h->mirror_n.assign(NFIELDS, 0);
+    *out = h;
+    return CSI_OK;
+}
+
+int csi_destroy(csi_handle *h)
+{
+    if (!h) return CSI_ERR_ARG;
+    cudaSetDevice(h->cfg.device);
+    if (h->fused) fused_destroy(h->fused);
+    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+    for (double *m : h->mirror) if (m) cudaFree(m);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->out_dev) cudaFree(h->out_dev);
+    if (h->mask_dev) cudaFree(h->mask_dev);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return CSI_OK;
+}
+
+int csi_evp_substeps(csi_handle *h, const csi_fields *f, double dt_stage, int32_t nsubsteps, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_MOMENTUM, &df);
+    if (rc) return rc;
+    if (nsubsteps < 0) return fail(h, CSI_ERR_ARG, "nsubsteps must be >= 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    Timed t(h, s);
+    return momentum_impl(h, df, dt_stage, nsubsteps, s);
+}
+
+int csi_compute_tracer_tendencies(csi_handle *h, const csi_fields *f, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_TRACERS, &df);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Timed t(h, s);
+    LaunchCtx c{s, &h->launches};
+    launch_tracer_tendencies(c, h->g, h->p, df);
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+int csi_dynamic_time_step(csi_handle *h, const csi_fields *f, double dt_stage, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_TRACERS | NEED_RK, &df);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Timed t(h, s);
+    LaunchCtx c{s, &h->launches};
+    const bool rk = h->cfg.timestepper == CSI_RK3;
+    launch_dynamic_step(c, h->g, df, rk ? df.hm : df.h, rk ? df.am : df.a, dt_stage);
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+int csi_cache_current_fields(csi_handle *h, const csi_fields *f, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_TRACERS | NEED_RK, &df);
+    if (rc) return rc;
+    if (h->cfg.timestepper != CSI_RK3) return CSI_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = copy_parent(h, df.hm, df.h, s))) return rc;
+    if ((rc = copy_parent(h, df.am, df.a, s))) return rc;
+    if ((rc = copy_parent(h, df.um, df.u, s))) return rc;
+    return copy_parent(h, df.vm, df.v, s);
+}
+
+int csi_update_state(csi_handle *h, const csi_fields *f, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_TRACERS & ~0, &df);
+    if (rc) return rc;
+    return update_state_impl(h, df, (cudaStream_t)stream);
+}
+
+int csi_fill_halos(csi_handle *h, const csi_array *a, int32_t loc_x, int32_t loc_y, int32_t which, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!a || !a->ptr) return fail(h, CSI_ERR_ARG, "csi_fill_halos: NULL array");
+    FieldInfo fi{"array", loc_x ? 1 : 0, loc_y ? 1 : 0};
+    int rc = check_array(h, *a, fi, true);
+    if (rc) return rc;
+    LaunchCtx c{(cudaStream_t)stream, &h->launches};
+    launch_fill_halo(c, h->g, h->p, to_darr(*a), fi.lx, fi.ly, which);
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+int csi_time_step(csi_handle *h, const csi_fields *f, double dt, int32_t first, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_MOMENTUM | NEED_TRACERS | NEED_RK, &df);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Timed t(h, s);
+    return time_step_impl(h, df, dt, first, s);
+}
+
+static int reduce_to_host(csi_handle *h, const csi_fields *f, double *host6, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, 0, &df);
+    if (rc) return rc;
+    if (!df.u.p || !df.v.p) return fail(h, CSI_ERR_ARG, "u and v are required");
+    cudaStream_t s = (cudaStream_t)stream;
+    LaunchCtx c{s, &h->launches};
+    launch_diagnostics(c, h->g, df, h->scratch, h->nscratch, h->out_dev);
+    CSI_CUDA(h, cudaMemcpyAsync(host6, h->out_dev, sizeof(double) * 6, cudaMemcpyDeviceToHost, s));
+    CSI_CUDA(h, cudaStreamSynchronize(s));
+    return CSI_OK;
+}
+
+int csi_cell_advection_timescale(csi_handle *h, const csi_fields *f, double *out_host, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!out_host) return fail(h, CSI_ERR_ARG, "out_host is NULL");
+    double tmp[6];
+    int rc = reduce_to_host(h, f, tmp, stream);
+    if (rc) return rc;
+    *out_host = tmp[5];
+    return CSI_OK;
+}
+
+int csi_diagnostics(csi_handle *h, const csi_fields *f, double *out_host5, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!out_host5) return fail(h, CSI_ERR_ARG, "out_host5 is NULL");
+    double tmp[6];
+    int rc = reduce_to_host(h, f, tmp, stream);
+    if (rc) return rc;
+    for (int k = 0; k < 5; k++) out_host5[k] = tmp[k];
+    return CSI_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------
+static int upload_all(csi_handle *h, const csi_fields *hf, csi_fields *dev, cudaStream_t s)
+{
+    for (int k = 0; k < NFIELDS; k++) {
+        const csi_array &a = field_at(*hf, k);
+        csi_array &d = field_at(*dev, k);
+        d = a;
+        if (!a.ptr) continue;
+        const size_t n = (size_t)a.nx_tot * a.ny_tot;
+        if (h->mirror_n[k] != n) {
+            if (h->mirror[k]) cudaFree(h->mirror[k]);
+            h->mirror[k] = nullptr;
+            CSI_CUDA(h, cudaMalloc(&h->mirror[k], n * sizeof(double)));
+            h->mirror_n[k] = n;
+        }
+        CSI_CUDA(h, cudaMemcpyAsync(h->mirror[k], a.ptr, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        d.ptr = h->mirror[k];
+    }
+    return CSI_OK;
+}
+static int download(csi_handle *h, const csi_fields *hf, const int *which, int n, cudaStream_t s)
+{
+    for (int q = 0; q < n; q++) {
+        const int k = which[q];
+        const csi_array &a = field_at(*hf, k);
+        if (!a.ptr) continue;
+        CSI_CUDA(h, cudaMemcpyAsync(a.ptr, h->mirror[k], h->mirror_n[k] * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    return CSI_OK;
+}
+
+int csi_time_step_host(csi_handle *h, const csi_fields *hf, double dt, int32_t nsteps, int32_t first)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!hf) return fail(h, CSI_ERR_ARG, "csi_fields pointer is NULL");
+    cudaSetDevice(h->cfg.device);
+    if (!h->own_stream) CSI_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->own_stream;
+    csi_fields dev;
+    int rc = upload_all(h, hf, &dev, s);
+    if (rc) return rc;
+    DFields df;
+    if ((rc = convert_fields(h, &dev, NEED_MOMENTUM | NEED_TRACERS | NEED_RK, &df))) return rc;
+    {
+        Timed t(h, s);
+        for (int k = 0; k < nsteps; k++)
+            if ((rc = time_step_impl(h, df, dt, first && k == 0, s))) return rc;
+    }
+    const int outs[] = {0, 1, 2, 3, 4, 5, 6, 10};  // u v h a s11 s22 s12 alpha
+    if ((rc = download(h, hf, outs, 8, s))) return rc;
+    CSI_CUDA(h, cudaStreamSynchronize(s));
+    return CSI_OK;
+}
+
+int csi_evp_substeps_host(csi_handle *h, const csi_fields *hf, double dt_stage, int32_t nsubsteps)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!hf) return fail(h, CSI_ERR_ARG, "csi_fields pointer is NULL");
+    cudaSetDevice(h->cfg.device);
+    if (!h->own_stream) CSI_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->own_stream;
+    csi_fields dev;
+    int rc = upload_all(h, hf, &dev, s);
+    if (rc) return rc;
+    DFields df;
+    if ((rc = convert_fields(h, &dev, NEED_MOMENTUM, &df))) return rc;
+    {
+        Timed t(h, s);
+        if ((rc = momentum_impl(h, df, dt_stage, nsubsteps, s))) return rc;
+    }
+    const int outs[] = {0, 1, 4, 5, 6, 10};  // u v s11 s22 s12 alpha
+    if ((rc = download(h, hf, outs, 6, s))) return rc;
+    CSI_CUDA(h, cudaStreamSynchronize(s));
+    return CSI_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+int csi_nccl_unique_id(uint8_t out128[128])
+{
+    if (!out128) return CSI_ERR_ARG;
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(nullptr, CSI_ERR_NCCL_MISSING, "libnccl.so.2 could not be loaded");
+    nccl_uid id;
+    int rc = api.GetUniqueId(&id);
+    if (rc) return fail(nullptr, 1000 + rc, "ncclGetUniqueId failed");
+    memcpy(out128, id.internal, 128);
+    return CSI_OK;
+}
+
+int csi_comm_init(csi_handle *h, const uint8_t id128[128], int32_t rank, int32_t nranks)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, CSI_ERR_ARG, "csi_comm_init: bad arguments");
+    if (nranks != h->nranks || rank != h->rank) return fail(h, CSI_ERR_ARG, "csi_comm_init: rank/nranks differ from csi_config");
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(h, CSI_ERR_NCCL_MISSING, "libnccl.so.2 could not be loaded");
+    cudaSetDevice(h->cfg.device);
+    nccl_uid id;
+    memcpy(id.internal, id128, 128);
+    int rc = api.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc) return fail(h, 1000 + rc, std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+    return CSI_OK;
+}
+
+int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!arrays || narrays < 1 || narrays > 16) return fail(h, CSI_ERR_ARG, "csi_exchange_halos: bad arguments");
+    DArr d[16];
+    for (int k = 0; k < narrays; k++) d[k] = to_darr(arrays[k]);
+    return exchange_slab_halos(h, d, narrays, width, (cudaStream_t)stream);
+}
+
+int64_t csi_launch_count(const csi_handle *h) { return h ? h->launches : 0; }
+
+double csi_last_elapsed_ms(const csi_handle *h)
+{
+    if (!h || !h->timed) return 0.0;
+    float ms = 0.f;
+    cudaEventSynchronize(h->ev1);
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return 0.0;
+    return (double)ms;
+}
+
+int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage, int32_t reps, double *out_ms, char *name64,
+                             int32_t *bytes_per_cell, csi_stream stream)
+{
+    DFields df;
+    int rc = convert_fields(h, f, NEED_MOMENTUM, &df);
+    if (rc) return rc;
+    if (!out_ms || !name64 || !bytes_per_cell || reps < 1) return fail(h, CSI_ERR_ARG, "csi_time_dominant_kernel: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    LaunchCtx c{s, &h->launches};
+    bool use_fused = false;
+    if (h->cfg.solver_impl != CSI_SOLVER_UNFUSED && !h->fused_failed) {
+        char why[256];
+        use_fused = fused_supported(h->g, h->p, df, why, sizeof why) != 0;
+    }
+    char err[256] = {0};
+    if (use_fused && !h->fused) {
+        h->fused = fused_create(h->g, h->p, err, sizeof err);
+        if (!h->fused) return fail(h, 1, std::string("fused_create: ") + err);
+    }
+    // one untimed launch first (module load, tensor maps)
+    if (use_fused) rc = fused_run(h->fused, c, h->g, h->p, df, dt_stage, 1, 2, err, sizeof err);
+    else launch_evp_stress(c, h->g, h->p, df, dt_stage);
+    if (rc) return fail(h, rc, err);
+    CSI_CUDA(h, cudaEventRecord(h->ev0, s));
+    if (use_fused) rc = fused_run(h->fused, c, h->g, h->p, df, dt_stage, 1, reps, err, sizeof err);
+    else for (int k = 0; k < reps; k++) launch_evp_stress(c, h->g, h->p, df, dt_stage);
+    if (rc) return fail(h, rc, err);
+    CSI_CUDA(h, cudaEventRecord(h->ev1, s));
+    CSI_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CSI_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *out_ms = (double)ms / reps;
+    snprintf(name64, 64, "%s", use_fused ? "k_evp_substep_fused" : "k_evp_stress");
+    *bytes_per_cell = use_fused ? 144 : 120;
+    return CSI_OK;
+}
+
+double csi_host_exp(double x) { return csi::exp_cr(x); }
+double csi_host_div_by_const(double x, double c) { return csi::div_by(x, csi::make_recip(c)); }
+int csi_host_halo_width(int32_t k) { return 2 * k + 3; }
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// csi_cell.cuh -- per-node formulas of the EVP substep, evaluated straight from global memory.
+//
+// Used by the UNFUSED kernels (csi_unfused.cu), which keep the reference's launch structure
+// (stress kernel, u kernel, v kernel, halo fills) and serve as the general path for every
+// topology.  Each function names the reference function it stands for
+// (evp = src/Rheologies/elasto_visco_plastic_rheology.jl, isd = src/Rheologies/ice_stress_divergence.jl,
+//  mt = src/SeaIceDynamics/momentum_tendencies_kernel_functions.jl,
+//  ext = src/SeaIceDynamics/sea_ice_external_stress.jl, se = src/SeaIceDynamics/split_explicit_momentum_equations.jl).
+// Expression trees keep Julia's left-to-right association; compiled with -fmad=false.
+#pragma once
+#include "../../include/climaseaice_b200.h"
+#include "csi_math.cuh"
+#include "csi_types.cuh"
+
+namespace csi {
+
+// ---- node activity (Oceananigans inactive_cell / peripheral_node) ----------------------------
+__device__ __forceinline__ bool outside_domain(const DGrid &g, int i, int j)
+{
+    // a slab's connected south / north side is a rank boundary, not a wall
+    return (g.topo_x == CSI_BOUNDED && (i < 1 || i > g.Nx)) ||
+           (g.topo_y == CSI_BOUNDED && ((j < 1 && !g.conn_s) || (j > g.Ny && !g.conn_n)));
+}
+__device__ __forceinline__ bool immersed_cell(const DGrid &g, int i, int j)
+{
+    if (!g.mask) return false;
+    const int sx = g.Nx + 2 * g.Hx, sy = g.Ny + 2 * g.Hy;
+    int pi = min(max(i - 1 + g.Hx, 0), sx - 1), pj = min(max(j - 1 + g.Hy, 0), sy - 1);
+    return g.mask[(size_t)pi + (size_t)pj * sx] != 0;
+}
+__device__ __forceinline__ bool inactive_cell(const DGrid &g, int i, int j) { return outside_domain(g, i, j) || immersed_cell(g, i, j); }
+__device__ __forceinline__ bool peripheral_fc(const DGrid &g, int i, int j) { return inactive_cell(g, i - 1, j) || inactive_cell(g, i, j); }
+__device__ __forceinline__ bool peripheral_cf(const DGrid &g, int i, int j) { return inactive_cell(g, i, j - 1) || inactive_cell(g, i, j); }
+__device__ __forceinline__ bool imm_peripheral_cc(const DGrid &g, int i, int j) { return inactive_cell(g, i, j) && !outside_domain(g, i, j); }
+__device__ __forceinline__ bool imm_peripheral_ff(const DGrid &g, int i, int j)
+{
+    const bool per = inactive_cell(g, i - 1, j - 1) || inactive_cell(g, i, j - 1) || inactive_cell(g, i - 1, j) || inactive_cell(g, i, j);
+    const bool und = outside_domain(g, i - 1, j - 1) || outside_domain(g, i, j - 1) || outside_domain(g, i - 1, j) || outside_domain(g, i, j);
+    return per && !und;
+}
+__device__ __forceinline__ bool imm_peripheral_fc(const DGrid &g, int i, int j)
+{
+    return peripheral_fc(g, i, j) && !(outside_domain(g, i - 1, j) || outside_domain(g, i, j));
+}
+__device__ __forceinline__ bool imm_peripheral_cf(const DGrid &g, int i, int j)
+{
+    return peripheral_cf(g, i, j) && !(outside_domain(g, i, j - 1) || outside_domain(g, i, j));
+}
+
+// ---- averages (Oceananigans: y-average of x-averages) -----------------------------------------
+template <class Fn> __device__ __forceinline__ double avg_ff(Fn q, int i, int j) { return ((q(i - 1, j - 1) + q(i, j - 1)) / 2 + (q(i - 1, j) + q(i, j)) / 2) / 2; }
+template <class Fn> __device__ __forceinline__ double avg_cc(Fn q, int i, int j) { return ((q(i, j) + q(i + 1, j)) / 2 + (q(i, j + 1) + q(i + 1, j + 1)) / 2) / 2; }
+template <class Fn> __device__ __forceinline__ double avg_fc(Fn q, int i, int j) { return ((q(i - 1, j) + q(i, j)) / 2 + (q(i - 1, j + 1) + q(i, j + 1)) / 2) / 2; }
+template <class Fn> __device__ __forceinline__ double avg_cf(Fn q, int i, int j) { return ((q(i, j - 1) + q(i + 1, j - 1)) / 2 + (q(i, j) + q(i + 1, j)) / 2) / 2; }
+
+// ---- strain rates: evp:360-375 (regular metrics: every dx*, dy* is the scalar, Az = dx*dy) ----
+__device__ __forceinline__ double eps_D(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
+{
+    return ((g.dy * at(u, i + 1, j) - g.dy * at(u, i, j)) + (g.dx * at(v, i, j + 1) - g.dx * at(v, i, j))) / g.az;
+}
+__device__ __forceinline__ double eps_T(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
+{
+    return (g.dy * g.dy * (at(u, i + 1, j) / g.dy - at(u, i, j) / g.dy) - g.dx * g.dx * (at(v, i, j + 1) / g.dx - at(v, i, j) / g.dx)) / g.az;
+}
+__device__ __forceinline__ double eps_S(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
+{
+    return (g.dx * g.dx * (at(u, i, j) / g.dx - at(u, i, j - 1) / g.dx) + g.dy * g.dy * (at(v, i, j) / g.dy - at(v, i - 1, j) / g.dy)) / g.az;
+}
+__device__ __forceinline__ double strain_xx(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) + eps_T(g, u, v, i, j)) / 2; }
+__device__ __forceinline__ double strain_yy(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) - eps_T(g, u, v, i, j)) / 2; }
+__device__ __forceinline__ double strain_xy(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return eps_S(g, u, v, i, j) / 2; }
+
+// ice_mass: src/ClimaSeaIce.jl:42
+__device__ __forceinline__ double ice_mass(const DParams &p, const DFields &f, int i, int j) { return at(f.h, i, j) * p.rho_i * at(f.a, i, j); }
+
+// ---- _compute_evp_viscosities! + _compute_evp_stresses! at one node: evp:236-354 --------------
+__device__ __forceinline__ void evp_stress_node(const DGrid &g, const DParams &p, const DFields &f, double dt, int i, int j)
+{
+    const DArr &u = f.u, &v = f.v;
+    auto exx = [&](int a, int b) { return strain_xx(g, u, v, a, b); };
+    auto eyy = [&](int a, int b) { return strain_yy(g, u, v, a, b); };
+    auto exy = [&](int a, int b) { return strain_xy(g, u, v, a, b); };
+    auto PP = [&](int a, int b) { return at(f.P, a, b); };
+    auto mm = [&](int a, int b) { return ice_mass(p, f, a, b); };
+
+    const double e11c = exx(i, j), e22c = eyy(i, j), e12f = exy(i, j);
+    const double e11f = avg_ff(exx, i, j), e22f = avg_ff(eyy, i, j), e12c = avg_cc(exy, i, j);
+    const double dc = e11c + e22c, df = e11f + e22f;
+    const double sc = sqrt((e11c - e22c) * (e11c - e22c) + 4 * (e12c * e12c));
+    const double sf = sqrt((e11f - e22f) * (e11f - e22f) + 4 * (e12f * e12f));
+    const double Dc = jl_max(sqrt(dc * dc + sc * sc * p.em2), p.Dmin);
+    const double Df = jl_max(sqrt(df * df + sf * sf * p.em2), p.Dmin);
+    const double Pc = PP(i, j), Pf = avg_ff(PP, i, j);
+    const double zf = Pf / (2 * Df), zc = Pc / (2 * Dc);
+    at(f.zf, i, j) = zf;
+    at(f.zc, i, j) = zc;
+    at(f.delta, i, j) = Dc;
+
+    // stresses (the strain rates of evp:310-312 are the same expressions as e11c, e22c, e12f)
+    const double Pr = p.pform == CSI_ICE_STRENGTH ? Pc : Pc * Dc / (Dc + p.Dmin);
+    const double ec = zc * p.em2, ef = zf * p.em2;
+    const double s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+    const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+    const double s12n = 2 * ef * e12f;
+    const double mc = mm(i, j), mf = avg_ff(mm, i, j);
+    double g2c = zc * p.ca * dt / mc / g.az;
+    g2c = (g2c != g2c) ? p.amax * p.amax : g2c;
+    const double gc = jl_clamp(sqrt(g2c), p.amin, p.amax);
+    double g2f = zf * p.ca * dt / mf / g.az;
+    g2f = (g2f != g2f) ? p.amax * p.amax : g2f;
+    const double gf = jl_clamp(sqrt(g2f), p.amin, p.amax);
+    const double d11 = (s11n - at(f.s11, i, j)) / gc;
+    const double d22 = (s22n - at(f.s22, i, j)) / gc;
+    const double d12 = (s12n - at(f.s12, i, j)) / gf;
+    at(f.s11, i, j) += (mc > 0 ? d11 : 0.0);
+    at(f.s22, i, j) += (mc > 0 ? d22 : 0.0);
+    at(f.s12, i, j) += (mf > 0 ? d12 : 0.0);
+    at(f.alpha, i, j) = gc;
+}
+
+// ---- stress divergence: isd:16-51 ------------------------------------------------------------
+__device__ __forceinline__ double stress_cc(const DGrid &g, const DArr &s, int i, int j) { return (g.mask && imm_peripheral_cc(g, i, j)) ? 0.0 : at(s, i, j); }
+__device__ __forceinline__ double stress_ff(const DGrid &g, const DArr &s, int i, int j) { return (g.mask && imm_peripheral_ff(g, i, j)) ? 0.0 : at(s, i, j); }
+__device__ __forceinline__ double sigD(const DGrid &g, const DFields &f, int i, int j) { return stress_cc(g, f.s11, i, j) + stress_cc(g, f.s22, i, j); }
+__device__ __forceinline__ double sigT(const DGrid &g, const DFields &f, int i, int j) { return stress_cc(g, f.s11, i, j) - stress_cc(g, f.s22, i, j); }
+__device__ __forceinline__ double div_sigma_1j(const DGrid &g, const DFields &f, int i, int j)
+{
+    const double d = g.dy * (sigD(g, f, i, j) - sigD(g, f, i - 1, j)) / 2;
+    const double t = (g.dy * g.dy * sigT(g, f, i, j) - g.dy * g.dy * sigT(g, f, i - 1, j)) / g.dy / 2;
+    const double S = (g.dx * g.dx * stress_ff(g, f.s12, i, j + 1) - g.dx * g.dx * stress_ff(g, f.s12, i, j)) / g.dx;
+    return (d + t + S) / g.az;
+}
+__device__ __forceinline__ double div_sigma_2j(const DGrid &g, const DFields &f, int i, int j)
+{
+    const double d = g.dx * (sigD(g, f, i, j) - sigD(g, f, i, j - 1)) / 2;
+    const double t = -(g.dx * g.dx * sigT(g, f, i, j) - g.dx * g.dx * sigT(g, f, i, j - 1)) / g.dx / 2;
+    const double S = (g.dy * g.dy * stress_ff(g, f.s12, i + 1, j) - g.dy * g.dy * stress_ff(g, f.s12, i, j)) / g.dy;
+    return (d + t + S) / g.az;
+}
+
+// ---- external stresses: ext:8-27,176-202 -------------------------------------------------------
+__device__ __forceinline__ double ue_at(const DParams &p, const DFields &f, int i, int j) { return f.ue.p ? at(f.ue, i, j) : p.ue_c; }
+__device__ __forceinline__ double ve_at(const DParams &p, const DFields &f, int i, int j) { return f.ve.p ? at(f.ve, i, j) : p.ve_c; }
+__device__ __forceinline__ double sis_speed_x(const DParams &p, const DFields &f, int i, int j)
+{
+    auto ve = [&](int a, int b) { return ve_at(p, f, a, b); };
+    auto vv = [&](int a, int b) { return at(f.v, a, b); };
+    const double du = ue_at(p, f, i, j) - at(f.u, i, j);
+    const double dv = avg_fc(ve, i, j) - avg_fc(vv, i, j);
+    return sqrt(du * du + dv * dv);
+}
+__device__ __forceinline__ double sis_speed_y(const DParams &p, const DFields &f, int i, int j)
+{
+    auto ue = [&](int a, int b) { return ue_at(p, f, a, b); };
+    auto uu = [&](int a, int b) { return at(f.u, a, b); };
+    const double dv = ve_at(p, f, i, j) - at(f.v, i, j);
+    const double du = avg_cf(ue, i, j) - avg_cf(uu, i, j);
+    return sqrt(du * du + dv * dv);
+}
+__device__ __forceinline__ double explicit_tx_top(const DParams &p, const DFields &f, int i, int j)
+{
+    return p.top_kind == CSI_STRESS_FIELD ? at(f.top_x, i, j) : (p.top_kind == CSI_STRESS_CONST ? p.ttx : 0.0);
+}
+__device__ __forceinline__ double explicit_ty_top(const DParams &p, const DFields &f, int i, int j)
+{
+    return p.top_kind == CSI_STRESS_FIELD ? at(f.top_y, i, j) : (p.top_kind == CSI_STRESS_CONST ? p.tty : 0.0);
+}
+
+// ---- _u_velocity_step! at one face: se:197-229 with mt:11-41, evp:384,391-395 -------------------
+__device__ __forceinline__ void u_step_node(const DGrid &g, const DParams &p, const DFields &f, double dt, int i, int j)
+{
+    auto mm = [&](int a, int b) { return ice_mass(p, f, a, b); };
+    auto vv = [&](int a, int b) { return at(f.v, a, b); };
+    const double mi = (mm(i, j) + mm(i - 1, j)) / 2;
+    const double ai = (at(f.a, i, j) + at(f.a, i - 1, j)) / 2;
+    const double abar = (at(f.alpha, i, j) + at(f.alpha, i - 1, j)) / 2;
+    const double dtau = dt / abar;
+    const bool sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
+    const double coef = sis ? p.rho_e * p.Cd * sis_speed_x(p, f, i, j) : 0.0;  // implicit_tx_coefficient
+    const double tbot = sis ? coef * ue_at(p, f, i, j) : 0.0;                  // explicit_tx
+    const double xcross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : -p.f * avg_fc(vv, i, j);
+    const double rheo = (at(f.un, i, j) - at(f.u, i, j)) / dtau / abar;
+    double Gu = -xcross - explicit_tx_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + 0.0 / mi + (0.0 + rheo);
+    Gu = mi <= 0 ? 0.0 : Gu;
+    double tau = (coef - 0.0) / mi * ai;
+    tau = mi <= 0 ? 0.0 : tau;
+    const double uD = (at(f.u, i, j) + dtau * Gu) / (1 + dtau * tau);
+    const double uF = 0.0;  // free_drift = nothing
+    const bool marginal = (mi > 2.220446049250313e-16) & (ai > 2.220446049250313e-16);
+    const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
+    const bool active = !peripheral_fc(g, i, j);
+    at(f.u, i, j) = jl_mul_bool(active_ice ? uD : (marginal ? uF : 0.0), active);
+}
+
+// ---- _v_velocity_step! at one face: se:231-264 with mt:44-74, evp:385,397-401 -------------------
+__device__ __forceinline__ void v_step_node(const DGrid &g, const DParams &p, const DFields &f, double dt, int i, int j)
+{
+    auto mm = [&](int a, int b) { return ice_mass(p, f, a, b); };
+    auto uu = [&](int a, int b) { return at(f.u, a, b); };
+    const double mi = (mm(i, j) + mm(i, j - 1)) / 2;
+    const double ai = (at(f.a, i, j) + at(f.a, i, j - 1)) / 2;
+    const double abar = (at(f.alpha, i, j) + at(f.alpha, i, j - 1)) / 2;
+    const double dtau = dt / abar;
+    const bool sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
+    const double coef = sis ? p.rho_e * p.Cd * sis_speed_y(p, f, i, j) : 0.0;
+    const double tbot = sis ? coef * ve_at(p, f, i, j) : 0.0;
+    const double ycross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : p.f * avg_cf(uu, i, j);
+    const double rheo = (at(f.vn, i, j) - at(f.v, i, j)) / dtau / abar;
+    double Gv = -ycross - explicit_ty_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + 0.0 / mi + (0.0 + rheo);
+    Gv = mi <= 0 ? 0.0 : Gv;
+    double tau = (coef - 0.0) / mi * ai;
+    tau = mi <= 0 ? 0.0 : tau;
+    const double vD = (at(f.v, i, j) + dtau * Gv) / (1 + dtau * tau);
+    const double vF = 0.0;
+    const bool marginal = (mi > 2.220446049250313e-16) & (ai > 2.220446049250313e-16);
+    const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
+    const bool active = !peripheral_cf(g, i, j);
+    at(f.v, i, j) = jl_mul_bool(active_ice ? vD : (marginal ? vF : 0.0), active);
+}
+
+}  // namespace csi

@@ -1,0 +1,139 @@
+// csi_halo.cu -- fill_halo_regions! for one field (Oceananigans BoundaryConditions, restated in
+// SURVEY.md Appendix A): call sites src/SeaIceDynamics/split_explicit_momentum_equations.jl:170-187,
+// src/Rheologies/elasto_visco_plastic_rheology.jl:275-280, src/sea_ice_model.jl:379-394.
+//
+// Order: non-periodic sides first over 1:N of the other axis, periodic sides last over the full
+// parent extent of the other axis, so corners hold periodic images.  Sides that are rank
+// boundaries of a slab partition are left to csi_exchange_halos (`only_local_halos = true`).
+//   no-flux (Center, Bounded):  c[0] = c[1], c[N+1] = c[N]
+//   value   (tangential velocity): c[0] = c[1] + ((c[1]-val)/(D/2))*(-D), c[N+1] = c[N] + ((val-c[N])/(D/2))*D
+//   impenetrable (normal velocity): c[1] = 0, c[N+1] = 0
+#include "csi_internal.h"
+
+namespace csi {
+
+enum { FILL_NONE = 0, FILL_NOFLUX = 1, FILL_VALUE = 2, FILL_IMPENETRABLE = 3 };
+
+__global__ void k_fill_x_periodic(DArr a, int Nx, int Hx)
+{
+    const int pj = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y + 1;
+    if (pj >= a.sy) return;
+    const int j = pj + 1 - a.oy;
+    at(a, 1 - k, j) = at(a, Nx + 1 - k, j);
+    at(a, Nx + k, j) = at(a, k, j);
+}
+
+__global__ void k_fill_y_periodic(DArr a, int Ny, int Hy)
+{
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y + 1;
+    if (pi >= a.sx) return;
+    const int i = pi + 1 - a.ox;
+    at(a, i, 1 - k) = at(a, i, Ny + 1 - k);
+    at(a, i, Ny + k) = at(a, i, k);
+}
+
+__global__ void k_fill_x_bounded(DArr a, int Nx, int Ny, int mode, double val, double D)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (j > Ny) return;
+    if (mode == FILL_NOFLUX) {
+        at(a, 0, j) = at(a, 1, j);
+        at(a, Nx + 1, j) = at(a, Nx, j);
+    } else if (mode == FILL_VALUE) {
+        const double c1 = at(a, 1, j), cN = at(a, Nx, j);
+        at(a, 0, j) = c1 + ((c1 - val) / (D / 2)) * (-D);
+        at(a, Nx + 1, j) = cN + ((val - cN) / (D / 2)) * D;
+    } else if (mode == FILL_IMPENETRABLE) {
+        at(a, 1, j) = 0.0;
+        at(a, Nx + 1, j) = 0.0;
+    }
+}
+
+__global__ void k_fill_y_bounded(DArr a, int Nx, int Ny, int mode, double val, double D, int do_south, int do_north)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > Nx) return;
+    if (mode == FILL_NOFLUX) {
+        if (do_south) at(a, i, 0) = at(a, i, 1);
+        if (do_north) at(a, i, Ny + 1) = at(a, i, Ny);
+    } else if (mode == FILL_VALUE) {
+        const double c1 = at(a, i, 1), cN = at(a, i, Ny);
+        if (do_south) at(a, i, 0) = c1 + ((c1 - val) / (D / 2)) * (-D);
+        if (do_north) at(a, i, Ny + 1) = cN + ((val - cN) / (D / 2)) * D;
+    } else if (mode == FILL_IMPENETRABLE) {
+        if (do_south) at(a, i, 1) = 0.0;
+        if (do_north) at(a, i, Ny + 1) = 0.0;
+    }
+}
+
+void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, const DArr &a, int lx, int ly, int which)
+{
+    if (!a.p) return;
+    const int T = 128;
+    if (g.topo_x == CSI_BOUNDED) {
+        int mode = FILL_NONE;
+        double val = 0.0;
+        if (lx == 0) {
+            mode = FILL_NOFLUX;
+            if (which == 2 && p.v_we_bc == CSI_BC_VALUE) { mode = FILL_VALUE; val = p.v_we_val; }
+        } else if (which == 1) {
+            mode = FILL_IMPENETRABLE;
+        }
+        if (mode != FILL_NONE) {
+            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(a, g.Nx, g.Ny, mode, val, g.dx);
+            ++*c.launches;
+        }
+    }
+    if (g.topo_y == CSI_BOUNDED && !(g.conn_s && g.conn_n)) {
+        int mode = FILL_NONE;
+        double val = 0.0;
+        if (ly == 0) {
+            mode = FILL_NOFLUX;
+            if (which == 1 && p.u_sn_bc == CSI_BC_VALUE) { mode = FILL_VALUE; val = p.u_sn_val; }
+        } else if (which == 2) {
+            mode = FILL_IMPENETRABLE;
+        }
+        if (mode != FILL_NONE) {
+            k_fill_y_bounded<<<(g.Nx + T - 1) / T, T, 0, c.stream>>>(a, g.Nx, g.Ny, mode, val, g.dy, !g.conn_s, !g.conn_n);
+            ++*c.launches;
+        }
+    }
+    if (g.topo_x == CSI_PERIODIC) {
+        k_fill_x_periodic<<<dim3((a.sy + T - 1) / T, g.Hx), T, 0, c.stream>>>(a, g.Nx, g.Hx);
+        ++*c.launches;
+    }
+    if (g.topo_y == CSI_PERIODIC && !g.conn_s && !g.conn_n) {
+        k_fill_y_periodic<<<dim3((a.sx + T - 1) / T, g.Hy), T, 0, c.stream>>>(a, g.Ny, g.Hy);
+        ++*c.launches;
+    }
+}
+
+// mask_immersed_field_xy!: zero a field on peripheral nodes of its own location (immersed grids)
+__global__ void k_mask_immersed(DGrid g, DArr a, int lx, int ly)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+    if (i > g.Nx || j > g.Ny) return;
+    auto imm = [&](int ii, int jj) {
+        const int sx = g.Nx + 2 * g.Hx, sy = g.Ny + 2 * g.Hy;
+        const int pi = min(max(ii - 1 + g.Hx, 0), sx - 1), pj = min(max(jj - 1 + g.Hy, 0), sy - 1);
+        const bool out = (g.topo_x == CSI_BOUNDED && (ii < 1 || ii > g.Nx)) ||
+                         (g.topo_y == CSI_BOUNDED && ((jj < 1 && !g.conn_s) || (jj > g.Ny && !g.conn_n)));
+        return out || g.mask[(size_t)pi + (size_t)pj * sx] != 0;
+    };
+    bool per;
+    if (lx && !ly) per = imm(i - 1, j) || imm(i, j);
+    else if (!lx && ly) per = imm(i, j - 1) || imm(i, j);
+    else per = imm(i, j);
+    if (per) at(a, i, j) = 0.0;
+}
+
+void launch_mask_immersed(const LaunchCtx &c, const DGrid &g, const DArr &a, int lx, int ly)
+{
+    if (!g.mask || !a.p) return;
+    k_mask_immersed<<<dim3((g.Nx + 127) / 128, g.Ny), 128, 0, c.stream>>>(g, a, lx, ly);
+    ++*c.launches;
+}
+
+}  // namespace csi

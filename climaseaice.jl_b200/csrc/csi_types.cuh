@@ -1,0 +1,52 @@
+// csi_types.cuh -- device-side views of the grid, parameters and fields (passed by value).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace csi {
+
+// Oceananigans parent array: element (i, j) (1-based) at p[(i-1+ox) + (j-1+oy)*sx]
+struct DArr {
+    double *p;
+    int sx, sy, ox, oy;
+};
+__device__ __forceinline__ double &at(const DArr &a, int i, int j)
+{
+    return a.p[(size_t)(i - 1 + a.ox) + (size_t)(j - 1 + a.oy) * (size_t)a.sx];
+}
+__device__ __forceinline__ double ld(const DArr &a, int i, int j)
+{
+    return __ldg(a.p + ((size_t)(i - 1 + a.ox) + (size_t)(j - 1 + a.oy) * (size_t)a.sx));
+}
+
+struct DGrid {
+    int Nx, Ny, Hx, Hy;
+    int topo_x, topo_y;     // CSI_PERIODIC / CSI_BOUNDED
+    int conn_s, conn_n;     // slab partition: south / north side is a rank boundary (halo exchanged)
+    double dx, dy, az;      // regular rectilinear metrics; az = dx*dy
+    const uint8_t *mask;    // optional immersed mask at centres (parent-shaped), device pointer
+};
+
+struct DParams {
+    double Pstar, C, em2, Dmin, amin, amax, ca;
+    int pform, cor;
+    double min_mass, min_conc, rho_i, f;
+    int top_kind, bot_kind;
+    double ttx, tty;
+    double rho_e, Cd, ue_c, ve_c;
+    int u_sn_bc, v_we_bc;
+    double u_sn_val, v_we_val;
+    int adv_order, pad_;
+};
+
+struct DFields {
+    DArr u, v, h, a, s11, s22, s12, zf, zc, delta, alpha, un, vn, P;
+    DArr top_x, top_y, ue, ve, Gh, Ga, hm, am, um, vm;
+};
+
+// index window a kernel runs over (inclusive, 1-based reference indices)
+struct Range2 {
+    int i0, i1, j0, j1;
+};
+
+}  // namespace csi

@@ -1,0 +1,85 @@
+"""Glue between synthetic `Case`s and the library: a device-resident SeaIceModel, and a
+host-buffer stepper that goes through the `*_host` entry points of the C ABI (the end-to-end path
+a Julia host with CPU arrays would take)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .model import (Bounded, FPlane, Field, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
+                    SplitExplicitSolver, UpwindBiased, ValueBoundaryCondition, WENO)
+from .synthetic import Case
+
+
+def grid_from_case(case: Case, device=None) -> RectilinearGrid:
+    return RectilinearGrid(size=(case.Nx, case.Ny), x=(0, case.Lx), y=(0, case.Ly), halo=(case.Hx, case.Hy),
+                           topology=(case.topology[0], case.topology[1], "Flat"), device=device)
+
+
+def model_from_case(case: Case, solver_impl="auto", partition=None, device=None) -> SeaIceModel:
+    grid = grid_from_case(case, device)
+    F = case.fields
+    ue = Field((1, 0), grid, F["ue"]) if "ue" in F else 0.0
+    ve = Field((0, 1), grid, F["ve"]) if "ve" in F else 0.0
+    top = dict(u=Field((1, 0), grid, F["top_x"]), v=Field((0, 1), grid, F["top_y"])) if "top_x" in F else None
+    dyn = SeaIceMomentumEquation(grid,
+                                 coriolis=FPlane(case.coriolis_f) if case.coriolis_f is not None else None,
+                                 top_momentum_stress=top,
+                                 bottom_momentum_stress=SemiImplicitStress(ue=ue, ve=ve, rho_e=case.rho_e, Cd=case.Cd),
+                                 solver=SplitExplicitSolver(substeps=case.substeps))
+    bcs = {}
+    if case.u_bc_value is not None:
+        bcs["u"] = dict(north=ValueBoundaryCondition(case.u_bc_value), south=ValueBoundaryCondition(case.u_bc_value))
+    if case.v_bc_value is not None:
+        bcs["v"] = dict(west=ValueBoundaryCondition(case.v_bc_value), east=ValueBoundaryCondition(case.v_bc_value))
+    adv = None if case.advection_order == 0 else (UpwindBiased(1) if case.advection_order == 1 else WENO(case.advection_order))
+    m = SeaIceModel(grid, dynamics=dyn, advection=adv, timestepper=case.timestepper, boundary_conditions=bcs,
+                    solver_impl=solver_impl, partition=partition)
+    m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
+    return m
+
+
+class HostStepper:
+    """Drives csi_time_step_host / csi_evp_substeps_host on pinned host arrays: every call uploads
+    the inputs, runs on the GPU and downloads the results (the end-to-end figure of bench.py)."""
+
+    def __init__(self, case: Case, solver_impl="auto", device_index=0):
+        self.case = case
+        self.model = model_from_case(case, solver_impl=solver_impl, device=f"cuda:{device_index}")
+        self.host = {}
+        for n, fld in self.model.all_fields().items():
+            t = torch.empty(fld.parent.shape, dtype=torch.float64).pin_memory()
+            t.copy_(fld.parent)
+            self.host[n] = t
+        self.fields = L.csi_fields()
+        for n, t in self.host.items():
+            a = L.csi_array()
+            a.ptr = t.data_ptr()
+            a.ny_tot, a.nx_tot = t.shape
+            a.off_x, a.off_y = case.Hx, case.Hy
+            setattr(self.fields, n, a)
+        self.iteration = 0
+
+    @property
+    def h2d_bytes(self):
+        return sum(t.numel() * 8 for t in self.host.values())
+
+    @property
+    def d2h_bytes(self):
+        return sum(self.host[n].numel() * 8 for n in ("u", "v", "h", "a", "s11", "s22", "s12", "alpha"))
+
+    @property
+    def d2h_bytes_momentum(self):
+        return sum(self.host[n].numel() * 8 for n in ("u", "v", "s11", "s22", "s12", "alpha"))
+
+    def time_step(self, dt, nsteps=1):
+        h = self.model._handle
+        L.check(L.lib().csi_time_step_host(h, C.byref(self.fields), float(dt), int(nsteps), 1 if self.iteration == 0 else 0), h)
+        self.iteration += nsteps
+
+    def evp_substeps(self, dt, nsub):
+        h = self.model._handle
+        L.check(L.lib().csi_evp_substeps_host(h, C.byref(self.fields), float(dt), int(nsub)), h)

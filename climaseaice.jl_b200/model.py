@@ -1,0 +1,382 @@
+"""Host-side mirror of the reference's user-facing interface for the hot path.
+
+Julia is not available in this image, so the Julia structs the reference's users touch are
+mirrored here with the same names, keyword arguments and defaults; every compute call goes
+through the C ABI of libclimaseaice_b200.so (the same entry points a Julia `ccall` shim binds,
+see INTEGRATION.md).  torch is used only to own device memory and streams.
+
+    RectilinearGrid(size, x, y, halo, topology)              Oceananigans.Grids
+    ElastoViscoPlasticRheology(...)     src/Rheologies/elasto_visco_plastic_rheology.jl:119-137
+    SplitExplicitSolver(grid; substeps) src/SeaIceDynamics/split_explicit_momentum_equations.jl:18-46
+    SemiImplicitStress(; ue, ve, rho_e, Cd)  src/SeaIceDynamics/sea_ice_external_stress.jl:84-130
+    SeaIceMomentumEquation(grid; ...)   src/SeaIceDynamics/sea_ice_momentum_equations.jl:67-94
+    SeaIceModel(grid; ...)              src/sea_ice_model.jl:140-297
+    time_step!(model, dt)               src/sea_ice_rk_substep.jl:81-94 / src/sea_ice_fe_step.jl:13-34
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field as dc_field
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+Periodic, Bounded, Flat = "Periodic", "Bounded", "Flat"
+Center, Face = 0, 1
+
+
+class RectilinearGrid:
+    """RectilinearGrid(size=(Nx, Ny), x=(x0, x1), y=(y0, y1), halo=(Hx, Hy), topology=(TX, TY, Flat))."""
+
+    def __init__(self, size, x, y, halo=(3, 3), topology=(Periodic, Periodic, Flat), device=None):
+        self.Nx, self.Ny = int(size[0]), int(size[1])
+        self.Hx, self.Hy = int(halo[0]), int(halo[1])
+        self.x, self.y = (float(x[0]), float(x[1])), (float(y[0]), float(y[1]))
+        self.topology = tuple(topology[:2])
+        for t in self.topology:
+            if t not in (Periodic, Bounded):
+                raise ValueError(f"unsupported topology {t!r}")
+        self.dx = (self.x[1] - self.x[0]) / self.Nx
+        self.dy = (self.y[1] - self.y[0]) / self.Ny
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    @property
+    def topo_codes(self):
+        return tuple(L.PERIODIC if t == Periodic else L.BOUNDED for t in self.topology)
+
+    def parent_shape(self, loc):
+        """(sy, sx) of a field's parent: Face fields carry N+1 points along Bounded axes."""
+        sx = self.Nx + 2 * self.Hx + (1 if (loc[0] == Face and self.topology[0] == Bounded) else 0)
+        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] == Bounded) else 0)
+        return sy, sx
+
+    def nodes(self, loc, with_halos=True):
+        """x(i), y(j) coordinate vectors of the parent array of a field at `loc`."""
+        sy, sx = self.parent_shape(loc)
+        i = np.arange(sx) - self.Hx + 1
+        j = np.arange(sy) - self.Hy + 1
+        xs = self.x[0] + ((i - 1) if loc[0] == Face else (i - 0.5)) * self.dx
+        ys = self.y[0] + ((j - 1) if loc[1] == Face else (j - 0.5)) * self.dy
+        return xs, ys
+
+
+class Field:
+    """Oceananigans-layout field: a dense (sy, sx) float64 parent (i fastest) with halos, on the GPU."""
+
+    def __init__(self, loc, grid, data=None):
+        self.loc, self.grid = tuple(loc), grid
+        shp = grid.parent_shape(self.loc)
+        if data is None:
+            self.parent = torch.zeros(shp, dtype=torch.float64, device=grid.device)
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(data, dtype=np.float64))
+            if tuple(t.shape) != shp:
+                raise ValueError(f"parent shape {tuple(t.shape)} != {shp}")
+            self.parent = t.to(grid.device).contiguous()
+
+    @property
+    def interior(self):
+        g = self.grid
+        sy, sx = self.parent.shape
+        return self.parent[g.Hy:sy - g.Hy, g.Hx:sx - g.Hx]
+
+    def set(self, value):
+        """set!(field, value): a number, an (x, y) function, or an interior-shaped / parent-shaped array."""
+        g = self.grid
+        if callable(value):
+            xs, ys = g.nodes(self.loc)
+            X, Y = np.meshgrid(xs, ys)
+            arr = np.asarray(value(X, Y), dtype=np.float64)
+            self.interior.copy_(torch.as_tensor(arr[g.Hy:arr.shape[0] - g.Hy, g.Hx:arr.shape[1] - g.Hx]).to(self.parent.device))
+        elif np.isscalar(value):
+            self.interior.fill_(float(value))
+        else:
+            arr = torch.as_tensor(np.asarray(value, dtype=np.float64)).to(self.parent.device)
+            if tuple(arr.shape) == tuple(self.parent.shape):
+                self.parent.copy_(arr)
+            else:
+                self.interior.copy_(arr)
+        return self
+
+    def as_csi(self):
+        a = L.csi_array()
+        a.ptr = self.parent.data_ptr()
+        a.ny_tot, a.nx_tot = self.parent.shape
+        a.off_x, a.off_y = self.grid.Hx, self.grid.Hy
+        return a
+
+    def numpy(self):
+        return self.parent.detach().cpu().numpy()
+
+
+@dataclass
+class ElastoViscoPlasticRheology:
+    ice_compressive_strength: float = 27500.0
+    ice_compaction_hardening: float = 20.0
+    yield_curve_eccentricity: float = 2.0
+    minimum_plastic_stress: float = 2e-9
+    min_relaxation_parameter: float = 50.0
+    max_relaxation_parameter: float = 300.0
+    relaxation_strength: float = math.pi ** 2
+    pressure_formulation: str = "ReplacementPressure"  # or "IceStrength"
+
+
+@dataclass
+class SplitExplicitSolver:
+    substeps: int = 120  # SplitExplicitSolver(grid; substeps=120)
+
+
+@dataclass
+class SemiImplicitStress:
+    ue: object = 0.0  # Field (f,c), or a number (ConstantField / ZeroField)
+    ve: object = 0.0  # Field (c,f), or a number
+    rho_e: float = 1026.0
+    Cd: float = 5.5e-3
+
+
+@dataclass
+class FPlane:
+    f: float = 1e-4
+
+
+@dataclass
+class WENO:
+    order: int = 5
+
+
+@dataclass
+class UpwindBiased:
+    order: int = 1
+
+
+@dataclass
+class ValueBoundaryCondition:
+    value: float = 0.0
+
+
+class SeaIceMomentumEquation:
+    def __init__(self, grid, coriolis=None, rheology=None, top_momentum_stress=None, bottom_momentum_stress=None,
+                 free_drift=None, solver=None, minimum_concentration=1e-3, minimum_mass=1.0):
+        if free_drift is not None:
+            raise NotImplementedError("free_drift other than `nothing` is a next-tier item (SURVEY section 8f)")
+        self.grid = grid
+        self.coriolis = coriolis
+        self.rheology = rheology or ElastoViscoPlasticRheology()
+        self.solver = solver or SplitExplicitSolver(substeps=150)
+        self.top = top_momentum_stress
+        self.bottom = bottom_momentum_stress
+        self.minimum_concentration = float(minimum_concentration)
+        self.minimum_mass = float(minimum_mass)
+        if self.bottom is not None and not isinstance(self.bottom, SemiImplicitStress):
+            raise NotImplementedError("bottom_momentum_stress must be `nothing` or a SemiImplicitStress")
+        # Auxiliaries(r::ElastoViscoPlasticRheology, grid): evp.jl:140-173
+        c, f = Center, Face
+        self.auxiliaries = dict(
+            s11=Field((c, c), grid), s22=Field((c, c), grid), s12=Field((f, f), grid),
+            zeta_f=Field((f, f), grid), zeta_c=Field((c, c), grid), delta=Field((c, c), grid),
+            alpha=Field((c, c), grid), un=Field((f, c), grid), vn=Field((c, f), grid), P=Field((c, c), grid))
+        self.auxiliaries["alpha"].parent.fill_(self.rheology.max_relaxation_parameter)  # evp.jl:161
+
+
+class SeaIceModel:
+    """SeaIceModel(grid; dynamics, advection, timestepper=:SplitRungeKutta3, boundary_conditions, ice_density=900)."""
+
+    def __init__(self, grid, dynamics=None, advection=None, timestepper="SplitRungeKutta3", boundary_conditions=None,
+                 ice_density=900.0, ice_thermodynamics=None, solver_impl="auto", immersed_mask=None,
+                 partition=None):
+        if ice_thermodynamics is not None:
+            raise NotImplementedError("thermodynamics is outside the hot path (SURVEY section 8f)")
+        if dynamics is None:
+            raise ValueError("this drop-in accelerates the dynamics path: pass a SeaIceMomentumEquation")
+        self.grid, self.dynamics = grid, dynamics
+        self.advection = advection
+        self.timestepper = timestepper
+        if timestepper not in ("SplitRungeKutta3", "ForwardEuler"):
+            raise ValueError(timestepper)
+        c, f = Center, Face
+        self.velocities = dict(u=Field((f, c), grid), v=Field((c, f), grid))
+        self.ice_thickness = Field((c, c), grid)
+        self.ice_concentration = Field((c, c), grid)
+        self.sea_ice_density = float(ice_density)
+        self.Gn = dict(h=Field((c, c), grid), a=Field((c, c), grid))
+        rk = timestepper == "SplitRungeKutta3"
+        self.Psi_m = dict(h=Field((c, c), grid), a=Field((c, c), grid), u=Field((f, c), grid), v=Field((c, f), grid)) if rk else None
+        self.iteration = 0
+        self.time = 0.0
+        bcs = boundary_conditions or {}
+        self._u_bc = bcs.get("u", {})
+        self._v_bc = bcs.get("v", {})
+        self.partition = partition  # (rank, nranks, exchange_every) for slab runs
+        self._mask = None if immersed_mask is None else np.ascontiguousarray(immersed_mask, dtype=np.uint8)
+        self._handle = C.c_void_p()
+        self._solver_impl = dict(auto=L.SOLVER_AUTO, unfused=L.SOLVER_UNFUSED, fused=L.SOLVER_FUSED)[solver_impl]
+        cfg = self._config()
+        L.check(L.lib().csi_create(C.byref(cfg), C.byref(self._handle)))
+        self._cfg = cfg
+
+    # -- configuration -> csi_config ---------------------------------------------------------
+    def _config(self):
+        g, d = self.grid, self.dynamics
+        r = d.rheology
+        cfg = L.csi_config()
+        cfg.abi_version = L.ABI_VERSION
+        cfg.device = g.device.index or 0
+        cfg.Nx, cfg.Ny, cfg.Hx, cfg.Hy = g.Nx, g.Ny, g.Hx, g.Hy
+        cfg.topo_x, cfg.topo_y = g.topo_codes
+        cfg.dx, cfg.dy = g.dx, g.dy
+        cfg.immersed_mask = self._mask.ctypes.data if self._mask is not None else None
+        cfg.ice_compressive_strength = r.ice_compressive_strength
+        cfg.ice_compaction_hardening = r.ice_compaction_hardening
+        cfg.yield_curve_eccentricity = r.yield_curve_eccentricity
+        cfg.minimum_plastic_stress = r.minimum_plastic_stress
+        cfg.min_relaxation_parameter = r.min_relaxation_parameter
+        cfg.max_relaxation_parameter = r.max_relaxation_parameter
+        cfg.relaxation_strength = r.relaxation_strength
+        cfg.pressure_formulation = L.ICE_STRENGTH if r.pressure_formulation == "IceStrength" else L.REPLACEMENT_PRESSURE
+        cfg.substeps = d.solver.substeps
+        cfg.minimum_mass, cfg.minimum_concentration = d.minimum_mass, d.minimum_concentration
+        cfg.ice_density = self.sea_ice_density
+        cfg.coriolis_kind = L.CORIOLIS_FPLANE if d.coriolis is not None else L.CORIOLIS_NONE
+        cfg.coriolis_f = d.coriolis.f if d.coriolis is not None else 0.0
+        top = d.top
+        if top is None:
+            cfg.top_stress_kind = L.STRESS_NONE
+        elif isinstance(top, dict) and isinstance(top["u"], Field):
+            cfg.top_stress_kind = L.STRESS_FIELD
+        elif isinstance(top, dict):
+            cfg.top_stress_kind = L.STRESS_CONST
+            cfg.top_tau_x, cfg.top_tau_y = float(top["u"]), float(top["v"])
+        else:
+            raise NotImplementedError("top_momentum_stress must be nothing or (u=..., v=...)")
+        if d.bottom is None:
+            cfg.bottom_stress_kind = L.STRESS_NONE
+        else:
+            cfg.bottom_stress_kind = L.STRESS_SEMI_IMPLICIT
+            cfg.rho_e, cfg.Cd = d.bottom.rho_e, d.bottom.Cd
+            if not isinstance(d.bottom.ue, Field):
+                cfg.ue_const, cfg.ve_const = float(d.bottom.ue), float(d.bottom.ve)
+        for side in ("south", "north"):
+            if side in self._u_bc:
+                cfg.u_south_north_bc, cfg.u_south_north_value = L.BC_VALUE, float(self._u_bc[side].value)
+        for side in ("west", "east"):
+            if side in self._v_bc:
+                cfg.v_west_east_bc, cfg.v_west_east_value = L.BC_VALUE, float(self._v_bc[side].value)
+        cfg.advection_order = 0 if self.advection is None else int(self.advection.order)
+        cfg.timestepper = L.RK3 if self.timestepper == "SplitRungeKutta3" else L.FE
+        cfg.solver_impl = self._solver_impl
+        if self.partition:
+            cfg.rank, cfg.nranks, cfg.exchange_every = self.partition
+        else:
+            cfg.rank, cfg.nranks, cfg.exchange_every = 0, 1, 0
+        return cfg
+
+    # -- fields -> csi_fields ----------------------------------------------------------------
+    def all_fields(self):
+        d = self.dynamics
+        out = dict(u=self.velocities["u"], v=self.velocities["v"], h=self.ice_thickness, a=self.ice_concentration,
+                   Gh=self.Gn["h"], Ga=self.Gn["a"])
+        out.update(d.auxiliaries)
+        if self.Psi_m:
+            out.update(hm=self.Psi_m["h"], am=self.Psi_m["a"], um=self.Psi_m["u"], vm=self.Psi_m["v"])
+        if isinstance(d.top, dict) and isinstance(d.top["u"], Field):
+            out.update(top_x=d.top["u"], top_y=d.top["v"])
+        if d.bottom is not None and isinstance(d.bottom.ue, Field):
+            out.update(ue=d.bottom.ue, ve=d.bottom.ve)
+        return out
+
+    def csi_fields(self):
+        f = L.csi_fields()
+        for n, fld in self.all_fields().items():
+            setattr(f, n, fld.as_csi())
+        return f
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.grid.device).cuda_stream)
+
+    # -- the reference's methods -----------------------------------------------------------------
+    def set(self, **kw):
+        """set!(model, h=..., ℵ=..., u=..., v=...) (use `a` for ℵ)."""
+        targets = dict(h=self.ice_thickness, a=self.ice_concentration, u=self.velocities["u"], v=self.velocities["v"])
+        for k, v in kw.items():
+            targets["a" if k in ("ℵ", "aice") else k].set(v)
+        return self
+
+    def time_step_momentum(self, dt, substeps=None):
+        """time_step_momentum!(model, dynamics, dt)"""
+        f = self.csi_fields()
+        n = self.dynamics.solver.substeps if substeps is None else int(substeps)
+        L.check(L.lib().csi_evp_substeps(self._handle, C.byref(f), float(dt), n, self._stream()), self._handle)
+
+    def compute_tracer_tendencies(self):
+        f = self.csi_fields()
+        L.check(L.lib().csi_compute_tracer_tendencies(self._handle, C.byref(f), self._stream()), self._handle)
+
+    def dynamic_time_step(self, dt):
+        f = self.csi_fields()
+        L.check(L.lib().csi_dynamic_time_step(self._handle, C.byref(f), float(dt), self._stream()), self._handle)
+
+    def cache_current_fields(self):
+        f = self.csi_fields()
+        L.check(L.lib().csi_cache_current_fields(self._handle, C.byref(f), self._stream()), self._handle)
+
+    def update_state(self):
+        f = self.csi_fields()
+        L.check(L.lib().csi_update_state(self._handle, C.byref(f), self._stream()), self._handle)
+
+    def time_step(self, dt):
+        """time_step!(model, dt)"""
+        f = self.csi_fields()
+        L.check(L.lib().csi_time_step(self._handle, C.byref(f), float(dt), 1 if self.iteration == 0 else 0, self._stream()),
+                self._handle)
+        self.iteration += 1
+        self.time += dt
+
+    def cell_advection_timescale(self):
+        f = self.csi_fields()
+        out = C.c_double()
+        L.check(L.lib().csi_cell_advection_timescale(self._handle, C.byref(f), C.byref(out), self._stream()), self._handle)
+        return out.value
+
+    def diagnostics(self):
+        f = self.csi_fields()
+        out = (C.c_double * 5)()
+        L.check(L.lib().csi_diagnostics(self._handle, C.byref(f), out, self._stream()), self._handle)
+        return dict(zip(("sum_h_Az", "sum_a_Az", "sum_ha_Az", "max_abs_u", "max_abs_v"), out))
+
+    def comm_init(self, unique_id: bytes):
+        rank, nranks, _ = self.partition
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        L.check(L.lib().csi_comm_init(self._handle, buf, rank, nranks), self._handle)
+
+    @property
+    def launch_count(self):
+        return L.lib().csi_launch_count(self._handle)
+
+    @property
+    def last_elapsed_ms(self):
+        return L.lib().csi_last_elapsed_ms(self._handle)
+
+    def close(self):
+        if self._handle:
+            L.lib().csi_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def time_step_b(model, dt):
+    """time_step!(model, dt) -- free-function spelling of the reference's API."""
+    model.time_step(dt)
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    L.check(L.lib().csi_nccl_unique_id(buf))
+    return bytes(buf)

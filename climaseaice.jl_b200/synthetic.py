@@ -1,0 +1,157 @@
+"""Seeded synthetic inputs for the hot path, as host numpy arrays.
+
+A `Case` is plain data -- sizes, physical settings and parent arrays (C-order (sy, sx), i fastest)
+-- so the same arrays can be fed to the GPU library and to the CPU oracle.  Configurations:
+
+  anticyclone_case(N): BASELINE config 1/2 -- examples/ice_advected_by_anticyclone.jl:35-126 scaled
+      to N x N (Bounded x Bounded, dx = 4 km, FPlane, wind-stress arrays, SemiImplicitStress ocean drag).
+  periodic_case(N):    BASELINE config 3 -- doubly periodic variant with every mask branch live.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SEED = 20260417
+
+
+@dataclass
+class Case:
+    name: str
+    Nx: int
+    Ny: int
+    Hx: int
+    Hy: int
+    topology: tuple          # ("Periodic"|"Bounded", "Periodic"|"Bounded")
+    Lx: float
+    Ly: float
+    dt: float = 120.0
+    substeps: int = 150
+    coriolis_f: float | None = 1e-4
+    advection_order: int = 7
+    timestepper: str = "SplitRungeKutta3"
+    u_bc_value: float | None = None   # ValueBoundaryCondition on u north/south (Bounded y)
+    v_bc_value: float | None = None   # ValueBoundaryCondition on v west/east (Bounded x)
+    rho_e: float = 1026.0
+    Cd: float = 5.5e-3
+    fields: dict = field(default_factory=dict)   # h, a, u, v, top_x, top_y, ue, ve parents
+
+    @property
+    def dx(self):
+        return self.Lx / self.Nx
+
+    @property
+    def dy(self):
+        return self.Ly / self.Ny
+
+    def parent_shape(self, loc):
+        sx = self.Nx + 2 * self.Hx + (1 if (loc[0] and self.topology[0] == "Bounded") else 0)
+        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] and self.topology[1] == "Bounded") else 0)
+        return sy, sx
+
+    def nodes(self, loc):
+        sy, sx = self.parent_shape(loc)
+        i = np.arange(sx) - self.Hx + 1
+        j = np.arange(sy) - self.Hy + 1
+        x = ((i - 1) if loc[0] else (i - 0.5)) * self.dx
+        y = ((j - 1) if loc[1] else (j - 0.5)) * self.dy
+        return np.meshgrid(x, y)
+
+
+LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1))
+
+
+def _wrap_periodic(case: Case, arr, loc):
+    """Fill halos of a host array with periodic images along Periodic axes (initial state only)."""
+    Hx, Hy, Nx, Ny = case.Hx, case.Hy, case.Nx, case.Ny
+    if case.topology[0] == "Periodic":
+        arr[:, :Hx] = arr[:, Nx:Nx + Hx]
+        arr[:, Nx + Hx:Nx + 2 * Hx] = arr[:, Hx:2 * Hx]
+    if case.topology[1] == "Periodic":
+        arr[:Hy, :] = arr[Ny:Ny + Hy, :]
+        arr[Ny + Hy:Ny + 2 * Hy, :] = arr[Hy:2 * Hy, :]
+    return arr
+
+
+def periodic_case(N, Ny=None, H=7, seed=SEED, aice="mixed", substeps=150, dt=120.0, advection_order=7,
+                  timestepper="SplitRungeKutta3", moving=True) -> Case:
+    """Doubly periodic domain, L = N * 4 km, smooth fields + seeded noise."""
+    Ny = N if Ny is None else Ny
+    c = Case("periodic", N, Ny, H, H, ("Periodic", "Periodic"), N * 4000.0, Ny * 4000.0, dt=dt, substeps=substeps,
+             advection_order=advection_order, timestepper=timestepper)
+    rng = np.random.default_rng(seed)
+    tp = 2 * np.pi
+    X, Y = c.nodes(LOC["h"])
+    h = 0.3 + 0.005 * (np.sin(3 * tp * X / c.Lx) + np.sin(2 * tp * Y / c.Ly)) + 1e-3 * rng.uniform(-1, 1, X.shape)
+    if aice == "ones":
+        a = np.ones_like(h)
+    else:
+        a = 0.9 + 0.1 * rng.uniform(0, 1, X.shape)
+        r = rng.uniform(0, 1, X.shape)
+        # a 5 % patch of marginal ice (below minimum_concentration) and 2 % of open water
+        patch = (np.abs(X / c.Lx - 0.3) < 0.11) & (np.abs(Y / c.Ly - 0.6) < 0.11)
+        a = np.where(patch & (r < 0.9), 5e-4 * r, a)
+        zero = (np.abs(X / c.Lx - 0.7) < 0.07) & (np.abs(Y / c.Ly - 0.25) < 0.07)
+        a = np.where(zero, 0.0, a)
+        h = np.where(zero, 0.0, h)
+    Xu, Yu = c.nodes(LOC["u"])
+    Xv, Yv = c.nodes(LOC["v"])
+    amp = 0.05 if moving else 0.0
+    u = amp * np.sin(tp * Yu / c.Ly) * np.cos(tp * Xu / c.Lx)
+    v = -amp * np.sin(tp * Xv / c.Lx) * np.cos(tp * Yv / c.Ly)
+    ue = 0.01 * np.sin(tp * Yu / c.Ly)
+    ve = 0.01 * np.sin(tp * Xv / c.Lx)
+    tx = 0.1 * np.sin(tp * Yu / c.Ly)
+    ty = 0.1 * np.cos(tp * Xv / c.Lx)
+    raw = dict(h=h, a=a, u=u, v=v, ue=ue, ve=ve, top_x=tx, top_y=ty)
+    c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
+    return c
+
+
+def anticyclone_case(N, H=7, seed=SEED, substeps=150, dt=120.0, advection_order=7, noise=1e-3,
+                     timestepper="SplitRungeKutta3") -> Case:
+    """examples/ice_advected_by_anticyclone.jl scaled to N x N at dx = 4 km (N = 128 is the shipped case)."""
+    L = N * 4000.0
+    c = Case("anticyclone", N, N, H, H, ("Bounded", "Bounded"), L, L, dt=dt, substeps=substeps,
+             advection_order=advection_order, timestepper=timestepper, u_bc_value=0.0, v_bc_value=0.0)
+    rng = np.random.default_rng(seed)
+    vo, va = 0.01, 30.0
+    s = L / 512e3  # stretch the eddy with the domain so every cell stays active at large N
+    Xc, Yc = c.nodes(LOC["h"])
+    Xu, Yu = c.nodes(LOC["u"])
+    Xv, Yv = c.nodes(LOC["v"])
+
+    def wind(x, y):
+        cen = 256e3 * s
+        r = np.sqrt((x - cen) ** 2 + (y - cen) ** 2)
+        sp = 1 / 100 * np.exp(-r / (100e3 * s))
+        ua = -va * sp * (np.cos(np.deg2rad(72)) * (x - cen) + np.sin(np.deg2rad(72)) * (y - cen)) / (1000 * s)
+        vaa = -va * sp * (-np.sin(np.deg2rad(72)) * (x - cen) + np.cos(np.deg2rad(72)) * (y - cen)) / (1000 * s)
+        return ua, vaa
+
+    uau, vau = wind(Xu, Yu)
+    uav, vav = wind(Xv, Yv)
+    tx = -uau * np.sqrt(uau ** 2 + vau ** 2) * 1.3 * 1.2e-3
+    ty = -vav * np.sqrt(uav ** 2 + vav ** 2) * 1.3 * 1.2e-3
+    ue = vo * (2 * Yu - L) / L
+    ve = vo * (L - 2 * Xv) / L
+    h = 0.3 + 0.005 * (np.sin(60 * Xc / 1000e3) + np.sin(30 * Yc / 1000e3)) + noise * rng.uniform(-1, 1, Xc.shape)
+    a = np.ones_like(h)
+    raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=ue, ve=ve, top_x=tx, top_y=ty)
+    c.fields = {k: np.ascontiguousarray(vv, dtype=np.float64) for k, vv in raw.items()}
+    return c
+
+
+def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
+    """Rank-local y-slab of a doubly periodic case with halo Hy (periodic images filled in)."""
+    assert case.topology == ("Periodic", "Periodic") and case.Ny % nranks == 0
+    ny = case.Ny // nranks
+    c = Case(case.name + f"-slab{rank}", case.Nx, ny, case.Hx, Hy, case.topology, case.Lx, case.Ly / nranks,
+             dt=case.dt, substeps=case.substeps, coriolis_f=case.coriolis_f, advection_order=case.advection_order,
+             timestepper=case.timestepper, rho_e=case.rho_e, Cd=case.Cd)
+    for k, arr in case.fields.items():
+        interior = arr[case.Hy:case.Hy + case.Ny, :]
+        rows = (np.arange(rank * ny - Hy, (rank + 1) * ny + Hy)) % case.Ny
+        c.fields[k] = np.ascontiguousarray(interior[rows, :])
+    return c

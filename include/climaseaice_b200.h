@@ -1,0 +1,186 @@
+/*
+ * climaseaice_b200.h -- C ABI of libclimaseaice_b200.so
+ *
+ * A B200-native (sm_100a) drop-in for ONE hot path of CliMA/ClimaSeaIce.jl v0.5.8: the
+ * split-explicit EVP momentum substep loop plus the h / aice advection update.  The reference
+ * has no FFI: its seam is Julia multiple dispatch.  Each entry point below replaces the method
+ * named beside it (paths relative to the reference tree); a Julia host overrides those methods
+ * for a `B200()` architecture tag and `ccall`s this library (INTEGRATION.md shows the shim).
+ *
+ * Data contract
+ *   - Every field is an Oceananigans `Field.data` parent: dense, column-major, i fastest,
+ *     Float64, extents (Nx + 2Hx [+1 if Face on a Bounded x]) x (Ny + 2Hy [+1 ...]) x 1.
+ *     Element (i, j) (1-based Julia index) lives at ptr[(i-1+off_x) + (j-1+off_y)*nx_tot].
+ *   - The caller owns every field buffer; the library updates them in place and owns only
+ *     scratch inside the handle (checkpointing / output on the Julia side keep working).
+ *   - Device entry points take DEVICE pointers and are asynchronous on the given CUDA stream.
+ *     `*_host` entry points take HOST pointers and include the host<->device copies.
+ *   - All functions return 0 on success, <0 for argument/shape errors, >0 for CUDA/NCCL errors;
+ *     `csi_last_error` returns the message.  Nothing throws or exits across the ABI.  There is no
+ *     CPU fallback: without a CUDA device every compute entry point fails with CSI_ERR_NO_DEVICE.
+ */
+#ifndef CLIMASEAICE_B200_H
+#define CLIMASEAICE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSI_ABI_VERSION 1
+
+typedef struct csi_handle csi_handle;
+typedef void *csi_stream; /* cudaStream_t */
+
+typedef struct {
+    double *ptr;            /* parent array base (device or host, see entry point) */
+    int32_t nx_tot, ny_tot; /* parent extents */
+    int32_t off_x, off_y;   /* halo offsets (Hx, Hy of the grid the field lives on) */
+} csi_array;
+
+enum { CSI_PERIODIC = 0, CSI_BOUNDED = 1 };
+enum { CSI_STRESS_NONE = 0, CSI_STRESS_CONST = 1, CSI_STRESS_FIELD = 2, CSI_STRESS_SEMI_IMPLICIT = 3 };
+enum { CSI_REPLACEMENT_PRESSURE = 0, CSI_ICE_STRENGTH = 1 };
+enum { CSI_CORIOLIS_NONE = 0, CSI_CORIOLIS_FPLANE = 1 };
+enum { CSI_BC_DEFAULT = 0, CSI_BC_VALUE = 1 };
+enum { CSI_RK3 = 0, CSI_FE = 1 };
+enum { CSI_SOLVER_AUTO = 0, CSI_SOLVER_UNFUSED = 1, CSI_SOLVER_FUSED = 2 };
+
+enum {
+    CSI_OK = 0,
+    CSI_ERR_ARG = -1,         /* null pointer, bad enum, non-positive size */
+    CSI_ERR_SHAPE = -2,       /* a csi_array does not match the grid */
+    CSI_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here yet */
+    CSI_ERR_NO_DEVICE = -4,   /* no CUDA device / wrong architecture */
+    CSI_ERR_NCCL_MISSING = -5
+};
+
+/* Mirrors the keyword constructors of the reference:
+ *   RectilinearGrid(size, x, y, halo, topology)                       (Oceananigans)
+ *   ElastoViscoPlasticRheology(...)      src/Rheologies/elasto_visco_plastic_rheology.jl:119-137
+ *   SplitExplicitSolver(grid; substeps)  src/SeaIceDynamics/split_explicit_momentum_equations.jl:18-46
+ *   SeaIceMomentumEquation(grid; ...)    src/SeaIceDynamics/sea_ice_momentum_equations.jl:67-94
+ *   SemiImplicitStress(; ue, ve, rho_e, Cd)  src/SeaIceDynamics/sea_ice_external_stress.jl:84-130
+ *   SeaIceModel(grid; advection, timestepper, boundary_conditions)  src/sea_ice_model.jl:140-158 */
+typedef struct {
+    int32_t abi_version; /* CSI_ABI_VERSION */
+    int32_t device;      /* CUDA device ordinal */
+    /* grid (the local block when partitioned) */
+    int32_t Nx, Ny, Hx, Hy;
+    int32_t topo_x, topo_y;
+    double dx, dy;
+    const uint8_t *immersed_mask; /* optional, centres, (Nx+2Hx) x (Ny+2Hy), 1 = immersed; NULL = none */
+    /* ElastoViscoPlasticRheology */
+    double ice_compressive_strength; /* P*   = 27500 */
+    double ice_compaction_hardening; /* C    = 20    */
+    double yield_curve_eccentricity; /* e    = 2     */
+    double minimum_plastic_stress;   /* Dmin = 2e-9  */
+    double min_relaxation_parameter; /* 50  */
+    double max_relaxation_parameter; /* 300 */
+    double relaxation_strength;      /* pi^2 */
+    int32_t pressure_formulation;
+    /* SplitExplicitSolver */
+    int32_t substeps;
+    /* SeaIceMomentumEquation */
+    double minimum_mass, minimum_concentration, ice_density;
+    int32_t coriolis_kind;
+    int32_t top_stress_kind;    /* NONE / CONST / FIELD (tau arrays in csi_fields.top_x/top_y) */
+    double coriolis_f;
+    double top_tau_x, top_tau_y;
+    int32_t bottom_stress_kind; /* NONE / SEMI_IMPLICIT (ue/ve arrays, or constants if ptr NULL) */
+    int32_t u_south_north_bc;   /* tangential BC of u on Bounded y: DEFAULT (no-flux) or VALUE */
+    double rho_e, Cd, ue_const, ve_const;
+    double u_south_north_value;
+    int32_t v_west_east_bc;
+    int32_t advection_order;    /* 0 none, 1 upwind, 3/5/7 WENO(order) */
+    double v_west_east_value;
+    int32_t timestepper;        /* CSI_RK3 (":SplitRungeKutta3", default) or CSI_FE */
+    int32_t solver_impl;        /* CSI_SOLVER_* : kernel formulation used by csi_evp_substeps */
+    /* slab partition along y (rank-local block; halos of connected sides are exchanged) */
+    int32_t rank, nranks;
+    int32_t exchange_every;     /* K: substeps between halo exchanges (needs Hy >= 2K+3) */
+    int32_t reserved_;
+} csi_config;
+
+/* The arrays the hot path touches.  Unused ones may have ptr == NULL. */
+typedef struct {
+    csi_array u, v;                 /* model.velocities      (f,c) (c,f) */
+    csi_array h, a;                 /* ice_thickness, ice_concentration (c,c) */
+    csi_array s11, s22, s12;        /* auxiliaries.fields sigma11, sigma22 (c,c), sigma12 (f,f) */
+    csi_array zeta_f, zeta_c, delta, alpha, un, vn, P; /* remaining EVP auxiliaries (evp.jl:147-169) */
+    csi_array top_x, top_y;         /* top stress tau_x (f,c), tau_y (c,f) when FIELD */
+    csi_array ue, ve;               /* SemiImplicitStress external velocities (f,c) (c,f) */
+    csi_array Gh, Ga;               /* timestepper.G^n.h, .aice */
+    csi_array hm, am, um, vm;       /* timestepper.Psi^- (RK3) */
+} csi_fields;
+
+int csi_version(void);
+const char *csi_last_error(const csi_handle *h); /* h may be NULL: last error of csi_create */
+
+/* SeaIceModel(...) construction point: src/sea_ice_model.jl:140-297 */
+int csi_create(const csi_config *cfg, csi_handle **out);
+int csi_destroy(csi_handle *h);
+
+/* time_step_momentum!(model, ::SplitExplicitMomentumEquation, dt)
+ *   src/SeaIceDynamics/split_explicit_momentum_equations.jl:103-195
+ * = reset_velocities! (:87-93) + initialize_rheology! (evp.jl:192-216) + update_external_stress!
+ *   (sea_ice_external_stress.jl:72-78) + nsubsteps x {compute_stresses! (evp.jl:222-354);
+ *   alternating _u/_v_velocity_step! (:197-264) with local halo fills} + finalize_rheology!
+ *   (evp.jl:275-280). */
+int csi_evp_substeps(csi_handle *h, const csi_fields *f, double dt_stage, int32_t nsubsteps, csi_stream stream);
+
+/* compute_tracer_tendencies!(model)  src/tracer_tendency_kernel_functions.jl:9-45 */
+int csi_compute_tracer_tendencies(csi_handle *h, const csi_fields *f, csi_stream stream);
+/* dynamic_time_step!(model, dt)      src/sea_ice_rk_substep.jl:134-152, src/sea_ice_fe_step.jl:36-82 */
+int csi_dynamic_time_step(csi_handle *h, const csi_fields *f, double dt_stage, csi_stream stream);
+/* cache_current_fields!(model)       src/sea_ice_rk_substep.jl:29-42 */
+int csi_cache_current_fields(csi_handle *h, const csi_fields *f, csi_stream stream);
+/* update_state!(model)               src/sea_ice_model.jl:379-394 (mask + halo fill of h, aice, u, v) */
+int csi_update_state(csi_handle *h, const csi_fields *f, csi_stream stream);
+/* fill_halo_regions!(field): loc_x/loc_y 0 = Center, 1 = Face; which 0 = default BCs, 1 = u, 2 = v */
+int csi_fill_halos(csi_handle *h, const csi_array *a, int32_t loc_x, int32_t loc_y, int32_t which, csi_stream stream);
+/* time_step!(model, dt): src/sea_ice_fe_step.jl:13-34 / src/sea_ice_rk_substep.jl:81-94 driven by
+ * Oceananigans' SplitRungeKuttaTimeStepper; first != 0 mirrors `clock.iteration == 0`. */
+int csi_time_step(csi_handle *h, const csi_fields *f, double dt, int32_t first, csi_stream stream);
+/* cell_advection_timescale(model)    src/ClimaSeaIce.jl:66-69; synchronises the stream */
+int csi_cell_advection_timescale(csi_handle *h, const csi_fields *f, double *out_host, csi_stream stream);
+/* diagnostics (deterministic two-pass reductions; synchronises the stream):
+ * out[0] = sum h*Az, out[1] = sum aice*Az, out[2] = sum h*aice*Az, out[3] = max|u|, out[4] = max|v| */
+int csi_diagnostics(csi_handle *h, const csi_fields *f, double *out_host5, csi_stream stream);
+
+/* Same as csi_time_step but with HOST buffers: uploads every non-NULL array, runs `nsteps` model
+ * steps, downloads u, v, h, a, s11, s22, s12, alpha.  Blocking.  Used for the end-to-end metric. */
+int csi_time_step_host(csi_handle *h, const csi_fields *host_fields, double dt, int32_t nsteps, int32_t first);
+/* Same for the momentum solve alone (time_step_momentum! with host buffers). */
+int csi_evp_substeps_host(csi_handle *h, const csi_fields *host_fields, double dt_stage, int32_t nsubsteps);
+
+/* Multi-GPU (one process per GPU, slabs along y).  The 128-byte NCCL unique id is produced on
+ * rank 0 and distributed by the host application (torch.distributed / MPI.jl broadcast). */
+int csi_nccl_unique_id(uint8_t out128[128]);
+int csi_comm_init(csi_handle *h, const uint8_t id128[128], int32_t rank, int32_t nranks);
+/* distributed fill_halo_regions! of one field across slab neighbours (Oceananigans
+ * DistributedComputations, used at src/sea_ice_model.jl:381-384, evp.jl:275-280) */
+int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream);
+
+/* Instrumentation: kernels launched by this handle so far; elapsed ms of the last device call
+ * measured with CUDA events on its stream. */
+int64_t csi_launch_count(const csi_handle *h);
+double csi_last_elapsed_ms(const csi_handle *h);
+
+/* Launches the dominant kernel of csi_evp_substeps (the fused substep kernel, or the stress kernel of
+ * the unfused formulation) `reps` times between two CUDA events on `stream` and returns the average
+ * duration per launch, its name and its algorithmic bytes per cell.  Advances the state
+ * by `reps` stress updates; for bench.py's roofline only.  Synchronises the stream. */
+int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage, int32_t reps, double *out_ms_per_launch,
+                             char *name64, int32_t *bytes_per_cell, csi_stream stream);
+
+/* Host-side helpers exported for CPU tests (no GPU needed). */
+double csi_host_exp(double x);                       /* the correctly rounded exp used for ice_strength */
+double csi_host_div_by_const(double x, double c);    /* the Markstein constant-division used in the kernels */
+int csi_host_halo_width(int32_t substeps_between_exchanges); /* 2K+3, se.jl:55-56 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

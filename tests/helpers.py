@@ -1,0 +1,57 @@
+"""Test helpers: build the CPU oracle from a synthetic Case, and compare fields.
+
+The oracle is the checker: it is imported only here, in smoke() and in bench.py's CPU legs."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle as O
+
+
+def oracle_params(case) -> dict:
+    p = dict(substeps=case.substeps, advection_order=case.advection_order,
+             timestepper=O.RK3 if case.timestepper == "SplitRungeKutta3" else O.FE,
+             coriolis_kind=0 if case.coriolis_f is None else 1, f=case.coriolis_f or 0.0,
+             top_kind=O.STRESS_FIELD if "top_x" in case.fields else O.STRESS_NONE,
+             bot_kind=O.STRESS_SEMI_IMPLICIT, rho_e=case.rho_e, Cd=case.Cd)
+    if case.u_bc_value is not None:
+        p.update(u_sn_bc=1, u_sn_val=case.u_bc_value)
+    if case.v_bc_value is not None:
+        p.update(v_we_bc=1, v_we_val=case.v_bc_value)
+    return p
+
+
+def oracle_from_case(case, **overrides) -> O.OracleModel:
+    topo = tuple(O.PERIODIC if t == "Periodic" else O.BOUNDED for t in case.topology)
+    p = oracle_params(case)
+    p.update(overrides)
+    return O.OracleModel(case.Nx, case.Ny, case.Hx, case.Hy, topo=topo, dx=case.dx, dy=case.dy, params=p,
+                         fields={k: v.copy() for k, v in case.fields.items()})
+
+
+# GPU field name -> oracle field name
+NAME_MAP = dict(u="u", v="v", h="h", a="a", s11="s11", s22="s22", s12="s12", alpha="alpha", zeta_c="zc", zeta_f="zf",
+                delta="delta", P="P", un="un", vn="vn", Gh="Gh", Ga="Ga")
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| (fields cross zero, SURVEY section 7 hard part 3)."""
+    d = float(np.max(np.abs(a - b)))
+    s = float(np.max(np.abs(b)))
+    return d / s if s > 0 else d
+
+
+def interior_of(arr, case):
+    return arr[case.Hy:arr.shape[0] - case.Hy, case.Hx:arr.shape[1] - case.Hx]
+
+
+def compare_model(model, oracle, case, names=("u", "v", "h", "a", "s11", "s22", "s12"), interior_only=True):
+    out = {}
+    F = model.all_fields()
+    for n in names:
+        g = F[n].numpy()
+        r = oracle.arr[NAME_MAP[n]]
+        if interior_only:
+            g, r = interior_of(g, case), interior_of(r, case)
+        out[n] = (rel_err(g, r), bool(np.array_equal(g, r)))
+    return out
