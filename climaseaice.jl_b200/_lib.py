@@ -9,7 +9,9 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libclimaseaice_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("CSI_B200_LIB", str(_HERE / "libclimaseaice_b200.so")))  # override only for kernel-variant experiments
 
 ABI_VERSION = 1
 PERIODIC, BOUNDED = 0, 1
@@ -77,7 +79,7 @@ EXPORTS = (
     "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
     "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
     "csi_evp_substeps_host", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count",
-    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
+    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_selftest_math", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
 )
 
 _lib = None
@@ -118,6 +120,7 @@ def lib():
     L.csi_last_elapsed_ms.argtypes = [H]
     L.csi_time_dominant_kernel.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.POINTER(C.c_double), C.c_char_p,
                                            C.POINTER(C.c_int32), C.c_void_p]
+    L.csi_selftest_math.argtypes = [C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
     L.csi_host_exp.restype = C.c_double
     L.csi_host_exp.argtypes = [C.c_double]
     L.csi_host_div_by_const.restype = C.c_double

@@ -247,6 +247,10 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
         }
         int rc = fused_run(h->fused, c, g, p, f, dt, 1, nsub, err, sizeof err);
         if (rc) return fail(h, rc, std::string("fused_run: ") + err);
+        // the in-loop fills of se.jl:180-187 happen inside the fused kernel on its internal layout;
+        // refresh the caller-visible halos once
+        launch_fill_halo(c, g, p, f.u, 1, 0, 1);
+        launch_fill_halo(c, g, p, f.v, 0, 1, 2);
     } else {
         const Range2 r = velocity_range(g);
         const int K = h->cfg.exchange_every > 0 ? h->cfg.exchange_every : nsub;
@@ -758,6 +762,20 @@ int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage
     snprintf(name64, 64, "%s", use_fused ? "k_evp_substep_fused" : "k_evp_stress");
     *bytes_per_cell = use_fused ? 144 : 120;
     return CSI_OK;
+}
+
+int csi_selftest_math(int64_t samples, uint64_t seed, int32_t exponent_span, uint64_t *out5)
+{
+    if (!out5 || samples < 1 || exponent_span < 0 || exponent_span > 1000) return CSI_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CSI_ERR_NO_DEVICE, "csi_selftest_math: no CUDA device");
+    }
+    unsigned long long tmp[5];
+    int rc = csi::fz::selftest_math(samples, seed, exponent_span, tmp);
+    for (int k = 0; k < 5; k++) out5[k] = tmp[k];
+    return rc;
 }
 
 double csi_host_exp(double x) { return csi::exp_cr(x); }

@@ -40,4 +40,8 @@ void fused_destroy(FusedPlan *);
 int fused_run(FusedPlan *, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, int first_sub,
               int nsub, char *err, int nerr);
 
+namespace fz {
+int selftest_math(long long samples, unsigned long long seed, int span, unsigned long long *out5);
+}
+
 }  // namespace csi

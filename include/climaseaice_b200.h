@@ -175,6 +175,12 @@ double csi_last_elapsed_ms(const csi_handle *h);
 int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage, int32_t reps, double *out_ms_per_launch,
                              char *name64, int32_t *bytes_per_cell, csi_stream stream);
 
+/* Device self test: compares the kernels' branch-free division / reciprocal / square root / constant
+ * quotient with the hardware IEEE operators on `samples` random operand sets whose exponents spread
+ * over +-2^exponent_span.  out5 = {rcp, div, sqrt, constant-quotient mismatches, samples outside the
+ * fast windows}.  A correct build returns zeros in out5[0..3]. */
+int csi_selftest_math(int64_t samples, uint64_t seed, int32_t exponent_span, uint64_t *out5);
+
 /* Host-side helpers exported for CPU tests (no GPU needed). */
 double csi_host_exp(double x);                       /* the correctly rounded exp used for ice_strength */
 double csi_host_div_by_const(double x, double c);    /* the Markstein constant-division used in the kernels */

@@ -143,3 +143,17 @@ def test_full_size_properties_4096():
     after = a.diagnostics()
     assert abs(after["sum_h_Az"] - before["sum_h_Az"]) / before["sum_h_Az"] < 1e-12
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("span", [30, 250])
+def test_fast_arithmetic_equals_ieee_operators(span):
+    """The kernels' branch-free rcp / div / sqrt / constant-quotient return the IEEE results bit for bit
+    (2e9 random operand sets per span, incl. perfect squares, near-equal operands and signed zeros)."""
+    import ctypes as C
+    from climaseaice_b200 import lib
+    out = (C.c_uint64 * 5)()
+    rc = lib().csi_selftest_math(2_000_000_000, 20260417 + span, span, out)
+    assert rc == 0
+    assert list(out)[:4] == [0, 0, 0, 0], list(out)
+    if span <= 250:
+        assert out[4] < 0.01 * 2e9   # these exponent ranges stay inside the fast windows (bar the all-ones guard)
