@@ -6,7 +6,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=${CSI_OUT:-../libclimaseaice_b200.so}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
-      -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -ffp-contract=off -shared -DCSI_FUSED_NC=${CSI_FUSED_NC:-1} -DCSI_FUSED_MINB=${CSI_FUSED_MINB:-1} \
+      -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -ffp-contract=off -shared -DCSI_FUSED_MINB=${CSI_FUSED_MINB:-3} \
       ${CSI_NVCC_EXTRA} \
       -o $OUT csi_api.cu csi_unfused.cu csi_halo.cu csi_advection.cu csi_reduce.cu csi_fused.cu \
       -cudart static -ldl

@@ -2,26 +2,29 @@
 //
 // Replaces, per substep, the reference's four kernels + two local halo fills
 // (compute_stresses! evp:222-354, _u/_v_velocity_step! se:197-264, fill_halo_regions! se:170-187)
-// with a single streaming kernel:
+// with a single tiled kernel:
 //
 //   * Fields live in an internal planar layout owned by the plan: one allocation
 //     [field][row][pitch], pitch a multiple of 16 doubles, interior column 1 at a 128-byte
 //     boundary, a halo ring of W cells.  One 3-D TMA tensor map describes all of it.
-//   * A CTA owns a strip of columns and marches along y.  Warp 0 is the TMA producer: each step it
-//     issues one `cp.async.bulk.tensor` row load (128 columns) per input field into a shared-memory
-//     stage, completion on a `full` mbarrier; consumer warps release stages through `empty`
-//     mbarriers.  There is no block-wide barrier anywhere in the loop.
-//   * Each consumer warp owns 32*NC columns (NC columns per lane) and is autonomous: row history
-//     (strain rates, P, m, alpha, new stresses, first velocity of the previous rows) lives in
-//     register shift-registers, x-neighbours come from warp shuffles.  Per step a warp computes
-//     strain rates (row t, t+1), the stress update (row t), the first velocity (row t or t-1) and the
-//     second velocity (row t-1).  Warps overlap by 4 columns (2 per side) and recompute them.
+//   * A CTA (256 threads) owns a tile: stresses on BX x BY = 32 x 16 nodes, velocities on the
+//     30 x 14 cells inside.  One elected thread issues one `cp.async.bulk.tensor` per stencil field
+//     (u, v, h, aice, P, s11, s22, s12, ue, ve): a 34 x 18 box = tile + halo, landing in shared
+//     memory, completion on an mbarrier.  Then four phases, separated by block barriers:
+//       A  strain rates e11, e22, e12 and ice mass on the haloed tile      (evp:360-375)
+//       B  viscosities, replacement pressure, stress relaxation, alpha     (evp:236-354)
+//       C  first velocity component on the tile + 1 ring                   (se:197-264)
+//       D  second velocity component on the output cells
+//     Strain rates, zeta, Delta, alpha, the new stresses and the first velocity never touch HBM
+//     between phases.  About 73 KB of shared memory per CTA: three CTAs (24 warps) per SM, which is
+//     what hides the 12-cycle FP64 latency (the earlier warp-marching variant kept all history in
+//     registers, ran 8-12 warps per SM and was latency-bound; see git history and DESIGN.md).
 //   * The five evolving fields are double buffered in HBM (read set A, write set B), so there is
 //     no hazard between CTAs; the owner of a cell also stores its periodic images / wall values,
 //     which replaces the two halo-fill launches per substep.
-//   * Arithmetic keeps the reference's Float64 expression trees (compiled with -fmad=false).
-//     Divisions by the constant metrics and by divisors used several times (m_i, alpha_bar,
-//     gamma) go through the Markstein quotient of csi_math.cuh, which returns the IEEE quotient.
+//   * Arithmetic keeps the reference's Float64 expression trees (compiled with -fmad=false) and
+//     uses the bit-exact FAST policy below; a tile whose operands leave the FAST windows is
+//     recomputed with plain IEEE operators.
 //
 // Algorithmic HBM traffic: 14 loads + 5 stores per cell-update (u, v, s11, s22, s12 r/w; h, aice,
 // P, un, vn, tau_x, tau_y, ue, ve read) = 152 B, 144 B by the SURVEY convention (P recomputable).
@@ -36,28 +39,21 @@ namespace csi {
 
 namespace fz {
 
-constexpr int BOX = 128;         // columns per TMA row box = columns per CTA strip (incl. overlap)
+constexpr int BX = 32, BY = 16;  // stress nodes per tile
+constexpr int OUTX = BX - 2, OUTY = BY - 2;  // velocity cells per tile
+constexpr int SXD = BX + 2, SYD = BY + 2;    // shared-memory tile = TMA box: tile + 1 halo ring
+constexpr int NT = 256;                       // threads per CTA
+constexpr int ASTRIDE = ((SXD * SYD * 8 + 127) / 128) * 128 / 8;  // doubles between shared arrays (TMA destinations are 128-byte aligned)
 constexpr int W = 3;             // halo ring kept valid in the internal layout
 constexpr int OX = 16;           // internal column of i = 1 (128-byte aligned)
-constexpr int NSTAGE = 3;        // TMA stages in flight per CTA
-constexpr int NIN = 14;          // input rows per stage
 
 // internal field indices
 enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, F_S12_1,
        F_H, F_A, F_P, F_UN, F_VN, F_TX, F_TY, F_UE, F_VE, F_ALPHA, F_ZC, F_ZF, F_DELTA, NF };
-// stage slots
-enum { I_U = 0, I_V, I_H, I_A, I_P, I_S11, I_S22, I_S12, I_UN, I_VN, I_TX, I_TY, I_UE, I_VE };
+// shared-memory arrays (each SXD x SYD doubles)
+enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E22, A_E12, A_AL, A_W, NARR };
 
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * NIN * BOX * sizeof(double) + 2 * NSTAGE * sizeof(uint64_t) + 128;
-
-// geometry of one kernel variant: NC columns per lane
-template <int NC> struct Geo {
-    static constexpr int WCOLS = 32 * NC;              // columns per consumer warp
-    static constexpr int WOUT = WCOLS - 4;             // output columns per warp (2 overlap per side)
-    static constexpr int NCW = (BOX - 4) / WOUT;       // consumer warps per CTA
-    static constexpr int OUTX = NCW * WOUT;            // output columns per CTA
-    static constexpr int THREADS = (NCW + 1) * 32;     // + the producer warp
-};
+constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64;
 
 struct Params {
     int Nx, Ny;          // interior size
@@ -69,7 +65,6 @@ struct Params {
     int sx0, sx1, sy0, sy1;  // stresses
     int vx0, vx1, vy0, vy1;  // velocities
     int cx0, cx1, cy0, cy1;  // cells whose velocity is evolved (periodic images included); others keep their value
-    int LY;                  // output rows per CTA
     int a0;                  // first column of strip 0 (chosen so every TMA box starts 16-byte aligned)
     int use_top, use_ue;     // field arrays present
     int u_sn_bc, v_we_bc;
@@ -219,39 +214,6 @@ struct MathSlow {
     __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
-// ---- per-lane state ---------------------------------------------------------------------------
-// rows of this step taken from the TMA stage
-template <int NC> struct In {
-    double u_n[NC], v_n[NC], h0[NC], a0[NC], P0[NC], o11[NC], o22[NC], o12[NC], un_[NC], vn_[NC], tx_[NC], ty_[NC], ue0[NC], ve0[NC];
-};
-// row history kept in registers (own columns)
-template <int NC> struct Hist {
-    double u_c[NC], u_p[NC], v_c[NC], v_p[NC], udx_c[NC], vdx_c[NC];
-    double e11_p[NC], e22_p[NC], e12_c[NC];
-    double P_p[NC], m_p[NC], m_pp[NC], a_p[NC], a_pp[NC], al_p[NC], al_pp[NC];
-    double s11_p[NC], s22_p[NC], s12_p[NC], s11_pp[NC], s22_pp[NC];
-    double w_p[NC], ue_p[NC], ue_pp[NC], ve_p[NC];
-};
-// everything one step produces
-template <int NC> struct Out {
-    double e11_c[NC], e22_c[NC], e12_n[NC], m_c[NC], undx[NC], vndx[NC];
-    double n11[NC], n22[NC], n12[NC], gc[NC], zc[NC], zf[NC], Dc[NC];
-    double w1[NC], w2[NC];  // first / second velocity of the step
-};
-
-template <int NC> __device__ __forceinline__ void lefts(const double (&x)[NC], double (&o)[NC])
-{
-    const double s = __shfl_up_sync(0xffffffffu, x[NC - 1], 1);
-#pragma unroll
-    for (int k = 0; k < NC; k++) o[k] = k > 0 ? x[k - 1] : s;
-}
-template <int NC> __device__ __forceinline__ void rights(const double (&x)[NC], double (&o)[NC])
-{
-    const double s = __shfl_down_sync(0xffffffffu, x[0], 1);
-#pragma unroll
-    for (int k = 0; k < NC; k++) o[k] = k < NC - 1 ? x[k + 1] : s;
-}
-
 // u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
 template <class M>
 __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
@@ -311,412 +273,272 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, do
     return jl_mul_bool(active_ice ? vD : 0.0, active);
 }
 
-// One marching step of one lane: strain rates (rows t, t+1), stress update (row t), first and
-// second velocity.  Pure function of (history, this step's rows); all lanes of the warp call it
-// together (shuffles inside).  updC / updD: whether the first / second velocity cell is evolved.
-template <int NC, bool VFIRST, class M>
-__device__ __forceinline__ void compute_step(M &mm, const Params &p, const Hist<NC> &h, const In<NC> &in, Out<NC> &o, const bool (&actu)[NC],
-                                             bool actv1, bool actv2, const bool (&updC)[NC], const bool (&updD)[NC])
-{
-    // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) --------
-    {
-        double u_r[NC], v_l[NC];
-        rights<NC>(h.u_c, u_r);
-        lefts<NC>(in.v_n, v_l);
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            const double D = mm.divc((p.dy * u_r[k] - p.dy * h.u_c[k]) + (p.dx * in.v_n[k] - p.dx * h.v_c[k]), p.az, p.raz);
-            o.vndx[k] = mm.divc(in.v_n[k], p.dx, p.rdx);
-            const double T = mm.divc(p.dy2 * (mm.divc(u_r[k], p.dy, p.rdy) - mm.divc(h.u_c[k], p.dy, p.rdy)) - p.dx2 * (o.vndx[k] - h.vdx_c[k]), p.az, p.raz);
-            o.undx[k] = mm.divc(in.u_n[k], p.dx, p.rdx);
-            const double S = mm.divc(p.dx2 * (o.undx[k] - h.udx_c[k]) + p.dy2 * (mm.divc(in.v_n[k], p.dy, p.rdy) - mm.divc(v_l[k], p.dy, p.rdy)), p.az, p.raz);
-            o.e11_c[k] = (D + T) / 2;
-            o.e22_c[k] = (D - T) / 2;
-            o.e12_n[k] = S / 2;
-            o.m_c[k] = in.h0[k] * p.rho_i * in.a0[k];
-        }
-    }
-    // ---------------- phase B: viscosities + stress update (evp:236-354) at row t ---------------
-    {
-        double e12c_r[NC], e12n_r[NC], e11p_l[NC], e11c_l[NC], e22p_l[NC], e22c_l[NC], Pp_l[NC], P0_l[NC], mp_l[NC], mc_l[NC];
-        rights<NC>(h.e12_c, e12c_r);
-        rights<NC>(o.e12_n, e12n_r);
-        lefts<NC>(h.e11_p, e11p_l);
-        lefts<NC>(o.e11_c, e11c_l);
-        lefts<NC>(h.e22_p, e22p_l);
-        lefts<NC>(o.e22_c, e22c_l);
-        lefts<NC>(h.P_p, Pp_l);
-        lefts<NC>(in.P0, P0_l);
-        lefts<NC>(h.m_p, mp_l);
-        lefts<NC>(o.m_c, mc_l);
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            const double e11c = o.e11_c[k], e22c = o.e22_c[k], e12f = h.e12_c[k];
-            const double e12c = ((h.e12_c[k] + e12c_r[k]) / 2 + (o.e12_n[k] + e12n_r[k]) / 2) / 2;
-            const double e11f = ((e11p_l[k] + h.e11_p[k]) / 2 + (e11c_l[k] + o.e11_c[k]) / 2) / 2;
-            const double e22f = ((e22p_l[k] + h.e22_p[k]) / 2 + (e22c_l[k] + o.e22_c[k]) / 2) / 2;
-            const double dc = e11c + e22c, df = e11f + e22f;
-            const double sc = mm.sqrt_((e11c - e22c) * (e11c - e22c) + 4 * (e12c * e12c));
-            const double sf = mm.sqrt_((e11f - e22f) * (e11f - e22f) + 4 * (e12f * e12f));
-            const double Dc = jl_max(mm.sqrt_(dc * dc + sc * sc * p.em2), p.Dmin);
-            const double Df = jl_max(mm.sqrt_(df * df + sf * sf * p.em2), p.Dmin);
-            const double Pc = in.P0[k];
-            const double Pf = ((Pp_l[k] + h.P_p[k]) / 2 + (P0_l[k] + in.P0[k]) / 2) / 2;
-            const double zf = mm.div(Pf, 2 * Df), zc = mm.div(Pc, 2 * Dc);
-            const double Pr = p.pform == CSI_ICE_STRENGTH ? Pc : mm.div(Pc * Dc, Dc + p.Dmin);
-            const double ec = zc * p.em2, ef = zf * p.em2;
-            const double s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
-            const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
-            const double s12n = 2 * ef * e12f;
-            const double mc = o.m_c[k];
-            const double mf = ((mp_l[k] + h.m_p[k]) / 2 + (mc_l[k] + o.m_c[k]) / 2) / 2;
-            double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), p.az, p.raz);
-            g2c = (g2c != g2c) ? p.amax2 : g2c;
-            const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
-            double g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), p.az, p.raz);
-            g2f = (g2f != g2f) ? p.amax2 : g2f;
-            const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
-            const NodeRecip Rg = mm.recip(gc);
-            const double d11 = mm.divn(s11n - in.o11[k], Rg), d22 = mm.divn(s22n - in.o22[k], Rg), d12 = mm.div(s12n - in.o12[k], gf);
-            o.n11[k] = in.o11[k] + (mc > 0 ? d11 : 0.0);
-            o.n22[k] = in.o22[k] + (mc > 0 ? d22 : 0.0);
-            o.n12[k] = in.o12[k] + (mf > 0 ? d12 : 0.0);
-            o.gc[k] = gc;
-            o.zc[k] = zc;
-            o.zf[k] = zf;
-            o.Dc[k] = Dc;
-        }
-    }
-    // ---------------- velocity updates -------------------------------------------------------------
-    if (VFIRST) {
-        {  // C: v at row t (reads old u rows t-1, t)
-            double up_r[NC], uc_r[NC], uep_r[NC], ue0_r[NC], n12_r[NC];
-            rights<NC>(h.u_p, up_r);
-            rights<NC>(h.u_c, uc_r);
-            rights<NC>(h.ue_p, uep_r);
-            rights<NC>(in.ue0, ue0_r);
-            rights<NC>(o.n12, n12_r);
-#pragma unroll
-            for (int k = 0; k < NC; k++) {
-                const double ubar = ((h.u_p[k] + up_r[k]) / 2 + (h.u_c[k] + uc_r[k]) / 2) / 2;
-                const double uebar = ((h.ue_p[k] + uep_r[k]) / 2 + (in.ue0[k] + ue0_r[k]) / 2) / 2;
-                const double val = v_node(mm, p, actv1, o.m_c[k], h.m_p[k], in.a0[k], h.a_p[k], o.gc[k], h.al_p[k], h.v_c[k], ubar, in.ve0[k], uebar,
-                                          in.ty_[k], in.vn_[k], o.n11[k] + o.n22[k], h.s11_p[k] + h.s22_p[k], o.n11[k] - o.n22[k],
-                                          h.s11_p[k] - h.s22_p[k], n12_r[k], o.n12[k]);
-                o.w1[k] = updC[k] ? val : h.v_c[k];
-            }
-        }
-        {  // D: u at row t-1 (reads new v rows t-1, t)
-            double mp_l[NC], ap_l[NC], alp_l[NC], wp_l[NC], wn_l[NC], vep_l[NC], ve0_l[NC], s11p_l[NC], s22p_l[NC];
-            lefts<NC>(h.m_p, mp_l);
-            lefts<NC>(h.a_p, ap_l);
-            lefts<NC>(h.al_p, alp_l);
-            lefts<NC>(h.w_p, wp_l);
-            lefts<NC>(o.w1, wn_l);
-            lefts<NC>(h.ve_p, vep_l);
-            lefts<NC>(in.ve0, ve0_l);
-            lefts<NC>(h.s11_p, s11p_l);
-            lefts<NC>(h.s22_p, s22p_l);
-#pragma unroll
-            for (int k = 0; k < NC; k++) {
-                const double vbar = ((wp_l[k] + h.w_p[k]) / 2 + (wn_l[k] + o.w1[k]) / 2) / 2;
-                const double vebar = ((vep_l[k] + h.ve_p[k]) / 2 + (ve0_l[k] + in.ve0[k]) / 2) / 2;
-                const double val = u_node(mm, p, actu[k], h.m_p[k], mp_l[k], h.a_p[k], ap_l[k], h.al_p[k], alp_l[k], h.u_p[k], vbar, h.ue_p[k], vebar,
-                                          in.tx_[k], in.un_[k], h.s11_p[k] + h.s22_p[k], s11p_l[k] + s22p_l[k], h.s11_p[k] - h.s22_p[k],
-                                          s11p_l[k] - s22p_l[k], o.n12[k], h.s12_p[k]);
-                o.w2[k] = updD[k] ? val : h.u_p[k];
-            }
-        }
-    } else {
-        {  // C: u at row t-1 (reads old v rows t-1, t)
-            double mp_l[NC], ap_l[NC], alp_l[NC], vp_l[NC], vc_l[NC], vep_l[NC], ve0_l[NC], s11p_l[NC], s22p_l[NC];
-            lefts<NC>(h.m_p, mp_l);
-            lefts<NC>(h.a_p, ap_l);
-            lefts<NC>(h.al_p, alp_l);
-            lefts<NC>(h.v_p, vp_l);
-            lefts<NC>(h.v_c, vc_l);
-            lefts<NC>(h.ve_p, vep_l);
-            lefts<NC>(in.ve0, ve0_l);
-            lefts<NC>(h.s11_p, s11p_l);
-            lefts<NC>(h.s22_p, s22p_l);
-#pragma unroll
-            for (int k = 0; k < NC; k++) {
-                const double vbar = ((vp_l[k] + h.v_p[k]) / 2 + (vc_l[k] + h.v_c[k]) / 2) / 2;
-                const double vebar = ((vep_l[k] + h.ve_p[k]) / 2 + (ve0_l[k] + in.ve0[k]) / 2) / 2;
-                const double val = u_node(mm, p, actu[k], h.m_p[k], mp_l[k], h.a_p[k], ap_l[k], h.al_p[k], alp_l[k], h.u_p[k], vbar, h.ue_p[k], vebar,
-                                          in.tx_[k], in.un_[k], h.s11_p[k] + h.s22_p[k], s11p_l[k] + s22p_l[k], h.s11_p[k] - h.s22_p[k],
-                                          s11p_l[k] - s22p_l[k], o.n12[k], h.s12_p[k]);
-                o.w1[k] = updC[k] ? val : h.u_p[k];
-            }
-        }
-        {  // D: v at row t-1 (reads new u rows t-2, t-1)
-            double wp_r[NC], wn_r[NC], uepp_r[NC], uep_r[NC], s12p_r[NC];
-            rights<NC>(h.w_p, wp_r);
-            rights<NC>(o.w1, wn_r);
-            rights<NC>(h.ue_pp, uepp_r);
-            rights<NC>(h.ue_p, uep_r);
-            rights<NC>(h.s12_p, s12p_r);
-#pragma unroll
-            for (int k = 0; k < NC; k++) {
-                const double ubar = ((h.w_p[k] + wp_r[k]) / 2 + (o.w1[k] + wn_r[k]) / 2) / 2;
-                const double uebar = ((h.ue_pp[k] + uepp_r[k]) / 2 + (h.ue_p[k] + uep_r[k]) / 2) / 2;
-                const double val = v_node(mm, p, actv2, h.m_p[k], h.m_pp[k], h.a_p[k], h.a_pp[k], h.al_p[k], h.al_pp[k], h.v_p[k], ubar, h.ve_p[k], uebar,
-                                          in.ty_[k], in.vn_[k], h.s11_p[k] + h.s22_p[k], h.s11_pp[k] + h.s22_pp[k], h.s11_p[k] - h.s22_p[k],
-                                          h.s11_pp[k] - h.s22_pp[k], s12p_r[k], h.s12_p[k]);
-                o.w2[k] = updD[k] ? val : h.v_p[k];
-            }
-        }
-    }
-}
-
 // ---- the kernel ----------------------------------------------------------------------------
-// NC: columns per lane.  VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).
-// AUX: also write alpha, zeta_c, zeta_f, Delta (last substep of a stage).
-template <int NC, bool VFIRST, bool AUX>
-__global__ void __launch_bounds__(Geo<NC>::THREADS, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
-{
-    using G = Geo<NC>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stages = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(stages + (size_t)NSTAGE * NIN * BOX);
-    uint64_t *empty = full + NSTAGE;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ia = p.a0 + blockIdx.x * G::OUTX;  // first output column of this strip
-    const int y0 = p.sy0 < p.vy0 ? p.sy0 : p.vy0, y1 = p.sy1 > p.vy1 ? p.sy1 : p.vy1;
-    const int ja = y0 + blockIdx.y * p.LY;
-    const int jb = min(ja + p.LY - 1, y1);
-    const int fin = p.in_set ? F_U1 : F_U0, fout = p.out_set ? F_U1 : F_U0;
-    const int t_begin = ja - 3, t_end = jb + 1;
+// Tile-local coordinates: (sx, sy) in [0,BX) x [0,BY) are the stress nodes; node (sx, sy) is the
+// reference index (I0-1+sx, J0-1+sy), so the velocity cells of the tile are sx in [1,30], sy in [1,14].
+// Shared arrays hold [-1, BX] x [-1, BY]; S(a, sx, sy) addresses them.
+#define S(a, sx, sy) (sm[(a) * ASTRIDE + ((sy) + 1) * SXD + ((sx) + 1)])
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], G::NCW);
+struct TileCtx {
+    int I0, J0;  // reference index of the first velocity cell of the tile
+    int fin, fout;
+};
+
+// All phases of one tile under one arithmetic policy.  Returns (via `bad`) whether any thread left
+// the policy's windows.  Global stores happen only when the pass is clean (or is the SLOW pass).
+template <bool VFIRST, bool AUX, class M>
+__device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc)
+{
+    const int tid = threadIdx.x;
+    const size_t plane = (size_t)p.pitch * p.rows;
+    // ---- TMA: tile + halo of every stencil field ----
+    if (tid == 0) {
+        const int x = tc.I0 - 2 - 1 + OX, y = tc.J0 - 2 - 1 + p.oy;
+        int n = 8;
+        auto ld = [&](int arr, int field) { tma_load_row(sm + arr * ASTRIDE, tmap, bar, x, y, field); };
+        ld(A_U, tc.fin + 0);
+        ld(A_V, tc.fin + 1);
+        ld(A_H, F_H);
+        ld(A_A, F_A);
+        ld(A_P, F_P);
+        ld(A_S11, tc.fin + 2);
+        ld(A_S22, tc.fin + 3);
+        ld(A_S12, tc.fin + 4);
+        if (p.use_ue) {
+            ld(A_UE, F_UE);
+            ld(A_VE, F_VE);
+            n += 2;
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)n * SXD * SYD * sizeof(double));
+    }
+    mbar_wait(bar, parity);
+
+    M mm;
+    // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) ----------------
+    // e11, e22 on [-1, BX-1] x [-1, BY-1]; e12 on [0, BX] x [0, BY]; m everywhere (in place over h)
+    for (int n = tid; n < SXD * SYD; n += NT) {
+        const int sx = n % SXD - 1, sy = n / SXD - 1;
+        if (sx < BX && sy < BY) {
+            const double u00 = S(A_U, sx, sy), u10 = S(A_U, sx + 1, sy), v00 = S(A_V, sx, sy), v01 = S(A_V, sx, sy + 1);
+            const double D = mm.divc((p.dy * u10 - p.dy * u00) + (p.dx * v01 - p.dx * v00), p.az, p.raz);
+            const double T = mm.divc(p.dy2 * (mm.divc(u10, p.dy, p.rdy) - mm.divc(u00, p.dy, p.rdy)) -
+                                         p.dx2 * (mm.divc(v01, p.dx, p.rdx) - mm.divc(v00, p.dx, p.rdx)),
+                                     p.az, p.raz);
+            S(A_E11, sx, sy) = (D + T) / 2;
+            S(A_E22, sx, sy) = (D - T) / 2;
+        }
+        if (sx >= 0 && sy >= 0) {
+            const double u00 = S(A_U, sx, sy), u0m = S(A_U, sx, sy - 1), v00 = S(A_V, sx, sy), vm0 = S(A_V, sx - 1, sy);
+            const double Sh = mm.divc(p.dx2 * (mm.divc(u00, p.dx, p.rdx) - mm.divc(u0m, p.dx, p.rdx)) +
+                                          p.dy2 * (mm.divc(v00, p.dy, p.rdy) - mm.divc(vm0, p.dy, p.rdy)),
+                                      p.az, p.raz);
+            S(A_E12, sx, sy) = Sh / 2;
+        }
+        S(A_H, sx, sy) = S(A_H, sx, sy) * p.rho_i * S(A_A, sx, sy);  // h -> m
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            const int xcoord = ia - 2 - 1 + OX;  // internal column of the strip's first (overlap) column
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = t_begin; t <= t_end; t++) {
-                if (t - t_begin >= NSTAGE) mbar_wait(&empty[s], ph ^ 1);
-                double *st = stages + (size_t)s * NIN * BOX;
-                const int ru = t - 1, rv = VFIRST ? t : t - 1;  // rows of the u / v updates of this step
-                int n = 10;
-                auto ld = [&](int slot, int field, int r) { tma_load_row(st + slot * BOX, &tmap, &full[s], xcoord, r - 1 + p.oy, field); };
-                ld(I_U, fin + 0, t + 1);
-                ld(I_V, fin + 1, t + 1);
-                ld(I_H, F_H, t);
-                ld(I_A, F_A, t);
-                ld(I_P, F_P, t);
-                ld(I_S11, fin + 2, t);
-                ld(I_S22, fin + 3, t);
-                ld(I_S12, fin + 4, t);
-                ld(I_UN, F_UN, ru);
-                ld(I_VN, F_VN, rv);
-                if (p.use_top) {
-                    ld(I_TX, F_TX, ru);
-                    ld(I_TY, F_TY, rv);
-                    n += 2;
-                }
-                if (p.use_ue) {
-                    ld(I_UE, F_UE, t);
-                    ld(I_VE, F_VE, t);
-                    n += 2;
-                }
-                mbar_expect_tx(&full[s], (uint32_t)n * BOX * sizeof(double));
-                if (++s == NSTAGE) {
-                    s = 0;
-                    ph ^= 1;
-                }
-            }
+    // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
+    double aux_zc[2], aux_zf[2], aux_Dc[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int n = tid + q * NT, sx = n % BX, sy = n / BX;
+        const double e11c = S(A_E11, sx, sy), e22c = S(A_E22, sx, sy), e12f = S(A_E12, sx, sy);
+        const double e12c = ((S(A_E12, sx, sy) + S(A_E12, sx + 1, sy)) / 2 + (S(A_E12, sx, sy + 1) + S(A_E12, sx + 1, sy + 1)) / 2) / 2;
+        const double e11f = ((S(A_E11, sx - 1, sy - 1) + S(A_E11, sx, sy - 1)) / 2 + (S(A_E11, sx - 1, sy) + S(A_E11, sx, sy)) / 2) / 2;
+        const double e22f = ((S(A_E22, sx - 1, sy - 1) + S(A_E22, sx, sy - 1)) / 2 + (S(A_E22, sx - 1, sy) + S(A_E22, sx, sy)) / 2) / 2;
+        const double dc = e11c + e22c, df = e11f + e22f;
+        const double sc = mm.sqrt_((e11c - e22c) * (e11c - e22c) + 4 * (e12c * e12c));
+        const double sf = mm.sqrt_((e11f - e22f) * (e11f - e22f) + 4 * (e12f * e12f));
+        const double Dc = jl_max(mm.sqrt_(dc * dc + sc * sc * p.em2), p.Dmin);
+        const double Df = jl_max(mm.sqrt_(df * df + sf * sf * p.em2), p.Dmin);
+        const double Pc = S(A_P, sx, sy);
+        const double Pf = ((S(A_P, sx - 1, sy - 1) + S(A_P, sx, sy - 1)) / 2 + (S(A_P, sx - 1, sy) + S(A_P, sx, sy)) / 2) / 2;
+        const double zf = mm.div(Pf, 2 * Df), zc = mm.div(Pc, 2 * Dc);
+        const double Pr = p.pform == CSI_ICE_STRENGTH ? Pc : mm.div(Pc * Dc, Dc + p.Dmin);
+        const double ec = zc * p.em2, ef = zf * p.em2;
+        const double s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+        const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+        const double s12n = 2 * ef * e12f;
+        const double mc = S(A_H, sx, sy);
+        const double mf = ((S(A_H, sx - 1, sy - 1) + S(A_H, sx, sy - 1)) / 2 + (S(A_H, sx - 1, sy) + S(A_H, sx, sy)) / 2) / 2;
+        double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), p.az, p.raz);
+        g2c = (g2c != g2c) ? p.amax2 : g2c;
+        const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
+        double g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), p.az, p.raz);
+        g2f = (g2f != g2f) ? p.amax2 : g2f;
+        const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
+        const NodeRecip Rg = mm.recip(gc);
+        const double o11 = S(A_S11, sx, sy), o22 = S(A_S22, sx, sy), o12 = S(A_S12, sx, sy);
+        const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.div(s12n - o12, gf);
+        // in place: each thread owns its node of the sigma arrays
+        S(A_S11, sx, sy) = o11 + (mc > 0 ? d11 : 0.0);
+        S(A_S22, sx, sy) = o22 + (mc > 0 ? d22 : 0.0);
+        S(A_S12, sx, sy) = o12 + (mf > 0 ? d12 : 0.0);
+        S(A_AL, sx, sy) = gc;
+        aux_zc[q] = zc;
+        aux_zf[q] = zf;
+        aux_Dc[q] = Dc;
+    }
+    __syncthreads();
+
+    // per-node helpers for the velocity phases
+    const double *gUN = p.base + (size_t)F_UN * plane, *gVN = p.base + (size_t)F_VN * plane;
+    const double *gTX = p.base + (size_t)F_TX * plane, *gTY = p.base + (size_t)F_TY * plane;
+    // offset of node (sx, sy) in a plane of the internal layout, clamped into the plane (edge tiles reach past the
+    // allocation; those nodes are never stored)
+    auto goff = [&](int sx, int sy) {
+        const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
+        return (size_t)row * p.pitch + (size_t)col;
+    };
+    // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
+    auto u_at = [&](int sx, int sy, int VS) -> double {
+        const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
+        const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
+        const bool active = !(p.bounded_x && (i <= 1 || i > p.Nx));
+        const double vbar = ((S(VS, sx - 1, sy) + S(VS, sx, sy)) / 2 + (S(VS, sx - 1, sy + 1) + S(VS, sx, sy + 1)) / 2) / 2;
+        double ue = p.ue_c, vebar = ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
+        if (p.use_ue) {
+            ue = S(A_UE, sx, sy);
+            vebar = ((S(A_VE, sx - 1, sy) + S(A_VE, sx, sy)) / 2 + (S(A_VE, sx - 1, sy + 1) + S(A_VE, sx, sy + 1)) / 2) / 2;
         }
-        return;
+        const size_t g = goff(sx, sy);
+        const double ttop = p.use_top ? __ldg(gTX + g) : p.ttx, un = __ldg(gUN + g), uold = S(A_U, sx, sy);
+        const double a1 = S(A_S11, sx, sy), b1 = S(A_S22, sx, sy), a0 = S(A_S11, sx - 1, sy), b0 = S(A_S22, sx - 1, sy);
+        const double val = u_node(mm, p, active, S(A_H, sx, sy), S(A_H, sx - 1, sy), S(A_A, sx, sy), S(A_A, sx - 1, sy), S(A_AL, sx, sy),
+                                  S(A_AL, sx - 1, sy), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, S(A_S12, sx, sy + 1),
+                                  S(A_S12, sx, sy));
+        return upd ? val : uold;
+    };
+    auto v_at = [&](int sx, int sy, int US) -> double {
+        const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
+        const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
+        const bool active = !(p.bounded_y && (r <= 1 || r > p.Ny));
+        const double ubar = ((S(US, sx, sy - 1) + S(US, sx + 1, sy - 1)) / 2 + (S(US, sx, sy) + S(US, sx + 1, sy)) / 2) / 2;
+        double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
+        if (p.use_ue) {
+            ve = S(A_VE, sx, sy);
+            uebar = ((S(A_UE, sx, sy - 1) + S(A_UE, sx + 1, sy - 1)) / 2 + (S(A_UE, sx, sy) + S(A_UE, sx + 1, sy)) / 2) / 2;
+        }
+        const size_t g = goff(sx, sy);
+        const double ttop = p.use_top ? __ldg(gTY + g) : p.tty, vn = __ldg(gVN + g), vold = S(A_V, sx, sy);
+        const double a1 = S(A_S11, sx, sy), b1 = S(A_S22, sx, sy), a0 = S(A_S11, sx, sy - 1), b0 = S(A_S22, sx, sy - 1);
+        const double val = v_node(mm, p, active, S(A_H, sx, sy), S(A_H, sx, sy - 1), S(A_A, sx, sy), S(A_A, sx, sy - 1), S(A_AL, sx, sy),
+                                  S(A_AL, sx, sy - 1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, S(A_S12, sx + 1, sy),
+                                  S(A_S12, sx, sy));
+        return upd ? val : vold;
+    };
+
+    // ---------------- phase C: first velocity on the cells the second one reads -------------------------
+    // odd (v first): v on sx in [0,30], sy in [1,15] ; even (u first): u on sx in [1,31], sy in [0,14]
+    constexpr int CW = OUTX + 1, CH = OUTY + 1;
+    for (int n = tid; n < CW * CH; n += NT) {
+        const int cx = n % CW, cy = n / CW;
+        if (VFIRST) S(A_W, cx, cy + 1) = v_at(cx, cy + 1, A_U);
+        else S(A_W, cx + 1, cy) = u_at(cx + 1, cy, A_V);
     }
+    __syncthreads();
 
-    // ================= consumer warps =================
-    const int cw = warp - 1;                  // consumer warp index
-    const int q0 = cw * G::WOUT + NC * lane;  // strip-local index of this lane's first column
-    const int i0 = ia - 2 + q0;               // reference column index of it
-
-    // per-column constants of the march: output predicates, image offsets, wall masks
-    bool st_s[NC], st_v[NC], actu[NC], evx[NC];
-    int ix[NC];
+    // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
+    double w2[2];
+    int d_sx[2], d_sy[2];
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-        const int wq = NC * lane + k, i = i0 + k;
-        const bool outc = wq >= 2 && wq <= G::WCOLS - 3;
-        st_s[k] = outc && i >= p.sx0 && i <= p.sx1;
-        st_v[k] = outc && i >= p.vx0 && i <= p.vx1;
-        actu[k] = !(p.bounded_x && (i <= 1 || i > p.Nx));  // !peripheral_node(f,c,c)
-        evx[k] = i >= p.cx0 && i <= p.cx1;
-        ix[k] = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
-    }
-    const size_t plane = (size_t)p.pitch * p.rows;
-    double *const bS11 = p.base + (size_t)(fout + 2) * plane + (size_t)(i0 - 1 + OX);
-    double *const bS22 = p.base + (size_t)(fout + 3) * plane + (size_t)(i0 - 1 + OX);
-    double *const bS12 = p.base + (size_t)(fout + 4) * plane + (size_t)(i0 - 1 + OX);
-    double *const bU = p.base + (size_t)(fout + 0) * plane + (size_t)(i0 - 1 + OX);
-    double *const bV = p.base + (size_t)(fout + 1) * plane + (size_t)(i0 - 1 + OX);
-
-    Hist<NC> h;
-    {
-        double *z = reinterpret_cast<double *>(&h);
-#pragma unroll
-        for (int k = 0; k < (int)(sizeof(Hist<NC>) / sizeof(double)); k++) z[k] = 0.0;
+    for (int q = 0; q < 2; q++) {
+        const int n = tid + q * NT;
+        d_sx[q] = n % OUTX + 1;
+        d_sy[q] = n / OUTX + 1;
+        w2[q] = 0.0;
+        if (n < OUTX * OUTY) w2[q] = VFIRST ? u_at(d_sx[q], d_sy[q], A_W) : v_at(d_sx[q], d_sy[q], A_W);
     }
 
-    // store val at (column k, row r) of the array starting at b, plus its periodic images
-    auto put = [&](double *b, int k, int r, int iy, double val) {
-        double *q = b + (size_t)(r - 1 + p.oy) * p.pitch + k;
+    const bool bad = __syncthreads_or(mm.bad());
+    if (bad) return true;
+
+    // ---------------- stores: home cell + periodic images + wall cells ----------------------------------
+    auto put = [&](int field, int i, int r, double val) {
+        double *q = p.base + (size_t)field * plane + (size_t)(r - 1 + p.oy) * p.pitch + (size_t)(i - 1 + OX);
+        const int ix = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
+        const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
         q[0] = val;
-        if (ix[k]) q[ix[k]] = val;
+        if (ix) q[ix] = val;
         if (iy) {
             q += (ptrdiff_t)iy * p.pitch;
             q[0] = val;
-            if (ix[k]) q[ix[k]] = val;
+            if (ix) q[ix] = val;
         }
     };
-
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = t_begin; t <= t_end; t++) {
-        // ---- take this step's rows out of the stage, then hand the stage back ----
-        mbar_wait(&full[s], ph);
-        const double *st = stages + (size_t)s * NIN * BOX + q0;
-        In<NC> in;
+    auto put_vel = [&](int field, int i, int r, double val, bool is_u) {
+        if (!(i >= p.vx0 && i <= p.vx1 && r >= p.vy0 && r <= p.vy1)) return;
+        put(field, i, r, val);
+        double *q = p.base + (size_t)field * plane + (size_t)(r - 1 + p.oy) * p.pitch + (size_t)(i - 1 + OX);
+        // walls: one tangential halo cell (value / no-flux BC), as fill_halo_regions! does
+        if (is_u && p.bounded_y) {
+            if (r == 1) q[-p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val;
+            if (r == p.Ny) q[p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (p.dy / 2)) * p.dy : val;
+        }
+        if (!is_u && p.bounded_x) {
+            if (i == 1) q[-1] = p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (p.dx / 2)) * (-p.dx) : val;
+            if (i == p.Nx) q[1] = p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (p.dx / 2)) * p.dx : val;
+        }
+    };
 #pragma unroll
-        for (int k = 0; k < NC; k++) {
-            in.u_n[k] = st[I_U * BOX + k];
-            in.v_n[k] = st[I_V * BOX + k];
-            in.h0[k] = st[I_H * BOX + k];
-            in.a0[k] = st[I_A * BOX + k];
-            in.P0[k] = st[I_P * BOX + k];
-            in.o11[k] = st[I_S11 * BOX + k];
-            in.o22[k] = st[I_S22 * BOX + k];
-            in.o12[k] = st[I_S12 * BOX + k];
-            in.un_[k] = st[I_UN * BOX + k];
-            in.vn_[k] = st[I_VN * BOX + k];
-            in.tx_[k] = p.use_top ? st[I_TX * BOX + k] : p.ttx;
-            in.ty_[k] = p.use_top ? st[I_TY * BOX + k] : p.tty;
-            in.ue0[k] = p.use_ue ? st[I_UE * BOX + k] : p.ue_c;
-            in.ve0[k] = p.use_ue ? st[I_VE * BOX + k] : p.ve_c;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == NSTAGE) {
-            s = 0;
-            ph ^= 1;
-        }
-
-        // rows of the two velocity updates of this step and whether those cells evolve
-        const int rC = VFIRST ? t : t - 1, rD = t - 1;
-        const bool evC = rC >= p.cy0 && rC <= p.cy1, evD = rD >= p.cy0 && rD <= p.cy1;
-        bool updC[NC], updD[NC];
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            updC[k] = evC && evx[k];
-            updD[k] = evD && evx[k];
-        }
-        const bool actv1 = !(p.bounded_y && (t <= 1 || t > p.Ny));          // v at row t (VFIRST, phase C)
-        const bool actv2 = !(p.bounded_y && (t - 1 <= 1 || t - 1 > p.Ny));  // v at row t-1 (phase D)
-
-        Out<NC> o;
-        {
-            MathFast mf;
-            compute_step<NC, VFIRST>(mf, p, h, in, o, actu, actv1, actv2, updC, updD);
-            if (__any_sync(0xffffffffu, mf.bad())) {
-                // an operand left the exponent window of the shortcut quotients: redo this step with IEEE divisions
-                MathSlow ms;
-                compute_step<NC, VFIRST>(ms, p, h, in, o, actu, actv1, actv2, updC, updD);
+    for (int q = 0; q < 2; q++) {
+        // stresses (and aux) of the node this thread updated in phase B
+        const int n = tid + q * NT, sx = n % BX, sy = n / BX;
+        const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
+        if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY && i >= p.sx0 && i <= p.sx1 && r >= p.sy0 && r <= p.sy1) {
+            put(tc.fout + 2, i, r, S(A_S11, sx, sy));
+            put(tc.fout + 3, i, r, S(A_S22, sx, sy));
+            put(tc.fout + 4, i, r, S(A_S12, sx, sy));
+            if (AUX) {
+                put(F_ALPHA, i, r, S(A_AL, sx, sy));
+                put(F_ZC, i, r, aux_zc[q]);
+                put(F_ZF, i, r, aux_zf[q]);
+                put(F_DELTA, i, r, aux_Dc[q]);
             }
         }
-
-        // ---- stores (home cell + periodic images + wall cells) ----
-        {
-            const bool row_s = t >= ja && t <= jb && t >= p.sy0 && t <= p.sy1;
-            if (row_s) {
-                const int iy = p.py ? (t <= W ? p.Ny : (t > p.Ny - W ? -p.Ny : 0)) : 0;
-#pragma unroll
-                for (int k = 0; k < NC; k++)
-                    if (st_s[k]) {
-                        put(bS11, k, t, iy, o.n11[k]);
-                        put(bS22, k, t, iy, o.n22[k]);
-                        put(bS12, k, t, iy, o.n12[k]);
-                        if (AUX) {
-                            const ptrdiff_t d = (ptrdiff_t)plane;
-                            put(bS11 + ((ptrdiff_t)F_ALPHA - (fout + 2)) * d, k, t, iy, o.gc[k]);
-                            put(bS11 + ((ptrdiff_t)F_ZC - (fout + 2)) * d, k, t, iy, o.zc[k]);
-                            put(bS11 + ((ptrdiff_t)F_ZF - (fout + 2)) * d, k, t, iy, o.zf[k]);
-                            put(bS11 + ((ptrdiff_t)F_DELTA - (fout + 2)) * d, k, t, iy, o.Dc[k]);
-                        }
-                    }
-            }
-            auto store_vel = [&](double *b, int r, const double (&val)[NC], bool is_u) {
-                if (!(r >= ja && r <= jb && r >= p.vy0 && r <= p.vy1)) return;
-                const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
-#pragma unroll
-                for (int k = 0; k < NC; k++)
-                    if (st_v[k]) {
-                        put(b, k, r, iy, val[k]);
-                        // walls: one tangential halo cell (value / no-flux BC), as fill_halo_regions! does
-                        double *q = b + (size_t)(r - 1 + p.oy) * p.pitch + k;
-                        const int i = i0 + k;
-                        if (is_u && p.bounded_y) {
-                            if (r == 1) q[-p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val[k] + ((val[k] - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val[k];
-                            if (r == p.Ny) q[p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val[k] + ((p.u_sn_val - val[k]) / (p.dy / 2)) * p.dy : val[k];
-                        }
-                        if (!is_u && p.bounded_x) {
-                            if (i == 1) q[-1] = p.v_we_bc == CSI_BC_VALUE ? val[k] + ((val[k] - p.v_we_val) / (p.dx / 2)) * (-p.dx) : val[k];
-                            if (i == p.Nx) q[1] = p.v_we_bc == CSI_BC_VALUE ? val[k] + ((p.v_we_val - val[k]) / (p.dx / 2)) * p.dx : val[k];
-                        }
-                    }
-            };
+        // velocities of the output cell this thread updated in phase D
+        if (n < OUTX * OUTY) {
+            const int ui = tc.I0 - 1 + d_sx[q], ur = tc.J0 - 1 + d_sy[q];
             if (VFIRST) {
-                store_vel(bV, rC, o.w1, false);
-                store_vel(bU, rD, o.w2, true);
+                put_vel(tc.fout + 0, ui, ur, w2[q], true);
+                put_vel(tc.fout + 1, ui, ur, S(A_W, d_sx[q], d_sy[q]), false);
             } else {
-                store_vel(bU, rC, o.w1, true);
-                store_vel(bV, rD, o.w2, false);
+                put_vel(tc.fout + 1, ui, ur, w2[q], false);
+                put_vel(tc.fout + 0, ui, ur, S(A_W, d_sx[q], d_sy[q]), true);
             }
-        }
-
-        // ---- shift the row history ----
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            h.u_p[k] = h.u_c[k];
-            h.u_c[k] = in.u_n[k];
-            h.v_p[k] = h.v_c[k];
-            h.v_c[k] = in.v_n[k];
-            h.udx_c[k] = o.undx[k];
-            h.vdx_c[k] = o.vndx[k];
-            h.e11_p[k] = o.e11_c[k];
-            h.e22_p[k] = o.e22_c[k];
-            h.e12_c[k] = o.e12_n[k];
-            h.P_p[k] = in.P0[k];
-            h.m_pp[k] = h.m_p[k];
-            h.m_p[k] = o.m_c[k];
-            h.a_pp[k] = h.a_p[k];
-            h.a_p[k] = in.a0[k];
-            h.al_pp[k] = h.al_p[k];
-            h.al_p[k] = o.gc[k];
-            h.s11_pp[k] = h.s11_p[k];
-            h.s22_pp[k] = h.s22_p[k];
-            h.s11_p[k] = o.n11[k];
-            h.s22_p[k] = o.n22[k];
-            h.s12_p[k] = o.n12[k];
-            h.w_p[k] = o.w1[k];
-            h.ue_pp[k] = h.ue_p[k];
-            h.ue_p[k] = in.ue0[k];
-            h.ve_p[k] = in.ve0[k];
         }
     }
+    return false;
 }
+
+// VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
+// alpha, zeta_c, zeta_f, Delta (last substep of a stage).
+template <bool VFIRST, bool AUX>
+__global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + NARR * ASTRIDE);
+    const int y0 = p.sy0 < p.vy0 ? p.sy0 : p.vy0;
+    TileCtx tc;
+    tc.I0 = p.a0 + blockIdx.x * OUTX;
+    tc.J0 = y0 + blockIdx.y * OUTY;
+    tc.fin = p.in_set ? F_U1 : F_U0;
+    tc.fout = p.out_set ? F_U1 : F_U0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tile_pass<VFIRST, AUX, MathFast>(sm, bar, 0, &tmap, p, tc)) {
+        // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, denormals ...):
+        // reload the tile and redo it with plain IEEE operators
+        __syncthreads();
+        tile_pass<VFIRST, AUX, MathSlow>(sm, bar, 1, &tmap, p, tc);
+    }
+}
+#undef S
 
 // ---- self test of the FAST arithmetic against the IEEE operators ---------------------------------
 // Each thread draws pseudo-random operands (splitmix64; random significands, exponents spread over
@@ -743,7 +565,8 @@ __global__ void k_selftest_math(unsigned long long *out, uint64_t seed, int iter
     uint64_t s = seed + (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0x632be59bd9b4e019ull;
     unsigned long long bad[5] = {0, 0, 0, 0, 0};
     for (int it = 0; it < iters; it++) {
-        double x = rnd_double(s, span, false), y = rnd_double(s, span, false), z = rnd_double(s, span, true);
+        // divisors are positive in every kernel use (metrics, masses, alpha, gamma, Delta, 1 + dtau*tau)
+        double x = rnd_double(s, span, false), y = rnd_double(s, span, true), z = rnd_double(s, span, true);
         if ((it & 15) == 0) {  // near-special operands: perfect squares, powers of two, x close to y
             const double t = rnd_double(s, 20, true);
             z = t * t;
@@ -867,7 +690,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     if (!enc) { snprintf(err, nerr, "cuTensorMapEncodeTiled unavailable"); cudaFree(pl->base); delete pl; return nullptr; }
     cuuint64_t dims[3] = {(cuuint64_t)pl->pitch, (cuuint64_t)pl->rows, (cuuint64_t)NF};
     cuuint64_t strides[2] = {(cuuint64_t)pl->pitch * 8, (cuuint64_t)pl->pitch * pl->rows * 8};
-    cuuint32_t box[3] = {(cuuint32_t)BOX, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)SXD, (cuuint32_t)SYD, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, pl->base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -882,18 +705,16 @@ void fused_destroy(FusedPlan *pl)
     delete pl;
 }
 
-constexpr int FUSED_NC = CSI_FUSED_NC;  // columns per lane of the production variant
-
 template <bool VFIRST, bool AUX> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<FUSED_NC, VFIRST, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_evp_substep_fused<FUSED_NC, VFIRST, AUX><<<grid, Geo<FUSED_NC>::THREADS, SMEM_BYTES, s>>>(pl->tmap, P);
+    k_evp_substep_fused<VFIRST, AUX><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
     return cudaGetLastError();
 }
 
@@ -932,42 +753,12 @@ int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.base = pl->base;
 
-    // the TMA box of strip k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
+    // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
     P.a0 = P.sx0 < P.vx0 ? P.sx0 : P.vx0;
     if ((P.a0 - 3 + OX) & 1) P.a0 -= 1;
     const int ncols = (P.sx1 > P.vx1 ? P.sx1 : P.vx1) - P.a0 + 1;
     const int nrows = (P.sy1 > P.vy1 ? P.sy1 : P.vy1) - (P.sy0 < P.vy0 ? P.sy0 : P.vy0) + 1;
-    const int OUTX = Geo<FUSED_NC>::OUTX;
-    const int strips = (ncols + OUTX - 1) / OUTX;
-    // rows per CTA: aim for a whole number of waves of 2 CTAs per SM over 148 SMs
-    int LY = 128;
-    {
-        static int per_sm = 0;
-        if (!per_sm) {
-            int a = 1, b = 1, nsm = 148;
-            cudaFuncSetAttribute(k_evp_substep_fused<FUSED_NC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-            cudaFuncSetAttribute(k_evp_substep_fused<FUSED_NC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_evp_substep_fused<FUSED_NC, true, false>, Geo<FUSED_NC>::THREADS, SMEM_BYTES);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_evp_substep_fused<FUSED_NC, false, false>, Geo<FUSED_NC>::THREADS, SMEM_BYTES);
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-            per_sm = (a < b ? a : b) * nsm;
-            if (per_sm < 1) per_sm = 148;
-        }
-        const int slots = per_sm;
-        int best = 128;
-        double best_eff = 0.0;
-        for (int ly = 48; ly <= 512; ly += 8) {
-            const int ctas = strips * ((nrows + ly - 1) / ly);
-            const int waves = (ctas + slots - 1) / slots;
-            const double eff = (double)ctas / (waves * slots) * ((double)ly / (ly + 5));
-            if (eff > best_eff) { best_eff = eff; best = ly; }
-        }
-        LY = best;
-    }
-    P.LY = LY;
-    dim3 grid(strips, (nrows + LY - 1) / LY);
+    dim3 grid((ncols + OUTX - 1) / OUTX, (nrows + OUTY - 1) / OUTY);
 
     // pack: caller parents -> internal layout (window includes W halo cells; evolving fields into both copies)
     const int w = W;

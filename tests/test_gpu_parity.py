@@ -152,7 +152,7 @@ def test_fast_arithmetic_equals_ieee_operators(span):
     import ctypes as C
     from climaseaice_b200 import lib
     out = (C.c_uint64 * 5)()
-    rc = lib().csi_selftest_math(2_000_000_000, 20260417 + span, span, out)
+    rc = lib().csi_selftest_math(2_000_000_000, 20260417 + span, span, out)  # divisors are drawn positive, as in every kernel use
     assert rc == 0
     assert list(out)[:4] == [0, 0, 0, 0], list(out)
     if span <= 250:
