@@ -53,7 +53,7 @@ enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, 
 // shared-memory arrays (each SXD x SYD doubles)
 enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E22, A_E12, A_AL, A_W, NARR };
 
-constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64;
+constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64;  // + two mbarriers
 
 struct Params {
     int Nx, Ny;          // interior size
@@ -215,7 +215,7 @@ struct MathSlow {
 };
 
 // u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
-template <class M>
+template <bool GEN, class M>
 __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
                                          double uold, double vbar, double ue, double vebar, double ttop, double un, double sD1, double sD0,
                                          double sT1, double sT0, double s12hi, double s12lo)
@@ -224,12 +224,12 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
     const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
     const double dtau = mm.divn(p.dt, Ra);
     double coef = 0.0, tbot = 0.0;
-    if (p.sis) {
+    if (GEN ? p.sis != 0 : true) {
         const double du = ue - uold, dv = vebar - vbar;
         coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
         tbot = coef * ue;
     }
-    const double xcross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : -p.f * vbar;
+    const double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : -p.f * vbar;
     const double rheo = mm.divn(mm.div(un - uold, dtau), Ra);
     const double d = p.dy * (sD1 - sD0) / 2;
     const double tt = mm.divc(p.dy2 * sT1 - p.dy2 * sT0, p.dy, p.rdy) / 2;
@@ -244,7 +244,7 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
     return jl_mul_bool(active_ice ? uD : 0.0, active);  // free_drift = nothing: marginal ice -> 0
 }
 // v at (i, r): se:231-264, mt:44-74, ext:183-202, isd:46-51, evp:385,397-401.  *0 = row r-1.
-template <class M>
+template <bool GEN, class M>
 __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
                                          double vold, double ubar, double ve, double uebar, double ttop, double vn, double sD1, double sD0,
                                          double sT1, double sT0, double s12hi, double s12lo)
@@ -253,12 +253,12 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, do
     const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
     const double dtau = mm.divn(p.dt, Ra);
     double coef = 0.0, tbot = 0.0;
-    if (p.sis) {
+    if (GEN ? p.sis != 0 : true) {
         const double dv = ve - vold, du = uebar - ubar;
         coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
         tbot = coef * ve;
     }
-    const double ycross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : p.f * ubar;
+    const double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : p.f * ubar;
     const double rheo = mm.divn(mm.div(vn - vold, dtau), Ra);
     const double d = p.dx * (sD1 - sD0) / 2;
     const double tt = mm.divc(-(p.dx2 * sT1 - p.dx2 * sT0), p.dx, p.rdx) / 2;
@@ -276,92 +276,131 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, do
 // ---- the kernel ----------------------------------------------------------------------------
 // Tile-local coordinates: (sx, sy) in [0,BX) x [0,BY) are the stress nodes; node (sx, sy) is the
 // reference index (I0-1+sx, J0-1+sy), so the velocity cells of the tile are sx in [1,30], sy in [1,14].
-// Shared arrays hold [-1, BX] x [-1, BY]; S(a, sx, sy) addresses them.
+// Shared arrays hold [-1, BX] x [-1, BY].  S(a, sx, sy) addresses them; SB(b, a, dx, dy) does the
+// same relative to a node pointer b = &S(0, sx, sy), with compile-time offsets.
 #define S(a, sx, sy) (sm[(a) * ASTRIDE + ((sy) + 1) * SXD + ((sx) + 1)])
+#define SB(b, a, dx, dy) ((b)[(a) * ASTRIDE + (dy) * SXD + (dx)])
 
 struct TileCtx {
     int I0, J0;  // reference index of the first velocity cell of the tile
     int fin, fout;
 };
 
-// All phases of one tile under one arithmetic policy.  Returns (via `bad`) whether any thread left
-// the policy's windows.  Global stores happen only when the pass is clean (or is the SLOW pass).
-template <bool VFIRST, bool AUX, class M>
+// All phases of one tile under one arithmetic policy.  Returns whether any thread left the policy's
+// windows; global stores happen only when the pass is clean (the SLOW pass always is).
+// GEN = false compiles the common configuration (SemiImplicitStress with velocity arrays, wind-stress
+// arrays, FPlane, ReplacementPressure) without its run-time switches.
+template <bool VFIRST, bool AUX, bool GEN, class M>
 __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const size_t plane = (size_t)p.pitch * p.rows;
-    // ---- TMA: tile + halo of every stencil field ----
+    const bool use_ue = GEN ? p.use_ue != 0 : true, use_top = GEN ? p.use_top != 0 : true;
+    // ---- TMA: tile + halo of every stencil field; u, v first (phase A starts on them) ----
     if (tid == 0) {
         const int x = tc.I0 - 2 - 1 + OX, y = tc.J0 - 2 - 1 + p.oy;
-        int n = 8;
-        auto ld = [&](int arr, int field) { tma_load_row(sm + arr * ASTRIDE, tmap, bar, x, y, field); };
-        ld(A_U, tc.fin + 0);
-        ld(A_V, tc.fin + 1);
-        ld(A_H, F_H);
-        ld(A_A, F_A);
-        ld(A_P, F_P);
-        ld(A_S11, tc.fin + 2);
-        ld(A_S22, tc.fin + 3);
-        ld(A_S12, tc.fin + 4);
-        if (p.use_ue) {
-            ld(A_UE, F_UE);
-            ld(A_VE, F_VE);
+        auto ld = [&](int arr, int field, uint64_t *b) { tma_load_row(sm + arr * ASTRIDE, tmap, b, x, y, field); };
+        ld(A_U, tc.fin + 0, &bar[0]);
+        ld(A_V, tc.fin + 1, &bar[0]);
+        mbar_expect_tx(&bar[0], 2u * SXD * SYD * sizeof(double));
+        int n = 6;
+        ld(A_H, F_H, &bar[1]);
+        ld(A_A, F_A, &bar[1]);
+        ld(A_P, F_P, &bar[1]);
+        ld(A_S11, tc.fin + 2, &bar[1]);
+        ld(A_S22, tc.fin + 3, &bar[1]);
+        ld(A_S12, tc.fin + 4, &bar[1]);
+        if (use_ue) {
+            ld(A_UE, F_UE, &bar[1]);
+            ld(A_VE, F_VE, &bar[1]);
             n += 2;
         }
-        mbar_expect_tx(bar, (uint32_t)n * SXD * SYD * sizeof(double));
+        mbar_expect_tx(&bar[1], (uint32_t)n * SXD * SYD * sizeof(double));
     }
-    mbar_wait(bar, parity);
+    // global offsets of the nodes this thread updates in phases C and D (32-wide rows: lane = column)
+    // C: odd  -> v at sx = lane (0..30), sy = 1 + wrp + 8 q (<= 15);  even -> u at sx = lane + 1 (1..31), sy = wrp + 8 q (<= 14)
+    // D: sx = lane + 1 (1..30), sy = 1 + wrp + 8 q (<= 14)
+    const int c_sx = VFIRST ? lane : lane + 1, c_sy0 = VFIRST ? 1 + wrp : wrp;
+    const bool c_on[2] = {lane < OUTX + 1, lane < OUTX + 1 && c_sy0 + 8 <= (VFIRST ? OUTY + 1 : OUTY)};
+    const int d_sx = lane + 1, d_sy0 = 1 + wrp;
+    const bool d_on[2] = {lane < OUTX, lane < OUTX && d_sy0 + 8 <= OUTY};
+    auto goff = [&](int sx, int sy) {
+        // clamped into the plane: edge tiles reach past the allocation (those nodes are never stored)
+        const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
+        return (size_t)row * p.pitch + (size_t)col;
+    };
+    const double *gC1 = p.base + (size_t)(VFIRST ? F_VN : F_UN) * plane, *gC2 = p.base + (size_t)(VFIRST ? F_TY : F_TX) * plane;
+    const double *gD1 = p.base + (size_t)(VFIRST ? F_UN : F_VN) * plane, *gD2 = p.base + (size_t)(VFIRST ? F_TX : F_TY) * plane;
+    size_t c_g[2], d_g[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        c_g[q] = goff(c_sx, c_sy0 + 8 * q);
+        d_g[q] = goff(d_sx, d_sy0 + 8 * q);
+        // pull the pointwise inputs of phases C / D towards L2/L1 while the tile lands and A, B run
+        if (c_on[q]) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gC1 + c_g[q]));
+            if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gC2 + c_g[q]));
+        }
+        if (d_on[q]) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gD1 + d_g[q]));
+            if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gD2 + d_g[q]));
+        }
+    }
 
     M mm;
     // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) ----------------
     // e11, e22 on [-1, BX-1] x [-1, BY-1]; e12 on [0, BX] x [0, BY]; m everywhere (in place over h)
+    mbar_wait(&bar[0], parity);
     for (int n = tid; n < SXD * SYD; n += NT) {
         const int sx = n % SXD - 1, sy = n / SXD - 1;
+        double *b = sm + n;  // = &S(0, sx, sy)
+        const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0);
         if (sx < BX && sy < BY) {
-            const double u00 = S(A_U, sx, sy), u10 = S(A_U, sx + 1, sy), v00 = S(A_V, sx, sy), v01 = S(A_V, sx, sy + 1);
+            const double u10 = SB(b, A_U, 1, 0), v01 = SB(b, A_V, 0, 1);
             const double D = mm.divc((p.dy * u10 - p.dy * u00) + (p.dx * v01 - p.dx * v00), p.az, p.raz);
             const double T = mm.divc(p.dy2 * (mm.divc(u10, p.dy, p.rdy) - mm.divc(u00, p.dy, p.rdy)) -
                                          p.dx2 * (mm.divc(v01, p.dx, p.rdx) - mm.divc(v00, p.dx, p.rdx)),
                                      p.az, p.raz);
-            S(A_E11, sx, sy) = (D + T) / 2;
-            S(A_E22, sx, sy) = (D - T) / 2;
+            SB(b, A_E11, 0, 0) = (D + T) / 2;
+            SB(b, A_E22, 0, 0) = (D - T) / 2;
         }
         if (sx >= 0 && sy >= 0) {
-            const double u00 = S(A_U, sx, sy), u0m = S(A_U, sx, sy - 1), v00 = S(A_V, sx, sy), vm0 = S(A_V, sx - 1, sy);
+            const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
             const double Sh = mm.divc(p.dx2 * (mm.divc(u00, p.dx, p.rdx) - mm.divc(u0m, p.dx, p.rdx)) +
                                           p.dy2 * (mm.divc(v00, p.dy, p.rdy) - mm.divc(vm0, p.dy, p.rdy)),
                                       p.az, p.raz);
-            S(A_E12, sx, sy) = Sh / 2;
+            SB(b, A_E12, 0, 0) = Sh / 2;
         }
-        S(A_H, sx, sy) = S(A_H, sx, sy) * p.rho_i * S(A_A, sx, sy);  // h -> m
     }
+    mbar_wait(&bar[1], parity);
+    for (int n = tid; n < SXD * SYD; n += NT) sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
     __syncthreads();
 
     // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
     double aux_zc[2], aux_zf[2], aux_Dc[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        const int n = tid + q * NT, sx = n % BX, sy = n / BX;
-        const double e11c = S(A_E11, sx, sy), e22c = S(A_E22, sx, sy), e12f = S(A_E12, sx, sy);
-        const double e12c = ((S(A_E12, sx, sy) + S(A_E12, sx + 1, sy)) / 2 + (S(A_E12, sx, sy + 1) + S(A_E12, sx + 1, sy + 1)) / 2) / 2;
-        const double e11f = ((S(A_E11, sx - 1, sy - 1) + S(A_E11, sx, sy - 1)) / 2 + (S(A_E11, sx - 1, sy) + S(A_E11, sx, sy)) / 2) / 2;
-        const double e22f = ((S(A_E22, sx - 1, sy - 1) + S(A_E22, sx, sy - 1)) / 2 + (S(A_E22, sx - 1, sy) + S(A_E22, sx, sy)) / 2) / 2;
+        const int sx = lane, sy = wrp + 8 * q;
+        double *b = &S(0, sx, sy);
+        const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
+        const double e12c = ((e12f + SB(b, A_E12, 1, 0)) / 2 + (SB(b, A_E12, 0, 1) + SB(b, A_E12, 1, 1)) / 2) / 2;
+        const double e11f = ((SB(b, A_E11, -1, -1) + SB(b, A_E11, 0, -1)) / 2 + (SB(b, A_E11, -1, 0) + e11c) / 2) / 2;
+        const double e22f = ((SB(b, A_E22, -1, -1) + SB(b, A_E22, 0, -1)) / 2 + (SB(b, A_E22, -1, 0) + e22c) / 2) / 2;
         const double dc = e11c + e22c, df = e11f + e22f;
         const double sc = mm.sqrt_((e11c - e22c) * (e11c - e22c) + 4 * (e12c * e12c));
         const double sf = mm.sqrt_((e11f - e22f) * (e11f - e22f) + 4 * (e12f * e12f));
         const double Dc = jl_max(mm.sqrt_(dc * dc + sc * sc * p.em2), p.Dmin);
         const double Df = jl_max(mm.sqrt_(df * df + sf * sf * p.em2), p.Dmin);
-        const double Pc = S(A_P, sx, sy);
-        const double Pf = ((S(A_P, sx - 1, sy - 1) + S(A_P, sx, sy - 1)) / 2 + (S(A_P, sx - 1, sy) + S(A_P, sx, sy)) / 2) / 2;
+        const double Pc = SB(b, A_P, 0, 0);
+        const double Pf = ((SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) / 2 + (SB(b, A_P, -1, 0) + Pc) / 2) / 2;
         const double zf = mm.div(Pf, 2 * Df), zc = mm.div(Pc, 2 * Dc);
-        const double Pr = p.pform == CSI_ICE_STRENGTH ? Pc : mm.div(Pc * Dc, Dc + p.Dmin);
+        const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.div(Pc * Dc, Dc + p.Dmin);
         const double ec = zc * p.em2, ef = zf * p.em2;
         const double s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
         const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
         const double s12n = 2 * ef * e12f;
-        const double mc = S(A_H, sx, sy);
-        const double mf = ((S(A_H, sx - 1, sy - 1) + S(A_H, sx, sy - 1)) / 2 + (S(A_H, sx - 1, sy) + S(A_H, sx, sy)) / 2) / 2;
+        const double mc = SB(b, A_H, 0, 0);
+        const double mf = ((SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) / 2 + (SB(b, A_H, -1, 0) + mc) / 2) / 2;
         double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), p.az, p.raz);
         g2c = (g2c != g2c) ? p.amax2 : g2c;
         const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
@@ -369,87 +408,76 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         g2f = (g2f != g2f) ? p.amax2 : g2f;
         const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
         const NodeRecip Rg = mm.recip(gc);
-        const double o11 = S(A_S11, sx, sy), o22 = S(A_S22, sx, sy), o12 = S(A_S12, sx, sy);
+        const double o11 = SB(b, A_S11, 0, 0), o22 = SB(b, A_S22, 0, 0), o12 = SB(b, A_S12, 0, 0);
         const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.div(s12n - o12, gf);
         // in place: each thread owns its node of the sigma arrays
-        S(A_S11, sx, sy) = o11 + (mc > 0 ? d11 : 0.0);
-        S(A_S22, sx, sy) = o22 + (mc > 0 ? d22 : 0.0);
-        S(A_S12, sx, sy) = o12 + (mf > 0 ? d12 : 0.0);
-        S(A_AL, sx, sy) = gc;
+        SB(b, A_S11, 0, 0) = o11 + (mc > 0 ? d11 : 0.0);
+        SB(b, A_S22, 0, 0) = o22 + (mc > 0 ? d22 : 0.0);
+        SB(b, A_S12, 0, 0) = o12 + (mf > 0 ? d12 : 0.0);
+        SB(b, A_AL, 0, 0) = gc;
         aux_zc[q] = zc;
         aux_zf[q] = zf;
         aux_Dc[q] = Dc;
     }
     __syncthreads();
 
-    // per-node helpers for the velocity phases
-    const double *gUN = p.base + (size_t)F_UN * plane, *gVN = p.base + (size_t)F_VN * plane;
-    const double *gTX = p.base + (size_t)F_TX * plane, *gTY = p.base + (size_t)F_TY * plane;
-    // offset of node (sx, sy) in a plane of the internal layout, clamped into the plane (edge tiles reach past the
-    // allocation; those nodes are never stored)
-    auto goff = [&](int sx, int sy) {
-        const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
-        return (size_t)row * p.pitch + (size_t)col;
-    };
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
-    auto u_at = [&](int sx, int sy, int VS) -> double {
+    auto u_at = [&](int sx, int sy, int VS, double un, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
         const bool active = !(p.bounded_x && (i <= 1 || i > p.Nx));
-        const double vbar = ((S(VS, sx - 1, sy) + S(VS, sx, sy)) / 2 + (S(VS, sx - 1, sy + 1) + S(VS, sx, sy + 1)) / 2) / 2;
+        const double *b = &S(0, sx, sy);
+        const double vbar = ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
         double ue = p.ue_c, vebar = ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
-        if (p.use_ue) {
-            ue = S(A_UE, sx, sy);
-            vebar = ((S(A_VE, sx - 1, sy) + S(A_VE, sx, sy)) / 2 + (S(A_VE, sx - 1, sy + 1) + S(A_VE, sx, sy + 1)) / 2) / 2;
+        if (use_ue) {
+            ue = SB(b, A_UE, 0, 0);
+            vebar = ((SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) / 2 + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1)) / 2) / 2;
         }
-        const size_t g = goff(sx, sy);
-        const double ttop = p.use_top ? __ldg(gTX + g) : p.ttx, un = __ldg(gUN + g), uold = S(A_U, sx, sy);
-        const double a1 = S(A_S11, sx, sy), b1 = S(A_S22, sx, sy), a0 = S(A_S11, sx - 1, sy), b0 = S(A_S22, sx - 1, sy);
-        const double val = u_node(mm, p, active, S(A_H, sx, sy), S(A_H, sx - 1, sy), S(A_A, sx, sy), S(A_A, sx - 1, sy), S(A_AL, sx, sy),
-                                  S(A_AL, sx - 1, sy), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, S(A_S12, sx, sy + 1),
-                                  S(A_S12, sx, sy));
+        const double uold = SB(b, A_U, 0, 0);
+        const double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, -1, 0), b0 = SB(b, A_S22, -1, 0);
+        const double val = u_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
+                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, SB(b, A_S12, 0, 1),
+                                       SB(b, A_S12, 0, 0));
         return upd ? val : uold;
     };
-    auto v_at = [&](int sx, int sy, int US) -> double {
+    auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
         const bool active = !(p.bounded_y && (r <= 1 || r > p.Ny));
-        const double ubar = ((S(US, sx, sy - 1) + S(US, sx + 1, sy - 1)) / 2 + (S(US, sx, sy) + S(US, sx + 1, sy)) / 2) / 2;
+        const double *b = &S(0, sx, sy);
+        const double ubar = ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
         double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
-        if (p.use_ue) {
-            ve = S(A_VE, sx, sy);
-            uebar = ((S(A_UE, sx, sy - 1) + S(A_UE, sx + 1, sy - 1)) / 2 + (S(A_UE, sx, sy) + S(A_UE, sx + 1, sy)) / 2) / 2;
+        if (use_ue) {
+            ve = SB(b, A_VE, 0, 0);
+            uebar = ((SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) / 2 + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0)) / 2) / 2;
         }
-        const size_t g = goff(sx, sy);
-        const double ttop = p.use_top ? __ldg(gTY + g) : p.tty, vn = __ldg(gVN + g), vold = S(A_V, sx, sy);
-        const double a1 = S(A_S11, sx, sy), b1 = S(A_S22, sx, sy), a0 = S(A_S11, sx, sy - 1), b0 = S(A_S22, sx, sy - 1);
-        const double val = v_node(mm, p, active, S(A_H, sx, sy), S(A_H, sx, sy - 1), S(A_A, sx, sy), S(A_A, sx, sy - 1), S(A_AL, sx, sy),
-                                  S(A_AL, sx, sy - 1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, S(A_S12, sx + 1, sy),
-                                  S(A_S12, sx, sy));
+        const double vold = SB(b, A_V, 0, 0);
+        const double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, 0, -1), b0 = SB(b, A_S22, 0, -1);
+        const double val = v_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, SB(b, A_S12, 1, 0),
+                                       SB(b, A_S12, 0, 0));
         return upd ? val : vold;
     };
 
     // ---------------- phase C: first velocity on the cells the second one reads -------------------------
-    // odd (v first): v on sx in [0,30], sy in [1,15] ; even (u first): u on sx in [1,31], sy in [0,14]
-    constexpr int CW = OUTX + 1, CH = OUTY + 1;
-    for (int n = tid; n < CW * CH; n += NT) {
-        const int cx = n % CW, cy = n / CW;
-        if (VFIRST) S(A_W, cx, cy + 1) = v_at(cx, cy + 1, A_U);
-        else S(A_W, cx + 1, cy) = u_at(cx + 1, cy, A_V);
-    }
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+        if (c_on[q]) {
+            const int sy = c_sy0 + 8 * q;
+            const double n1 = __ldg(gC1 + c_g[q]), t1 = use_top ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
+            S(A_W, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
+        }
     __syncthreads();
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
-    double w2[2];
-    int d_sx[2], d_sy[2];
+    double w2[2] = {0.0, 0.0};
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int n = tid + q * NT;
-        d_sx[q] = n % OUTX + 1;
-        d_sy[q] = n / OUTX + 1;
-        w2[q] = 0.0;
-        if (n < OUTX * OUTY) w2[q] = VFIRST ? u_at(d_sx[q], d_sy[q], A_W) : v_at(d_sx[q], d_sy[q], A_W);
-    }
+    for (int q = 0; q < 2; q++)
+        if (d_on[q]) {
+            const int sy = d_sy0 + 8 * q;
+            const double n1 = __ldg(gD1 + d_g[q]), t1 = use_top ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
+            w2[q] = VFIRST ? u_at(d_sx, sy, A_W, n1, t1) : v_at(d_sx, sy, A_W, n1, t1);
+        }
 
     const bool bad = __syncthreads_or(mm.bad());
     if (bad) return true;
@@ -484,7 +512,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         // stresses (and aux) of the node this thread updated in phase B
-        const int n = tid + q * NT, sx = n % BX, sy = n / BX;
+        const int sx = lane, sy = wrp + 8 * q;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY && i >= p.sx0 && i <= p.sx1 && r >= p.sy0 && r <= p.sy1) {
             put(tc.fout + 2, i, r, S(A_S11, sx, sy));
@@ -498,14 +526,15 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             }
         }
         // velocities of the output cell this thread updated in phase D
-        if (n < OUTX * OUTY) {
-            const int ui = tc.I0 - 1 + d_sx[q], ur = tc.J0 - 1 + d_sy[q];
+        if (d_on[q]) {
+            const int dsy = d_sy0 + 8 * q;
+            const int ui = tc.I0 - 1 + d_sx, ur = tc.J0 - 1 + dsy;
             if (VFIRST) {
                 put_vel(tc.fout + 0, ui, ur, w2[q], true);
-                put_vel(tc.fout + 1, ui, ur, S(A_W, d_sx[q], d_sy[q]), false);
+                put_vel(tc.fout + 1, ui, ur, S(A_W, d_sx, dsy), false);
             } else {
                 put_vel(tc.fout + 1, ui, ur, w2[q], false);
-                put_vel(tc.fout + 0, ui, ur, S(A_W, d_sx[q], d_sy[q]), true);
+                put_vel(tc.fout + 0, ui, ur, S(A_W, d_sx, dsy), true);
             }
         }
     }
@@ -513,8 +542,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 }
 
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
-// alpha, zeta_c, zeta_f, Delta (last substep of a stage).
-template <bool VFIRST, bool AUX>
+// alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
+template <bool VFIRST, bool AUX, bool GEN>
 __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -527,18 +556,20 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
     tc.fin = p.in_set ? F_U1 : F_U0;
     tc.fout = p.out_set ? F_U1 : F_U0;
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tile_pass<VFIRST, AUX, MathFast>(sm, bar, 0, &tmap, p, tc)) {
+    if (tile_pass<VFIRST, AUX, GEN, MathFast>(sm, bar, 0, &tmap, p, tc)) {
         // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, denormals ...):
         // reload the tile and redo it with plain IEEE operators
         __syncthreads();
-        tile_pass<VFIRST, AUX, MathSlow>(sm, bar, 1, &tmap, p, tc);
+        tile_pass<VFIRST, AUX, GEN, MathSlow>(sm, bar, 1, &tmap, p, tc);
     }
 }
 #undef S
+#undef SB
 
 // ---- self test of the FAST arithmetic against the IEEE operators ---------------------------------
 // Each thread draws pseudo-random operands (splitmix64; random significands, exponents spread over
@@ -705,17 +736,22 @@ void fused_destroy(FusedPlan *pl)
     delete pl;
 }
 
-template <bool VFIRST, bool AUX> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
+template <bool VFIRST, bool AUX, bool GEN> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_evp_substep_fused<VFIRST, AUX><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
+    k_evp_substep_fused<VFIRST, AUX, GEN><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
     return cudaGetLastError();
+}
+template <bool GEN> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
+{
+    if (vfirst) return aux ? launch_one<true, true, GEN>(pl, P, grid, s) : launch_one<true, false, GEN>(pl, P, grid, s);
+    return aux ? launch_one<false, true, GEN>(pl, P, grid, s) : launch_one<false, false, GEN>(pl, P, grid, s);
 }
 
 int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, int first_sub, int nsub,
@@ -782,9 +818,9 @@ int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &
         P.out_set = in_set ^ 1;
         const bool vfirst = (sub % 2) != 0;  // se.jl:178-187: odd substeps update v first
         const bool aux = k == nsub - 1;
-        cudaError_t e;
-        if (vfirst) e = aux ? launch_one<true, true>(pl, P, grid, c.stream) : launch_one<true, false>(pl, P, grid, c.stream);
-        else e = aux ? launch_one<false, true>(pl, P, grid, c.stream) : launch_one<false, false>(pl, P, grid, c.stream);
+        // the common configuration runs the variant compiled without run-time switches
+        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE;
+        const cudaError_t e = common ? launch_sub<false>(pl, P, grid, c.stream, vfirst, aux) : launch_sub<true>(pl, P, grid, c.stream, vfirst, aux);
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
         ++*c.launches;
         in_set ^= 1;
