@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -229,6 +230,13 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
     }
     launch_fill_halo(c, g, p, f.u, 1, 0, 1);  // se.jl:170-171
     launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+    if (h->nranks > 1) {
+        // the reference fills the external fields' halos with a full (communicating) fill_halo_regions!
+        // (ext.jl:57-61,72-78); P, un, vn are computed over the whole parent from exchanged h, aice, u, v
+        const DArr ext[4] = {f.top_x, f.top_y, f.ue, f.ve};
+        int rc = exchange_slab_halos(h, ext, 4, g.Hy, s);
+        if (rc) return rc;
+    }
 
     bool use_fused = false;
     if (h->cfg.solver_impl != CSI_SOLVER_UNFUSED && !h->fused_failed) {
@@ -245,8 +253,22 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
                 return fail(h, 1, std::string("fused_create: ") + err);
             }
         }
-        int rc = fused_run(h->fused, c, g, p, f, dt, 1, nsub, err, sizeof err);
-        if (rc) return fail(h, rc, std::string("fused_run: ") + err);
+        // pack -> blocks of K substeps with a slab halo exchange of the internal (double-buffered) fields
+        // in between -> unpack.  K = exchange_every (halo Hy >= 2K+3, se.jl:55-56); one block when serial.
+        int rc = fused_begin(h->fused, c, g, p, f, dt, err, sizeof err);
+        if (rc) return fail(h, rc, std::string("fused_begin: ") + err);
+        const int K = (h->nranks > 1 && h->cfg.exchange_every > 0) ? h->cfg.exchange_every : nsub;
+        for (int sub = 1; sub <= nsub; sub += K) {
+            const int n = std::min(K, nsub - sub + 1);
+            if (h->nranks > 1 && sub > 1) {
+                DArr views[5];
+                fused_views(h->fused, views);
+                if ((rc = exchange_slab_halos(h, views, 5, g.Hy, s))) return rc;
+            }
+            rc = fused_steps(h->fused, c, sub, n, sub + n - 1 == nsub, err, sizeof err);
+            if (rc) return fail(h, rc, std::string("fused_steps: ") + err);
+        }
+        if (nsub > 0 && (rc = fused_end(h->fused, c, f, err, sizeof err))) return fail(h, rc, std::string("fused_end: ") + err);
         // the in-loop fills of se.jl:180-187 happen inside the fused kernel on its internal layout;
         // refresh the caller-visible halos once
         launch_fill_halo(c, g, p, f.u, 1, 0, 1);
@@ -359,14 +381,12 @@ int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaS
         double *recv_s = a.p + (size_t)(a.oy - width) * row;             // halo rows 1-width..0
         double *send_n = a.p + (size_t)(a.oy + g.Ny - width) * row;      // interior rows Ny-width+1..Ny
         double *recv_n = a.p + (size_t)(a.oy + g.Ny) * row;              // halo rows Ny+1..Ny+width
-        if (south >= 0) {
-            api.Send(send_s, cnt, NCCL_FLOAT64, south, h->comm, s);
-            api.Recv(recv_s, cnt, NCCL_FLOAT64, south, h->comm, s);
-        }
-        if (north >= 0) {
-            api.Send(send_n, cnt, NCCL_FLOAT64, north, h->comm, s);
-            api.Recv(recv_n, cnt, NCCL_FLOAT64, north, h->comm, s);
-        }
+        // order matters when both neighbours are the same rank (2 slabs, periodic): my southward send
+        // must pair with the peer's receive from its north, and vice versa
+        if (south >= 0) api.Send(send_s, cnt, NCCL_FLOAT64, south, h->comm, s);
+        if (north >= 0) api.Recv(recv_n, cnt, NCCL_FLOAT64, north, h->comm, s);
+        if (north >= 0) api.Send(send_n, cnt, NCCL_FLOAT64, north, h->comm, s);
+        if (south >= 0) api.Recv(recv_s, cnt, NCCL_FLOAT64, south, h->comm, s);
     }
     int rc = api.GroupEnd();
     if (rc != 0) return fail(h, 1000 + rc, std::string("ncclGroupEnd: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
@@ -746,18 +766,23 @@ int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage
         h->fused = fused_create(h->g, h->p, err, sizeof err);
         if (!h->fused) return fail(h, 1, std::string("fused_create: ") + err);
     }
-    // one untimed launch first (module load, tensor maps)
-    if (use_fused) rc = fused_run(h->fused, c, h->g, h->p, df, dt_stage, 1, 2, err, sizeof err);
-    else launch_evp_stress(c, h->g, h->p, df, dt_stage);
+    // one untimed launch first (module load, tensor maps); the timed region holds kernel launches only
+    if (use_fused) {
+        rc = fused_begin(h->fused, c, h->g, h->p, df, dt_stage, err, sizeof err);
+        if (!rc) rc = fused_steps(h->fused, c, 1, 2, false, err, sizeof err);
+    } else {
+        launch_evp_stress(c, h->g, h->p, df, dt_stage);
+    }
     if (rc) return fail(h, rc, err);
     CSI_CUDA(h, cudaEventRecord(h->ev0, s));
-    if (use_fused) rc = fused_run(h->fused, c, h->g, h->p, df, dt_stage, 1, reps, err, sizeof err);
+    if (use_fused) rc = fused_steps(h->fused, c, 1, reps, false, err, sizeof err);
     else for (int k = 0; k < reps; k++) launch_evp_stress(c, h->g, h->p, df, dt_stage);
     if (rc) return fail(h, rc, err);
     CSI_CUDA(h, cudaEventRecord(h->ev1, s));
     CSI_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     CSI_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (use_fused && (rc = fused_end(h->fused, c, df, err, sizeof err))) return fail(h, rc, err);
     *out_ms = (double)ms / reps;
     snprintf(name64, 64, "%s", use_fused ? "k_evp_substep_fused" : "k_evp_stress");
     *bytes_per_cell = use_fused ? 144 : 120;

@@ -669,6 +669,9 @@ __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 
 // ---- host side ----------------------------------------------------------------------------------
 struct FusedPlan {
+    fz::Params P;
+    dim3 grid;
+    int cur_set = 0;
     double *base = nullptr;
     int pitch = 0, rows = 0, oy = 0;
     CUtensorMap tmap;
@@ -754,11 +757,11 @@ template <bool GEN> static cudaError_t launch_sub(const FusedPlan *pl, const fz:
     return aux ? launch_one<false, true, GEN>(pl, P, grid, s) : launch_one<false, false, GEN>(pl, P, grid, s);
 }
 
-int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, int first_sub, int nsub,
-              char *err, int nerr)
+int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, char *err, int nerr)
 {
     using namespace fz;
-    Params P;
+    Params &P = pl->P;
+
     memset(&P, 0, sizeof P);
     P.Nx = g.Nx; P.Ny = g.Ny; P.pitch = pl->pitch; P.rows = pl->rows; P.oy = pl->oy;
     P.px = g.topo_x == CSI_PERIODIC;
@@ -811,20 +814,57 @@ int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &
     if (P.use_top) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
     if (P.use_ue) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
 
-    int in_set = 0;
+    pl->grid = grid;
+    pl->cur_set = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, nerr, "pack: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+// `nsub` substeps starting at substep index `first_sub` (odd substeps update v first, se.jl:178-187);
+// `aux_last`: the last of them also writes alpha, zeta, Delta.
+int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool aux_last, char *err, int nerr)
+{
+    using namespace fz;
+    Params &P = pl->P;
+    const dim3 grid = pl->grid;
     for (int k = 0; k < nsub; k++) {
         const int sub = first_sub + k;
-        P.in_set = in_set;
-        P.out_set = in_set ^ 1;
-        const bool vfirst = (sub % 2) != 0;  // se.jl:178-187: odd substeps update v first
-        const bool aux = k == nsub - 1;
+        P.in_set = pl->cur_set;
+        P.out_set = pl->cur_set ^ 1;
+        const bool vfirst = (sub % 2) != 0;
+        const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
         const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE;
         const cudaError_t e = common ? launch_sub<false>(pl, P, grid, c.stream, vfirst, aux) : launch_sub<true>(pl, P, grid, c.stream, vfirst, aux);
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
         ++*c.launches;
-        in_set ^= 1;
+        pl->cur_set ^= 1;
     }
+    return 0;
+}
+
+// views of the current copy of the evolving fields (u, v, s11, s22, s12) in the internal layout,
+// for the slab halo exchange between blocks of substeps
+void fused_views(const FusedPlan *pl, DArr out[5])
+{
+    using namespace fz;
+    const size_t plane = (size_t)pl->pitch * pl->rows;
+    for (int k = 0; k < 5; k++) {
+        out[k].p = pl->base + (size_t)((pl->cur_set ? F_U1 : F_U0) + k) * plane;
+        out[k].sx = pl->pitch;
+        out[k].sy = pl->rows;
+        out[k].ox = OX;
+        out[k].oy = pl->oy;
+    }
+}
+
+int fused_end(FusedPlan *pl, const LaunchCtx &c, const DFields &f, char *err, int nerr)
+{
+    using namespace fz;
+    Params &P = pl->P;
+    const int in_set = pl->cur_set;
+    const int nsub = 1;
     // unpack the final copy into the caller's arrays (interior / stress window); halos are refilled by the caller
     auto unpack = [&](const DArr &a, int field, int i0, int i1, int j0, int j1) {
         if (!a.p) return;
@@ -848,6 +888,16 @@ int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, nerr, "%s", cudaGetErrorString(e)); return (int)e; }
     return 0;
+}
+
+
+int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, int first_sub, int nsub,
+              char *err, int nerr)
+{
+    int rc = fused_begin(pl, c, g, p, f, dt, err, nerr);
+    if (rc) return rc;
+    if ((rc = fused_steps(pl, c, first_sub, nsub, true, err, nerr))) return rc;
+    return nsub > 0 ? fused_end(pl, c, f, err, nerr) : 0;
 }
 
 }  // namespace csi
