@@ -139,6 +139,9 @@ struct MathFast {
     static constexpr uint32_t DLO = 0x300u << 21, DHI = (0x500u << 21) - 1u;  // |d| in [2^-255, 2^257)
     __device__ __forceinline__ void chkq(double q)
     {
+#ifdef CSI_EXPERIMENT_NOCHECK
+        return;
+#endif
         const uint32_t g = (uint32_t)__double2hiint(q) << 1;
         qmx = max(qmx, g);
         qmn = min(qmn, g - 1u);  // g == 0 (a zero) wraps to 0xffffffff and is ignored
@@ -509,6 +512,40 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             if (i == p.Nx) q[1] = p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (p.dx / 2)) * p.dx : val;
         }
     };
+    // interior tiles (the vast majority): every output cell is inside all store windows and has no periodic
+    // image or wall neighbour -> plain stores at one precomputed offset
+    {
+        const int i_lo = tc.I0, i_hi = tc.I0 + OUTX - 1, r_lo = tc.J0, r_hi = tc.J0 + OUTY - 1;
+        const bool inside = i_lo >= max(p.sx0, p.vx0) && i_hi <= min(p.sx1, p.vx1) && r_lo >= max(p.sy0, p.vy0) && r_hi <= min(p.sy1, p.vy1);
+        const bool no_img = (!p.px || (i_lo > W && i_hi <= p.Nx - W)) && (!p.py || (r_lo > W && r_hi <= p.Ny - W));
+        const bool no_wall = (!p.bounded_x || (i_lo > 1 && i_hi < p.Nx)) && (!p.bounded_y || (r_lo > 1 && r_hi < p.Ny));
+        if (inside && no_img && no_wall) {
+            double *o = p.base + (size_t)(tc.J0 - 2 + p.oy) * p.pitch + (size_t)(tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int sx = lane, sy = wrp + 8 * q;
+                if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
+                    double *g = o + (size_t)sy * p.pitch + sx;
+                    g[(size_t)(tc.fout + 2) * plane] = S(A_S11, sx, sy);
+                    g[(size_t)(tc.fout + 3) * plane] = S(A_S22, sx, sy);
+                    g[(size_t)(tc.fout + 4) * plane] = S(A_S12, sx, sy);
+                    if (AUX) {
+                        g[(size_t)F_ALPHA * plane] = S(A_AL, sx, sy);
+                        g[(size_t)F_ZC * plane] = aux_zc[q];
+                        g[(size_t)F_ZF * plane] = aux_zf[q];
+                        g[(size_t)F_DELTA * plane] = aux_Dc[q];
+                    }
+                }
+                if (d_on[q]) {
+                    const int dsy = d_sy0 + 8 * q;
+                    double *g = o + (size_t)dsy * p.pitch + d_sx;
+                    g[(size_t)(tc.fout + (VFIRST ? 0 : 1)) * plane] = w2[q];
+                    g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(A_W, d_sx, dsy);
+                }
+            }
+            return false;
+        }
+    }
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         // stresses (and aux) of the node this thread updated in phase B
