@@ -244,7 +244,8 @@ def run_gpu(args):
         for _ in range(n_e2e):
             hs.evp_substeps(DT_STAGE, SUBSTEPS)
         wall = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": cells * SUBSTEPS / wall, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes_momentum,
+        h2d, d2h = hs.last_transfer_bytes()
+        e2e = {"value": cells * SUBSTEPS / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": wall * 1e3, "call": "csi_evp_substeps_host (pinned host arrays)"}
         hs.model.close()
 
@@ -342,7 +343,7 @@ def main():
     ap.add_argument("--periodic", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-n", type=int, default=1024)
+    ap.add_argument("--cpu-n", type=int, default=2048)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -78,7 +78,7 @@ EXPORTS = (
     "csi_version", "csi_last_error", "csi_create", "csi_destroy", "csi_evp_substeps",
     "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
     "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
-    "csi_evp_substeps_host", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count",
+    "csi_evp_substeps_host", "csi_last_transfer_bytes", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count",
     "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_selftest_math", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
 )
 
@@ -111,6 +111,7 @@ def lib():
     L.csi_diagnostics.argtypes = [H, C.POINTER(csi_fields), C.POINTER(C.c_double), C.c_void_p]
     L.csi_time_step_host.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.c_int32]
     L.csi_evp_substeps_host.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32]
+    L.csi_last_transfer_bytes.argtypes = [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.csi_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.csi_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
     L.csi_exchange_halos.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_void_p]

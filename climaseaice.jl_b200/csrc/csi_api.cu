@@ -86,6 +86,7 @@ struct csi_handle {
     std::vector<double *> mirror;
     std::vector<size_t> mirror_n;
     cudaStream_t own_stream = nullptr;
+    size_t last_h2d = 0, last_d2h = 0;  // bytes moved by the last *_host call
     // slab partition
     void *comm = nullptr;
     int rank = 0, nranks = 1;
@@ -624,7 +625,9 @@ int csi_diagnostics(csi_handle *h, const csi_fields *f, double *out_host5, csi_s
 }
 
 // ---- host-buffer entry points ------------------------------------------------------------------
-static int upload_all(csi_handle *h, const csi_fields *hf, csi_fields *dev, cudaStream_t s)
+// Mirrors every non-NULL host array on the device; copies only the ones in `inputs` (a bit mask over
+// csi_fields member indices): arrays the call merely writes (P, un, vn, zeta, Delta, alpha, G^n ...) are not uploaded.
+static int upload_all(csi_handle *h, const csi_fields *hf, csi_fields *dev, cudaStream_t s, uint32_t inputs, size_t *h2d_bytes)
 {
     for (int k = 0; k < NFIELDS; k++) {
         const csi_array &a = field_at(*hf, k);
@@ -638,7 +641,10 @@ static int upload_all(csi_handle *h, const csi_fields *hf, csi_fields *dev, cuda
             CSI_CUDA(h, cudaMalloc(&h->mirror[k], n * sizeof(double)));
             h->mirror_n[k] = n;
         }
-        CSI_CUDA(h, cudaMemcpyAsync(h->mirror[k], a.ptr, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (inputs & (1u << k)) {
+            CSI_CUDA(h, cudaMemcpyAsync(h->mirror[k], a.ptr, n * sizeof(double), cudaMemcpyHostToDevice, s));
+            if (h2d_bytes) *h2d_bytes += n * sizeof(double);
+        }
         d.ptr = h->mirror[k];
     }
     return CSI_OK;
@@ -650,6 +656,7 @@ static int download(csi_handle *h, const csi_fields *hf, const int *which, int n
         const csi_array &a = field_at(*hf, k);
         if (!a.ptr) continue;
         CSI_CUDA(h, cudaMemcpyAsync(a.ptr, h->mirror[k], h->mirror_n[k] * sizeof(double), cudaMemcpyDeviceToHost, s));
+        h->last_d2h += h->mirror_n[k] * sizeof(double);
     }
     return CSI_OK;
 }
@@ -662,7 +669,10 @@ int csi_time_step_host(csi_handle *h, const csi_fields *hf, double dt, int32_t n
     if (!h->own_stream) CSI_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     cudaStream_t s = h->own_stream;
     csi_fields dev;
-    int rc = upload_all(h, hf, &dev, s);
+    // inputs of time_step!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17); Psi^- is written before it is read
+    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14);  // + alpha (10): only its interior is rewritten, the halo must survive the round trip
+    h->last_h2d = h->last_d2h = 0;
+    int rc = upload_all(h, hf, &dev, s, in_mask, &h->last_h2d);
     if (rc) return rc;
     DFields df;
     if ((rc = convert_fields(h, &dev, NEED_MOMENTUM | NEED_TRACERS | NEED_RK, &df))) return rc;
@@ -685,7 +695,10 @@ int csi_evp_substeps_host(csi_handle *h, const csi_fields *hf, double dt_stage, 
     if (!h->own_stream) CSI_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     cudaStream_t s = h->own_stream;
     csi_fields dev;
-    int rc = upload_all(h, hf, &dev, s);
+    // inputs of time_step_momentum!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17), and Psi^-.u, .v (22, 23) under RK3
+    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14) | (h->cfg.timestepper == CSI_RK3 ? (0x3u << 22) : 0u);
+    h->last_h2d = h->last_d2h = 0;
+    int rc = upload_all(h, hf, &dev, s, in_mask, &h->last_h2d);
     if (rc) return rc;
     DFields df;
     if ((rc = convert_fields(h, &dev, NEED_MOMENTUM, &df))) return rc;
@@ -801,6 +814,14 @@ int csi_selftest_math(int64_t samples, uint64_t seed, int32_t exponent_span, uin
     int rc = csi::fz::selftest_math(samples, seed, exponent_span, tmp);
     for (int k = 0; k < 5; k++) out5[k] = tmp[k];
     return rc;
+}
+
+int csi_last_transfer_bytes(const csi_handle *h, uint64_t *h2d, uint64_t *d2h)
+{
+    if (!h || !h2d || !d2h) return CSI_ERR_ARG;
+    *h2d = h->last_h2d;
+    *d2h = h->last_d2h;
+    return CSI_OK;
 }
 
 double csi_host_exp(double x) { return csi::exp_cr(x); }

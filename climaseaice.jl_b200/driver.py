@@ -63,17 +63,11 @@ class HostStepper:
             setattr(self.fields, n, a)
         self.iteration = 0
 
-    @property
-    def h2d_bytes(self):
-        return sum(t.numel() * 8 for t in self.host.values())
-
-    @property
-    def d2h_bytes(self):
-        return sum(self.host[n].numel() * 8 for n in ("u", "v", "h", "a", "s11", "s22", "s12", "alpha"))
-
-    @property
-    def d2h_bytes_momentum(self):
-        return sum(self.host[n].numel() * 8 for n in ("u", "v", "s11", "s22", "s12", "alpha"))
+    def last_transfer_bytes(self):
+        """(host->device, device->host) bytes of the last call, as counted by the library."""
+        a, b = C.c_uint64(), C.c_uint64()
+        L.check(L.lib().csi_last_transfer_bytes(self.model._handle, C.byref(a), C.byref(b)), self.model._handle)
+        return a.value, b.value
 
     def time_step(self, dt, nsteps=1):
         h = self.model._handle

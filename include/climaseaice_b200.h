@@ -155,6 +155,9 @@ int csi_time_step_host(csi_handle *h, const csi_fields *host_fields, double dt, 
 /* Same for the momentum solve alone (time_step_momentum! with host buffers). */
 int csi_evp_substeps_host(csi_handle *h, const csi_fields *host_fields, double dt_stage, int32_t nsubsteps);
 
+/* Bytes the last *_host call copied host->device and device->host (inputs only go up, results only come down). */
+int csi_last_transfer_bytes(const csi_handle *h, uint64_t *h2d, uint64_t *d2h);
+
 /* Multi-GPU (one process per GPU, slabs along y).  The 128-byte NCCL unique id is produced on
  * rank 0 and distributed by the host application (torch.distributed / MPI.jl broadcast). */
 int csi_nccl_unique_id(uint8_t out128[128]);
