@@ -502,14 +502,24 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if (!(i >= p.vx0 && i <= p.vx1 && r >= p.vy0 && r <= p.vy1)) return;
         put(field, i, r, val);
         double *q = p.base + (size_t)field * plane + (size_t)(r - 1 + p.oy) * p.pitch + (size_t)(i - 1 + OX);
-        // walls: one tangential halo cell (value / no-flux BC), as fill_halo_regions! does
-        if (is_u && p.bounded_y) {
-            if (r == 1) q[-p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val;
-            if (r == p.Ny) q[p.pitch] = p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (p.dy / 2)) * p.dy : val;
+        // walls: one tangential halo cell (value / no-flux BC), as fill_halo_regions! does -- and, on a mixed
+        // topology, its periodic image along the other axis (the reference fills the periodic axis last,
+        // over the full parent extent, so corners hold images of the wall cells)
+        if (is_u && p.bounded_y && (r == 1 || r == p.Ny)) {
+            const int ix = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
+            const double wv = r == 1 ? (p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val)
+                                     : (p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (p.dy / 2)) * p.dy : val);
+            double *w = r == 1 ? q - p.pitch : q + p.pitch;
+            w[0] = wv;
+            if (ix) w[ix] = wv;
         }
-        if (!is_u && p.bounded_x) {
-            if (i == 1) q[-1] = p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (p.dx / 2)) * (-p.dx) : val;
-            if (i == p.Nx) q[1] = p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (p.dx / 2)) * p.dx : val;
+        if (!is_u && p.bounded_x && (i == 1 || i == p.Nx)) {
+            const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
+            const double wv = i == 1 ? (p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (p.dx / 2)) * (-p.dx) : val)
+                                     : (p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (p.dx / 2)) * p.dx : val);
+            double *w = i == 1 ? q - 1 : q + 1;
+            w[0] = wv;
+            if (iy) w[(ptrdiff_t)iy * p.pitch] = wv;
         }
     };
     // interior tiles (the vast majority): every output cell is inside all store windows and has no periodic

@@ -157,3 +157,129 @@ def test_fast_arithmetic_equals_ieee_operators(span):
     assert list(out)[:4] == [0, 0, 0, 0], list(out)
     if span <= 250:
         assert out[4] < 0.01 * 2e9   # these exponent ranges stay inside the fast windows (bar the all-ones guard)
+
+
+def _variant_case(kind):
+    """Configurations off the benchmark's common path: every run-time switch of the kernels."""
+    from climaseaice_b200.synthetic import Case
+    if kind == "no_top_no_coriolis":
+        c = periodic_case(37, Ny=23, substeps=7, aice="mixed")
+        c.coriolis_f = None
+        del c.fields["top_x"], c.fields["top_y"]
+    elif kind == "const_ocean":
+        c = periodic_case(33, Ny=41, substeps=6, aice="ones")
+        del c.fields["ue"], c.fields["ve"]
+    elif kind == "periodic_x_bounded_y":
+        c = periodic_case(40, Ny=36, substeps=9, aice="mixed")
+        c.topology = ("Periodic", "Bounded")
+        c.u_bc_value = 0.0
+        for k in ("v", "top_y", "ve"):   # Face-y fields carry Ny+1 rows on a Bounded y axis
+            c.fields[k] = np.ascontiguousarray(np.vstack([c.fields[k], c.fields[k][-1:]]))
+    elif kind == "bounded_x_periodic_y":
+        c = periodic_case(36, Ny=40, substeps=9, aice="mixed")
+        c.topology = ("Bounded", "Periodic")
+        c.v_bc_value = 0.0
+        for k in ("u", "top_x", "ue"):
+            c.fields[k] = np.ascontiguousarray(np.hstack([c.fields[k], c.fields[k][:, -1:]]))
+    elif kind == "tiny_grid":
+        c = periodic_case(9, Ny=8, substeps=5, aice="ones")
+    elif kind == "halo3":
+        c = periodic_case(48, Ny=32, H=4, substeps=8, aice="mixed", advection_order=5)
+    else:
+        raise KeyError(kind)
+    return c
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kind", ["no_top_no_coriolis", "const_ocean", "periodic_x_bounded_y", "bounded_x_periodic_y", "tiny_grid", "halo3"])
+def test_configuration_switches(impl, kind):
+    case = _variant_case(kind)
+    over = {}
+    if kind == "const_ocean":
+        over = dict(ue_c=0.03, ve_c=-0.02)
+    m = model_from_case(case, solver_impl=impl)
+    if kind == "const_ocean":
+        m.close()
+        from climaseaice_b200 import SemiImplicitStress
+        from climaseaice_b200.driver import grid_from_case
+        import climaseaice_b200 as csi
+        grid = grid_from_case(case)
+        F = case.fields
+        dyn = csi.SeaIceMomentumEquation(grid, coriolis=csi.FPlane(case.coriolis_f),
+                                         top_momentum_stress=dict(u=csi.Field((1, 0), grid, F["top_x"]), v=csi.Field((0, 1), grid, F["top_y"])),
+                                         bottom_momentum_stress=SemiImplicitStress(ue=0.03, ve=-0.02), solver=csi.SplitExplicitSolver(substeps=case.substeps))
+        m = csi.SeaIceModel(grid, dynamics=dyn, advection=csi.WENO(7), solver_impl=impl)
+        m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
+    o = oracle_from_case(case, **over)
+    m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    m.close()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_ice_strength_pressure_and_forward_euler(impl):
+    case = periodic_case(40, Ny=30, substeps=11, aice="mixed", timestepper="ForwardEuler")
+    import climaseaice_b200 as csi
+    from climaseaice_b200.driver import grid_from_case
+    grid = grid_from_case(case)
+    F = case.fields
+    dyn = csi.SeaIceMomentumEquation(grid, coriolis=csi.FPlane(case.coriolis_f),
+                                     rheology=csi.ElastoViscoPlasticRheology(pressure_formulation="IceStrength", min_relaxation_parameter=30.0),
+                                     top_momentum_stress=dict(u=0.05, v=-0.02),
+                                     bottom_momentum_stress=csi.SemiImplicitStress(ue=csi.Field((1, 0), grid, F["ue"]), ve=csi.Field((0, 1), grid, F["ve"])),
+                                     solver=csi.SplitExplicitSolver(substeps=case.substeps))
+    m = csi.SeaIceModel(grid, dynamics=dyn, advection=csi.WENO(7), timestepper="ForwardEuler", solver_impl=impl)
+    m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
+    del case.fields["top_x"], case.fields["top_y"]
+    from oracle import oracle as O
+    o = oracle_from_case(case, pressure_formulation=1, alpha_min=30.0, top_kind=O.STRESS_CONST, top_tx=0.05, top_ty=-0.02)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    m.close()
+
+
+def test_shape_errors_are_reported():
+    """A field whose parent does not match the grid is refused with CSI_ERR_SHAPE, not silently accepted."""
+    import climaseaice_b200 as csi
+    case = periodic_case(24, substeps=2)
+    m = model_from_case(case)
+    other = csi.RectilinearGrid(size=(25, 24), x=(0, 1e5), y=(0, 1e5), halo=(7, 7))
+    m.ice_thickness = csi.Field((0, 0), other)
+    with pytest.raises(csi.CsiError) as e:
+        m.time_step(case.dt)
+    assert e.value.code == -2 and "field 'h'" in str(e.value)
+    m.close()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_immersed_mask(impl):
+    """Immersed-boundary land mask (BASELINE config 4 ingredients: masked stresses isd:16-24, peripheral-node
+    velocity mask se:226,261, zero flux through immersed faces, mask_immersed_field_xy! in update_state!).
+    Masks run on the unfused kernels; solver_impl='auto' must pick them and give the same answer."""
+    case = periodic_case(40, Ny=36, substeps=9, aice="mixed")
+    X, Y = case.nodes((0, 0))
+    sy, sx = case.parent_shape((0, 0))
+    mask = (((X / case.Lx - 0.5) ** 2 + (Y / case.Ly - 0.45) ** 2) < 0.03).astype(np.uint8)   # an island
+    mask[:, :case.Hx] = mask[:, case.Nx:case.Nx + case.Hx]; mask[:, case.Nx + case.Hx:] = mask[:, case.Hx:2 * case.Hx]
+    mask[:case.Hy, :] = mask[case.Ny:case.Ny + case.Hy, :]; mask[case.Ny + case.Hy:, :] = mask[case.Hy:2 * case.Hy, :]
+    import climaseaice_b200 as csi
+    from climaseaice_b200.driver import grid_from_case
+    grid = grid_from_case(case)
+    F = case.fields
+    dyn = csi.SeaIceMomentumEquation(grid, coriolis=csi.FPlane(case.coriolis_f),
+                                     top_momentum_stress=dict(u=csi.Field((1, 0), grid, F["top_x"]), v=csi.Field((0, 1), grid, F["top_y"])),
+                                     bottom_momentum_stress=csi.SemiImplicitStress(ue=csi.Field((1, 0), grid, F["ue"]), ve=csi.Field((0, 1), grid, F["ve"])),
+                                     solver=csi.SplitExplicitSolver(substeps=case.substeps))
+    m = csi.SeaIceModel(grid, dynamics=dyn, advection=csi.WENO(7), solver_impl=impl, immersed_mask=mask)
+    m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
+    from oracle import oracle as O
+    from tests.helpers import oracle_params
+    o = O.OracleModel(case.Nx, case.Ny, case.Hx, case.Hy, dx=case.dx, dy=case.dy, params=oracle_params(case),
+                      fields={k: v.copy() for k, v in case.fields.items()}, mask=mask)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    inside = mask[case.Hy:-case.Hy, case.Hx:-case.Hx].astype(bool)
+    assert np.all(interior_of(m.all_fields()["h"].numpy(), case)[inside] == 0)   # land stays ice free
+    m.close()
