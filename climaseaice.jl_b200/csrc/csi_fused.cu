@@ -133,10 +133,15 @@ struct NodeRecip {
 };
 
 struct MathFast {
-    // exponent field << 21 of: quotients / radicands (zero allowed) and divisors (zero not allowed)
-    uint32_t qmn = 0xffffffffu, qmx = 0u, dmn = 0xffffffffu, dmx = 0u, lo1 = 0xffffffffu, neg = 0u;
-    static constexpr uint32_t QLO = 0x200u << 21, QHI = (0x600u << 21) - 1u;  // |q| in [2^-511, 2^513)
-    static constexpr uint32_t DLO = 0x300u << 21, DHI = (0x500u << 21) - 1u;  // |d| in [2^-255, 2^257)
+    // Window accumulators on the high word of each checked double (exponent field = bits 30..20):
+    //  * quotients (any sign, zero allowed): g = hi << 1; qmx = max g, qmn = min (g - 1)  -> |q| in [2^-511, 2^513) or q == 0
+    //  * divisors  (positive, non-zero): dacc = umax(hi - DLO)  -> d in [2^-255, 2^257); zeros, negatives, NaN wrap high
+    //  * radicands: checked like quotients (a zero radicand -- ice exactly at rest -- is legitimate), plus a sign accumulator
+    // With these windows the numerators x = q d stay in [2^-766, 2^770), far from where the exact
+    // residual d q0 - x could underflow (2^-969) or anything could overflow.
+    uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u;
+    static constexpr uint32_t QLO = 0x200u << 21, QHI = (0x600u << 21) - 1u;
+    static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;
     __device__ __forceinline__ void chkq(double q)
     {
 #ifdef CSI_EXPERIMENT_NOCHECK
@@ -148,12 +153,10 @@ struct MathFast {
     }
     __device__ __forceinline__ void chkd(double d)
     {
-        const uint32_t g = (uint32_t)__double2hiint(d) << 1;
-        dmx = max(dmx, g);
-        dmn = min(dmn, g);
+        dacc = max(dacc, (uint32_t)__double2hiint(d) - DLO);
         lo1 = min(lo1, (uint32_t)__double2loint(d) + 1u);  // 0 if the low word is all ones (superset of "significand all ones")
     }
-    __device__ __forceinline__ bool bad() const { return (qmn < QLO - 1u) | (qmx > QHI) | (dmn < DLO) | (dmx > DHI) | (lo1 == 0u) | ((neg >> 31) != 0u); }
+    __device__ __forceinline__ bool bad() const { return (qmn < QLO - 1u) | (qmx > QHI) | (dacc > DSPAN) | ((neg >> 31) != 0u) | (lo1 == 0u); }
 
     __device__ __forceinline__ double rcp(double y)
     {
@@ -195,8 +198,7 @@ struct MathFast {
         g = __fma_rn(g, e, g);
         h = __fma_rn(h, e, h);
         e = __fma_rn(-h, g, 0.5);
-        g = __fma_rn(g, e, g);
-        h = __fma_rn(h, e, h);
+        g = __fma_rn(g, e, g);  // (h keeps its 2^-44 accuracy: enough for the correction term)
         const double d = __fma_rn(-g, g, x);
         g = __fma_rn(d, h, g);
         return x > 0.0 ? g : x;  // sqrt(+-0) = +-0

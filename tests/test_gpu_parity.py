@@ -156,7 +156,7 @@ def test_fast_arithmetic_equals_ieee_operators(span):
     assert rc == 0
     assert list(out)[:4] == [0, 0, 0, 0], list(out)
     if span <= 250:
-        assert out[4] < 0.01 * 2e9   # these exponent ranges stay inside the fast windows (bar the all-ones guard)
+        assert out[4] < 0.03 * 2e9   # these exponent ranges stay inside the fast windows (bar the all-ones guard)
 
 
 def _variant_case(kind):
