@@ -42,6 +42,13 @@ namespace fz {
 constexpr int BX = 32, BY = 16;  // stress nodes per tile
 constexpr int OUTX = BX - 2, OUTY = BY - 2;  // velocity cells per tile
 constexpr int SXD = BX + 2, SYD = BY + 2;    // shared-memory tile = TMA box: tile + 1 halo ring
+#ifndef CSI_UNROLL_B
+#define CSI_UNROLL_B 2
+#endif
+#ifndef CSI_UNROLL_CD
+#define CSI_UNROLL_CD 2
+#endif
+constexpr int UNROLL_B = CSI_UNROLL_B, UNROLL_CD = CSI_UNROLL_CD;
 constexpr int NT = 256;                       // threads per CTA
 constexpr int ASTRIDE = ((SXD * SYD * 8 + 127) / 128) * 128 / 8;  // doubles between shared arrays (TMA destinations are 128-byte aligned)
 constexpr int W = 3;             // halo ring kept valid in the internal layout
@@ -383,7 +390,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 
     // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
     double aux_zc[2], aux_zf[2], aux_Dc[2];
-#pragma unroll
+#pragma unroll UNROLL_B
     for (int q = 0; q < 2; q++) {
         const int sx = lane, sy = wrp + 8 * q;
         double *b = &S(0, sx, sy);
@@ -465,7 +472,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     };
 
     // ---------------- phase C: first velocity on the cells the second one reads -------------------------
-#pragma unroll
+#pragma unroll UNROLL_CD
     for (int q = 0; q < 2; q++)
         if (c_on[q]) {
             const int sy = c_sy0 + 8 * q;
@@ -476,7 +483,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
     double w2[2] = {0.0, 0.0};
-#pragma unroll
+#pragma unroll UNROLL_CD
     for (int q = 0; q < 2; q++)
         if (d_on[q]) {
             const int sy = d_sy0 + 8 * q;
