@@ -80,6 +80,7 @@ struct csi_handle {
     int nscratch = 0;
     double *out_dev = nullptr;
     uint8_t *mask_dev = nullptr;
+    std::vector<uint8_t> mask_host;
     FusedPlan *fused = nullptr;
     bool fused_failed = false;
     // device mirrors for the *_host entry points, in csi_fields member order
@@ -445,6 +446,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.conn_s = g.conn_n = h->nranks > 1 ? 1 : 0;
     g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
     g.mask = nullptr;
+    g.mask_host = nullptr;
     DParams &p = h->p;
     p.Pstar = cfg->ice_compressive_strength;
     p.C = cfg->ice_compaction_hardening;
@@ -482,6 +484,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         if ((e = cudaMalloc(&h->mask_dev, n)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(mask)"); }
         cudaMemcpy(h->mask_dev, cfg->immersed_mask, n, cudaMemcpyDefault);
         g.mask = h->mask_dev;
+        h->mask_host.assign(cfg->immersed_mask, cfg->immersed_mask + n);
+        g.mask_host = h->mask_host.data();
     }
     h->mirror.assign(NFIELDS, nullptr);
     h->mirror_n.assign(NFIELDS, 0);

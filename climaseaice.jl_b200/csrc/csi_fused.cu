@@ -32,6 +32,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "csi_cell.cuh"
 #include "csi_internal.h"
 
@@ -60,7 +63,7 @@ enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, 
 // shared-memory arrays (each SXD x SYD doubles)
 enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E22, A_E12, A_AL, A_W, NARR };
 
-constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64;  // + two mbarriers
+constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64 + ((SXD * SYD + 63) / 64) * 64;  // + two mbarriers + node flags
 
 struct Params {
     int Nx, Ny;          // interior size
@@ -83,6 +86,7 @@ struct Params {
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     double *base;         // internal allocation
+    const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
 };
 
 
@@ -359,6 +363,16 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
     }
 
+    // immersed-boundary node flags of the tile (bit 0: centre masked, 1: corner masked, 2: u face peripheral, 3: v face peripheral)
+    uint8_t *smf = reinterpret_cast<uint8_t *>(bar + 8);
+    const bool has_mask = GEN && p.flags != nullptr;
+    if (has_mask)
+        for (int n = tid; n < SXD * SYD; n += NT) {
+            const int row = min(max(tc.J0 - 2 + n / SXD - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 2 + n % SXD - 1 + OX, 0), p.pitch - 1);
+            smf[n] = p.flags[(size_t)row * p.pitch + col];
+        }
+#define FLG(sx, sy) (smf[((sy) + 1) * SXD + ((sx) + 1)])
+
     M mm;
     // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) ----------------
     // e11, e22 on [-1, BX-1] x [-1, BY-1]; e12 on [0, BX] x [0, BY]; m everywhere (in place over h)
@@ -437,7 +451,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     auto u_at = [&](int sx, int sy, int VS, double un, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool active = !(p.bounded_x && (i <= 1 || i > p.Nx));
+        const bool wall_active = !(p.bounded_x && (i <= 1 || i > p.Nx));
         const double *b = &S(0, sx, sy);
         const double vbar = ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
         double ue = p.ue_c, vebar = ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
@@ -446,16 +460,24 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             vebar = ((SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) / 2 + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1)) / 2) / 2;
         }
         const double uold = SB(b, A_U, 0, 0);
-        const double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, -1, 0), b0 = SB(b, A_S22, -1, 0);
+        double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, -1, 0), b0 = SB(b, A_S22, -1, 0);
+        double s12hi = SB(b, A_S12, 0, 1), s12lo = SB(b, A_S12, 0, 0);
+        bool active = wall_active;
+        if (has_mask) {  // isd:21-24: stresses read as 0 on immersed-peripheral nodes; se:226: peripheral u faces stay at rest
+            if (FLG(sx, sy) & 1) a1 = b1 = 0.0;
+            if (FLG(sx - 1, sy) & 1) a0 = b0 = 0.0;
+            if (FLG(sx, sy + 1) & 2) s12hi = 0.0;
+            if (FLG(sx, sy) & 2) s12lo = 0.0;
+            active = active && !(FLG(sx, sy) & 4);
+        }
         const double val = u_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, SB(b, A_S12, 0, 1),
-                                       SB(b, A_S12, 0, 0));
+                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo);
         return upd ? val : uold;
     };
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool active = !(p.bounded_y && (r <= 1 || r > p.Ny));
+        const bool wall_active = !(p.bounded_y && (r <= 1 || r > p.Ny));
         const double *b = &S(0, sx, sy);
         const double ubar = ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
         double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
@@ -464,10 +486,18 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             uebar = ((SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) / 2 + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0)) / 2) / 2;
         }
         const double vold = SB(b, A_V, 0, 0);
-        const double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, 0, -1), b0 = SB(b, A_S22, 0, -1);
+        double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, 0, -1), b0 = SB(b, A_S22, 0, -1);
+        double s12hi = SB(b, A_S12, 1, 0), s12lo = SB(b, A_S12, 0, 0);
+        bool active = wall_active;
+        if (has_mask) {
+            if (FLG(sx, sy) & 1) a1 = b1 = 0.0;
+            if (FLG(sx, sy - 1) & 1) a0 = b0 = 0.0;
+            if (FLG(sx + 1, sy) & 2) s12hi = 0.0;
+            if (FLG(sx, sy) & 2) s12lo = 0.0;
+            active = active && !(FLG(sx, sy) & 8);
+        }
         const double val = v_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, SB(b, A_S12, 1, 0),
-                                       SB(b, A_S12, 0, 0));
+                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo);
         return upd ? val : vold;
     };
 
@@ -626,6 +656,7 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
 }
 #undef S
 #undef SB
+#undef FLG
 
 // ---- self test of the FAST arithmetic against the IEEE operators ---------------------------------
 // Each thread draws pseudo-random operands (splitmix64; random significands, exponents spread over
@@ -725,6 +756,7 @@ __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 
 // ---- host side ----------------------------------------------------------------------------------
 struct FusedPlan {
+    uint8_t *flags = nullptr;
     fz::Params P;
     dim3 grid;
     int cur_set = 0;
@@ -753,7 +785,6 @@ static EncodeTiledFn get_encode()
 
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
-    if (g.mask) { snprintf(why, nwhy, "immersed masks run on the unfused path"); return 0; }
     if (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az)) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.topo_y == CSI_BOUNDED && (g.conn_s || g.conn_n)) { snprintf(why, nwhy, "Bounded y with slabs"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
@@ -776,6 +807,33 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
     cudaMemset(pl->base, 0, bytes);
     cudaDeviceSynchronize();  // the plan may be used next from a non-blocking stream
+    if (g.mask_host) {
+        // node flags from the centre mask, with the reference's inactive_cell / immersed_peripheral_node logic
+        const int msx = g.Nx + 2 * g.Hx, msy = g.Ny + 2 * g.Hy;
+        auto outside = [&](int i, int j) {
+            return (g.topo_x == CSI_BOUNDED && (i < 1 || i > g.Nx)) || (g.topo_y == CSI_BOUNDED && ((j < 1 && !g.conn_s) || (j > g.Ny && !g.conn_n)));
+        };
+        auto immersed = [&](int i, int j) {
+            const int pi = std::min(std::max(i - 1 + g.Hx, 0), msx - 1), pj = std::min(std::max(j - 1 + g.Hy, 0), msy - 1);
+            return g.mask_host[(size_t)pi + (size_t)pj * msx] != 0;
+        };
+        auto inactive = [&](int i, int j) { return outside(i, j) || immersed(i, j); };
+        std::vector<uint8_t> fl((size_t)pl->pitch * pl->rows, 0);
+        for (int r = 0; r < pl->rows; r++)
+            for (int c = 0; c < pl->pitch; c++) {
+                const int i = c + 1 - OX, j = r + 1 - pl->oy;
+                uint8_t f = 0;
+                if (inactive(i, j) && !outside(i, j)) f |= 1;
+                const bool per = inactive(i - 1, j - 1) || inactive(i, j - 1) || inactive(i - 1, j) || inactive(i, j);
+                const bool und = outside(i - 1, j - 1) || outside(i, j - 1) || outside(i - 1, j) || outside(i, j);
+                if (per && !und) f |= 2;
+                if (immersed(i - 1, j) || immersed(i, j)) f |= 4;
+                if (immersed(i, j - 1) || immersed(i, j)) f |= 8;
+                fl[(size_t)r * pl->pitch + c] = f;
+            }
+        if (cudaMalloc(&pl->flags, fl.size()) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flags)"); cudaFree(pl->base); delete pl; return nullptr; }
+        cudaMemcpy(pl->flags, fl.data(), fl.size(), cudaMemcpyHostToDevice);
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) { snprintf(err, nerr, "cuTensorMapEncodeTiled unavailable"); cudaFree(pl->base); delete pl; return nullptr; }
     cuuint64_t dims[3] = {(cuuint64_t)pl->pitch, (cuuint64_t)pl->rows, (cuuint64_t)NF};
@@ -792,6 +850,7 @@ void fused_destroy(FusedPlan *pl)
 {
     if (!pl) return;
     if (pl->base) cudaFree(pl->base);
+    if (pl->flags) cudaFree(pl->flags);
     delete pl;
 }
 
@@ -847,6 +906,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.ue_c = p.ue_c; P.ve_c = p.ve_c;
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.base = pl->base;
+    P.flags = pl->flags;
 
     // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
     P.a0 = P.sx0 < P.vx0 ? P.sx0 : P.vx0;
@@ -891,7 +951,7 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         const bool vfirst = (sub % 2) != 0;
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
-        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE;
+        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags;
         const cudaError_t e = common ? launch_sub<false>(pl, P, grid, c.stream, vfirst, aux) : launch_sub<true>(pl, P, grid, c.stream, vfirst, aux);
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
         ++*c.launches;

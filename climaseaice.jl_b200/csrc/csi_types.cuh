@@ -25,6 +25,7 @@ struct DGrid {
     int conn_s, conn_n;     // slab partition: south / north side is a rank boundary (halo exchanged)
     double dx, dy, az;      // regular rectilinear metrics; az = dx*dy
     const uint8_t *mask;    // optional immersed mask at centres (parent-shaped), device pointer
+    const uint8_t *mask_host;  // the same mask in host memory (plan construction only)
 };
 
 struct DParams {
