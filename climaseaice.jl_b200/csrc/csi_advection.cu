@@ -108,11 +108,13 @@ __device__ __forceinline__ double face_value_dyn(int b, const double *cm, int st
 }
 }  // namespace weno
 
-// order reduction next to Bounded walls: buffer = min(B, face-1, N+1-face), at least 1
-__device__ __forceinline__ int buffer_at(int B, bool bounded, int N, int face)
+// order reduction next to Bounded walls: buffer = min(B, face-1, N+1-face), at least 1; a slab's connected
+// side is not a wall
+__device__ __forceinline__ int buffer_at(int B, bool wall_lo, bool wall_hi, int N, int face)
 {
-    if (!bounded) return B;
-    int b = min(B, min(face - 1, N + 1 - face));
+    int b = B;
+    if (wall_lo) b = min(b, face - 1);
+    if (wall_hi) b = min(b, N + 1 - face);
     return b < 1 ? 1 : b;
 }
 
@@ -139,14 +141,14 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         sh[1][lj][li] = at(f.a, gi, gj);
     }
     __syncthreads();
-    const bool bx = g.topo_x == CSI_BOUNDED, by = g.topo_y == CSI_BOUNDED && !g.conn_s && !g.conn_n;
+    const bool bx = g.topo_x == CSI_BOUNDED, by_lo = g.topo_y == CSI_BOUNDED && !g.conn_s, by_hi = g.topo_y == CSI_BOUNDED && !g.conn_n;
     // x faces: (ATX+1) x ATY
     for (int t = tid; t < (ATX + 1) * ATY; t += ATX * ATY) {
         const int li = t % (ATX + 1), lj = t / (ATX + 1);
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx + 1 && j <= g.Ny) {
             const double U = at(f.u, min(i, f.u.sx - f.u.ox), j);
-            const int b = buffer_at(B, bx, g.Nx, i);
+            const int b = buffer_at(B, bx, bx, g.Nx, i);
             const bool imm = g.mask && imm_peripheral_fc(g, i, j);
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx && j <= g.Ny + 1) {
             const double V = at(f.v, i, min(j, f.v.sy - f.v.oy));
-            const int b = buffer_at(B, by, g.Ny, j);
+            const int b = buffer_at(B, by_lo, by_hi, g.Ny, j);
             const bool imm = g.mask && imm_peripheral_cf(g, i, j);
 #pragma unroll
             for (int q = 0; q < 2; q++) {

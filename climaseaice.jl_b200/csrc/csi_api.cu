@@ -370,6 +370,7 @@ int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaS
     if (!h->comm) return fail(h, CSI_ERR_ARG, "csi_comm_init has not been called on this handle");
     NcclApi &api = nccl();
     const DGrid &g = h->g;
+    // conn_s / conn_n already encode the topology: a Bounded y axis has no wrap-around neighbour
     const int south = g.conn_s ? (h->rank + h->nranks - 1) % h->nranks : -1;
     const int north = g.conn_n ? (h->rank + 1) % h->nranks : -1;
     if (width > g.Hy) width = g.Hy;
@@ -419,8 +420,6 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED");
     if (!(cfg->dx > 0) || !(cfg->dy > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: dx, dy must be positive");
     if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
-    if (cfg->nranks > 1 && cfg->topo_y != CSI_PERIODIC)
-        return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: slab partitions need a Periodic y axis in this version");
     if (cfg->nranks > 1) {
         const int K = cfg->exchange_every > 0 ? cfg->exchange_every : cfg->substeps;
         if (cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: slab partitions need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
@@ -443,7 +442,9 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     DGrid &g = h->g;
     g.Nx = cfg->Nx; g.Ny = cfg->Ny; g.Hx = cfg->Hx; g.Hy = cfg->Hy;
     g.topo_x = cfg->topo_x; g.topo_y = cfg->topo_y;
-    g.conn_s = g.conn_n = h->nranks > 1 ? 1 : 0;
+    // slab partition along y: a side is "connected" when another rank owns the rows beyond it
+    g.conn_s = h->nranks > 1 && (cfg->topo_y == CSI_PERIODIC || h->rank > 0);
+    g.conn_n = h->nranks > 1 && (cfg->topo_y == CSI_PERIODIC || h->rank < h->nranks - 1);
     g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
     g.mask = nullptr;
     g.mask_host = nullptr;

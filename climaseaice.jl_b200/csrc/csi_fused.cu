@@ -71,6 +71,7 @@ struct Params {
     int oy;              // internal row of j = 1 is (oy)
     int px, py;          // periodic images along x / y
     int bounded_x, bounded_y;
+    int wall_s, wall_n;  // physical walls of a Bounded y axis on this rank (a slab's connected side is not a wall)
     // store windows (reference indices, inclusive)
     int sx0, sx1, sy0, sy1;  // stresses
     int vx0, vx1, vy0, vy1;  // velocities
@@ -477,7 +478,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool wall_active = !(p.bounded_y && (r <= 1 || r > p.Ny));
+        const bool wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
         const double *b = &S(0, sx, sy);
         const double ubar = ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
         double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
@@ -544,7 +545,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // walls: one tangential halo cell (value / no-flux BC), as fill_halo_regions! does -- and, on a mixed
         // topology, its periodic image along the other axis (the reference fills the periodic axis last,
         // over the full parent extent, so corners hold images of the wall cells)
-        if (is_u && p.bounded_y && (r == 1 || r == p.Ny)) {
+        if (is_u && ((p.wall_s && r == 1) || (p.wall_n && r == p.Ny))) {
             const int ix = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
             const double wv = r == 1 ? (p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val)
                                      : (p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (p.dy / 2)) * p.dy : val);
@@ -567,7 +568,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int i_lo = tc.I0, i_hi = tc.I0 + OUTX - 1, r_lo = tc.J0, r_hi = tc.J0 + OUTY - 1;
         const bool inside = i_lo >= max(p.sx0, p.vx0) && i_hi <= min(p.sx1, p.vx1) && r_lo >= max(p.sy0, p.vy0) && r_hi <= min(p.sy1, p.vy1);
         const bool no_img = (!p.px || (i_lo > W && i_hi <= p.Nx - W)) && (!p.py || (r_lo > W && r_hi <= p.Ny - W));
-        const bool no_wall = (!p.bounded_x || (i_lo > 1 && i_hi < p.Nx)) && (!p.bounded_y || (r_lo > 1 && r_hi < p.Ny));
+        const bool no_wall = (!p.bounded_x || (i_lo > 1 && i_hi < p.Nx)) && (!p.wall_s || r_lo > 1) && (!p.wall_n || r_hi < p.Ny);
         if (inside && no_img && no_wall) {
             double *o = p.base + (size_t)(tc.J0 - 2 + p.oy) * p.pitch + (size_t)(tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
 #pragma unroll
@@ -786,7 +787,6 @@ static EncodeTiledFn get_encode()
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
     if (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az)) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
-    if (g.topo_y == CSI_BOUNDED && (g.conn_s || g.conn_n)) { snprintf(why, nwhy, "Bounded y with slabs"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
@@ -883,10 +883,12 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.py = g.topo_y == CSI_PERIODIC && !g.conn_s && !g.conn_n;
     P.bounded_x = g.topo_x == CSI_BOUNDED;
     P.bounded_y = g.topo_y == CSI_BOUNDED;
+    P.wall_s = P.bounded_y && !g.conn_s;
+    P.wall_n = P.bounded_y && !g.conn_n;
     // stresses: interior for periodic axes, one extra ring on Bounded axes (boundary nodes of sigma12 and
     // the first halo cell, which the reference also evolves, evp.jl:145); slabs: the widened range
     P.sx0 = P.bounded_x ? 0 : 1; P.sx1 = P.bounded_x ? g.Nx + 1 : g.Nx;
-    P.sy0 = P.bounded_y ? 0 : 1; P.sy1 = P.bounded_y ? g.Ny + 1 : g.Ny;
+    P.sy0 = P.wall_s ? 0 : 1; P.sy1 = P.wall_n ? g.Ny + 1 : g.Ny;
     P.vx0 = 1; P.vx1 = g.Nx; P.vy0 = 1; P.vy1 = g.Ny;
     if (g.conn_s) { P.sy0 = -g.Hy + 2; P.vy0 = -g.Hy + 2; }
     if (g.conn_n) { P.sy1 = g.Ny + g.Hy - 1; P.vy1 = g.Ny + g.Hy - 1; }

@@ -14,13 +14,13 @@ from .model import (Bounded, FPlane, Field, Periodic, RectilinearGrid, SeaIceMod
 from .synthetic import Case
 
 
-def grid_from_case(case: Case, device=None) -> RectilinearGrid:
+def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearGrid:
     return RectilinearGrid(size=(case.Nx, case.Ny), x=(0, case.Lx), y=(0, case.Ly), halo=(case.Hx, case.Hy),
-                           topology=(case.topology[0], case.topology[1], "Flat"), device=device)
+                           topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y)
 
 
 def model_from_case(case: Case, solver_impl="auto", partition=None, device=None) -> SeaIceModel:
-    grid = grid_from_case(case, device)
+    grid = grid_from_case(case, device, partitioned_y=partition is not None)
     F = case.fields
     ue = Field((1, 0), grid, F["ue"]) if "ue" in F else 0.0
     ve = Field((0, 1), grid, F["ve"]) if "ve" in F else 0.0

@@ -31,7 +31,10 @@ Center, Face = 0, 1
 class RectilinearGrid:
     """RectilinearGrid(size=(Nx, Ny), x=(x0, x1), y=(y0, y1), halo=(Hx, Hy), topology=(TX, TY, Flat))."""
 
-    def __init__(self, size, x, y, halo=(3, 3), topology=(Periodic, Periodic, Flat), device=None):
+    def __init__(self, size, x, y, halo=(3, 3), topology=(Periodic, Periodic, Flat), device=None, partitioned_y=False):
+        # partitioned_y: this grid is a rank-local y-slab; Face fields then carry no extra row on a Bounded y axis
+        # (the wall row lives in the slab's halo), as with Oceananigans' Distributed grids
+        self.partitioned_y = bool(partitioned_y)
         self.Nx, self.Ny = int(size[0]), int(size[1])
         self.Hx, self.Hy = int(halo[0]), int(halo[1])
         self.x, self.y = (float(x[0]), float(x[1])), (float(y[0]), float(y[1]))
@@ -50,7 +53,7 @@ class RectilinearGrid:
     def parent_shape(self, loc):
         """(sy, sx) of a field's parent: Face fields carry N+1 points along Bounded axes."""
         sx = self.Nx + 2 * self.Hx + (1 if (loc[0] == Face and self.topology[0] == Bounded) else 0)
-        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] == Bounded) else 0)
+        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] == Bounded and not self.partitioned_y) else 0)
         return sy, sx
 
     def nodes(self, loc, with_halos=True):

@@ -144,14 +144,28 @@ def anticyclone_case(N, H=7, seed=SEED, substeps=150, dt=120.0, advection_order=
 
 
 def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
-    """Rank-local y-slab of a doubly periodic case with halo Hy (periodic images filled in)."""
-    assert case.topology == ("Periodic", "Periodic") and case.Ny % nranks == 0
+    """Rank-local y-slab (halo Hy) of a case whose x axis is anything and whose y axis is Periodic (halo rows =
+    periodic images) or Bounded (halo rows = the global parent's rows where it has them, zeros beyond)."""
+    assert case.Ny % nranks == 0
     ny = case.Ny // nranks
     c = Case(case.name + f"-slab{rank}", case.Nx, ny, case.Hx, Hy, case.topology, case.Lx, case.Ly / nranks,
              dt=case.dt, substeps=case.substeps, coriolis_f=case.coriolis_f, advection_order=case.advection_order,
-             timestepper=case.timestepper, rho_e=case.rho_e, Cd=case.Cd)
+             timestepper=case.timestepper, u_bc_value=case.u_bc_value, v_bc_value=case.v_bc_value, rho_e=case.rho_e, Cd=case.Cd)
+    j = np.arange(rank * ny - Hy, (rank + 1) * ny + Hy)          # 0-based global interior row of every slab row
     for k, arr in case.fields.items():
-        interior = arr[case.Hy:case.Hy + case.Ny, :]
-        rows = (np.arange(rank * ny - Hy, (rank + 1) * ny + Hy)) % case.Ny
-        c.fields[k] = np.ascontiguousarray(interior[rows, :])
+        if case.topology[1] == "Periodic":
+            interior = arr[case.Hy:case.Hy + case.Ny, :]
+            c.fields[k] = np.ascontiguousarray(interior[j % case.Ny, :])
+        else:
+            out = np.zeros((ny + 2 * Hy, arr.shape[1]))
+            pj = j + case.Hy                                      # row in the global parent
+            ok = (pj >= 0) & (pj < arr.shape[0])
+            out[ok, :] = arr[pj[ok], :]
+            c.fields[k] = out
     return c
+
+
+def slab_rows(case: Case, rank: int, nranks: int):
+    """Rows of the global parent array that rank's interior covers."""
+    ny = case.Ny // nranks
+    return slice(case.Hy + rank * ny, case.Hy + (rank + 1) * ny)

@@ -27,7 +27,13 @@ def main():
     nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    topo = sys.argv[4] if len(sys.argv) > 4 else "periodic"
     case = periodic_case(96, Ny=32 * world, substeps=10, aice="mixed")
+    if topo == "bounded_y":   # Periodic x Bounded: walls at the south of rank 0 and the north of the last rank
+        case.topology = ("Periodic", "Bounded")
+        case.u_bc_value = 0.0
+        for k in ("v", "top_y", "ve"):
+            case.fields[k] = np.ascontiguousarray(np.vstack([case.fields[k], case.fields[k][-1:]]))
     Hy = max(2 * K + 3, 7)
     sl = slab_of(case, rank, world, Hy)
     m = model_from_case(sl, solver_impl=solver, partition=(rank, world, K), device=f"cuda:{local}")

@@ -28,10 +28,11 @@ def test_slab_partition_logic_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,K", [("unfused", 3), ("auto", 3), ("auto", 10)])
-def test_two_gpus_equal_one_gpu(solver, K):
+@pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 10, "periodic"),
+                                            ("unfused", 3, "bounded_y"), ("auto", 4, "bounded_y")])
+def test_two_gpus_equal_one_gpu(solver, K, topo):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(ROOT / "tests" / "multigpu_check.py", 2, solver, K, 2)
+    r = _torchrun(ROOT / "tests" / "multigpu_check.py", 2, solver, K, 2, topo)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU_OK" in r.stdout
