@@ -58,6 +58,7 @@ class csi_config(C.Structure):
         ("timestepper", C.c_int32), ("solver_impl", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("exchange_every", C.c_int32), ("reserved_", C.c_int32),
+        ("immersed_drag_u", C.c_double), ("immersed_drag_v", C.c_double),
     ]
 
 

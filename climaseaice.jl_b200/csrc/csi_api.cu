@@ -470,6 +470,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     p.u_sn_val = cfg->u_south_north_value; p.v_we_val = cfg->v_west_east_value;
     p.adv_order = cfg->advection_order;
     p.pad_ = 0;
+    p.imm_u = cfg->immersed_drag_u;
+    p.imm_v = cfg->immersed_drag_v;
     cudaError_t e;
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
         delete h;

@@ -138,6 +138,26 @@ __device__ __forceinline__ double div_sigma_2j(const DGrid &g, const DFields &f,
     return (d + t + S) / g.az;
 }
 
+// ---- immersed stress divergence: isd:57-123 with the linear-drag FluxBoundaryCondition -C*u (coastline example) ----
+__device__ __forceinline__ double immersed_div_sigma_1j(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
+{
+    if (!g.mask || p.imm_u == 0.0) return 0.0;
+    const double bc = (-p.imm_u) * at(f.u, i, j);
+    const double qW = 0.0 * (g.dy * 1.0), qE = 0.0 * (g.dy * 1.0);
+    const double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (g.dx * 1.0);
+    const double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (g.dx * 1.0);
+    return (qE - qW + qN - qS) / (g.az * 1.0);
+}
+__device__ __forceinline__ double immersed_div_sigma_2j(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
+{
+    if (!g.mask || p.imm_v == 0.0) return 0.0;
+    const double bc = (-p.imm_v) * at(f.v, i, j);
+    const double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (g.dy * 1.0);
+    const double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (g.dy * 1.0);
+    const double qS = 0.0 * (g.dx * 1.0), qN = 0.0 * (g.dx * 1.0);
+    return (qE - qW + qN - qS) / (g.az * 1.0);
+}
+
 // ---- external stresses: ext:8-27,176-202 -------------------------------------------------------
 __device__ __forceinline__ double ue_at(const DParams &p, const DFields &f, int i, int j) { return f.ue.p ? at(f.ue, i, j) : p.ue_c; }
 __device__ __forceinline__ double ve_at(const DParams &p, const DFields &f, int i, int j) { return f.ve.p ? at(f.ve, i, j) : p.ve_c; }
@@ -180,7 +200,7 @@ __device__ __forceinline__ void u_step_node(const DGrid &g, const DParams &p, co
     const double tbot = sis ? coef * ue_at(p, f, i, j) : 0.0;                  // explicit_tx
     const double xcross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : -p.f * avg_fc(vv, i, j);
     const double rheo = (at(f.un, i, j) - at(f.u, i, j)) / dtau / abar;
-    double Gu = -xcross - explicit_tx_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + 0.0 / mi + (0.0 + rheo);
+    double Gu = -xcross - explicit_tx_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + immersed_div_sigma_1j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gu = mi <= 0 ? 0.0 : Gu;
     double tau = (coef - 0.0) / mi * ai;
     tau = mi <= 0 ? 0.0 : tau;
@@ -206,7 +226,7 @@ __device__ __forceinline__ void v_step_node(const DGrid &g, const DParams &p, co
     const double tbot = sis ? coef * ve_at(p, f, i, j) : 0.0;
     const double ycross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : p.f * avg_cf(uu, i, j);
     const double rheo = (at(f.vn, i, j) - at(f.v, i, j)) / dtau / abar;
-    double Gv = -ycross - explicit_ty_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + 0.0 / mi + (0.0 + rheo);
+    double Gv = -ycross - explicit_ty_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + immersed_div_sigma_2j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gv = mi <= 0 ? 0.0 : Gv;
     double tau = (coef - 0.0) / mi * ai;
     tau = mi <= 0 ? 0.0 : tau;

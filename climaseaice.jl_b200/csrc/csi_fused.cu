@@ -84,6 +84,7 @@ struct Params {
     double dx, dy, az, dx2, dy2, rdx, rdy, raz;
     double em2, Dmin, amin, amax, amax2, ca, rho_i, rhoCd, f, min_mass, min_conc;
     double ttx, tty, ue_c, ve_c;
+    double imm_u, imm_v;  // immersed linear-drag flux BC (0 = none)
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     double *base;         // internal allocation
@@ -235,7 +236,7 @@ struct MathSlow {
 template <bool GEN, class M>
 __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
                                          double uold, double vbar, double ue, double vebar, double ttop, double un, double sD1, double sD0,
-                                         double sT1, double sT0, double s12hi, double s12lo)
+                                         double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
 {
     const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
     const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
@@ -252,7 +253,7 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
     const double tt = mm.divc(p.dy2 * sT1 - p.dy2 * sT0, p.dy, p.rdy) / 2;
     const double SS = mm.divc(p.dx2 * s12hi - p.dx2 * s12lo, p.dx, p.rdx);
     const double dsig = mm.divc(d + tt + SS, p.az, p.raz);
-    double G = -xcross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + 0.0 + (0.0 + rheo);
+    double G = -xcross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
     G = mi <= 0 ? 0.0 : G;
     double tau = mm.divn(coef - 0.0, Rm) * ai;
     tau = mi <= 0 ? 0.0 : tau;
@@ -264,7 +265,7 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
 template <bool GEN, class M>
 __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
                                          double vold, double ubar, double ve, double uebar, double ttop, double vn, double sD1, double sD0,
-                                         double sT1, double sT0, double s12hi, double s12lo)
+                                         double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
 {
     const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
     const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
@@ -281,7 +282,7 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, do
     const double tt = mm.divc(-(p.dx2 * sT1 - p.dx2 * sT0), p.dx, p.rdx) / 2;
     const double SS = mm.divc(p.dy2 * s12hi - p.dy2 * s12lo, p.dy, p.rdy);
     const double dsig = mm.divc(d + tt + SS, p.az, p.raz);
-    double G = -ycross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + 0.0 + (0.0 + rheo);
+    double G = -ycross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
     G = mi <= 0 ? 0.0 : G;
     double tau = mm.divn(coef - 0.0, Rm) * ai;
     tau = mi <= 0 ? 0.0 : tau;
@@ -471,8 +472,18 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             if (FLG(sx, sy) & 2) s12lo = 0.0;
             active = active && !(FLG(sx, sy) & 4);
         }
+        // immersed stress divergence (isd:65-82) for the linear-drag flux BC -C*u on south/north immersed faces
+        const bool has_imm = has_mask && p.imm_u != 0.0;
+        double imm = 0.0;
+        if (has_imm) {
+            const double bc = (-p.imm_u) * uold;
+            const double qW = 0.0 * (p.dy * 1.0), qE = 0.0 * (p.dy * 1.0);
+            const double qS = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (p.dx * 1.0);
+            const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (p.dx * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, p.az * 1.0, p.raz);
+        }
         const double val = u_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo);
+                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : uold;
     };
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
@@ -497,8 +508,17 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             if (FLG(sx, sy) & 2) s12lo = 0.0;
             active = active && !(FLG(sx, sy) & 8);
         }
+        const bool has_imm = has_mask && p.imm_v != 0.0;
+        double imm = 0.0;
+        if (has_imm) {  // isd:84-101, -C*v on west/east immersed faces
+            const double bc = (-p.imm_v) * vold;
+            const double qW = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (p.dy * 1.0);
+            const double qE = ((FLG(sx + 1, sy) & 2) ? bc : 0.0) * (p.dy * 1.0);
+            const double qS = 0.0 * (p.dx * 1.0), qN = 0.0 * (p.dx * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, p.az * 1.0, p.raz);
+        }
         const double val = v_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo);
+                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
     };
 
@@ -906,6 +926,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.ttx = p.top_kind == CSI_STRESS_CONST ? p.ttx : 0.0;
     P.tty = p.top_kind == CSI_STRESS_CONST ? p.tty : 0.0;
     P.ue_c = p.ue_c; P.ve_c = p.ve_c;
+    P.imm_u = p.imm_u; P.imm_v = p.imm_v;
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.base = pl->base;
     P.flags = pl->flags;

@@ -38,6 +38,7 @@ struct DParams {
     int u_sn_bc, v_we_bc;
     double u_sn_val, v_we_val;
     int adv_order, pad_;
+    double imm_u, imm_v;  // immersed linear-drag flux BC coefficients (0 = none)
 };
 
 struct DFields {

@@ -22,9 +22,13 @@ def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearG
 def model_from_case(case: Case, solver_impl="auto", partition=None, device=None) -> SeaIceModel:
     grid = grid_from_case(case, device, partitioned_y=partition is not None)
     F = case.fields
-    ue = Field((1, 0), grid, F["ue"]) if "ue" in F else 0.0
-    ve = Field((0, 1), grid, F["ve"]) if "ve" in F else 0.0
-    top = dict(u=Field((1, 0), grid, F["top_x"]), v=Field((0, 1), grid, F["top_y"])) if "top_x" in F else None
+    oc = case.ocean_const or (0.0, 0.0)
+    ue = Field((1, 0), grid, F["ue"]) if "ue" in F else oc[0]
+    ve = Field((0, 1), grid, F["ve"]) if "ve" in F else oc[1]
+    if "top_x" in F:
+        top = dict(u=Field((1, 0), grid, F["top_x"]), v=Field((0, 1), grid, F["top_y"]))
+    else:
+        top = dict(u=case.top_const[0], v=case.top_const[1]) if case.top_const else None
     dyn = SeaIceMomentumEquation(grid,
                                  coriolis=FPlane(case.coriolis_f) if case.coriolis_f is not None else None,
                                  top_momentum_stress=top,
@@ -37,7 +41,7 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
         bcs["v"] = dict(west=ValueBoundaryCondition(case.v_bc_value), east=ValueBoundaryCondition(case.v_bc_value))
     adv = None if case.advection_order == 0 else (UpwindBiased(1) if case.advection_order == 1 else WENO(case.advection_order))
     m = SeaIceModel(grid, dynamics=dyn, advection=adv, timestepper=case.timestepper, boundary_conditions=bcs,
-                    solver_impl=solver_impl, partition=partition)
+                    solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag)
     m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
     return m
 

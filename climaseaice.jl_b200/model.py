@@ -189,7 +189,7 @@ class SeaIceModel:
 
     def __init__(self, grid, dynamics=None, advection=None, timestepper="SplitRungeKutta3", boundary_conditions=None,
                  ice_density=900.0, ice_thermodynamics=None, solver_impl="auto", immersed_mask=None,
-                 partition=None):
+                 partition=None, immersed_drag=(0.0, 0.0)):
         if ice_thermodynamics is not None:
             raise NotImplementedError("thermodynamics is outside the hot path (SURVEY section 8f)")
         if dynamics is None:
@@ -213,6 +213,9 @@ class SeaIceModel:
         self._u_bc = bcs.get("u", {})
         self._v_bc = bcs.get("v", {})
         self.partition = partition  # (rank, nranks, exchange_every) for slab runs
+        # ImmersedBoundaryCondition with the discrete-form flux -C*u (u: south/north) and -C*v (v: west/east), as in
+        # examples/ice_advected_on_coastline.jl:91-98
+        self.immersed_drag = (float(immersed_drag[0]), float(immersed_drag[1]))
         self._mask = None if immersed_mask is None else np.ascontiguousarray(immersed_mask, dtype=np.uint8)
         self._handle = C.c_void_p()
         self._solver_impl = dict(auto=L.SOLVER_AUTO, unfused=L.SOLVER_UNFUSED, fused=L.SOLVER_FUSED)[solver_impl]
@@ -270,6 +273,7 @@ class SeaIceModel:
         cfg.advection_order = 0 if self.advection is None else int(self.advection.order)
         cfg.timestepper = L.RK3 if self.timestepper == "SplitRungeKutta3" else L.FE
         cfg.solver_impl = self._solver_impl
+        cfg.immersed_drag_u, cfg.immersed_drag_v = self.immersed_drag
         if self.partition:
             cfg.rank, cfg.nranks, cfg.exchange_every = self.partition
         else:

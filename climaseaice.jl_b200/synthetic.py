@@ -36,6 +36,10 @@ class Case:
     rho_e: float = 1026.0
     Cd: float = 5.5e-3
     fields: dict = field(default_factory=dict)   # h, a, u, v, top_x, top_y, ue, ve parents
+    top_const: tuple | None = None       # constant (tau_x, tau_y) when there are no top_x/top_y arrays
+    ocean_const: tuple | None = None     # constant (ue, ve) when there are no ue/ve arrays
+    mask: object = None                  # immersed mask at centres, uint8 (Ny+2Hy, Nx+2Hx), 1 = land
+    immersed_drag: tuple = (0.0, 0.0)    # linear-drag immersed flux BC coefficients for u and v
 
     @property
     def dx(self):
@@ -169,3 +173,22 @@ def slab_rows(case: Case, rank: int, nranks: int):
     """Rows of the global parent array that rank's interior covers."""
     ny = case.Ny // nranks
     return slice(case.Hy + rank * ny, case.Hy + (rank + 1) * ny)
+
+
+def coastline_case(Ny=128, H=4, substeps=150, dt=300.0, seed=SEED, noise=1e-3) -> Case:
+    """examples/ice_advected_on_coastline.jl:32-125 scaled to 2Ny x Ny (BASELINE config 4 at Ny = 4096):
+    Periodic x Bounded, dx = dy = 2 km, triangular immersed coastline, uniform wind stress, ocean at rest
+    (SemiImplicitStress with zero velocity), u = 0 on the walls, linear immersed drag C = 3e-3, h = aice = 1."""
+    Nx = 2 * Ny
+    c = Case("coastline", Nx, Ny, H, H, ("Periodic", "Bounded"), Nx * 2000.0, Ny * 2000.0, dt=dt, substeps=substeps,
+             coriolis_f=None, u_bc_value=0.0, top_const=(-1.3 * 1.2e-3 * 10.0 ** 2, 0.0), ocean_const=(0.0, 0.0),
+             immersed_drag=(3e-3, 3e-3))
+    rng = np.random.default_rng(seed)
+    Xc, Yc = c.nodes(LOC["h"])
+    x = Xc - c.Lx / 2                                     # the example's x runs over (-Lx/2, Lx/2)
+    land = (Yc <= c.Ly / 2) & (np.abs(x / c.Lx) * Nx + Yc / c.Ly * Ny <= 24 * (Ny / 128))
+    c.mask = np.ascontiguousarray(land.astype(np.uint8))
+    h = np.ones_like(Xc) + noise * rng.uniform(-1, 1, Xc.shape)
+    raw = dict(h=h, a=np.ones_like(h), u=np.zeros(c.parent_shape(LOC["u"])), v=np.zeros(c.parent_shape(LOC["v"])))
+    c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
+    return c

@@ -101,6 +101,9 @@ typedef struct {
     int32_t rank, nranks;
     int32_t exchange_every;     /* K: substeps between halo exchanges (needs Hy >= 2K+3) */
     int32_t reserved_;
+    /* ImmersedBoundaryCondition of examples/ice_advected_on_coastline.jl:91-98: discrete-form flux -C*u on the
+     * south/north immersed faces of u and -C*v on the west/east ones of v (isd.jl:57-123); 0 = none */
+    double immersed_drag_u, immersed_drag_v;
 } csi_config;
 
 /* The arrays the hot path touches.  Unused ones may have ptr == NULL. */

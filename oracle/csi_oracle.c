@@ -334,6 +334,33 @@ static inline double y_f_cross_U(P p, const csio_state *s, int i, int j)
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Immersed stress divergence.  ref: src/Rheologies/ice_stress_divergence.jl:57-123.  Without an
+ * ImmersedBoundaryCondition it is zero(grid).  With the discrete-form FluxBoundaryCondition -C*u of
+ * examples/ice_advected_on_coastline.jl:91-98 on south/north (u) and west/east (v), the other sides
+ * `nothing`:  ib_*_south/west = -getbc, ib_*_north/east = +getbc (isd.jl:116-123), getbc = (-C)*u[i,j].
+ * [OCN-recall] index_left(i, Center) = i, index_right(i, Center) = i+1; conditional_flux_ffc picks the
+ * boundary flux on immersed-peripheral (f,f) nodes.
+ * ------------------------------------------------------------------------------------------- */
+static inline double immersed_div_sigma_1j(G g, P p, const csio_state *s, int i, int j)
+{
+    if (!g->mask || p->imm_drag_u == 0.0) return 0.0;
+    double bc = (-p->imm_drag_u) * F(s->u, i, j);
+    double qW = 0.0 * (dycc(g, i - 1, j) * 1.0), qE = 0.0 * (dycc(g, i, j) * 1.0);
+    double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dxff(g, i, j) * 1.0);
+    double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (dxff(g, i, j + 1) * 1.0);
+    return (qE - qW + qN - qS) / (azfc(g, i, j) * 1.0);
+}
+static inline double immersed_div_sigma_2j(G g, P p, const csio_state *s, int i, int j)
+{
+    if (!g->mask || p->imm_drag_v == 0.0) return 0.0;
+    double bc = (-p->imm_drag_v) * F(s->v, i, j);
+    double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dyff(g, i, j) * 1.0);
+    double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (dyff(g, i + 1, j) * 1.0);
+    double qS = 0.0 * (dxcc(g, i, j - 1) * 1.0), qN = 0.0 * (dxcc(g, i, j) * 1.0);
+    return (qE - qW + qN - qS) / (azcf(g, i, j) * 1.0);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * u / v tendencies.  ref: src/SeaIceDynamics/momentum_tendencies_kernel_functions.jl:11-74
  * `dtau` is what the reference passes as "dt" (the local substep, se.jl:207-211), so the EVP
  * relaxation forcing (evp.jl:391-401) is evaluated literally as (un-u)/dtau/alpha_bar.
@@ -347,7 +374,7 @@ static inline double u_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->un, i, j) - F(s->u, i, j)) / dtau / ((AL(i, j) + AL(i - 1, j)) / 2);
     double Gu = -x_f_cross_U(p, s, i, j) - explicit_tx_top(p, i, j) / mi * ai + explicit_tx_bot(p, s, i, j) / mi * ai +
-                div_sigma_1j(g, s, i, j) / mi + 0.0 / mi + (user_forcing + rheology_forcing);
+                div_sigma_1j(g, s, i, j) / mi + immersed_div_sigma_1j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gu;
 }
 static inline double v_velocity_tendency(G g, P p, const csio_state *s, int i, int j, double dtau)
@@ -357,7 +384,7 @@ static inline double v_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->vn, i, j) - F(s->v, i, j)) / dtau / ((AL(i, j) + AL(i, j - 1)) / 2);
     double Gv = -y_f_cross_U(p, s, i, j) - explicit_ty_top(p, i, j) / mi * ai + explicit_ty_bot(p, s, i, j) / mi * ai +
-                div_sigma_2j(g, s, i, j) / mi + 0.0 / mi + (user_forcing + rheology_forcing);
+                div_sigma_2j(g, s, i, j) / mi + immersed_div_sigma_2j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gv;
 }
 

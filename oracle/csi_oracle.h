@@ -83,6 +83,9 @@ typedef struct {
     /* advection: 0 = nothing, 1 = first-order upwind, 3/5/7 = WENO(order) */
     int32_t advection_order;
     int32_t timestepper;            /* CSIO_RK3 / CSIO_FE */
+    /* immersed boundary condition of examples/ice_advected_on_coastline.jl:91-98: discrete-form
+     * FluxBoundaryCondition -C*u on the south/north immersed faces of u, -C*v on west/east of v; 0 = none */
+    double imm_drag_u, imm_drag_v;
 } csio_params;
 
 typedef struct {

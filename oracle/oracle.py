@@ -61,6 +61,7 @@ class Params(C.Structure):
         ("ue", Field), ("ve", Field),
         ("u_sn_bc", C.c_int32), ("v_we_bc", C.c_int32), ("u_sn_val", C.c_double), ("v_we_val", C.c_double),
         ("advection_order", C.c_int32), ("timestepper", C.c_int32),
+        ("imm_drag_u", C.c_double), ("imm_drag_v", C.c_double),
     ]
 
 
@@ -119,7 +120,7 @@ DEFAULT_PARAMS = dict(
     pressure_formulation=0, substeps=150, min_mass=1.0, min_conc=1e-3, rho_ice=900.0,
     coriolis_kind=0, f=0.0, top_kind=STRESS_NONE, top_tx=0.0, top_ty=0.0,
     bot_kind=STRESS_NONE, rho_e=1026.0, Cd=5.5e-3, ue_c=0.0, ve_c=0.0,
-    u_sn_bc=0, v_we_bc=0, u_sn_val=0.0, v_we_val=0.0, advection_order=7, timestepper=RK3,
+    u_sn_bc=0, v_we_bc=0, u_sn_val=0.0, v_we_val=0.0, advection_order=7, timestepper=RK3, imm_drag_u=0.0, imm_drag_v=0.0,
 )
 
 

@@ -14,6 +14,11 @@ def oracle_params(case) -> dict:
              coriolis_kind=0 if case.coriolis_f is None else 1, f=case.coriolis_f or 0.0,
              top_kind=O.STRESS_FIELD if "top_x" in case.fields else O.STRESS_NONE,
              bot_kind=O.STRESS_SEMI_IMPLICIT, rho_e=case.rho_e, Cd=case.Cd)
+    if case.top_const and "top_x" not in case.fields:
+        p.update(top_kind=O.STRESS_CONST, top_tx=case.top_const[0], top_ty=case.top_const[1])
+    if case.ocean_const and "ue" not in case.fields:
+        p.update(ue_c=case.ocean_const[0], ve_c=case.ocean_const[1])
+    p.update(imm_drag_u=case.immersed_drag[0], imm_drag_v=case.immersed_drag[1])
     if case.u_bc_value is not None:
         p.update(u_sn_bc=1, u_sn_val=case.u_bc_value)
     if case.v_bc_value is not None:
@@ -26,7 +31,7 @@ def oracle_from_case(case, **overrides) -> O.OracleModel:
     p = oracle_params(case)
     p.update(overrides)
     return O.OracleModel(case.Nx, case.Ny, case.Hx, case.Hy, topo=topo, dx=case.dx, dy=case.dy, params=p,
-                         fields={k: v.copy() for k, v in case.fields.items()})
+                         fields={k: v.copy() for k, v in case.fields.items()}, mask=case.mask)
 
 
 # GPU field name -> oracle field name

@@ -283,3 +283,20 @@ def test_immersed_mask(impl):
     inside = mask[case.Hy:-case.Hy, case.Hx:-case.Hx].astype(bool)
     assert np.all(interior_of(m.all_fields()["h"].numpy(), case)[inside] == 0)   # land stays ice free
     m.close()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_coastline_config4_reduced(impl):
+    """BASELINE config 4 (examples/ice_advected_on_coastline.jl) at reduced size: Periodic x Bounded, immersed
+    triangular coast, uniform wind, ocean at rest, wall BCs and the linear immersed drag flux BC."""
+    from climaseaice_b200.synthetic import coastline_case
+    case = coastline_case(Ny=48, substeps=30)
+    assert case.mask.any() and not case.mask.all()
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    u = interior_of(m.all_fields()["u"].numpy(), case)
+    assert np.abs(u).max() > 1e-4          # the wind moved the ice
+    m.close()

@@ -174,3 +174,18 @@ def test_weno_reconstruction_is_exact_for_polynomials():
             got = m.reconstruct(0, "h", order, bias, i, 5)
             want = np.polyval(coef[::-1], float(i - 1))     # face i sits at x = i-1
             assert abs(got - want) < 1e-12, (order, bias, got, want)
+
+
+def test_immersed_drag_slows_the_ice_along_the_coast():
+    """The linear immersed drag BC (isd.jl:57-123 with the coastline example's -C*u flux) only acts on faces next to
+    land and opposes the motion."""
+    from climaseaice_b200.synthetic import coastline_case
+    case = coastline_case(Ny=32, substeps=20)
+    a = oracle_from_case(case)
+    case.immersed_drag = (0.0, 0.0)
+    b = oracle_from_case(case)
+    for _ in range(2):
+        a.time_step(case.dt); b.time_step(case.dt)
+    ua, ub = a.interior("u"), b.interior("u")
+    assert np.isfinite(ua).all() and not np.array_equal(ua, ub)
+    assert np.abs(ua).sum() < np.abs(ub).sum()
