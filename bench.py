@@ -94,6 +94,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_rate(n, steps, warmup, threads=None):
     """Times the oracle's time_step_momentum! (150 substeps) on an n x n anticyclone sample."""
+    import __graft_entry__ as entry
+    entry.load_package()
     from climaseaice_b200.synthetic import anticyclone_case
     from oracle import oracle as O
     from tests.helpers import oracle_from_case

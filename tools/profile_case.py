@@ -7,8 +7,14 @@ import torch
 from climaseaice_b200.driver import model_from_case
 from climaseaice_b200.synthetic import anticyclone_case, periodic_case
 N = int(sys.argv[1]); nsub = int(sys.argv[2]); solver = sys.argv[3] if len(sys.argv) > 3 else "auto"
-bounded = len(sys.argv) > 4 and sys.argv[4] == "bounded"
-case = anticyclone_case(N, substeps=nsub) if bounded else periodic_case(N, substeps=nsub, aice="mixed")
+kind = sys.argv[4] if len(sys.argv) > 4 else "periodic"
+if kind == "bounded":
+    case = anticyclone_case(N, substeps=nsub)
+elif kind == "coastline":
+    from climaseaice_b200.synthetic import coastline_case
+    case = coastline_case(Ny=N, substeps=nsub)
+else:
+    case = periodic_case(N, substeps=nsub, aice="mixed")
 m = model_from_case(case, solver_impl=solver)
 m.update_state()
 m.time_step_momentum(case.dt, nsub)
@@ -16,4 +22,5 @@ torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record(); m.time_step_momentum(case.dt, nsub); ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1)
-print(f"{case.name} {N}x{N} {solver}: {ms:.3f} ms for {nsub} substeps -> {ms/nsub:.4f} ms/substep, {N*N*nsub/ms/1e6:.3f} G cell-updates/s")
+cells = case.Nx * case.Ny
+print(f"{case.name} {case.Nx}x{case.Ny} {solver}: {ms:.3f} ms for {nsub} substeps -> {ms/nsub:.4f} ms/substep, {cells*nsub/ms/1e6:.3f} G cell-updates/s")
