@@ -5,7 +5,7 @@ modules here are the host-side mirror of the reference's user interface for that
 """
 from . import _lib
 from ._lib import CsiError, lib
-from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid,
+from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid, LatitudeLongitudeGrid,
                     SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress, SplitExplicitSolver, UpwindBiased,
                     ValueBoundaryCondition, WENO, nccl_unique_id, time_step_b)
 

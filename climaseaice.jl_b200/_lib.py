@@ -21,6 +21,7 @@ CORIOLIS_NONE, CORIOLIS_FPLANE = 0, 1
 BC_DEFAULT, BC_VALUE = 0, 1
 RK3, FE = 0, 1
 SOLVER_AUTO, SOLVER_UNFUSED, SOLVER_FUSED = 0, 1, 2
+METRIC_REGULAR, METRIC_J = 0, 1
 
 ERRORS = {-1: "CSI_ERR_ARG", -2: "CSI_ERR_SHAPE", -3: "CSI_ERR_UNSUPPORTED", -4: "CSI_ERR_NO_DEVICE", -5: "CSI_ERR_NCCL_MISSING"}
 
@@ -59,6 +60,7 @@ class csi_config(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("exchange_every", C.c_int32), ("reserved_", C.c_int32),
         ("immersed_drag_u", C.c_double), ("immersed_drag_v", C.c_double),
+        ("metric_kind", C.c_int32), ("reserved2_", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
     ]
 
 

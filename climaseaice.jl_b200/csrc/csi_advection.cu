@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH][li + AH - 1], 1, U > 0);
-                const double fl = (g.dy * 1.0) * U * ct;
+                const double fl = (dyfc(g, j) * 1.0) * U * ct;
                 fx[q][lj][li] = imm ? 0.0 : fl;
             }
         }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH - 1][li + AH], SX, V > 0);
-                const double fl = (g.dx * 1.0) * V * ct;
+                const double fl = (dxcf(g, j) * 1.0) * V * ct;
                 fy[q][lj][li] = imm ? 0.0 : fl;
             }
         }
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
     __syncthreads();
     const int li = threadIdx.x, lj = threadIdx.y, i = i0 + li, j = j0 + lj;
     if (i <= g.Nx && j <= g.Ny) {
-        const double V = g.az * 1.0;
+        const double V = azcc(g, j) * 1.0;
         at(f.Gh, i, j) = -(1 / V * ((fx[0][lj][li + 1] - fx[0][lj][li]) + (fy[0][lj + 1][li] - fy[0][lj][li])));
         at(f.Ga, i, j) = -(1 / V * ((fx[1][lj][li + 1] - fx[1][lj][li]) + (fy[1][lj + 1][li] - fy[1][lj][li])));
     }

@@ -80,6 +80,7 @@ struct csi_handle {
     int nscratch = 0;
     double *out_dev = nullptr;
     uint8_t *mask_dev = nullptr;
+    double *met_dev = nullptr;
     std::vector<uint8_t> mask_host;
     FusedPlan *fused = nullptr;
     bool fused_failed = false;
@@ -418,7 +419,17 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     if (cfg->Hx < B || cfg->Hy < B) return fail(nullptr, CSI_ERR_ARG, "csi_create: halo smaller than the advection stencil");
     if ((cfg->topo_x != CSI_PERIODIC && cfg->topo_x != CSI_BOUNDED) || (cfg->topo_y != CSI_PERIODIC && cfg->topo_y != CSI_BOUNDED))
         return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED");
-    if (!(cfg->dx > 0) || !(cfg->dy > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: dx, dy must be positive");
+    if (cfg->metric_kind != CSI_METRIC_REGULAR && cfg->metric_kind != CSI_METRIC_J) return fail(nullptr, CSI_ERR_ARG, "csi_create: metric_kind must be CSI_METRIC_REGULAR or CSI_METRIC_J");
+    if (cfg->metric_kind == CSI_METRIC_REGULAR && (!(cfg->dx > 0) || !(cfg->dy > 0))) return fail(nullptr, CSI_ERR_ARG, "csi_create: dx, dy must be positive");
+    if (cfg->metric_kind == CSI_METRIC_J) {
+        const int L = cfg->Ny + 2 * cfg->Hy + 1;
+        for (int k = 0; k < 12; k++) {
+            if (!cfg->metrics[k]) return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_METRIC_J needs all 12 metric arrays");
+            // rows the stencils touch: j = 0 .. Ny+2 (stress ring + the j+1 metrics it reads)
+            for (int j = 0; j <= cfg->Ny + 2; j++)
+                if (j - 1 + cfg->Hy < L && !(cfg->metrics[k][j - 1 + cfg->Hy] > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive");
+        }
+    }
     if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
     if (cfg->nranks > 1) {
         const int K = cfg->exchange_every > 0 ? cfg->exchange_every : cfg->substeps;
@@ -448,6 +459,9 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
     g.mask = nullptr;
     g.mask_host = nullptr;
+    g.met = nullptr;
+    g.metL = 0;
+    g.pad_ = 0;
     DParams &p = h->p;
     p.Pstar = cfg->ice_compressive_strength;
     p.C = cfg->ice_compaction_hardening;
@@ -490,6 +504,14 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         h->mask_host.assign(cfg->immersed_mask, cfg->immersed_mask + n);
         g.mask_host = h->mask_host.data();
     }
+    if (cfg->metric_kind == CSI_METRIC_J) {
+        const int L = cfg->Ny + 2 * cfg->Hy + 1;
+        if ((e = cudaMalloc(&h->met_dev, sizeof(double) * 12 * L)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(metrics)"); }
+        for (int k = 0; k < 12; k++) cudaMemcpy(h->met_dev + (size_t)k * L, cfg->metrics[k], sizeof(double) * L, cudaMemcpyDefault);
+        g.met = h->met_dev;
+        g.metL = L;
+        for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;  // the caller's arrays are not retained
+    }
     h->mirror.assign(NFIELDS, nullptr);
     h->mirror_n.assign(NFIELDS, 0);
     *out = h;
@@ -507,6 +529,7 @@ int csi_destroy(csi_handle *h)
     if (h->scratch) cudaFree(h->scratch);
     if (h->out_dev) cudaFree(h->out_dev);
     if (h->mask_dev) cudaFree(h->mask_dev);
+    if (h->met_dev) cudaFree(h->met_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -53,18 +53,22 @@ template <class Fn> __device__ __forceinline__ double avg_cc(Fn q, int i, int j)
 template <class Fn> __device__ __forceinline__ double avg_fc(Fn q, int i, int j) { return ((q(i - 1, j) + q(i, j)) / 2 + (q(i - 1, j + 1) + q(i, j + 1)) / 2) / 2; }
 template <class Fn> __device__ __forceinline__ double avg_cf(Fn q, int i, int j) { return ((q(i, j - 1) + q(i + 1, j - 1)) / 2 + (q(i, j) + q(i + 1, j)) / 2) / 2; }
 
-// ---- strain rates: evp:360-375 (regular metrics: every dx*, dy* is the scalar, Az = dx*dy) ----
+// ---- strain rates: evp:360-375 (metrics: scalars on a RectilinearGrid, functions of j on a lat-lon grid) ----
 __device__ __forceinline__ double eps_D(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    return ((g.dy * at(u, i + 1, j) - g.dy * at(u, i, j)) + (g.dx * at(v, i, j + 1) - g.dx * at(v, i, j))) / g.az;
+    return ((dyfc(g, j) * at(u, i + 1, j) - dyfc(g, j) * at(u, i, j)) + (dxcf(g, j + 1) * at(v, i, j + 1) - dxcf(g, j) * at(v, i, j))) / azcc(g, j);
 }
 __device__ __forceinline__ double eps_T(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    return (g.dy * g.dy * (at(u, i + 1, j) / g.dy - at(u, i, j) / g.dy) - g.dx * g.dx * (at(v, i, j + 1) / g.dx - at(v, i, j) / g.dx)) / g.az;
+    const double dy = dycc(g, j), dx = dxcc(g, j);
+    return (dy * dy * (at(u, i + 1, j) / dyfc(g, j) - at(u, i, j) / dyfc(g, j)) - dx * dx * (at(v, i, j + 1) / dxcf(g, j + 1) - at(v, i, j) / dxcf(g, j))) /
+           azcc(g, j);
 }
 __device__ __forceinline__ double eps_S(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    return (g.dx * g.dx * (at(u, i, j) / g.dx - at(u, i, j - 1) / g.dx) + g.dy * g.dy * (at(v, i, j) / g.dy - at(v, i - 1, j) / g.dy)) / g.az;
+    const double dx = dxff(g, j), dy = dyff(g, j);
+    return (dx * dx * (at(u, i, j) / dxfc(g, j) - at(u, i, j - 1) / dxfc(g, j - 1)) + dy * dy * (at(v, i, j) / dycf(g, j) - at(v, i - 1, j) / dycf(g, j))) /
+           azff(g, j);
 }
 __device__ __forceinline__ double strain_xx(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) + eps_T(g, u, v, i, j)) / 2; }
 __device__ __forceinline__ double strain_yy(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) - eps_T(g, u, v, i, j)) / 2; }
@@ -103,10 +107,10 @@ __device__ __forceinline__ void evp_stress_node(const DGrid &g, const DParams &p
     const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
     const double s12n = 2 * ef * e12f;
     const double mc = mm(i, j), mf = avg_ff(mm, i, j);
-    double g2c = zc * p.ca * dt / mc / g.az;
+    double g2c = zc * p.ca * dt / mc / azcc(g, j);
     g2c = (g2c != g2c) ? p.amax * p.amax : g2c;
     const double gc = jl_clamp(sqrt(g2c), p.amin, p.amax);
-    double g2f = zf * p.ca * dt / mf / g.az;
+    double g2f = zf * p.ca * dt / mf / azff(g, j);
     g2f = (g2f != g2f) ? p.amax * p.amax : g2f;
     const double gf = jl_clamp(sqrt(g2f), p.amin, p.amax);
     const double d11 = (s11n - at(f.s11, i, j)) / gc;
@@ -125,17 +129,17 @@ __device__ __forceinline__ double sigD(const DGrid &g, const DFields &f, int i, 
 __device__ __forceinline__ double sigT(const DGrid &g, const DFields &f, int i, int j) { return stress_cc(g, f.s11, i, j) - stress_cc(g, f.s22, i, j); }
 __device__ __forceinline__ double div_sigma_1j(const DGrid &g, const DFields &f, int i, int j)
 {
-    const double d = g.dy * (sigD(g, f, i, j) - sigD(g, f, i - 1, j)) / 2;
-    const double t = (g.dy * g.dy * sigT(g, f, i, j) - g.dy * g.dy * sigT(g, f, i - 1, j)) / g.dy / 2;
-    const double S = (g.dx * g.dx * stress_ff(g, f.s12, i, j + 1) - g.dx * g.dx * stress_ff(g, f.s12, i, j)) / g.dx;
-    return (d + t + S) / g.az;
+    const double d = dyfc(g, j) * (sigD(g, f, i, j) - sigD(g, f, i - 1, j)) / 2;
+    const double t = (dycc(g, j) * dycc(g, j) * sigT(g, f, i, j) - dycc(g, j) * dycc(g, j) * sigT(g, f, i - 1, j)) / dyfc(g, j) / 2;
+    const double S = (dxff(g, j + 1) * dxff(g, j + 1) * stress_ff(g, f.s12, i, j + 1) - dxff(g, j) * dxff(g, j) * stress_ff(g, f.s12, i, j)) / dxfc(g, j);
+    return (d + t + S) / azfc(g, j);
 }
 __device__ __forceinline__ double div_sigma_2j(const DGrid &g, const DFields &f, int i, int j)
 {
-    const double d = g.dx * (sigD(g, f, i, j) - sigD(g, f, i, j - 1)) / 2;
-    const double t = -(g.dx * g.dx * sigT(g, f, i, j) - g.dx * g.dx * sigT(g, f, i, j - 1)) / g.dx / 2;
-    const double S = (g.dy * g.dy * stress_ff(g, f.s12, i + 1, j) - g.dy * g.dy * stress_ff(g, f.s12, i, j)) / g.dy;
-    return (d + t + S) / g.az;
+    const double d = dxcf(g, j) * (sigD(g, f, i, j) - sigD(g, f, i, j - 1)) / 2;
+    const double t = -(dxcc(g, j) * dxcc(g, j) * sigT(g, f, i, j) - dxcc(g, j - 1) * dxcc(g, j - 1) * sigT(g, f, i, j - 1)) / dxcf(g, j) / 2;
+    const double S = (dyff(g, j) * dyff(g, j) * stress_ff(g, f.s12, i + 1, j) - dyff(g, j) * dyff(g, j) * stress_ff(g, f.s12, i, j)) / dycf(g, j);
+    return (d + t + S) / azcf(g, j);
 }
 
 // ---- immersed stress divergence: isd:57-123 with the linear-drag FluxBoundaryCondition -C*u (coastline example) ----
@@ -143,19 +147,19 @@ __device__ __forceinline__ double immersed_div_sigma_1j(const DGrid &g, const DP
 {
     if (!g.mask || p.imm_u == 0.0) return 0.0;
     const double bc = (-p.imm_u) * at(f.u, i, j);
-    const double qW = 0.0 * (g.dy * 1.0), qE = 0.0 * (g.dy * 1.0);
-    const double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (g.dx * 1.0);
-    const double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (g.dx * 1.0);
-    return (qE - qW + qN - qS) / (g.az * 1.0);
+    const double qW = 0.0 * (dycc(g, j) * 1.0), qE = 0.0 * (dycc(g, j) * 1.0);
+    const double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dxff(g, j) * 1.0);
+    const double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (dxff(g, j + 1) * 1.0);
+    return (qE - qW + qN - qS) / (azfc(g, j) * 1.0);
 }
 __device__ __forceinline__ double immersed_div_sigma_2j(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
 {
     if (!g.mask || p.imm_v == 0.0) return 0.0;
     const double bc = (-p.imm_v) * at(f.v, i, j);
-    const double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (g.dy * 1.0);
-    const double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (g.dy * 1.0);
-    const double qS = 0.0 * (g.dx * 1.0), qN = 0.0 * (g.dx * 1.0);
-    return (qE - qW + qN - qS) / (g.az * 1.0);
+    const double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dyff(g, j) * 1.0);
+    const double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (dyff(g, j) * 1.0);
+    const double qS = 0.0 * (dxcc(g, j - 1) * 1.0), qN = 0.0 * (dxcc(g, j) * 1.0);
+    return (qE - qW + qN - qS) / (azcf(g, j) * 1.0);
 }
 
 // ---- external stresses: ext:8-27,176-202 -------------------------------------------------------

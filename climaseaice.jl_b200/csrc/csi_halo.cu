@@ -34,10 +34,11 @@ __global__ void k_fill_y_periodic(DArr a, int Ny, int Hy)
     at(a, i, Ny + k) = at(a, i, k);
 }
 
-__global__ void k_fill_x_bounded(DArr a, int Nx, int Ny, int mode, double val, double D)
+__global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (j > Ny) return;
+    const double D = dxff(g, j);  // Delta x at (Face, Face) on the wall, as Oceananigans' left/right_gradient uses
     if (mode == FILL_NOFLUX) {
         at(a, 0, j) = at(a, 1, j);
         at(a, Nx + 1, j) = at(a, Nx, j);
@@ -51,17 +52,18 @@ __global__ void k_fill_x_bounded(DArr a, int Nx, int Ny, int mode, double val, d
     }
 }
 
-__global__ void k_fill_y_bounded(DArr a, int Nx, int Ny, int mode, double val, double D, int do_south, int do_north)
+__global__ void k_fill_y_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val, int do_south, int do_north)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > Nx) return;
+    const double Ds = dyff(g, 1), Dn = dyff(g, Ny + 1);
     if (mode == FILL_NOFLUX) {
         if (do_south) at(a, i, 0) = at(a, i, 1);
         if (do_north) at(a, i, Ny + 1) = at(a, i, Ny);
     } else if (mode == FILL_VALUE) {
         const double c1 = at(a, i, 1), cN = at(a, i, Ny);
-        if (do_south) at(a, i, 0) = c1 + ((c1 - val) / (D / 2)) * (-D);
-        if (do_north) at(a, i, Ny + 1) = cN + ((val - cN) / (D / 2)) * D;
+        if (do_south) at(a, i, 0) = c1 + ((c1 - val) / (Ds / 2)) * (-Ds);
+        if (do_north) at(a, i, Ny + 1) = cN + ((val - cN) / (Dn / 2)) * Dn;
     } else if (mode == FILL_IMPENETRABLE) {
         if (do_south) at(a, i, 1) = 0.0;
         if (do_north) at(a, i, Ny + 1) = 0.0;
@@ -82,7 +84,7 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             mode = FILL_IMPENETRABLE;
         }
         if (mode != FILL_NONE) {
-            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(a, g.Nx, g.Ny, mode, val, g.dx);
+            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val);
             ++*c.launches;
         }
     }
@@ -96,7 +98,7 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             mode = FILL_IMPENETRABLE;
         }
         if (mode != FILL_NONE) {
-            k_fill_y_bounded<<<(g.Nx + T - 1) / T, T, 0, c.stream>>>(a, g.Nx, g.Ny, mode, val, g.dy, !g.conn_s, !g.conn_n);
+            k_fill_y_bounded<<<(g.Nx + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val, !g.conn_s, !g.conn_n);
             ++*c.launches;
         }
     }

@@ -26,7 +26,30 @@ struct DGrid {
     double dx, dy, az;      // regular rectilinear metrics; az = dx*dy
     const uint8_t *mask;    // optional immersed mask at centres (parent-shaped), device pointer
     const uint8_t *mask_host;  // the same mask in host memory (plan construction only)
+    // j-dependent metrics (LatitudeLongitudeGrid): 12 arrays of metL doubles, entry for index j at [j-1+Hy];
+    // order dxcc dxfc dxcf dxff dycc dyfc dycf dyff azcc azfc azcf azff.  NULL on a regular RectilinearGrid.
+    const double *met;
+    int metL, pad_;
 };
+
+// grid metrics at row j (they do not depend on i on the supported grids)
+enum { M_DXCC = 0, M_DXFC, M_DXCF, M_DXFF, M_DYCC, M_DYFC, M_DYCF, M_DYFF, M_AZCC, M_AZFC, M_AZCF, M_AZFF };
+__device__ __forceinline__ double metric(const DGrid &g, int which, int j, double regular)
+{
+    return g.met ? __ldg(g.met + (size_t)which * g.metL + (j - 1 + g.Hy)) : regular;
+}
+__device__ __forceinline__ double dxcc(const DGrid &g, int j) { return metric(g, M_DXCC, j, g.dx); }
+__device__ __forceinline__ double dxfc(const DGrid &g, int j) { return metric(g, M_DXFC, j, g.dx); }
+__device__ __forceinline__ double dxcf(const DGrid &g, int j) { return metric(g, M_DXCF, j, g.dx); }
+__device__ __forceinline__ double dxff(const DGrid &g, int j) { return metric(g, M_DXFF, j, g.dx); }
+__device__ __forceinline__ double dycc(const DGrid &g, int j) { return metric(g, M_DYCC, j, g.dy); }
+__device__ __forceinline__ double dyfc(const DGrid &g, int j) { return metric(g, M_DYFC, j, g.dy); }
+__device__ __forceinline__ double dycf(const DGrid &g, int j) { return metric(g, M_DYCF, j, g.dy); }
+__device__ __forceinline__ double dyff(const DGrid &g, int j) { return metric(g, M_DYFF, j, g.dy); }
+__device__ __forceinline__ double azcc(const DGrid &g, int j) { return metric(g, M_AZCC, j, g.az); }
+__device__ __forceinline__ double azfc(const DGrid &g, int j) { return metric(g, M_AZFC, j, g.az); }
+__device__ __forceinline__ double azcf(const DGrid &g, int j) { return metric(g, M_AZCF, j, g.az); }
+__device__ __forceinline__ double azff(const DGrid &g, int j) { return metric(g, M_AZFF, j, g.az); }
 
 struct DParams {
     double Pstar, C, em2, Dmin, amin, amax, ca;

@@ -9,12 +9,18 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .model import (Bounded, FPlane, Field, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
+from .model import (Bounded, FPlane, Field, LatitudeLongitudeGrid, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
                     SplitExplicitSolver, UpwindBiased, ValueBoundaryCondition, WENO)
 from .synthetic import Case
 
 
 def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearGrid:
+    if case.latlon is not None:
+        if partitioned_y:
+            raise NotImplementedError("slab partitions of a LatitudeLongitudeGrid")
+        return LatitudeLongitudeGrid(size=(case.Nx, case.Ny), longitude=case.latlon[0], latitude=case.latlon[1],
+                                     halo=(case.Hx, case.Hy), topology=(case.topology[0], case.topology[1], "Flat"),
+                                     device=device, metrics=case.metrics())
     return RectilinearGrid(size=(case.Nx, case.Ny), x=(0, case.Lx), y=(0, case.Ly), halo=(case.Hx, case.Hy),
                            topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y)
 

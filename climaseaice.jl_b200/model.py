@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .metrics import METRIC_NAMES, latitude_longitude_metrics
 
 Periodic, Bounded, Flat = "Periodic", "Bounded", "Flat"
 Center, Face = 0, 1
@@ -64,6 +65,29 @@ class RectilinearGrid:
         xs = self.x[0] + ((i - 1) if loc[0] == Face else (i - 0.5)) * self.dx
         ys = self.y[0] + ((j - 1) if loc[1] == Face else (j - 0.5)) * self.dy
         return xs, ys
+
+
+class LatitudeLongitudeGrid(RectilinearGrid):
+    """LatitudeLongitudeGrid(size=(Nx, Ny), longitude=(l0, l1), latitude=(p0, p1), halo, topology, radius).
+
+    Regularly spaced in degrees; the horizontal metrics depend on j only (Oceananigans' precomputed-metrics layout:
+    dx = R cos(phi) dlambda at centre / face latitudes, dy = R dphi, Az = R^2 dlambda (sin phi_north - sin phi_south)).
+    `metrics[name][j - 1 + Hy]` is the value at index j, for j = 1-Hy .. Ny+Hy+1 -- the arrays csi_config.metrics takes.
+    `nodes()` returns degrees.  Only the general (per-kernel) solver formulation supports this grid.
+    """
+
+    def __init__(self, size, longitude, latitude, halo=(3, 3), topology=(Bounded, Bounded, Flat), radius=6371e3, device=None,
+                 metrics=None):
+        super().__init__(size, longitude, latitude, halo=halo, topology=topology, device=device)
+        self.radius = float(radius)
+        if metrics is None:
+            metrics = latitude_longitude_metrics(self.Nx, self.Ny, self.Hy, self.x, self.y, self.radius)
+        self.metrics = {}
+        for n in METRIC_NAMES:
+            a = np.ascontiguousarray(metrics[n], dtype=np.float64).copy()
+            if a.shape != (self.Ny + 2 * self.Hy + 1,):
+                raise ValueError(f"metric {n}: expected {self.Ny + 2 * self.Hy + 1} entries, got {a.shape}")
+            self.metrics[n] = a
 
 
 class Field:
@@ -233,6 +257,10 @@ class SeaIceModel:
         cfg.Nx, cfg.Ny, cfg.Hx, cfg.Hy = g.Nx, g.Ny, g.Hx, g.Hy
         cfg.topo_x, cfg.topo_y = g.topo_codes
         cfg.dx, cfg.dy = g.dx, g.dy
+        if isinstance(g, LatitudeLongitudeGrid):
+            cfg.metric_kind = L.METRIC_J
+            for k, n in enumerate(METRIC_NAMES):
+                cfg.metrics[k] = g.metrics[n].ctypes.data_as(C.POINTER(C.c_double))
         cfg.immersed_mask = self._mask.ctypes.data if self._mask is not None else None
         cfg.ice_compressive_strength = r.ice_compressive_strength
         cfg.ice_compaction_hardening = r.ice_compaction_hardening

@@ -6,12 +6,16 @@ A `Case` is plain data -- sizes, physical settings and parent arrays (C-order (s
   anticyclone_case(N): BASELINE config 1/2 -- examples/ice_advected_by_anticyclone.jl:35-126 scaled
       to N x N (Bounded x Bounded, dx = 4 km, FPlane, wind-stress arrays, SemiImplicitStress ocean drag).
   periodic_case(N):    BASELINE config 3 -- doubly periodic variant with every mask branch live.
+  coastline_case(Ny):  BASELINE config 4 -- examples/ice_advected_on_coastline.jl with its immersed coastline.
+  latlon_case(N):      a basin on a LatitudeLongitudeGrid (j-dependent metrics).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass, field
 
 import numpy as np
+
+from .metrics import latitude_longitude_metrics
 
 SEED = 20260417
 
@@ -40,6 +44,13 @@ class Case:
     ocean_const: tuple | None = None     # constant (ue, ve) when there are no ue/ve arrays
     mask: object = None                  # immersed mask at centres, uint8 (Ny+2Hy, Nx+2Hx), 1 = land
     immersed_drag: tuple = (0.0, 0.0)    # linear-drag immersed flux BC coefficients for u and v
+    latlon: tuple | None = None          # ((lon0, lon1), (lat0, lat1)) in degrees: LatitudeLongitudeGrid; Lx, Ly = extents in degrees
+
+    def metrics(self):
+        """j-indexed metric arrays of a lat-lon case (None on a RectilinearGrid)."""
+        if self.latlon is None:
+            return None
+        return latitude_longitude_metrics(self.Nx, self.Ny, self.Hy, self.latlon[0], self.latlon[1])
 
     @property
     def dx(self):
@@ -144,6 +155,33 @@ def anticyclone_case(N, H=7, seed=SEED, substeps=150, dt=120.0, advection_order=
     a = np.ones_like(h)
     raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=ue, ve=ve, top_x=tx, top_y=ty)
     c.fields = {k: np.ascontiguousarray(vv, dtype=np.float64) for k, vv in raw.items()}
+    return c
+
+
+def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7, timestepper="SplitRungeKutta3",
+                topology=("Bounded", "Bounded")) -> Case:
+    """A basin on a LatitudeLongitudeGrid (the grid of test/test_rheology_energy_budget.jl:18-24 and of the coupled
+    ClimaOcean set-ups): lambda in (0, 60), phi in (20, 70), closed or zonally periodic, rotating wind stress,
+    sheared ocean current, variable ice cover.  The metrics vary by a factor ~2.7 across the rows."""
+    lon, lat = (0.0, 60.0), (20.0, 70.0)
+    c = Case("latlon", N, N, H, H, tuple(topology), lon[1] - lon[0], lat[1] - lat[0], dt=dt, substeps=substeps,
+             advection_order=advection_order, timestepper=timestepper, latlon=(lon, lat),
+             u_bc_value=0.0 if topology[1] == "Bounded" else None, v_bc_value=0.0 if topology[0] == "Bounded" else None)
+    rng = np.random.default_rng(seed)
+    tp = 2 * np.pi
+    X, Y = c.nodes(LOC["h"])
+    Xu, Yu = c.nodes(LOC["u"])
+    Xv, Yv = c.nodes(LOC["v"])
+    fx = lambda x: x / c.Lx
+    fy = lambda y: y / c.Ly
+    h = 0.5 + 0.2 * np.sin(tp * fx(X)) * np.cos(tp * fy(Y)) + 1e-3 * rng.uniform(-1, 1, X.shape)
+    a = np.clip(0.95 + 0.05 * np.cos(2 * tp * fx(X)) - 0.3 * (fy(Y) < 0.15), 0.0, 1.0)
+    tx = 0.1 * np.cos(tp * fy(Yu))
+    ty = 0.1 * np.sin(tp * fx(Xv))
+    ue = 0.05 * np.sin(tp * fy(Yu))
+    ve = 0.05 * np.sin(tp * fx(Xv))
+    raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=ue, ve=ve, top_x=tx, top_y=ty)
+    c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
     return c
 
 

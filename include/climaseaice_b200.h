@@ -104,6 +104,13 @@ typedef struct {
     /* ImmersedBoundaryCondition of examples/ice_advected_on_coastline.jl:91-98: discrete-form flux -C*u on the
      * south/north immersed faces of u and -C*v on the west/east ones of v (isd.jl:57-123); 0 = none */
     double immersed_drag_u, immersed_drag_v;
+    /* LatitudeLongitudeGrid (or any grid whose metrics depend on j only): metric_kind = CSI_METRIC_J and
+     * metrics[k] -> host array of Ny + 2*Hy + 1 doubles, the value at index j stored at [j - 1 + Hy], in the
+     * order dx{cc,fc,cf,ff}, dy{cc,fc,cf,ff}, Az{cc,fc,cf,ff} (Oceananigans' Delta-x/Delta-y/Az at the four
+     * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above. */
+    int32_t metric_kind;
+    int32_t reserved2_;
+    const double *metrics[12];
 } csi_config;
 
 /* The arrays the hot path touches.  Unused ones may have ptr == NULL. */
@@ -117,6 +124,8 @@ typedef struct {
     csi_array Gh, Ga;               /* timestepper.G^n.h, .aice */
     csi_array hm, am, um, vm;       /* timestepper.Psi^- (RK3) */
 } csi_fields;
+
+enum { CSI_METRIC_REGULAR = 0, CSI_METRIC_J = 1 };
 
 int csi_version(void);
 const char *csi_last_error(const csi_handle *h); /* h may be NULL: last error of csi_create */

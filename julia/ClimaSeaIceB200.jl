@@ -55,6 +55,20 @@ Base.@kwdef struct CsiConfig
     v_west_east_value :: Float64 = 0.0
     timestepper :: Int32 = 0; solver_impl :: Int32 = 0
     rank :: Int32 = 0; nranks :: Int32 = 1; exchange_every :: Int32 = 0; reserved_ :: Int32 = 0
+    immersed_drag_u :: Float64 = 0.0; immersed_drag_v :: Float64 = 0.0
+    metric_kind :: Int32 = 0; reserved2_ :: Int32 = 0
+    metrics :: NTuple{12, Ptr{Float64}} = ntuple(_ -> Ptr{Float64}(C_NULL), 12)
+end
+
+# LatitudeLongitudeGrid: the twelve j-indexed metric vectors csi_config.metrics takes (metric_kind = 1), each
+# Ny + 2Hy + 1 long with index j at [j - 1 + Hy] (1-based: [j + Hy]).  Evaluated with Oceananigans' own operators so
+# the library sees exactly the numbers the reference kernels would; keep `vecs` alive until csi_create returns.
+function metric_vectors(grid)
+    _, Ny, _ = size(grid); _, Hy, _ = halo_size(grid)
+    ops = (Δxᶜᶜᶜ, Δxᶠᶜᶜ, Δxᶜᶠᶜ, Δxᶠᶠᶜ, Δyᶜᶜᶜ, Δyᶠᶜᶜ, Δyᶜᶠᶜ, Δyᶠᶠᶜ, Azᶜᶜᶜ, Azᶠᶜᶜ, Azᶜᶠᶜ, Azᶠᶠᶜ)
+    cpu = on_architecture(CPU(), grid)
+    vecs = [Float64[op(1, j, 1, cpu) for j in 1-Hy:Ny+Hy+1] for op in ops]
+    return vecs, ntuple(k -> pointer(vecs[k]), 12)
 end
 
 # csi_fields: 24 csi_array in header order
@@ -78,8 +92,11 @@ function create(model::SeaIceModel)
     dyn, r = model.dynamics, model.dynamics.rheology
     Nx, Ny, _ = size(grid); Hx, Hy, _ = halo_size(grid); TX, TY, _ = topology(grid)
     bottom = dyn.external_momentum_stresses.bottom
+    regular = grid isa RectilinearGrid      # else: LatitudeLongitudeGrid, metrics depend on j
+    vecs, metrics = regular ? (nothing, ntuple(_ -> Ptr{Float64}(C_NULL), 12)) : metric_vectors(grid)
     cfg = CsiConfig(; Nx, Ny, Hx, Hy, topo_x = topo_code(TX), topo_y = topo_code(TY),
-                    dx = grid.Δxᶜᵃᵃ, dy = grid.Δyᵃᶜᵃ, device = CUDA.deviceid(),
+                    dx = regular ? grid.Δxᶜᵃᵃ : 0.0, dy = regular ? grid.Δyᵃᶜᵃ : 0.0, device = CUDA.deviceid(),
+                    metric_kind = regular ? 0 : 1, metrics,
                     ice_compressive_strength = r.ice_compressive_strength, ice_compaction_hardening = r.ice_compaction_hardening,
                     yield_curve_eccentricity = r.yield_curve_eccentricity, minimum_plastic_stress = r.minimum_plastic_stress,
                     min_relaxation_parameter = r.min_relaxation_parameter, max_relaxation_parameter = r.max_relaxation_parameter,
@@ -91,7 +108,7 @@ function create(model::SeaIceModel)
                     bottom_stress_kind = bottom isa SemiImplicitStress ? 3 : 0,
                     rho_e = bottom isa SemiImplicitStress ? bottom.ρₑ : 1026.0, Cd = bottom isa SemiImplicitStress ? bottom.Cᴰ : 5.5e-3)
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:csi_create, LIB), Cint, (Ref{CsiConfig}, Ref{Ptr{Cvoid}}), cfg, out))
+    GC.@preserve vecs check(ccall((:csi_create, LIB), Cint, (Ref{CsiConfig}, Ref{Ptr{Cvoid}}), cfg, out))
     h = Handle(out[])
     finalizer(x -> ccall((:csi_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
     return h

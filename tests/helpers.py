@@ -31,7 +31,7 @@ def oracle_from_case(case, **overrides) -> O.OracleModel:
     p = oracle_params(case)
     p.update(overrides)
     return O.OracleModel(case.Nx, case.Ny, case.Hx, case.Hy, topo=topo, dx=case.dx, dy=case.dy, params=p,
-                         fields={k: v.copy() for k, v in case.fields.items()}, mask=case.mask)
+                         fields={k: v.copy() for k, v in case.fields.items()}, mask=case.mask, metrics=case.metrics())
 
 
 # GPU field name -> oracle field name

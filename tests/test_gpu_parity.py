@@ -300,3 +300,41 @@ def test_coastline_config4_reduced(impl):
     u = interior_of(m.all_fields()["u"].numpy(), case)
     assert np.abs(u).max() > 1e-4          # the wind moved the ice
     m.close()
+
+
+@pytest.mark.parametrize("topology", [("Bounded", "Bounded"), ("Periodic", "Bounded")])
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_latitude_longitude_grid(topology, timestepper):
+    """j-dependent metrics (LatitudeLongitudeGrid, the grid of test/test_rheology_energy_budget.jl:18-24): every
+    dx/dy/Az in the strain rates, the SBP stress divergence, the relaxation factors, the flux divergence, the value
+    BCs and the CFL reduction is the row's own.  The general kernels serve this grid ("auto" must route there)."""
+    from climaseaice_b200.synthetic import latlon_case
+    case = latlon_case(48, substeps=20, topology=topology, timestepper=timestepper)
+    met = case.metrics()
+    assert met["dxcc"].max() / met["dxcc"].min() > 2          # the metrics really vary
+    m = model_from_case(case, solver_impl="auto")
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "delta")))
+    assert np.abs(interior_of(m.all_fields()["u"].numpy(), case)).max() > 1e-4
+    assert m.cell_advection_timescale() == pytest.approx(o.cell_advection_timescale(), rel=1e-15)
+    d = m.diagnostics()
+    az = met["azcc"][case.Hy:case.Hy + case.Ny][:, None]
+    assert d["sum_h_Az"] == pytest.approx((o.interior("h") * az).sum(), rel=1e-13)
+    m.close()
+
+
+def test_latitude_longitude_grid_rejects_fused_and_bad_metrics():
+    from climaseaice_b200.synthetic import latlon_case
+    case = latlon_case(32, substeps=4)
+    m = model_from_case(case, solver_impl="fused")
+    with pytest.raises(RuntimeError, match="j-dependent grid metrics"):
+        m.time_step(case.dt)
+    m.close()
+    bad = latlon_case(32, substeps=4)
+    met = bad.metrics()
+    met["azff"][bad.Hy + 3] = 0.0
+    bad.metrics = lambda: met
+    with pytest.raises(RuntimeError, match="metrics must be positive"):
+        model_from_case(bad)

@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     # sizes computed by hand from include/climaseaice_b200.h (natural alignment)
     assert C.sizeof(L.csi_array) == 24
     assert C.sizeof(L.csi_fields) == 24 * len(L.FIELD_NAMES)
-    assert C.sizeof(L.csi_config) == 8 + 24 + 16 + 8 + 56 + 8 + 24 + 8 + 24 + 8 + 40 + 8 + 8 + 8 + 16 + 16
+    assert C.sizeof(L.csi_config) == 8 + 24 + 16 + 8 + 56 + 8 + 24 + 8 + 24 + 8 + 40 + 8 + 8 + 8 + 16 + 16 + 8 + 96
 
 
 def test_correctly_rounded_exp_matches_binary128():
