@@ -5,7 +5,7 @@ modules here are the host-side mirror of the reference's user interface for that
 """
 from . import _lib
 from ._lib import CsiError, lib
-from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid, LatitudeLongitudeGrid,
+from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid, LatitudeLongitudeGrid, StressBalanceFreeDrift,
                     SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress, SplitExplicitSolver, UpwindBiased,
                     ValueBoundaryCondition, WENO, nccl_unique_id, time_step_b)
 

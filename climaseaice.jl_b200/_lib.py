@@ -22,6 +22,7 @@ BC_DEFAULT, BC_VALUE = 0, 1
 RK3, FE = 0, 1
 SOLVER_AUTO, SOLVER_UNFUSED, SOLVER_FUSED = 0, 1, 2
 METRIC_REGULAR, METRIC_J = 0, 1
+FD_NONE, FD_FIELDS, FD_STRESS_BALANCE = 0, 1, 2
 
 ERRORS = {-1: "CSI_ERR_ARG", -2: "CSI_ERR_SHAPE", -3: "CSI_ERR_UNSUPPORTED", -4: "CSI_ERR_NO_DEVICE", -5: "CSI_ERR_NCCL_MISSING"}
 
@@ -61,15 +62,17 @@ class csi_config(C.Structure):
         ("exchange_every", C.c_int32), ("reserved_", C.c_int32),
         ("immersed_drag_u", C.c_double), ("immersed_drag_v", C.c_double),
         ("metric_kind", C.c_int32), ("reserved2_", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
+        ("free_drift_kind", C.c_int32), ("reserved3_", C.c_int32), ("top_rho_e", C.c_double), ("top_Cd", C.c_double),
     ]
 
 
 FIELD_NAMES = ("u", "v", "h", "a", "s11", "s22", "s12", "zeta_f", "zeta_c", "delta", "alpha", "un", "vn", "P",
-               "top_x", "top_y", "ue", "ve", "Gh", "Ga", "hm", "am", "um", "vm")
+               "top_x", "top_y", "ue", "ve", "Gh", "Ga", "hm", "am", "um", "vm", "hs", "Ghs", "hsm", "fd_u", "fd_v")
 # (face_x, face_y) of every field, same order
 FIELD_LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), s11=(0, 0), s22=(0, 0), s12=(1, 1), zeta_f=(1, 1),
                  zeta_c=(0, 0), delta=(0, 0), alpha=(0, 0), un=(1, 0), vn=(0, 1), P=(0, 0), top_x=(1, 0),
-                 top_y=(0, 1), ue=(1, 0), ve=(0, 1), Gh=(0, 0), Ga=(0, 0), hm=(0, 0), am=(0, 0), um=(1, 0), vm=(0, 1))
+                 top_y=(0, 1), ue=(1, 0), ve=(0, 1), Gh=(0, 0), Ga=(0, 0), hm=(0, 0), am=(0, 0), um=(1, 0), vm=(0, 1),
+                 hs=(0, 0), Ghs=(0, 0), hsm=(0, 0), fd_u=(1, 0), fd_v=(0, 1))
 
 
 class csi_fields(C.Structure):

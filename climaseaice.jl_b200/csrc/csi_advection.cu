@@ -120,15 +120,15 @@ __device__ __forceinline__ int buffer_at(int B, bool wall_lo, bool wall_hi, int 
 
 static constexpr int ATX = 32, ATY = 8, AH = 4;  // tile and the widest stencil halo (WENO7)
 
-// G^n.h = -div(U h), G^n.aice = -div(U aice)
-template <int B>
+// G^n.h = -div(U h), G^n.aice = -div(U aice) and, with snow (NQ = 3), G^n.hs = -div(U hs)  (tracer_tendency:27-52)
+template <int B, int NQ>
 __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_constant__ DGrid g, const __grid_constant__ DParams p,
                                                                  const __grid_constant__ DFields f)
 {
     constexpr int SX = ATX + 2 * AH, SY = ATY + 2 * AH;
-    __shared__ double sh[2][SY][SX];          // h, aice with halo
-    __shared__ double fx[2][ATY][ATX + 1];    // x-face fluxes
-    __shared__ double fy[2][ATY + 1][ATX];    // y-face fluxes
+    __shared__ double sh[NQ][SY][SX];          // h, aice (, hs) with halo
+    __shared__ double fx[NQ][ATY][ATX + 1];    // x-face fluxes
+    __shared__ double fy[NQ][ATY + 1][ATX];    // y-face fluxes
     const int i0 = blockIdx.x * ATX + 1, j0 = blockIdx.y * ATY + 1;
     const int tid = threadIdx.y * ATX + threadIdx.x;
     for (int t = tid; t < SX * SY; t += ATX * ATY) {
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         gj = min(max(gj, 1 - g.Hy), g.Ny + g.Hy);
         sh[0][lj][li] = at(f.h, gi, gj);
         sh[1][lj][li] = at(f.a, gi, gj);
+        if (NQ > 2) sh[NQ - 1][lj][li] = at(f.hs, gi, gj);
     }
     __syncthreads();
     const bool bx = g.topo_x == CSI_BOUNDED, by_lo = g.topo_y == CSI_BOUNDED && !g.conn_s, by_hi = g.topo_y == CSI_BOUNDED && !g.conn_n;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
             const int b = buffer_at(B, bx, bx, g.Nx, i);
             const bool imm = g.mask && imm_peripheral_fc(g, i, j);
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH][li + AH - 1], 1, U > 0);
                 const double fl = (dyfc(g, j) * 1.0) * U * ct;
                 fx[q][lj][li] = imm ? 0.0 : fl;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
             const int b = buffer_at(B, by_lo, by_hi, g.Ny, j);
             const bool imm = g.mask && imm_peripheral_cf(g, i, j);
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH - 1][li + AH], SX, V > 0);
                 const double fl = (dxcf(g, j) * 1.0) * V * ct;
                 fy[q][lj][li] = imm ? 0.0 : fl;
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         const double V = azcc(g, j) * 1.0;
         at(f.Gh, i, j) = -(1 / V * ((fx[0][lj][li + 1] - fx[0][lj][li]) + (fy[0][lj + 1][li] - fy[0][lj][li])));
         at(f.Ga, i, j) = -(1 / V * ((fx[1][lj][li + 1] - fx[1][lj][li]) + (fy[1][lj + 1][li] - fy[1][lj][li])));
+        if (NQ > 2) at(f.Ghs, i, j) = -(1 / V * ((fx[NQ - 1][lj][li + 1] - fx[NQ - 1][lj][li]) + (fy[NQ - 1][lj + 1][li] - fy[NQ - 1][lj][li])));
     }
 }
 
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) k_zero_tendencies(const __grid_constant__
     if (i > g.Nx || j > g.Ny) return;
     at(f.Gh, i, j) = -0.0;  // -zero(grid)
     at(f.Ga, i, j) = -0.0;
+    if (f.hs.p) at(f.Ghs, i, j) = -0.0;
 }
 
 void launch_tracer_tendencies(const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f)
@@ -196,16 +199,21 @@ void launch_tracer_tendencies(const LaunchCtx &c, const DGrid &g, const DParams 
     dim3 grid((g.Nx + ATX - 1) / ATX, (g.Ny + ATY - 1) / ATY), block(ATX, ATY);
     switch (p.adv_order) {
     case 0: k_zero_tendencies<<<dim3((g.Nx + 255) / 256, g.Ny), 256, 0, c.stream>>>(g, f); break;
-    case 1: k_tracer_tendencies<1><<<grid, block, 0, c.stream>>>(g, p, f); break;
-    case 3: k_tracer_tendencies<2><<<grid, block, 0, c.stream>>>(g, p, f); break;
-    case 5: k_tracer_tendencies<3><<<grid, block, 0, c.stream>>>(g, p, f); break;
-    default: k_tracer_tendencies<4><<<grid, block, 0, c.stream>>>(g, p, f); break;
+#define CSI_TT(B_)                                                                     \
+    if (f.hs.p) k_tracer_tendencies<B_, 3><<<grid, block, 0, c.stream>>>(g, p, f);     \
+    else k_tracer_tendencies<B_, 2><<<grid, block, 0, c.stream>>>(g, p, f);            \
+    break
+    case 1: CSI_TT(1);
+    case 3: CSI_TT(2);
+    case 5: CSI_TT(3);
+    default: CSI_TT(4);
+#undef CSI_TT
     }
     ++*c.launches;
 }
 
-// _dynamic_step_tracers!: fe:56-82
-__global__ void __launch_bounds__(256) k_dynamic_step(const __grid_constant__ DGrid g, const __grid_constant__ DFields f, DArr hn, DArr an, double dt)
+// _dynamic_step_tracers!: fe:56-82, dynamic_step_snow!: fe:84-94
+__global__ void __launch_bounds__(256) k_dynamic_step(const __grid_constant__ DGrid g, const __grid_constant__ DFields f, DArr hn, DArr an, DArr hsn, double dt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
     if (i > g.Nx || j > g.Ny) return;
@@ -216,13 +224,20 @@ __global__ void __launch_bounds__(256) k_dynamic_step(const __grid_constant__ DG
     ap = (hp == 0) ? 0.0 : ap;
     hp = (ap == 0) ? 0.0 : hp;
     const double Vp = hp * ap;
-    at(f.a, i, j) = ap > 1 ? 1.0 : ap;
+    const double anew = ap > 1 ? 1.0 : ap;
+    at(f.a, i, j) = anew;
     at(f.h, i, j) = ap > 1 ? Vp : hp;
+    if (f.hs.p) {
+        double sp = at(hsn, i, j) + dt * at(f.Ghs, i, j);
+        sp = jl_max(0.0, sp);
+        sp = (anew <= 0) ? 0.0 : sp;
+        at(f.hs, i, j) = sp;
+    }
 }
 
-void launch_dynamic_step(const LaunchCtx &c, const DGrid &g, const DFields &f, const DArr &hn, const DArr &an, double dt)
+void launch_dynamic_step(const LaunchCtx &c, const DGrid &g, const DFields &f, const DArr &hn, const DArr &an, const DArr &hsn, double dt)
 {
-    k_dynamic_step<<<dim3((g.Nx + 255) / 256, g.Ny), 256, 0, c.stream>>>(g, f, hn, an, dt);
+    k_dynamic_step<<<dim3((g.Nx + 255) / 256, g.Ny), 256, 0, c.stream>>>(g, f, hn, an, hsn, dt);
     ++*c.launches;
 }
 

@@ -123,7 +123,9 @@ const FieldInfo FIELD_INFO[NFIELDS] = {
     {"u", 1, 0},     {"v", 0, 1},     {"h", 0, 0},      {"a", 0, 0},      {"s11", 0, 0},   {"s22", 0, 0},
     {"s12", 1, 1},   {"zeta_f", 1, 1}, {"zeta_c", 0, 0}, {"delta", 0, 0},  {"alpha", 0, 0}, {"un", 1, 0},
     {"vn", 0, 1},    {"P", 0, 0},     {"top_x", 1, 0},  {"top_y", 0, 1},  {"ue", 1, 0},    {"ve", 0, 1},
-    {"Gh", 0, 0},    {"Ga", 0, 0},    {"hm", 0, 0},     {"am", 0, 0},     {"um", 1, 0},    {"vm", 0, 1}};
+    {"Gh", 0, 0},    {"Ga", 0, 0},    {"hm", 0, 0},     {"am", 0, 0},     {"um", 1, 0},    {"vm", 0, 1},
+    {"hs", 0, 0},    {"Ghs", 0, 0},   {"hsm", 0, 0},    {"fd_u", 1, 0},   {"fd_v", 0, 1}};
+enum { K_UE = 16, K_VE = 17, K_HS = 24, K_GHS = 25, K_HSM = 26, K_FDU = 27, K_FDV = 28 };
 
 const csi_array &field_at(const csi_fields &f, int k) { return reinterpret_cast<const csi_array *>(&f)[k]; }
 csi_array &field_at(csi_fields &f, int k) { return reinterpret_cast<csi_array *>(&f)[k]; }
@@ -169,15 +171,20 @@ int convert_fields(csi_handle *h, const csi_fields *f, int need, DFields *out)
             req |= (n == "u" || n == "v" || n == "h" || n == "a" || n == "s11" || n == "s22" || n == "s12" || n == "zeta_f" ||
                     n == "zeta_c" || n == "delta" || n == "alpha" || n == "un" || n == "vn" || n == "P");
             if (c.top_stress_kind == CSI_STRESS_FIELD) req |= (n == "top_x" || n == "top_y");
+            if (c.bottom_stress_kind == CSI_STRESS_FIELD) req |= (n == "ue" || n == "ve");
+            if (c.free_drift_kind == CSI_FD_FIELDS) req |= (n == "fd_u" || n == "fd_v");
         }
-        if (need & NEED_TRACERS) req |= (n == "u" || n == "v" || n == "h" || n == "a" || n == "Gh" || n == "Ga");
-        if ((need & NEED_RK) && c.timestepper == CSI_RK3) req |= (n == "hm" || n == "am" || n == "um" || n == "vm");
+        const bool snow = field_at(*f, K_HS).ptr != nullptr;
+        if (need & NEED_TRACERS) req |= (n == "u" || n == "v" || n == "h" || n == "a" || n == "Gh" || n == "Ga" || (snow && n == "Ghs"));
+        if ((need & NEED_RK) && c.timestepper == CSI_RK3) req |= (n == "hm" || n == "am" || n == "um" || n == "vm" || (snow && n == "hsm"));
         int rc = check_array(h, field_at(*f, k), FIELD_INFO[k], req);
         if (rc) return rc;
         reinterpret_cast<DArr *>(out)[k] = to_darr(field_at(*f, k));
     }
-    if ((field_at(*f, 16).ptr == nullptr) != (field_at(*f, 17).ptr == nullptr))
+    if ((field_at(*f, K_UE).ptr == nullptr) != (field_at(*f, K_VE).ptr == nullptr))
         return fail(h, CSI_ERR_ARG, "ue and ve must both be arrays or both be constants");
+    if ((field_at(*f, 14).ptr == nullptr) != (field_at(*f, 15).ptr == nullptr))
+        return fail(h, CSI_ERR_ARG, "top_x and top_y must both be arrays or both be constants");
     return CSI_OK;
 }
 
@@ -223,11 +230,11 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
     }
     launch_initialize_rheology(c, g, p, f);  // evp.jl:192-216
     // update_external_stress!  ext.jl:72-78,148-152
-    if (p.top_kind == CSI_STRESS_FIELD) {
+    if (p.top_kind == CSI_STRESS_FIELD || p.top_kind == CSI_STRESS_SEMI_IMPLICIT) {
         launch_fill_halo(c, g, p, f.top_x, 1, 0, 0);
         launch_fill_halo(c, g, p, f.top_y, 0, 1, 0);
     }
-    if (p.bot_kind == CSI_STRESS_SEMI_IMPLICIT) {
+    if (p.bot_kind == CSI_STRESS_FIELD || p.bot_kind == CSI_STRESS_SEMI_IMPLICIT) {
         launch_fill_halo(c, g, p, f.ue, 1, 0, 0);
         launch_fill_halo(c, g, p, f.ve, 0, 1, 0);
     }
@@ -322,13 +329,17 @@ int update_state_impl(csi_handle *h, const DFields &f, cudaStream_t s)
     launch_fill_halo(c, g, p, f.h, 0, 0, 0);
     launch_mask_immersed(c, g, f.a, 0, 0);
     launch_fill_halo(c, g, p, f.a, 0, 0, 0);
+    if (f.hs.p) {  // snow_fields(model.snow_thickness) follows h, aice among the prognostic fields
+        launch_mask_immersed(c, g, f.hs, 0, 0);
+        launch_fill_halo(c, g, p, f.hs, 0, 0, 0);
+    }
     launch_mask_immersed(c, g, f.u, 1, 0);
     launch_fill_halo(c, g, p, f.u, 1, 0, 1);
     launch_mask_immersed(c, g, f.v, 0, 1);
     launch_fill_halo(c, g, p, f.v, 0, 1, 2);
     if (h->nranks > 1) {
-        const DArr arrs[4] = {f.h, f.a, f.u, f.v};
-        int rc = exchange_slab_halos(h, arrs, 4, g.Hy, s);
+        const DArr arrs[5] = {f.h, f.a, f.u, f.v, f.hs};
+        int rc = exchange_slab_halos(h, arrs, 5, g.Hy, s);
         if (rc) return rc;
     }
     CSI_CUDA(h, cudaGetLastError());
@@ -346,19 +357,20 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
     if (h->cfg.timestepper == CSI_FE) {  // fe.jl:13-34
         launch_tracer_tendencies(c, g, p, f);
         if ((rc = momentum_impl(h, f, dt, nsub, s))) return rc;
-        launch_dynamic_step(c, g, f, f.h, f.a, dt);
+        launch_dynamic_step(c, g, f, f.h, f.a, f.hs, dt);
         return update_state_impl(h, f, s);
     }
     // cache_current_fields!  rk.jl:29-42
     if ((rc = copy_parent(h, f.hm, f.h, s))) return rc;
     if ((rc = copy_parent(h, f.am, f.a, s))) return rc;
+    if (f.hs.p && (rc = copy_parent(h, f.hsm, f.hs, s))) return rc;
     if ((rc = copy_parent(h, f.um, f.u, s))) return rc;
     if ((rc = copy_parent(h, f.vm, f.v, s))) return rc;
     for (int beta = 3; beta >= 1; beta--) {  // SplitRungeKutta3: dtau = dt / beta
         const double dtau = dt / beta;
         launch_tracer_tendencies(c, g, p, f);                      // rk.jl:84
         if ((rc = momentum_impl(h, f, dtau, nsub, s))) return rc;  // rk.jl:87
-        launch_dynamic_step(c, g, f, f.hm, f.am, dtau);            // rk.jl:89
+        launch_dynamic_step(c, g, f, f.hm, f.am, f.hsm, dtau);     // rk.jl:89
         if ((rc = update_state_impl(h, f, s))) return rc;
     }
     return CSI_OK;
@@ -431,6 +443,15 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         }
     }
     if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
+    for (int kind : {cfg->top_stress_kind, cfg->bottom_stress_kind})
+        if (kind < CSI_STRESS_NONE || kind > CSI_STRESS_SEMI_IMPLICIT) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad stress kind");
+    if (cfg->free_drift_kind < CSI_FD_NONE || cfg->free_drift_kind > CSI_FD_STRESS_BALANCE) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad free_drift_kind");
+    if (cfg->free_drift_kind == CSI_FD_STRESS_BALANCE) {
+        // stress_balance_free_drift.jl:21-35,111-116
+        const bool ts = cfg->top_stress_kind == CSI_STRESS_SEMI_IMPLICIT, bs = cfg->bottom_stress_kind == CSI_STRESS_SEMI_IMPLICIT;
+        if (ts && bs) return fail(nullptr, CSI_ERR_ARG, "csi_create: StressBalanceFreeDrift supports a SemiImplicitStress only for the top or the bottom stress, not both");
+        if (!ts && !bs) return fail(nullptr, CSI_ERR_ARG, "csi_create: StressBalanceFreeDrift requires a SemiImplicitStress for either the top or the bottom stress");
+    }
     if (cfg->nranks > 1) {
         const int K = cfg->exchange_every > 0 ? cfg->exchange_every : cfg->substeps;
         if (cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: slab partitions need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
@@ -486,6 +507,10 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     p.pad_ = 0;
     p.imm_u = cfg->immersed_drag_u;
     p.imm_v = cfg->immersed_drag_v;
+    p.fd_kind = cfg->free_drift_kind;
+    p.pad2_ = 0;
+    p.top_rho = cfg->top_rho_e;
+    p.top_Cd = cfg->top_Cd;
     cudaError_t e;
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
         delete h;
@@ -569,7 +594,7 @@ int csi_dynamic_time_step(csi_handle *h, const csi_fields *f, double dt_stage, c
     Timed t(h, s);
     LaunchCtx c{s, &h->launches};
     const bool rk = h->cfg.timestepper == CSI_RK3;
-    launch_dynamic_step(c, h->g, df, rk ? df.hm : df.h, rk ? df.am : df.a, dt_stage);
+    launch_dynamic_step(c, h->g, df, rk ? df.hm : df.h, rk ? df.am : df.a, rk ? df.hsm : df.hs, dt_stage);
     CSI_CUDA(h, cudaGetLastError());
     return CSI_OK;
 }
@@ -583,6 +608,7 @@ int csi_cache_current_fields(csi_handle *h, const csi_fields *f, csi_stream stre
     cudaStream_t s = (cudaStream_t)stream;
     if ((rc = copy_parent(h, df.hm, df.h, s))) return rc;
     if ((rc = copy_parent(h, df.am, df.a, s))) return rc;
+    if (df.hs.p && (rc = copy_parent(h, df.hsm, df.hs, s))) return rc;
     if ((rc = copy_parent(h, df.um, df.u, s))) return rc;
     return copy_parent(h, df.vm, df.v, s);
 }
@@ -700,7 +726,8 @@ int csi_time_step_host(csi_handle *h, const csi_fields *hf, double dt, int32_t n
     cudaStream_t s = h->own_stream;
     csi_fields dev;
     // inputs of time_step!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17); Psi^- is written before it is read
-    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14);  // + alpha (10): only its interior is rewritten, the halo must survive the round trip
+    // + alpha (10): only its interior is rewritten, the halo must survive the round trip; + hs (24), fd_u, fd_v (27, 28) when present
+    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14) | (1u << K_HS) | (3u << K_FDU);
     h->last_h2d = h->last_d2h = 0;
     int rc = upload_all(h, hf, &dev, s, in_mask, &h->last_h2d);
     if (rc) return rc;
@@ -711,8 +738,8 @@ int csi_time_step_host(csi_handle *h, const csi_fields *hf, double dt, int32_t n
         for (int k = 0; k < nsteps; k++)
             if ((rc = time_step_impl(h, df, dt, first && k == 0, s))) return rc;
     }
-    const int outs[] = {0, 1, 2, 3, 4, 5, 6, 10};  // u v h a s11 s22 s12 alpha
-    if ((rc = download(h, hf, outs, 8, s))) return rc;
+    const int outs[] = {0, 1, 2, 3, 4, 5, 6, 10, K_HS};  // u v h a s11 s22 s12 alpha (hs)
+    if ((rc = download(h, hf, outs, 9, s))) return rc;
     CSI_CUDA(h, cudaStreamSynchronize(s));
     return CSI_OK;
 }
@@ -726,7 +753,7 @@ int csi_evp_substeps_host(csi_handle *h, const csi_fields *hf, double dt_stage, 
     cudaStream_t s = h->own_stream;
     csi_fields dev;
     // inputs of time_step_momentum!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17), and Psi^-.u, .v (22, 23) under RK3
-    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14) | (h->cfg.timestepper == CSI_RK3 ? (0x3u << 22) : 0u);
+    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14) | (3u << K_FDU) | (h->cfg.timestepper == CSI_RK3 ? (0x3u << 22) : 0u);
     h->last_h2d = h->last_d2h = 0;
     int rc = upload_all(h, hf, &dev, s, in_mask, &h->last_h2d);
     if (rc) return rc;

@@ -162,32 +162,100 @@ __device__ __forceinline__ double immersed_div_sigma_2j(const DGrid &g, const DP
     return (qE - qW + qN - qS) / (azcf(g, j) * 1.0);
 }
 
-// ---- external stresses: ext:8-27,176-202 -------------------------------------------------------
-__device__ __forceinline__ double ue_at(const DParams &p, const DFields &f, int i, int j) { return f.ue.p ? at(f.ue, i, j) : p.ue_c; }
-__device__ __forceinline__ double ve_at(const DParams &p, const DFields &f, int i, int j) { return f.ve.p ? at(f.ve, i, j) : p.ve_c; }
-__device__ __forceinline__ double sis_speed_x(const DParams &p, const DFields &f, int i, int j)
+// ---- external stresses: ext:8-40,176-210 -----------------------------------------------------------
+// Either side (TOP: atmosphere, BOT: ocean) is nothing / a Number pair / a pair of arrays / a SemiImplicitStress.
+// ext_x/ext_y is the side's array-or-constant: the stress itself for CONST and FIELD, u_e / v_e for SEMI_IMPLICIT.
+enum { TOP = 0, BOT = 1 };
+__device__ __forceinline__ int stress_kind(const DParams &p, int w) { return w == TOP ? p.top_kind : p.bot_kind; }
+__device__ __forceinline__ double ext_x(const DParams &p, const DFields &f, int w, int i, int j)
 {
-    auto ve = [&](int a, int b) { return ve_at(p, f, a, b); };
+    if (w == TOP) return f.top_x.p ? at(f.top_x, i, j) : p.ttx;
+    return f.ue.p ? at(f.ue, i, j) : p.ue_c;
+}
+__device__ __forceinline__ double ext_y(const DParams &p, const DFields &f, int w, int i, int j)
+{
+    if (w == TOP) return f.top_y.p ? at(f.top_y, i, j) : p.tty;
+    return f.ve.p ? at(f.ve, i, j) : p.ve_c;
+}
+__device__ __forceinline__ double ext_rho(const DParams &p, int w) { return w == TOP ? p.top_rho : p.rho_e; }
+__device__ __forceinline__ double ext_Cd(const DParams &p, int w) { return w == TOP ? p.top_Cd : p.Cd; }
+__device__ __forceinline__ double sis_speed_x(const DParams &p, const DFields &f, int w, int i, int j)
+{
+    auto ey = [&](int a, int b) { return ext_y(p, f, w, a, b); };
     auto vv = [&](int a, int b) { return at(f.v, a, b); };
-    const double du = ue_at(p, f, i, j) - at(f.u, i, j);
-    const double dv = avg_fc(ve, i, j) - avg_fc(vv, i, j);
+    const double du = ext_x(p, f, w, i, j) - at(f.u, i, j);
+    const double dv = avg_fc(ey, i, j) - avg_fc(vv, i, j);
     return sqrt(du * du + dv * dv);
 }
-__device__ __forceinline__ double sis_speed_y(const DParams &p, const DFields &f, int i, int j)
+__device__ __forceinline__ double sis_speed_y(const DParams &p, const DFields &f, int w, int i, int j)
 {
-    auto ue = [&](int a, int b) { return ue_at(p, f, a, b); };
+    auto ex = [&](int a, int b) { return ext_x(p, f, w, a, b); };
     auto uu = [&](int a, int b) { return at(f.u, a, b); };
-    const double dv = ve_at(p, f, i, j) - at(f.v, i, j);
-    const double du = avg_cf(ue, i, j) - avg_cf(uu, i, j);
+    const double dv = ext_y(p, f, w, i, j) - at(f.v, i, j);
+    const double du = avg_cf(ex, i, j) - avg_cf(uu, i, j);
     return sqrt(du * du + dv * dv);
 }
-__device__ __forceinline__ double explicit_tx_top(const DParams &p, const DFields &f, int i, int j)
+// implicit_tau_x/y_coefficient (zero unless SemiImplicitStress) and explicit_tau_x/y
+__device__ __forceinline__ double implicit_tx(const DParams &p, const DFields &f, int w, int i, int j)
 {
-    return p.top_kind == CSI_STRESS_FIELD ? at(f.top_x, i, j) : (p.top_kind == CSI_STRESS_CONST ? p.ttx : 0.0);
+    return stress_kind(p, w) == CSI_STRESS_SEMI_IMPLICIT ? ext_rho(p, w) * ext_Cd(p, w) * sis_speed_x(p, f, w, i, j) : 0.0;
 }
-__device__ __forceinline__ double explicit_ty_top(const DParams &p, const DFields &f, int i, int j)
+__device__ __forceinline__ double implicit_ty(const DParams &p, const DFields &f, int w, int i, int j)
 {
-    return p.top_kind == CSI_STRESS_FIELD ? at(f.top_y, i, j) : (p.top_kind == CSI_STRESS_CONST ? p.tty : 0.0);
+    return stress_kind(p, w) == CSI_STRESS_SEMI_IMPLICIT ? ext_rho(p, w) * ext_Cd(p, w) * sis_speed_y(p, f, w, i, j) : 0.0;
+}
+__device__ __forceinline__ double explicit_tx(const DParams &p, const DFields &f, int w, int i, int j, double coef)
+{
+    const int k = stress_kind(p, w);
+    if (k == CSI_STRESS_NONE) return 0.0;
+    if (k == CSI_STRESS_SEMI_IMPLICIT) return coef * ext_x(p, f, w, i, j);  // (rho * Cd * sqrt(..)) * u_e, coef = implicit_tx
+    return ext_x(p, f, w, i, j);
+}
+__device__ __forceinline__ double explicit_ty(const DParams &p, const DFields &f, int w, int i, int j, double coef)
+{
+    const int k = stress_kind(p, w);
+    if (k == CSI_STRESS_NONE) return 0.0;
+    if (k == CSI_STRESS_SEMI_IMPLICIT) return coef * ext_y(p, f, w, i, j);
+    return ext_y(p, f, w, i, j);
+}
+// x/y_momentum_stress of a side that is not a SemiImplicitStress (ext:34-38): explicit - zero(grid) * u
+__device__ __forceinline__ double x_momentum_stress(const DParams &p, const DFields &f, int w, int i, int j)
+{
+    return explicit_tx(p, f, w, i, j, 0.0) - 0.0 * at(f.u, i, j);
+}
+__device__ __forceinline__ double y_momentum_stress(const DParams &p, const DFields &f, int w, int i, int j)
+{
+    return explicit_ty(p, f, w, i, j, 0.0) - 0.0 * at(f.v, i, j);
+}
+
+// ---- free drift: stress_balance_free_drift.jl:61-129 ---------------------------------------------
+// nothing -> 0; (u=, v=) arrays -> the array value; StressBalanceFreeDrift on the model's own stresses:
+// with d the SemiImplicitStress side and o the other, U_d - tau_o / sqrt(C_d * |tau_o|)
+__device__ __forceinline__ double free_drift_u(const DParams &p, const DFields &f, int i, int j)
+{
+    if (p.fd_kind == CSI_FD_NONE) return 0.0;
+    if (p.fd_kind == CSI_FD_FIELDS) return at(f.fd_u, i, j);
+    const int d = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT ? BOT : TOP, o = 1 - d;
+    auto yms = [&](int a, int b) { return y_momentum_stress(p, f, o, a, b); };
+    const double tx = x_momentum_stress(p, f, o, i, j);
+    const double ty = avg_fc(yms, i, j);
+    const double t = sqrt(tx * tx + ty * ty);
+    const double Ud = ext_x(p, f, d, i, j);
+    const double Cdrag = ext_rho(p, d) * ext_Cd(p, d);
+    return Ud - (t == 0 ? t : tx / sqrt(Cdrag * t));
+}
+__device__ __forceinline__ double free_drift_v(const DParams &p, const DFields &f, int i, int j)
+{
+    if (p.fd_kind == CSI_FD_NONE) return 0.0;
+    if (p.fd_kind == CSI_FD_FIELDS) return at(f.fd_v, i, j);
+    const int d = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT ? BOT : TOP, o = 1 - d;
+    auto xms = [&](int a, int b) { return x_momentum_stress(p, f, o, a, b); };
+    const double tx = avg_cf(xms, i, j);
+    const double ty = y_momentum_stress(p, f, o, i, j);
+    const double t = sqrt(tx * tx + ty * ty);
+    const double Ud = ext_y(p, f, d, i, j);
+    const double Cdrag = ext_rho(p, d) * ext_Cd(p, d);
+    return Ud - (t == 0 ? t : ty / sqrt(Cdrag * t));
 }
 
 // ---- _u_velocity_step! at one face: se:197-229 with mt:11-41, evp:384,391-395 -------------------
@@ -199,17 +267,16 @@ __device__ __forceinline__ void u_step_node(const DGrid &g, const DParams &p, co
     const double ai = (at(f.a, i, j) + at(f.a, i - 1, j)) / 2;
     const double abar = (at(f.alpha, i, j) + at(f.alpha, i - 1, j)) / 2;
     const double dtau = dt / abar;
-    const bool sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
-    const double coef = sis ? p.rho_e * p.Cd * sis_speed_x(p, f, i, j) : 0.0;  // implicit_tx_coefficient
-    const double tbot = sis ? coef * ue_at(p, f, i, j) : 0.0;                  // explicit_tx
+    const double cbot = implicit_tx(p, f, BOT, i, j), ctop = implicit_tx(p, f, TOP, i, j);  // implicit_tx_coefficient
+    const double tbot = explicit_tx(p, f, BOT, i, j, cbot), ttop = explicit_tx(p, f, TOP, i, j, ctop);
     const double xcross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : -p.f * avg_fc(vv, i, j);
     const double rheo = (at(f.un, i, j) - at(f.u, i, j)) / dtau / abar;
-    double Gu = -xcross - explicit_tx_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + immersed_div_sigma_1j(g, p, f, i, j) / mi + (0.0 + rheo);
+    double Gu = -xcross - ttop / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + immersed_div_sigma_1j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gu = mi <= 0 ? 0.0 : Gu;
-    double tau = (coef - 0.0) / mi * ai;
+    double tau = (cbot - ctop) / mi * ai;
     tau = mi <= 0 ? 0.0 : tau;
     const double uD = (at(f.u, i, j) + dtau * Gu) / (1 + dtau * tau);
-    const double uF = 0.0;  // free_drift = nothing
+    const double uF = free_drift_u(p, f, i, j);
     const bool marginal = (mi > 2.220446049250313e-16) & (ai > 2.220446049250313e-16);
     const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
     const bool active = !peripheral_fc(g, i, j);
@@ -225,17 +292,16 @@ __device__ __forceinline__ void v_step_node(const DGrid &g, const DParams &p, co
     const double ai = (at(f.a, i, j) + at(f.a, i, j - 1)) / 2;
     const double abar = (at(f.alpha, i, j) + at(f.alpha, i, j - 1)) / 2;
     const double dtau = dt / abar;
-    const bool sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
-    const double coef = sis ? p.rho_e * p.Cd * sis_speed_y(p, f, i, j) : 0.0;
-    const double tbot = sis ? coef * ve_at(p, f, i, j) : 0.0;
+    const double cbot = implicit_ty(p, f, BOT, i, j), ctop = implicit_ty(p, f, TOP, i, j);
+    const double tbot = explicit_ty(p, f, BOT, i, j, cbot), ttop = explicit_ty(p, f, TOP, i, j, ctop);
     const double ycross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : p.f * avg_cf(uu, i, j);
     const double rheo = (at(f.vn, i, j) - at(f.v, i, j)) / dtau / abar;
-    double Gv = -ycross - explicit_ty_top(p, f, i, j) / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + immersed_div_sigma_2j(g, p, f, i, j) / mi + (0.0 + rheo);
+    double Gv = -ycross - ttop / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + immersed_div_sigma_2j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gv = mi <= 0 ? 0.0 : Gv;
-    double tau = (coef - 0.0) / mi * ai;
+    double tau = (cbot - ctop) / mi * ai;
     tau = mi <= 0 ? 0.0 : tau;
     const double vD = (at(f.v, i, j) + dtau * Gv) / (1 + dtau * tau);
-    const double vF = 0.0;
+    const double vF = free_drift_v(p, f, i, j);
     const bool marginal = (mi > 2.220446049250313e-16) & (ai > 2.220446049250313e-16);
     const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
     const bool active = !peripheral_cf(g, i, j);

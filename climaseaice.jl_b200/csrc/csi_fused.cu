@@ -807,6 +807,9 @@ static EncodeTiledFn get_encode()
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
     if (g.met) { snprintf(why, nwhy, "j-dependent grid metrics (general kernels only)"); return 0; }
+    if (p.fd_kind != CSI_FD_NONE) { snprintf(why, nwhy, "free-drift velocities (general kernels only)"); return 0; }
+    if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT) { snprintf(why, nwhy, "SemiImplicitStress on top (general kernels only)"); return 0; }
+    if (p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD) { snprintf(why, nwhy, "prescribed bottom stress (general kernels only)"); return 0; }
     if (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az)) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }

@@ -25,7 +25,7 @@ void launch_mask_immersed(const LaunchCtx &c, const DGrid &g, const DArr &a, int
 
 // ---- advection (csi_advection.cu) ------------------------------------------------------------
 void launch_tracer_tendencies(const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f);
-void launch_dynamic_step(const LaunchCtx &c, const DGrid &g, const DFields &f, const DArr &hn, const DArr &an, double dt);
+void launch_dynamic_step(const LaunchCtx &c, const DGrid &g, const DFields &f, const DArr &hn, const DArr &an, const DArr &hsn, double dt);
 
 // ---- reductions (csi_reduce.cu); results land in `scratch` (device), final value in out_dev ------
 void launch_cfl(const LaunchCtx &c, const DGrid &g, const DFields &f, double *scratch, int nscratch, double *out_dev);

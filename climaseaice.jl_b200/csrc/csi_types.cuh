@@ -62,11 +62,14 @@ struct DParams {
     double u_sn_val, v_we_val;
     int adv_order, pad_;
     double imm_u, imm_v;  // immersed linear-drag flux BC coefficients (0 = none)
+    int fd_kind, pad2_;   // free drift: CSI_FD_NONE / FIELDS / STRESS_BALANCE
+    double top_rho, top_Cd;  // top SemiImplicitStress (u_e, v_e = top_x/top_y arrays or ttx/tty constants)
 };
 
 struct DFields {
     DArr u, v, h, a, s11, s22, s12, zf, zc, delta, alpha, un, vn, P;
     DArr top_x, top_y, ue, ve, Gh, Ga, hm, am, um, vm;
+    DArr hs, Ghs, hsm, fd_u, fd_v;
 };
 
 // index window a kernel runs over (inclusive, 1-based reference indices)

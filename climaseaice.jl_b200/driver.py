@@ -10,8 +10,8 @@ import torch
 
 from . import _lib as L
 from .model import (Bounded, FPlane, Field, LatitudeLongitudeGrid, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
-                    SplitExplicitSolver, UpwindBiased, ValueBoundaryCondition, WENO)
-from .synthetic import Case
+                    SplitExplicitSolver, StressBalanceFreeDrift, UpwindBiased, ValueBoundaryCondition, WENO)
+from .synthetic import LOC, Case
 
 
 def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearGrid:
@@ -29,16 +29,28 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
     grid = grid_from_case(case, device, partitioned_y=partition is not None)
     F = case.fields
     oc = case.ocean_const or (0.0, 0.0)
-    ue = Field((1, 0), grid, F["ue"]) if "ue" in F else oc[0]
-    ve = Field((0, 1), grid, F["ve"]) if "ve" in F else oc[1]
-    if "top_x" in F:
-        top = dict(u=Field((1, 0), grid, F["top_x"]), v=Field((0, 1), grid, F["top_y"]))
+    fld = lambda n: Field(LOC[n], grid, F[n])
+    # top: arrays or constants, read as the stress itself or as the atmosphere's velocity (SemiImplicitStress)
+    tu, tv = (fld("top_x"), fld("top_y")) if "top_x" in F else (case.top_const if case.top_const else (None, None))
+    if case.top_kind == "semi_implicit":
+        top = SemiImplicitStress(ue=tu, ve=tv, rho_e=case.top_rho_Cd[0], Cd=case.top_rho_Cd[1])
     else:
-        top = dict(u=case.top_const[0], v=case.top_const[1]) if case.top_const else None
+        top = None if tu is None else dict(u=tu, v=tv)
+    bu, bv = (fld("ue"), fld("ve")) if "ue" in F else oc
+    if case.bottom_kind == "semi_implicit":
+        bottom = SemiImplicitStress(ue=bu, ve=bv, rho_e=case.rho_e, Cd=case.Cd)
+    elif case.bottom_kind == "stress":
+        bottom = dict(u=bu, v=bv)
+    else:
+        bottom = None
+    free_drift = None
+    if case.free_drift == "fields":
+        free_drift = dict(u=fld("fd_u"), v=fld("fd_v"))
+    elif case.free_drift == "stress_balance":
+        free_drift = StressBalanceFreeDrift()
     dyn = SeaIceMomentumEquation(grid,
                                  coriolis=FPlane(case.coriolis_f) if case.coriolis_f is not None else None,
-                                 top_momentum_stress=top,
-                                 bottom_momentum_stress=SemiImplicitStress(ue=ue, ve=ve, rho_e=case.rho_e, Cd=case.Cd),
+                                 top_momentum_stress=top, bottom_momentum_stress=bottom, free_drift=free_drift,
                                  solver=SplitExplicitSolver(substeps=case.substeps))
     bcs = {}
     if case.u_bc_value is not None:
@@ -47,8 +59,10 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
         bcs["v"] = dict(west=ValueBoundaryCondition(case.v_bc_value), east=ValueBoundaryCondition(case.v_bc_value))
     adv = None if case.advection_order == 0 else (UpwindBiased(1) if case.advection_order == 1 else WENO(case.advection_order))
     m = SeaIceModel(grid, dynamics=dyn, advection=adv, timestepper=case.timestepper, boundary_conditions=bcs,
-                    solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag)
+                    solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag, snow_thickness="hs" in F)
     m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
+    if "hs" in F:
+        m.set(hs=F["hs"])
     return m
 
 

@@ -165,6 +165,15 @@ class SemiImplicitStress:
 
 
 @dataclass
+class StressBalanceFreeDrift:
+    """StressBalanceFreeDrift(): tau_a = tau_o closed form (stress_balance_free_drift.jl:61-109).  As in the reference
+    (sime.jl:80) it is repointed at the momentum equation's own top/bottom stresses, exactly one of which must be
+    a SemiImplicitStress."""
+    top_momentum_stress: object = None
+    bottom_momentum_stress: object = None
+
+
+@dataclass
 class FPlane:
     f: float = 1e-4
 
@@ -187,8 +196,18 @@ class ValueBoundaryCondition:
 class SeaIceMomentumEquation:
     def __init__(self, grid, coriolis=None, rheology=None, top_momentum_stress=None, bottom_momentum_stress=None,
                  free_drift=None, solver=None, minimum_concentration=1e-3, minimum_mass=1.0):
-        if free_drift is not None:
-            raise NotImplementedError("free_drift other than `nothing` is a next-tier item (SURVEY section 8f)")
+        # free_drift: nothing, (u=Field, v=Field), or StressBalanceFreeDrift()
+        if free_drift is not None and not isinstance(free_drift, (dict, StressBalanceFreeDrift)):
+            raise TypeError("free_drift must be nothing, dict(u=Field, v=Field) or StressBalanceFreeDrift()")
+        if isinstance(free_drift, StressBalanceFreeDrift):
+            ts, bs = isinstance(top_momentum_stress, SemiImplicitStress), isinstance(bottom_momentum_stress, SemiImplicitStress)
+            if ts and bs:
+                raise ValueError("`StressBalanceFreeDrift` supports a `SemiImplicitStress` only for the `top_momentum_stress` "
+                                 "or the `bottom_momentum_stress`, not both")
+            if not (ts or bs):
+                raise ValueError("`StressBalanceFreeDrift` requires using a `SemiImplicitStress` for either the "
+                                 "`top_momentum_stress` or the `bottom_momentum_stress`")
+        self.free_drift = free_drift
         self.grid = grid
         self.coriolis = coriolis
         self.rheology = rheology or ElastoViscoPlasticRheology()
@@ -197,8 +216,6 @@ class SeaIceMomentumEquation:
         self.bottom = bottom_momentum_stress
         self.minimum_concentration = float(minimum_concentration)
         self.minimum_mass = float(minimum_mass)
-        if self.bottom is not None and not isinstance(self.bottom, SemiImplicitStress):
-            raise NotImplementedError("bottom_momentum_stress must be `nothing` or a SemiImplicitStress")
         # Auxiliaries(r::ElastoViscoPlasticRheology, grid): evp.jl:140-173
         c, f = Center, Face
         self.auxiliaries = dict(
@@ -213,7 +230,7 @@ class SeaIceModel:
 
     def __init__(self, grid, dynamics=None, advection=None, timestepper="SplitRungeKutta3", boundary_conditions=None,
                  ice_density=900.0, ice_thermodynamics=None, solver_impl="auto", immersed_mask=None,
-                 partition=None, immersed_drag=(0.0, 0.0)):
+                 partition=None, immersed_drag=(0.0, 0.0), snow_thickness=False):
         if ice_thermodynamics is not None:
             raise NotImplementedError("thermodynamics is outside the hot path (SURVEY section 8f)")
         if dynamics is None:
@@ -231,6 +248,13 @@ class SeaIceModel:
         self.Gn = dict(h=Field((c, c), grid), a=Field((c, c), grid))
         rk = timestepper == "SplitRungeKutta3"
         self.Psi_m = dict(h=Field((c, c), grid), a=Field((c, c), grid), u=Field((f, c), grid), v=Field((c, f), grid)) if rk else None
+        # prognostic snow thickness hs (allocated by the reference when snow_thermodynamics is given, sea_ice_model.jl:203):
+        # here only its advection with the ice (tracer_tendency:47-52, fe.jl:84-94)
+        self.snow_thickness = Field((c, c), grid) if snow_thickness else None
+        if snow_thickness:
+            self.Gn["hs"] = Field((c, c), grid)
+            if rk:
+                self.Psi_m["hs"] = Field((c, c), grid)
         self.iteration = 0
         self.time = 0.0
         bcs = boundary_conditions or {}
@@ -275,23 +299,25 @@ class SeaIceModel:
         cfg.ice_density = self.sea_ice_density
         cfg.coriolis_kind = L.CORIOLIS_FPLANE if d.coriolis is not None else L.CORIOLIS_NONE
         cfg.coriolis_f = d.coriolis.f if d.coriolis is not None else 0.0
-        top = d.top
-        if top is None:
-            cfg.top_stress_kind = L.STRESS_NONE
-        elif isinstance(top, dict) and isinstance(top["u"], Field):
-            cfg.top_stress_kind = L.STRESS_FIELD
-        elif isinstance(top, dict):
-            cfg.top_stress_kind = L.STRESS_CONST
-            cfg.top_tau_x, cfg.top_tau_y = float(top["u"]), float(top["v"])
-        else:
-            raise NotImplementedError("top_momentum_stress must be nothing or (u=..., v=...)")
-        if d.bottom is None:
-            cfg.bottom_stress_kind = L.STRESS_NONE
-        else:
-            cfg.bottom_stress_kind = L.STRESS_SEMI_IMPLICIT
+        # either stress: nothing | (u=Number, v=Number) | (u=Field, v=Field) | SemiImplicitStress   (ext.jl:8-40,84-146)
+        def kind_of(st):
+            if st is None:
+                return L.STRESS_NONE, (0.0, 0.0)
+            if isinstance(st, SemiImplicitStress):
+                return L.STRESS_SEMI_IMPLICIT, ((0.0, 0.0) if isinstance(st.ue, Field) else (float(st.ue), float(st.ve)))
+            if isinstance(st, dict) and isinstance(st["u"], Field) and isinstance(st["v"], Field):
+                return L.STRESS_FIELD, (0.0, 0.0)
+            if isinstance(st, dict) and not isinstance(st["u"], Field) and not isinstance(st["v"], Field):
+                return L.STRESS_CONST, (float(st["u"]), float(st["v"]))
+            raise NotImplementedError("a momentum stress must be nothing, (u=, v=) numbers, (u=, v=) Fields or a SemiImplicitStress")
+        cfg.top_stress_kind, (cfg.top_tau_x, cfg.top_tau_y) = kind_of(d.top)
+        cfg.bottom_stress_kind, (cfg.ue_const, cfg.ve_const) = kind_of(d.bottom)
+        if isinstance(d.top, SemiImplicitStress):
+            cfg.top_rho_e, cfg.top_Cd = d.top.rho_e, d.top.Cd
+        if isinstance(d.bottom, SemiImplicitStress):
             cfg.rho_e, cfg.Cd = d.bottom.rho_e, d.bottom.Cd
-            if not isinstance(d.bottom.ue, Field):
-                cfg.ue_const, cfg.ve_const = float(d.bottom.ue), float(d.bottom.ve)
+        fd = d.free_drift
+        cfg.free_drift_kind = L.FD_NONE if fd is None else (L.FD_FIELDS if isinstance(fd, dict) else L.FD_STRESS_BALANCE)
         for side in ("south", "north"):
             if side in self._u_bc:
                 cfg.u_south_north_bc, cfg.u_south_north_value = L.BC_VALUE, float(self._u_bc[side].value)
@@ -316,10 +342,17 @@ class SeaIceModel:
         out.update(d.auxiliaries)
         if self.Psi_m:
             out.update(hm=self.Psi_m["h"], am=self.Psi_m["a"], um=self.Psi_m["u"], vm=self.Psi_m["v"])
-        if isinstance(d.top, dict) and isinstance(d.top["u"], Field):
-            out.update(top_x=d.top["u"], top_y=d.top["v"])
-        if d.bottom is not None and isinstance(d.bottom.ue, Field):
-            out.update(ue=d.bottom.ue, ve=d.bottom.ve)
+        for st, (nx, ny) in ((d.top, ("top_x", "top_y")), (d.bottom, ("ue", "ve"))):
+            if isinstance(st, dict) and isinstance(st["u"], Field):
+                out.update({nx: st["u"], ny: st["v"]})
+            if isinstance(st, SemiImplicitStress) and isinstance(st.ue, Field):
+                out.update({nx: st.ue, ny: st.ve})
+        if isinstance(d.free_drift, dict):
+            out.update(fd_u=d.free_drift["u"], fd_v=d.free_drift["v"])
+        if self.snow_thickness is not None:
+            out.update(hs=self.snow_thickness, Ghs=self.Gn["hs"])
+            if self.Psi_m:
+                out.update(hsm=self.Psi_m["hs"])
         return out
 
     def csi_fields(self):
@@ -335,6 +368,10 @@ class SeaIceModel:
     def set(self, **kw):
         """set!(model, h=..., ℵ=..., u=..., v=...) (use `a` for ℵ)."""
         targets = dict(h=self.ice_thickness, a=self.ice_concentration, u=self.velocities["u"], v=self.velocities["v"])
+        if "hs" in kw:
+            if self.snow_thickness is None:  # sea_ice_model.jl:307-311
+                raise ValueError("Cannot set snow thickness `hs` on a SeaIceModel without snow (model.snow_thickness is nothing).")
+            targets["hs"] = self.snow_thickness
         for k, v in kw.items():
             targets["a" if k in ("ℵ", "aice") else k].set(v)
         return self

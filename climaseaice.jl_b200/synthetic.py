@@ -44,6 +44,11 @@ class Case:
     ocean_const: tuple | None = None     # constant (ue, ve) when there are no ue/ve arrays
     mask: object = None                  # immersed mask at centres, uint8 (Ny+2Hy, Nx+2Hx), 1 = land
     immersed_drag: tuple = (0.0, 0.0)    # linear-drag immersed flux BC coefficients for u and v
+    top_kind: str = "auto"               # "auto": arrays -> (u=Field, v=Field), top_const -> numbers, else nothing;
+                                         # "semi_implicit": top_x/top_y (or top_const) are the atmosphere's u_e, v_e
+    top_rho_Cd: tuple = (1.3, 1.2e-3)    # rho_e, Cd of a top SemiImplicitStress
+    bottom_kind: str = "semi_implicit"   # "semi_implicit" (ue/ve or ocean_const = ocean velocity), "stress" (they hold tau), "none"
+    free_drift: str | None = None        # None, "fields" (fields fd_u, fd_v) or "stress_balance"
     latlon: tuple | None = None          # ((lon0, lon1), (lat0, lat1)) in degrees: LatitudeLongitudeGrid; Lx, Ly = extents in degrees
 
     def metrics(self):
@@ -74,7 +79,8 @@ class Case:
         return np.meshgrid(x, y)
 
 
-LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1))
+LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1), hs=(0, 0),
+           fd_u=(1, 0), fd_v=(0, 1))
 
 
 def _wrap_periodic(case: Case, arr, loc):
@@ -182,6 +188,75 @@ def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7,
     ve = 0.05 * np.sin(tp * fx(Xv))
     raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=ue, ve=ve, top_x=tx, top_y=ty)
     c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
+    return c
+
+
+def marginal_ice_case(N=64, H=5, seed=SEED, substeps=20, dt=120.0, variant="bottom_drag", snow=True,
+                      timestepper="SplitRungeKutta3", topology=("Periodic", "Periodic")) -> Case:
+    """A marginal ice zone: bands of compact ice, marginal ice (mass or concentration under the dynamical thresholds
+    but above eps -- the cells that take the free-drift velocity) and open water, plus a snow layer.  Variants:
+      "bottom_drag":  top = wind-stress arrays, bottom = SemiImplicitStress (ocean), StressBalanceFreeDrift  (TISB)
+      "top_drag":     top = SemiImplicitStress with wind arrays, bottom = prescribed stress arrays, StressBalanceFreeDrift (BISB)
+      "fields":       config-3 stresses, free_drift = (u = Field, v = Field)
+      "both_drag":    SemiImplicitStress on both sides, free_drift = nothing
+      "const_top_drag": top = SemiImplicitStress with constant wind, bottom = nothing
+    """
+    c = periodic_case(N, H=H, seed=seed, substeps=substeps, dt=dt, timestepper=timestepper) if topology == ("Periodic", "Periodic") else None
+    if c is None:
+        c = Case("marginal", N, N, H, H, tuple(topology), N * 4000.0, N * 4000.0, dt=dt, substeps=substeps, timestepper=timestepper,
+                 u_bc_value=0.0 if topology[1] == "Bounded" else None, v_bc_value=0.0 if topology[0] == "Bounded" else None)
+        base = periodic_case(N, H=H, seed=seed)
+        for k, arr in base.fields.items():
+            out = np.zeros(c.parent_shape(LOC[k]))
+            out[:arr.shape[0], :arr.shape[1]] = arr
+            c.fields[k] = out
+    c.name = "marginal-" + variant
+    rng = np.random.default_rng(seed + 1)
+    X, Y = c.nodes(LOC["h"])
+    a = c.fields["a"]
+    h = c.fields["h"]
+    band = (Y / c.Ly > 0.35) & (Y / c.Ly < 0.65)
+    a[band] = 2e-4 + 6e-4 * rng.uniform(0, 1, a.shape)[band]            # under minimum_concentration = 1e-3
+    thin = (X / c.Lx > 0.4) & (X / c.Lx < 0.6) & ~band
+    h[thin] = 5e-4 + 5e-4 * rng.uniform(0, 1, h.shape)[thin]              # mass under minimum_mass = 1 kg m^-2
+    tp = 2 * np.pi
+    Xu, Yu = c.nodes(LOC["u"])
+    Xv, Yv = c.nodes(LOC["v"])
+    if variant == "bottom_drag":
+        c.free_drift = "stress_balance"
+        # a patch without wind exercises the tau == 0 branch of the closed form
+        calm_u = (Xu / c.Lx < 0.2)
+        calm_v = (Xv / c.Lx < 0.2)
+        c.fields["top_x"] = np.where(calm_u, 0.0, c.fields["top_x"])
+        c.fields["top_y"] = np.where(calm_v, 0.0, c.fields["top_y"])
+    elif variant == "top_drag":
+        c.free_drift = "stress_balance"
+        c.top_kind = "semi_implicit"
+        c.fields["top_x"] = 8.0 * np.sin(tp * Yu / c.Ly) + 2.0          # wind, m/s
+        c.fields["top_y"] = 6.0 * np.cos(tp * Xv / c.Lx)
+        c.bottom_kind = "stress"
+        c.fields["ue"] = 0.02 * np.sin(tp * Yu / c.Ly)                    # prescribed ocean stress, N m^-2
+        c.fields["ve"] = 0.02 * np.cos(tp * Xv / c.Lx)
+    elif variant == "fields":
+        c.free_drift = "fields"
+        c.fields["fd_u"] = 0.03 * np.cos(tp * Yu / c.Ly)
+        c.fields["fd_v"] = 0.02 * np.sin(tp * Xv / c.Lx)
+    elif variant == "both_drag":
+        c.top_kind = "semi_implicit"
+        c.fields["top_x"] = 8.0 * np.sin(tp * Yu / c.Ly) + 2.0
+        c.fields["top_y"] = 6.0 * np.cos(tp * Xv / c.Lx)
+    elif variant == "const_top_drag":
+        c.top_kind = "semi_implicit"
+        c.fields.pop("top_x"); c.fields.pop("top_y")
+        c.top_const = (5.0, -3.0)
+        c.bottom_kind = "none"
+        c.fields.pop("ue"); c.fields.pop("ve")
+    else:
+        raise ValueError(variant)
+    if snow:
+        c.fields["hs"] = np.where(a > 0, 0.1 + 0.05 * np.sin(tp * X / c.Lx) * np.cos(tp * Y / c.Ly), 0.0)
+    for k in list(c.fields):
+        c.fields[k] = _wrap_periodic(c, np.ascontiguousarray(c.fields[k], dtype=np.float64), LOC[k])
     return c
 
 

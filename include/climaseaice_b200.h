@@ -44,6 +44,10 @@ enum { CSI_STRESS_NONE = 0, CSI_STRESS_CONST = 1, CSI_STRESS_FIELD = 2, CSI_STRE
 enum { CSI_REPLACEMENT_PRESSURE = 0, CSI_ICE_STRENGTH = 1 };
 enum { CSI_CORIOLIS_NONE = 0, CSI_CORIOLIS_FPLANE = 1 };
 enum { CSI_BC_DEFAULT = 0, CSI_BC_VALUE = 1 };
+/* free_drift of SeaIceMomentumEquation (src/SeaIceDynamics/stress_balance_free_drift.jl:61-129): nothing, a (u=, v=)
+ * pair of arrays, or StressBalanceFreeDrift (closed form from the model's own stresses, exactly one of which must be
+ * a SemiImplicitStress) */
+enum { CSI_FD_NONE = 0, CSI_FD_FIELDS = 1, CSI_FD_STRESS_BALANCE = 2 };
 enum { CSI_RK3 = 0, CSI_FE = 1 };
 enum { CSI_SOLVER_AUTO = 0, CSI_SOLVER_UNFUSED = 1, CSI_SOLVER_FUSED = 2 };
 
@@ -111,6 +115,13 @@ typedef struct {
     int32_t metric_kind;
     int32_t reserved2_;
     const double *metrics[12];
+    /* free drift velocity of marginal ice (mass or concentration under the thresholds but above eps): CSI_FD_* */
+    int32_t free_drift_kind;
+    int32_t reserved3_;
+    /* SemiImplicitStress as the TOP stress (top_stress_kind = CSI_STRESS_SEMI_IMPLICIT): rho_e, Cd of the atmosphere;
+     * its u_e, v_e are csi_fields.top_x/top_y, or the constants top_tau_x/top_tau_y when those are NULL.  Likewise the
+     * BOTTOM stress may be CSI_STRESS_CONST (ue_const, ve_const hold tau) or CSI_STRESS_FIELD (ue, ve hold tau). */
+    double top_rho_e, top_Cd;
 } csi_config;
 
 /* The arrays the hot path touches.  Unused ones may have ptr == NULL. */
@@ -123,6 +134,9 @@ typedef struct {
     csi_array ue, ve;               /* SemiImplicitStress external velocities (f,c) (c,f) */
     csi_array Gh, Ga;               /* timestepper.G^n.h, .aice */
     csi_array hm, am, um, vm;       /* timestepper.Psi^- (RK3) */
+    csi_array hs, Ghs, hsm;         /* optional snow_thickness (c,c), G^n.hs, Psi^-.hs: advected with h and aice
+                                       (src/tracer_tendency_kernel_functions.jl:47-52, src/sea_ice_fe_step.jl:84-94) */
+    csi_array fd_u, fd_v;           /* free-drift velocities (f,c) (c,f) when free_drift_kind = CSI_FD_FIELDS */
 } csi_fields;
 
 enum { CSI_METRIC_REGULAR = 0, CSI_METRIC_J = 1 };

@@ -58,6 +58,8 @@ Base.@kwdef struct CsiConfig
     immersed_drag_u :: Float64 = 0.0; immersed_drag_v :: Float64 = 0.0
     metric_kind :: Int32 = 0; reserved2_ :: Int32 = 0
     metrics :: NTuple{12, Ptr{Float64}} = ntuple(_ -> Ptr{Float64}(C_NULL), 12)
+    free_drift_kind :: Int32 = 0; reserved3_ :: Int32 = 0     # 0 nothing, 1 (u=, v=) arrays, 2 StressBalanceFreeDrift
+    top_rho_e :: Float64 = 1.3; top_Cd :: Float64 = 1.2e-3    # SemiImplicitStress as the top stress
 end
 
 # LatitudeLongitudeGrid: the twelve j-indexed metric vectors csi_config.metrics takes (metric_kind = 1), each
@@ -71,10 +73,10 @@ function metric_vectors(grid)
     return vecs, ntuple(k -> pointer(vecs[k]), 12)
 end
 
-# csi_fields: 24 csi_array in header order
+# csi_fields: 29 csi_array in header order
 const FIELD_ORDER = (:u, :v, :h, :a, :s11, :s22, :s12, :zeta_f, :zeta_c, :delta, :alpha, :un, :vn, :P,
-                     :top_x, :top_y, :ue, :ve, :Gh, :Ga, :hm, :am, :um, :vm)
-const CsiFields = NTuple{24, CsiArray}
+                     :top_x, :top_y, :ue, :ve, :Gh, :Ga, :hm, :am, :um, :vm, :hs, :Ghs, :hsm, :fd_u, :fd_v)
+const CsiFields = NTuple{29, CsiArray}
 
 mutable struct Handle
     ptr :: Ptr{Cvoid}

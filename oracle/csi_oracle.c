@@ -275,50 +275,107 @@ static inline double div_sigma_2j(G g, const csio_state *s, int i, int j)
 }
 
 /* ---------------------------------------------------------------------------------------------
- * External stresses.  ref: src/SeaIceDynamics/sea_ice_external_stress.jl:8-27,176-202
+ * External stresses.  ref: src/SeaIceDynamics/sea_ice_external_stress.jl:8-40,176-210
+ * Either side (w = TOP: atmosphere, BOT: ocean) is nothing / a Number pair / a pair of arrays / a
+ * SemiImplicitStress.  ext_x/ext_y is the side's array-or-constant: the stress itself for CONST and
+ * FIELD, the external velocity u_e, v_e for a SemiImplicitStress.
  * ------------------------------------------------------------------------------------------- */
-static inline double ue_at(P p, int i, int j) { return p->ue.p ? F(p->ue, i, j) : p->ue_c; }
-static inline double ve_at(P p, int i, int j) { return p->ve.p ? F(p->ve, i, j) : p->ve_c; }
-
-static inline double sis_speed_x(P p, const csio_state *s, int i, int j)
-{ /* sqrt(du^2+dv^2) at (f,c): ext.jl:177-180 */
-#define VE(I_, J_) ve_at(p, (I_), (J_))
+enum { TOP = 0, BOT = 1 };
+static inline int stress_kind(P p, int w) { return w == TOP ? p->top_kind : p->bot_kind; }
+static inline double ext_x(P p, int w, int i, int j)
+{
+    if (w == TOP) return p->top_x.p ? F(p->top_x, i, j) : p->top_tx;
+    return p->ue.p ? F(p->ue, i, j) : p->ue_c;
+}
+static inline double ext_y(P p, int w, int i, int j)
+{
+    if (w == TOP) return p->top_y.p ? F(p->top_y, i, j) : p->top_ty;
+    return p->ve.p ? F(p->ve, i, j) : p->ve_c;
+}
+static inline double ext_rho(P p, int w) { return w == TOP ? p->top_rho : p->rho_e; }
+static inline double ext_Cd(P p, int w) { return w == TOP ? p->top_Cd : p->Cd; }
 #define VV(I_, J_) F(s->v, (I_), (J_))
-    double du = ue_at(p, i, j) - F(s->u, i, j);
-    double dv = IXY_FC(VE, i, j) - IXY_FC(VV, i, j);
-    return sqrt(du * du + dv * dv);
-}
-static inline double sis_speed_y(P p, const csio_state *s, int i, int j)
-{ /* at (c,f): ext.jl:183-187 */
-#define UE(I_, J_) ue_at(p, (I_), (J_))
 #define UU(I_, J_) F(s->u, (I_), (J_))
-    double dv = ve_at(p, i, j) - F(s->v, i, j);
-    double du = IXY_CF(UE, i, j) - IXY_CF(UU, i, j);
+
+static inline double sis_speed_x(P p, const csio_state *s, int w, int i, int j)
+{ /* sqrt(du^2+dv^2) at (f,c): ext.jl:177-180 */
+#define EY(I_, J_) ext_y(p, w, (I_), (J_))
+    double du = ext_x(p, w, i, j) - F(s->u, i, j);
+    double dv = IXY_FC(EY, i, j) - IXY_FC(VV, i, j);
     return sqrt(du * du + dv * dv);
 }
-static inline double explicit_tx_top(P p, int i, int j)
+static inline double sis_speed_y(P p, const csio_state *s, int w, int i, int j)
+{ /* at (c,f): ext.jl:183-187 */
+#define EX(I_, J_) ext_x(p, w, (I_), (J_))
+    double dv = ext_y(p, w, i, j) - F(s->v, i, j);
+    double du = IXY_CF(EX, i, j) - IXY_CF(UU, i, j);
+    return sqrt(du * du + dv * dv);
+}
+/* explicit_tau_x/y: ext.jl:13-20 (nothing -> 0, Number, array) and :176-188 (rho_e * Cd * sqrt(..) * u_e) */
+static inline double explicit_tx(P p, const csio_state *s, int w, int i, int j)
 {
-    return p->top_kind == CSIO_STRESS_FIELD ? F(p->top_x, i, j) : (p->top_kind == CSIO_STRESS_CONST ? p->top_tx : 0.0);
+    int k = stress_kind(p, w);
+    if (k == CSIO_STRESS_NONE) return 0.0;
+    if (k == CSIO_STRESS_SEMI_IMPLICIT) return ext_rho(p, w) * ext_Cd(p, w) * sis_speed_x(p, s, w, i, j) * ext_x(p, w, i, j);
+    return ext_x(p, w, i, j);
 }
-static inline double explicit_ty_top(P p, int i, int j)
+static inline double explicit_ty(P p, const csio_state *s, int w, int i, int j)
 {
-    return p->top_kind == CSIO_STRESS_FIELD ? F(p->top_y, i, j) : (p->top_kind == CSIO_STRESS_CONST ? p->top_ty : 0.0);
+    int k = stress_kind(p, w);
+    if (k == CSIO_STRESS_NONE) return 0.0;
+    if (k == CSIO_STRESS_SEMI_IMPLICIT) return ext_rho(p, w) * ext_Cd(p, w) * sis_speed_y(p, s, w, i, j) * ext_y(p, w, i, j);
+    return ext_y(p, w, i, j);
 }
-static inline double explicit_tx_bot(P p, const csio_state *s, int i, int j)
-{ /* ext.jl:176-181:  rho_e * Cd * sqrt(..) * u_e */
-    return p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? p->rho_e * p->Cd * sis_speed_x(p, s, i, j) * ue_at(p, i, j) : 0.0;
-}
-static inline double explicit_ty_bot(P p, const csio_state *s, int i, int j)
+/* implicit_tau_x/y_coefficient: ext.jl:8-9 (zero for everything but a SemiImplicitStress) and :192-202 */
+static inline double implicit_tx(P p, const csio_state *s, int w, int i, int j)
 {
-    return p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? p->rho_e * p->Cd * sis_speed_y(p, s, i, j) * ve_at(p, i, j) : 0.0;
+    return stress_kind(p, w) == CSIO_STRESS_SEMI_IMPLICIT ? ext_rho(p, w) * ext_Cd(p, w) * sis_speed_x(p, s, w, i, j) : 0.0;
 }
-static inline double implicit_tx_bot(P p, const csio_state *s, int i, int j)
-{ /* ext.jl:192-196 */
-    return p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? p->rho_e * p->Cd * sis_speed_x(p, s, i, j) : 0.0;
-}
-static inline double implicit_ty_bot(P p, const csio_state *s, int i, int j)
+static inline double implicit_ty(P p, const csio_state *s, int w, int i, int j)
 {
-    return p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? p->rho_e * p->Cd * sis_speed_y(p, s, i, j) : 0.0;
+    return stress_kind(p, w) == CSIO_STRESS_SEMI_IMPLICIT ? ext_rho(p, w) * ext_Cd(p, w) * sis_speed_y(p, s, w, i, j) : 0.0;
+}
+/* x/y_momentum_stress of a stress that is NOT a SemiImplicitStress (ext.jl:34-38): explicit - zero(grid) * u */
+static inline double x_momentum_stress(P p, const csio_state *s, int w, int i, int j)
+{
+    return explicit_tx(p, s, w, i, j) - 0.0 * F(s->u, i, j);
+}
+static inline double y_momentum_stress(P p, const csio_state *s, int w, int i, int j)
+{
+    return explicit_ty(p, s, w, i, j) - 0.0 * F(s->v, i, j);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Free drift.  ref: src/SeaIceDynamics/stress_balance_free_drift.jl:61-129
+ *   nothing -> zero(grid) (:128-129);  (u=, v=) arrays -> the array value (:124-125);
+ *   StressBalanceFreeDrift, repointed at the model's own stresses (:43-45, sime.jl:80): with `d` the
+ *   side that is a SemiImplicitStress and `o` the other,  U_d - tau_o / sqrt(C_d * |tau_o|)  (:61-109).
+ * ------------------------------------------------------------------------------------------- */
+static inline double free_drift_u(P p, const csio_state *s, int i, int j)
+{
+    if (p->free_drift_kind == CSIO_FD_NONE) return 0.0;
+    if (p->free_drift_kind == CSIO_FD_FIELDS) return F(p->fd_u, i, j);
+    int d = p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? BOT : TOP, o = 1 - d;
+#define YMS(I_, J_) y_momentum_stress(p, s, o, (I_), (J_))
+    double tx = x_momentum_stress(p, s, o, i, j);
+    double ty = IXY_FC(YMS, i, j);
+    double t = sqrt(tx * tx + ty * ty);
+    double Ud = ext_x(p, d, i, j);
+    double Cdrag = ext_rho(p, d) * ext_Cd(p, d);
+    return Ud - (t == 0 ? t : tx / sqrt(Cdrag * t));
+}
+static inline double free_drift_v(P p, const csio_state *s, int i, int j)
+{
+    if (p->free_drift_kind == CSIO_FD_NONE) return 0.0;
+    if (p->free_drift_kind == CSIO_FD_FIELDS) return F(p->fd_v, i, j);
+    int d = p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT ? BOT : TOP, o = 1 - d;
+#define XMS(I_, J_) x_momentum_stress(p, s, o, (I_), (J_))
+    double tx = IXY_CF(XMS, i, j);
+    double ty = y_momentum_stress(p, s, o, i, j);
+    double t = sqrt(tx * tx + ty * ty);
+    double Ud = ext_y(p, d, i, j);
+    double Cdrag = ext_rho(p, d) * ext_Cd(p, d);
+    return Ud - (t == 0 ? t : ty / sqrt(Cdrag * t));
 }
 
 /* Coriolis [OCN-recall]: x_f_cross_U(FPlane) = -f * Ixy^fc(v); y_f_cross_U = +f * Ixy^cf(u) */
@@ -373,7 +430,7 @@ static inline double u_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double mi = (MM(i, j) + MM(i - 1, j)) / 2;
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->un, i, j) - F(s->u, i, j)) / dtau / ((AL(i, j) + AL(i - 1, j)) / 2);
-    double Gu = -x_f_cross_U(p, s, i, j) - explicit_tx_top(p, i, j) / mi * ai + explicit_tx_bot(p, s, i, j) / mi * ai +
+    double Gu = -x_f_cross_U(p, s, i, j) - explicit_tx(p, s, TOP, i, j) / mi * ai + explicit_tx(p, s, BOT, i, j) / mi * ai +
                 div_sigma_1j(g, s, i, j) / mi + immersed_div_sigma_1j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gu;
 }
@@ -383,7 +440,7 @@ static inline double v_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double mi = (MM(i, j) + MM(i, j - 1)) / 2;
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->vn, i, j) - F(s->v, i, j)) / dtau / ((AL(i, j) + AL(i, j - 1)) / 2);
-    double Gv = -y_f_cross_U(p, s, i, j) - explicit_ty_top(p, i, j) / mi * ai + explicit_ty_bot(p, s, i, j) / mi * ai +
+    double Gv = -y_f_cross_U(p, s, i, j) - explicit_ty(p, s, TOP, i, j) / mi * ai + explicit_ty(p, s, BOT, i, j) / mi * ai +
                 div_sigma_2j(g, s, i, j) / mi + immersed_div_sigma_2j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gv;
 }
@@ -402,10 +459,10 @@ int csio_u_velocity_step(G g, P p, csio_state *s, double dt)
             double ai = (AA(i, j) + AA(i - 1, j)) / 2;
             double dtau = dt / ((AL(i, j) + AL(i - 1, j)) / 2); /* evp.jl:384 */
             double Gu = u_velocity_tendency(g, p, s, i, j, dtau);
-            double tau = (implicit_tx_bot(p, s, i, j) - 0.0) / mi * ai; /* top stress has no implicit part (ext.jl:8-9,24) */
+            double tau = (implicit_tx(p, s, BOT, i, j) - implicit_tx(p, s, TOP, i, j)) / mi * ai; /* se.jl:214-215 */
             tau = mi <= 0 ? 0.0 : tau;
             double uD = (F(s->u, i, j) + dtau * Gu) / (1 + dtau * tau);
-            double uF = 0.0; /* free_drift = nothing: free_drift.jl:128 */
+            double uF = free_drift_u(p, s, i, j);
             int marginal = (mi > DBL_EPS) & (ai > DBL_EPS);
             int active_ice = (mi >= p->min_mass) & (ai >= p->min_conc);
             int active = !peripheral_fc(g, i, j);
@@ -424,10 +481,10 @@ int csio_v_velocity_step(G g, P p, csio_state *s, double dt)
             double ai = (AA(i, j) + AA(i, j - 1)) / 2;
             double dtau = dt / ((AL(i, j) + AL(i, j - 1)) / 2); /* evp.jl:385 */
             double Gv = v_velocity_tendency(g, p, s, i, j, dtau);
-            double tau = (implicit_ty_bot(p, s, i, j) - 0.0) / mi * ai;
+            double tau = (implicit_ty(p, s, BOT, i, j) - implicit_ty(p, s, TOP, i, j)) / mi * ai;
             tau = mi <= 0 ? 0.0 : tau;
             double vD = (F(s->v, i, j) + dtau * Gv) / (1 + dtau * tau);
-            double vF = 0.0;
+            double vF = free_drift_v(p, s, i, j);
             int marginal = (mi > DBL_EPS) & (ai > DBL_EPS);
             int active_ice = (mi >= p->min_mass) & (ai >= p->min_conc);
             int active = !peripheral_cf(g, i, j);
@@ -536,13 +593,13 @@ int csio_time_step_momentum(G g, P p, csio_state *s, double dt, int nsub)
     }
     csio_initialize_rheology(g, p, s); /* se.jl:130 */
     /* update_external_stress! (ext.jl:72-78,148-152): halo refresh of the stress inputs */
-    if (p->top_kind == CSIO_STRESS_FIELD) {
-        csio_fill_halo(g, p, &pm->top_x, 1, 0, 0);
-        csio_fill_halo(g, p, &pm->top_y, 0, 1, 0);
+    if (p->top_kind == CSIO_STRESS_FIELD || p->top_kind == CSIO_STRESS_SEMI_IMPLICIT) {
+        if (pm->top_x.p) csio_fill_halo(g, p, &pm->top_x, 1, 0, 0);
+        if (pm->top_y.p) csio_fill_halo(g, p, &pm->top_y, 0, 1, 0);
     }
-    if (p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT) {
-        csio_fill_halo(g, p, &pm->ue, 1, 0, 0);
-        csio_fill_halo(g, p, &pm->ve, 0, 1, 0);
+    if (p->bot_kind == CSIO_STRESS_FIELD || p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT) {
+        if (pm->ue.p) csio_fill_halo(g, p, &pm->ue, 1, 0, 0);
+        if (pm->ve.p) csio_fill_halo(g, p, &pm->ve, 0, 1, 0);
     }
     csio_fill_halo(g, p, &s->u, 1, 0, 1); /* se.jl:170-171 */
     csio_fill_halo(g, p, &s->v, 0, 1, 2);
@@ -598,6 +655,7 @@ int csio_compute_tracer_tendencies(G g, P p, csio_state *s)
         for (int i = 1; i <= g->Nx; i++) {
             F(s->Gh, i, j) = -horizontal_div_Uc(g, p, s, &s->h, i, j);
             F(s->Ga, i, j) = -horizontal_div_Uc(g, p, s, &s->a, i, j);
+            if (s->hs.p) F(s->Ghs, i, j) = -horizontal_div_Uc(g, p, s, &s->hs, i, j); /* tracer_tendency:47-52 */
         }
     return 0;
 }
@@ -607,6 +665,7 @@ int csio_dynamic_time_step(G g, P p, csio_state *s, double dt)
 {
     csio_field hn = (p->timestepper == CSIO_RK3) ? s->hm : s->h;
     csio_field an = (p->timestepper == CSIO_RK3) ? s->am : s->a;
+    csio_field hsn = (p->timestepper == CSIO_RK3) ? s->hsm : s->hs;
 #pragma omp parallel for schedule(static)
     for (int j = 1; j <= g->Ny; j++)
         for (int i = 1; i <= g->Nx; i++) {
@@ -619,6 +678,12 @@ int csio_dynamic_time_step(G g, P p, csio_state *s, double dt)
             double Vp = hp * ap;
             F(s->a, i, j) = ap > 1 ? 1.0 : ap;
             F(s->h, i, j) = ap > 1 ? Vp : hp;
+            if (s->hs.p) { /* dynamic_step_snow!: fe.jl:84-94 (reads the concentration just written) */
+                double sp = F(hsn, i, j) + dt * F(s->Ghs, i, j);
+                sp = jl_max(0.0, sp);
+                sp = (F(s->a, i, j) <= 0) ? 0.0 : sp;
+                F(s->hs, i, j) = sp;
+            }
         }
     return 0;
 }
@@ -641,6 +706,10 @@ int csio_update_state(G g, P p, csio_state *s)
     csio_fill_halo(g, p, &s->h, 0, 0, 0);
     mask_immersed(g, &s->a, 0, 0);
     csio_fill_halo(g, p, &s->a, 0, 0, 0);
+    if (s->hs.p) {
+        mask_immersed(g, &s->hs, 0, 0);
+        csio_fill_halo(g, p, &s->hs, 0, 0, 0);
+    }
     mask_immersed(g, &s->u, 1, 0);
     csio_fill_halo(g, p, &s->u, 1, 0, 1);
     mask_immersed(g, &s->v, 0, 1);
@@ -664,6 +733,7 @@ int csio_time_step(G g, P p, csio_state *s, double dt, int first)
     /* cache_current_fields! (rk.jl:29-42) */
     copy_parent(s->hm, s->h);
     copy_parent(s->am, s->a);
+    if (s->hs.p) copy_parent(s->hsm, s->hs);
     copy_parent(s->um, s->u);
     copy_parent(s->vm, s->v);
     for (int beta = 3; beta >= 1; beta--) {

@@ -59,6 +59,7 @@ enum { CSIO_REPLACEMENT_PRESSURE = 0, CSIO_ICE_STRENGTH = 1 };
 enum { CSIO_CORIOLIS_NONE = 0, CSIO_CORIOLIS_FPLANE = 1 };
 enum { CSIO_BC_DEFAULT = 0, CSIO_BC_VALUE = 1 };
 enum { CSIO_RK3 = 0, CSIO_FE = 1 };
+enum { CSIO_FD_NONE = 0, CSIO_FD_FIELDS = 1, CSIO_FD_STRESS_BALANCE = 2 };
 
 typedef struct {
     /* ElastoViscoPlasticRheology: elasto_visco_plastic_rheology.jl:14-25,119-137 */
@@ -86,6 +87,13 @@ typedef struct {
     /* immersed boundary condition of examples/ice_advected_on_coastline.jl:91-98: discrete-form
      * FluxBoundaryCondition -C*u on the south/north immersed faces of u, -C*v on west/east of v; 0 = none */
     double imm_drag_u, imm_drag_v;
+    /* free drift for marginal ice (stress_balance_free_drift.jl:61-129): NONE -> 0, FIELDS -> fd_u/fd_v arrays,
+     * STRESS_BALANCE -> closed form from the model's own stresses (exactly one side SEMI_IMPLICIT) */
+    int32_t free_drift_kind, pad3_;
+    csio_field fd_u, fd_v;
+    /* top SemiImplicitStress (top_kind == SEMI_IMPLICIT): u_e, v_e = top_x/top_y arrays or top_tx/top_ty constants.
+     * Likewise bot_kind may be CONST / FIELD, the stress then being ue/ve (arrays) or ue_c/ve_c (constants). */
+    double top_rho, top_Cd;
 } csio_params;
 
 typedef struct {
@@ -93,6 +101,7 @@ typedef struct {
     csio_field s11, s22, s12, zf, zc, delta, alpha, un, vn, P;  /* EVP Auxiliaries (evp.jl:147-169) */
     csio_field Gh, Ga;                                   /* timestepper.G^n */
     csio_field hm, am, um, vm;                           /* timestepper.Psi^- (RK3 only) */
+    csio_field hs, Ghs, hsm;                             /* optional snow thickness, its tendency, Psi^-.hs (p == NULL: no snow) */
 } csio_state;
 
 /* ---- entry points (all return 0 on success) ---- */

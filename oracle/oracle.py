@@ -62,11 +62,15 @@ class Params(C.Structure):
         ("u_sn_bc", C.c_int32), ("v_we_bc", C.c_int32), ("u_sn_val", C.c_double), ("v_we_val", C.c_double),
         ("advection_order", C.c_int32), ("timestepper", C.c_int32),
         ("imm_drag_u", C.c_double), ("imm_drag_v", C.c_double),
+        ("free_drift_kind", C.c_int32), ("pad3_", C.c_int32), ("fd_u", Field), ("fd_v", Field),
+        ("top_rho", C.c_double), ("top_Cd", C.c_double),
     ]
 
 
 _STATE_NAMES = ("u", "v", "h", "a", "s11", "s22", "s12", "zf", "zc", "delta", "alpha", "un", "vn", "P",
-                "Gh", "Ga", "hm", "am", "um", "vm")
+                "Gh", "Ga", "hm", "am", "um", "vm", "hs", "Ghs", "hsm")
+_SNOW_NAMES = ("hs", "Ghs", "hsm")
+FD_NONE, FD_FIELDS, FD_STRESS_BALANCE = 0, 1, 2
 
 
 class State(C.Structure):
@@ -76,7 +80,8 @@ class State(C.Structure):
 # location of every state field: (face_x, face_y)
 LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), s11=(0, 0), s22=(0, 0), s12=(1, 1), zf=(1, 1), zc=(0, 0),
            delta=(0, 0), alpha=(0, 0), un=(1, 0), vn=(0, 1), P=(0, 0), Gh=(0, 0), Ga=(0, 0),
-           hm=(0, 0), am=(0, 0), um=(1, 0), vm=(0, 1), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1))
+           hm=(0, 0), am=(0, 0), um=(1, 0), vm=(0, 1), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1),
+           hs=(0, 0), Ghs=(0, 0), hsm=(0, 0), fd_u=(1, 0), fd_v=(0, 1))
 
 _lib = None
 
@@ -121,6 +126,7 @@ DEFAULT_PARAMS = dict(
     coriolis_kind=0, f=0.0, top_kind=STRESS_NONE, top_tx=0.0, top_ty=0.0,
     bot_kind=STRESS_NONE, rho_e=1026.0, Cd=5.5e-3, ue_c=0.0, ve_c=0.0,
     u_sn_bc=0, v_we_bc=0, u_sn_val=0.0, v_we_val=0.0, advection_order=7, timestepper=RK3, imm_drag_u=0.0, imm_drag_v=0.0,
+    free_drift_kind=FD_NONE, top_rho=1.3, top_Cd=1.2e-3,
 )
 
 
@@ -135,12 +141,13 @@ class OracleModel:
         self.prm = prm
         fields = fields or {}
         self.arr = {}
-        for n in _STATE_NAMES + ("top_x", "top_y", "ue", "ve"):
+        snow = fields.get("hs") is not None
+        for n in _STATE_NAMES + ("top_x", "top_y", "ue", "ve", "fd_u", "fd_v"):
             shp = parent_shape(Nx, Ny, Hx, Hy, self.topo, LOC[n])
             if n in fields and fields[n] is not None:
                 a = np.ascontiguousarray(fields[n], dtype=np.float64).copy()
                 assert a.shape == shp, (n, a.shape, shp)
-            elif n in ("top_x", "top_y", "ue", "ve"):
+            elif n in ("top_x", "top_y", "ue", "ve", "fd_u", "fd_v") or (n in _SNOW_NAMES and not snow):
                 a = None
             else:
                 a = np.zeros(shp)
@@ -164,7 +171,7 @@ class OracleModel:
         self.p = Params()
         for k, v in prm.items():
             setattr(self.p, k, v)
-        for n in ("top_x", "top_y", "ue", "ve"):
+        for n in ("top_x", "top_y", "ue", "ve", "fd_u", "fd_v"):
             setattr(self.p, n, _as_field(self.arr[n], Hx, Hy))
         self.s = State()
         for n in _STATE_NAMES:

@@ -9,15 +9,27 @@ from oracle import oracle as O
 
 
 def oracle_params(case) -> dict:
+    F = case.fields
     p = dict(substeps=case.substeps, advection_order=case.advection_order,
              timestepper=O.RK3 if case.timestepper == "SplitRungeKutta3" else O.FE,
              coriolis_kind=0 if case.coriolis_f is None else 1, f=case.coriolis_f or 0.0,
-             top_kind=O.STRESS_FIELD if "top_x" in case.fields else O.STRESS_NONE,
-             bot_kind=O.STRESS_SEMI_IMPLICIT, rho_e=case.rho_e, Cd=case.Cd)
-    if case.top_const and "top_x" not in case.fields:
-        p.update(top_kind=O.STRESS_CONST, top_tx=case.top_const[0], top_ty=case.top_const[1])
-    if case.ocean_const and "ue" not in case.fields:
+             rho_e=case.rho_e, Cd=case.Cd, top_rho=case.top_rho_Cd[0], top_Cd=case.top_rho_Cd[1])
+    has_top = "top_x" in F or bool(case.top_const)
+    if case.top_kind == "semi_implicit":
+        p.update(top_kind=O.STRESS_SEMI_IMPLICIT)
+    else:
+        p.update(top_kind=O.STRESS_FIELD if "top_x" in F else (O.STRESS_CONST if has_top else O.STRESS_NONE))
+    if case.top_const and "top_x" not in F:
+        p.update(top_tx=case.top_const[0], top_ty=case.top_const[1])
+    if case.bottom_kind == "semi_implicit":
+        p.update(bot_kind=O.STRESS_SEMI_IMPLICIT)
+    elif case.bottom_kind == "stress":
+        p.update(bot_kind=O.STRESS_FIELD if "ue" in F else O.STRESS_CONST)
+    else:
+        p.update(bot_kind=O.STRESS_NONE)
+    if case.ocean_const and "ue" not in F:
         p.update(ue_c=case.ocean_const[0], ve_c=case.ocean_const[1])
+    p.update(free_drift_kind={None: O.FD_NONE, "fields": O.FD_FIELDS, "stress_balance": O.FD_STRESS_BALANCE}[case.free_drift])
     p.update(imm_drag_u=case.immersed_drag[0], imm_drag_v=case.immersed_drag[1])
     if case.u_bc_value is not None:
         p.update(u_sn_bc=1, u_sn_val=case.u_bc_value)
@@ -36,7 +48,7 @@ def oracle_from_case(case, **overrides) -> O.OracleModel:
 
 # GPU field name -> oracle field name
 NAME_MAP = dict(u="u", v="v", h="h", a="a", s11="s11", s22="s22", s12="s12", alpha="alpha", zeta_c="zc", zeta_f="zf",
-                delta="delta", P="P", un="un", vn="vn", Gh="Gh", Ga="Ga")
+                delta="delta", P="P", un="un", vn="vn", Gh="Gh", Ga="Ga", hs="hs", Ghs="Ghs")
 
 
 def rel_err(a, b):

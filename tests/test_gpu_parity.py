@@ -338,3 +338,64 @@ def test_latitude_longitude_grid_rejects_fused_and_bad_metrics():
     bad.metrics = lambda: met
     with pytest.raises(RuntimeError, match="metrics must be positive"):
         model_from_case(bad)
+
+
+@pytest.mark.parametrize("variant", ["bottom_drag", "top_drag", "fields", "both_drag", "const_top_drag"])
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_free_drift_top_drag_and_snow(variant, timestepper):
+    """free-drift velocities of marginal ice (StressBalanceFreeDrift closed forms for either side, and
+    (u=, v=) arrays: stress_balance_free_drift.jl:61-129), SemiImplicitStress as the top stress and prescribed
+    bottom stresses (ext.jl:8-40,176-210), and snow-thickness advection (tracer_tendency:47-52, fe.jl:84-94)."""
+    from climaseaice_b200.synthetic import marginal_ice_case
+    case = marginal_ice_case(48, substeps=12, variant=variant, timestepper=timestepper)
+    m = model_from_case(case, solver_impl="auto")
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "hs", "s11", "s22", "s12", "Ghs")))
+    u = interior_of(m.all_fields()["u"].numpy(), case)
+    assert np.isfinite(u).all() and np.abs(u).max() > 1e-3
+    m.close()
+
+
+def test_free_drift_on_a_bounded_domain_and_host_entry():
+    """Free drift + snow on a Bounded x Bounded domain, through the device and the host-buffer entry points."""
+    from climaseaice_b200.synthetic import marginal_ice_case
+    case = marginal_ice_case(40, substeps=8, variant="bottom_drag", topology=("Bounded", "Bounded"))
+    m = model_from_case(case)
+    o = oracle_from_case(case)
+    hs = HostStepper(case)
+    m.time_step(case.dt); o.time_step(case.dt); hs.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "hs", "s12")))
+    for n in ("u", "v", "h", "a", "hs"):
+        assert np.array_equal(interior_of(hs.host[n].numpy(), case), interior_of(m.all_fields()[n].numpy(), case)), n
+    m.close(); hs.model.close()
+
+
+def test_stress_balance_free_drift_argument_errors():
+    from climaseaice_b200 import SeaIceMomentumEquation, SemiImplicitStress, StressBalanceFreeDrift
+    from climaseaice_b200.driver import grid_from_case
+    grid = grid_from_case(periodic_case(16))
+    sis = SemiImplicitStress()
+    with pytest.raises(ValueError, match="not both"):
+        SeaIceMomentumEquation(grid, top_momentum_stress=sis, bottom_momentum_stress=sis, free_drift=StressBalanceFreeDrift())
+    with pytest.raises(ValueError, match="requires using a `SemiImplicitStress`"):
+        SeaIceMomentumEquation(grid, top_momentum_stress=dict(u=0.1, v=0.0), free_drift=StressBalanceFreeDrift())
+    # the library checks the same thing for callers that fill csi_config themselves
+    import ctypes as C
+    from climaseaice_b200 import _lib as L
+    case = periodic_case(16, substeps=2)
+    m = model_from_case(case)
+    cfg = m._config()
+    cfg.free_drift_kind = L.FD_STRESS_BALANCE
+    cfg.top_stress_kind = L.STRESS_SEMI_IMPLICIT
+    h = C.c_void_p()
+    assert L.lib().csi_create(C.byref(cfg), C.byref(h)) == -1 and b"not both" in L.lib().csi_last_error(None)
+    m.close()
+    # "fused" refuses what only the general kernels implement
+    from climaseaice_b200.synthetic import marginal_ice_case
+    mc = marginal_ice_case(32, substeps=2, variant="fields")
+    mf = model_from_case(mc, solver_impl="fused")
+    with pytest.raises(RuntimeError, match="free-drift"):
+        mf.time_step(mc.dt)
+    mf.close()

@@ -25,11 +25,25 @@ def test_every_declared_symbol_is_exported():
     assert lib.csi_version() == L.ABI_VERSION
 
 
-def test_struct_layout_matches_header():
-    # sizes computed by hand from include/climaseaice_b200.h (natural alignment)
-    assert C.sizeof(L.csi_array) == 24
-    assert C.sizeof(L.csi_fields) == 24 * len(L.FIELD_NAMES)
-    assert C.sizeof(L.csi_config) == 8 + 24 + 16 + 8 + 56 + 8 + 24 + 8 + 24 + 8 + 40 + 8 + 8 + 8 + 16 + 16 + 8 + 96
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors agree with what a C compiler makes of include/climaseaice_b200.h: total sizes and the
+    offset of every member of csi_config (members of csi_fields are all csi_array, in FIELD_NAMES order)."""
+    import subprocess
+    from pathlib import Path
+    inc = Path(__file__).resolve().parents[1] / "include"
+    members = [n for n, _ in L.csi_config._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "climaseaice_b200.h"', 'int main(void) {',
+             'printf("%zu %zu %zu\\n", sizeof(csi_array), sizeof(csi_fields), sizeof(csi_config));']
+    lines += [f'printf("%zu\\n", offsetof(csi_config, {m}));' for m in members]
+    lines += ['return 0; }']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(inc), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out[:3]] == [C.sizeof(L.csi_array), C.sizeof(L.csi_fields), C.sizeof(L.csi_config)]
+    assert [int(x) for x in out[3:]] == [getattr(L.csi_config, m).offset for m in members]
+    assert C.sizeof(L.csi_array) == 24 and C.sizeof(L.csi_fields) == 24 * len(L.FIELD_NAMES) == 24 * 29
 
 
 def test_correctly_rounded_exp_matches_binary128():

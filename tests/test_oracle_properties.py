@@ -207,3 +207,56 @@ def test_latlon_case_steps_and_conserves_volume():
         assert np.isfinite(o.arr[n]).all(), n
     assert np.abs(o.interior("u")).max() > 1e-5
     assert abs((o.interior("h") * az).sum() - v0) <= 1e-12 * abs(v0)
+
+
+@pytest.mark.parametrize("variant", ["bottom_drag", "top_drag"])
+def test_stress_balance_free_drift_balances_the_stresses(variant):
+    """stress_balance_free_drift.jl:61-109: marginal cells take U_d - tau_o / sqrt(C_d |tau_o|), i.e. the velocity at
+    which the velocity-dependent stress equals the prescribed one: C_d |U_d - u| (U_d - u) = tau_o, componentwise."""
+    from climaseaice_b200.synthetic import marginal_ice_case
+    from tests.helpers import oracle_from_case
+    case = marginal_ice_case(48, substeps=3, variant=variant, snow=False)
+    o = oracle_from_case(case)
+    o.update_state()
+    o.time_step_momentum(case.dt / 3, 3)
+    H, N = case.Hy, case.Ny
+    a = o.arr["a"]
+    ai = 0.5 * (a[:, 1:] + a[:, :-1])[H:H + N, H - 1:H - 1 + N]                 # aice at the u points 1..N
+    m = o.arr["h"] * 900.0 * a
+    mi = 0.5 * (m[:, 1:] + m[:, :-1])[H:H + N, H - 1:H - 1 + N]
+    marginal = ((mi < 1.0) | (ai < 1e-3)) & (mi > 2.3e-16) & (ai > 2.3e-16)
+    assert marginal.sum() > 100
+    u = o.interior("u")
+    d, oth = (("ue", "ve"), ("top_x", "top_y")) if variant == "bottom_drag" else (("top_x", "top_y"), ("ue", "ve"))
+    rho, Cd = (case.rho_e, case.Cd) if variant == "bottom_drag" else case.top_rho_Cd
+    Ud = o.arr[d[0]][H:H + N, H:H + N]
+    tx = o.arr[oth[0]][H:H + N, H:H + N]
+    ty4 = o.arr[oth[1]]
+    ty = 0.25 * (ty4[H:H + N, H - 1:H - 1 + N] + ty4[H:H + N, H:H + N] + ty4[H + 1:H + 1 + N, H - 1:H - 1 + N] + ty4[H + 1:H + 1 + N, H:H + N])
+    t = np.sqrt(tx ** 2 + ty ** 2)
+    drag_x = rho * Cd * np.sqrt(t / (rho * Cd)) * (Ud - u)                      # |U_d - u_F| = sqrt(|tau| / C)
+    sel = marginal & (t > 0)
+    assert np.allclose(drag_x[sel], tx[sel], rtol=1e-12, atol=1e-15)
+    calm = marginal & (t == 0)
+    assert np.array_equal(u[calm], Ud[calm])                                    # no stress: drift with the other medium
+
+
+def test_snow_is_advected_and_clipped_with_the_ice():
+    """tracer_tendency:47-52, fe.jl:84-94: hs moves with the same fluxes as h; it is zeroed where aice <= 0; its volume
+    sum(hs Az) is conserved by the flux form as long as no cell is clipped."""
+    from climaseaice_b200.synthetic import periodic_case
+    from tests.helpers import oracle_from_case
+    case = periodic_case(48, substeps=4, aice="ones", timestepper="ForwardEuler", advection_order=5)
+    case.fields["hs"] = 0.1 + 0.02 * np.sin(2 * np.pi * case.nodes((0, 0))[0] / case.Lx)
+    o = oracle_from_case(case)
+    o.update_state()
+    v0 = o.interior("hs").sum()
+    o.time_step(case.dt)
+    assert np.abs(o.interior("Ghs")).max() > 0
+    assert abs(o.interior("hs").sum() - v0) <= 1e-12 * v0
+    case2 = periodic_case(48, substeps=4, aice="mixed", timestepper="ForwardEuler")
+    case2.fields["hs"] = np.full_like(case2.fields["h"], 0.1)
+    o2 = oracle_from_case(case2)
+    o2.time_step(case2.dt)
+    assert np.all(o2.interior("hs")[o2.interior("a") <= 0] == 0.0)
+    assert (o2.interior("a") <= 0).any()
