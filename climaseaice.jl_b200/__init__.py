@@ -5,8 +5,11 @@ modules here are the host-side mirror of the reference's user interface for that
 """
 from . import _lib
 from ._lib import CsiError, lib
-from .model import (Bounded, Center, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, Periodic, RectilinearGrid, LatitudeLongitudeGrid, StressBalanceFreeDrift,
-                    SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress, SplitExplicitSolver, UpwindBiased,
-                    ValueBoundaryCondition, WENO, nccl_unique_id, time_step_b)
+from .model import (Bounded, Center, ConductiveFlux, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat,
+                    IceWaterThermalEquilibrium, LatitudeLongitudeGrid, LinearHeatFlux, MeltingConstrainedFluxBalance, Periodic,
+                    PhaseTransitions, PrescribedTemperature, RadiativeEmission, RectilinearGrid, SeaIceModel,
+                    SeaIceMomentumEquation, SemiImplicitStress, SlabThermodynamics, SplitExplicitSolver,
+                    StressBalanceFreeDrift, UpwindBiased, ValueBoundaryCondition, WENO, nccl_unique_id,
+                    sea_ice_slab_thermodynamics, snow_slab_thermodynamics, time_step_b)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -79,13 +79,44 @@ class csi_fields(C.Structure):
     _fields_ = [(n, csi_array) for n in FIELD_NAMES]
 
 
+TOP_FLUX_BALANCE, TOP_PRESCRIBED = 0, 1
+BOTTOM_EQUILIBRIUM, BOTTOM_PRESCRIBED = 0, 1
+FLUX_CONST, FLUX_ARRAY, FLUX_RADIATIVE_EMISSION, FLUX_CONDUCTIVE, FLUX_LINEAR = 0, 1, 2, 3, 4
+
+
+class csi_thermo_config(C.Structure):
+    _fields_ = [
+        ("density", C.c_double), ("heat_capacity", C.c_double), ("liquid_density", C.c_double),
+        ("liquid_heat_capacity", C.c_double), ("reference_latent_heat", C.c_double), ("reference_temperature", C.c_double),
+        ("liquidus_freshwater_melting_temperature", C.c_double), ("liquidus_slope", C.c_double),
+        ("top_heat_bc", C.c_int32), ("snow_top_heat_bc", C.c_int32), ("bottom_heat_bc", C.c_int32), ("layered", C.c_int32),
+        ("ice_conductivity", C.c_double), ("snow_conductivity", C.c_double),
+        ("bottom_salinity", C.c_double), ("bottom_temperature", C.c_double),
+        ("n_top_terms", C.c_int32), ("top_term_kind", C.c_int32 * 2), ("reserved_", C.c_int32),
+        ("top_flux_const", C.c_double), ("emissivity", C.c_double), ("stefan_boltzmann_constant", C.c_double),
+        ("emission_reference_temperature", C.c_double), ("bottom_flux_const", C.c_double),
+        ("snowfall", C.c_double), ("snow_density", C.c_double), ("ice_consolidation_thickness", C.c_double), ("ice_salinity", C.c_double),
+        ("secant_tolerance", C.c_double), ("secant_maxiters", C.c_int32), ("reserved2_", C.c_int32),
+        ("linear_coefficient", C.c_double), ("linear_temperature", C.c_double),
+        ("linear_times_concentration", C.c_int32), ("reserved3_", C.c_int32),
+    ]
+
+
+THERMO_FIELD_NAMES = ("h", "a", "hs", "Tu", "Tus", "S", "hc", "Qtop", "Qbot", "Sb", "Tb", "snowfall", "rho_s",
+                      "mf_ice", "mf_snow", "mf_snowfall")
+
+
+class csi_thermo_fields(C.Structure):
+    _fields_ = [(n, csi_array) for n in THERMO_FIELD_NAMES]
+
+
 # every symbol include/climaseaice_b200.h declares
 EXPORTS = (
     "csi_version", "csi_last_error", "csi_create", "csi_destroy", "csi_evp_substeps",
     "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
     "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
     "csi_evp_substeps_host", "csi_last_transfer_bytes", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count",
-    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_selftest_math", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
+    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_thermodynamic_time_step", "csi_attach_thermodynamics", "csi_selftest_math", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
 )
 
 _lib = None
@@ -111,6 +142,8 @@ def lib():
     L.csi_dynamic_time_step.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_void_p]
     L.csi_cache_current_fields.argtypes = [H, C.POINTER(csi_fields), C.c_void_p]
     L.csi_update_state.argtypes = [H, C.POINTER(csi_fields), C.c_void_p]
+    L.csi_thermodynamic_time_step.argtypes = [H, C.POINTER(csi_thermo_config), C.POINTER(csi_thermo_fields), C.c_double, C.c_void_p]
+    L.csi_attach_thermodynamics.argtypes = [H, C.POINTER(csi_thermo_config), C.POINTER(csi_thermo_fields)]
     L.csi_fill_halos.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.csi_time_step.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.c_void_p]
     L.csi_cell_advection_timescale.argtypes = [H, C.POINTER(csi_fields), C.POINTER(C.c_double), C.c_void_p]

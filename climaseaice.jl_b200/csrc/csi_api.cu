@@ -89,6 +89,10 @@ struct csi_handle {
     std::vector<size_t> mirror_n;
     cudaStream_t own_stream = nullptr;
     size_t last_h2d = 0, last_d2h = 0;  // bytes moved by the last *_host call
+    // attached thermodynamics (csi_attach_thermodynamics)
+    bool thermo_on = false;
+    csi_thermo_config thermo_cfg;
+    DThermoFields thermo_f;
     // slab partition
     void *comm = nullptr;
     int rank = 0, nranks = 1;
@@ -185,6 +189,39 @@ int convert_fields(csi_handle *h, const csi_fields *f, int need, DFields *out)
         return fail(h, CSI_ERR_ARG, "ue and ve must both be arrays or both be constants");
     if ((field_at(*f, 14).ptr == nullptr) != (field_at(*f, 15).ptr == nullptr))
         return fail(h, CSI_ERR_ARG, "top_x and top_y must both be arrays or both be constants");
+    return CSI_OK;
+}
+
+constexpr int NTHERMO = sizeof(csi_thermo_fields) / sizeof(csi_array);
+const char *THERMO_NAMES[NTHERMO] = {"h", "a", "hs", "Tu", "Tus", "S", "hc", "Qtop", "Qbot", "Sb", "Tb", "snowfall", "rho_s", "mf_ice", "mf_snow", "mf_snowfall"};
+
+int convert_thermo(csi_handle *h, const csi_thermo_config *cfg, const csi_thermo_fields *f, DThermoFields *out)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!cfg || !f) return fail(h, CSI_ERR_ARG, "csi_thermo_config / csi_thermo_fields pointer is NULL");
+    if (cfg->n_top_terms < 1 || cfg->n_top_terms > 2) return fail(h, CSI_ERR_ARG, "thermodynamics: n_top_terms must be 1 or 2");
+    bool need_qtop = false;
+    for (int t = 0; t < cfg->n_top_terms; t++) {
+        const int k = cfg->top_term_kind[t];
+        if (k < CSI_FLUX_CONST || k > CSI_FLUX_LINEAR) return fail(h, CSI_ERR_ARG, "thermodynamics: bad top flux term kind");
+        need_qtop |= k == CSI_FLUX_ARRAY;
+    }
+    for (int bc : {cfg->top_heat_bc, cfg->snow_top_heat_bc})
+        if (bc != CSI_TOP_MELTING_CONSTRAINED_FLUX_BALANCE && bc != CSI_TOP_PRESCRIBED_TEMPERATURE) return fail(h, CSI_ERR_ARG, "thermodynamics: bad top heat boundary condition");
+    if (cfg->bottom_heat_bc != CSI_BOTTOM_ICE_WATER_EQUILIBRIUM && cfg->bottom_heat_bc != CSI_BOTTOM_PRESCRIBED_TEMPERATURE)
+        return fail(h, CSI_ERR_ARG, "thermodynamics: bad bottom heat boundary condition");
+    if (!(cfg->secant_tolerance > 0) || cfg->secant_maxiters < 1) return fail(h, CSI_ERR_ARG, "thermodynamics: secant_tolerance and secant_maxiters must be positive");
+    for (int k = 0; k < NTHERMO; k++) {
+        const std::string n = THERMO_NAMES[k];
+        bool req = (n == "h" || n == "a" || n == "Tu");
+        if (cfg->layered) req |= (n == "hs" || n == "Tus");
+        if (need_qtop) req |= n == "Qtop";
+        FieldInfo fi{THERMO_NAMES[k], 0, 0};
+        const csi_array &a = reinterpret_cast<const csi_array *>(f)[k];
+        int rc = check_array(h, a, fi, req);
+        if (rc) return rc;
+        reinterpret_cast<DArr *>(out)[k] = to_darr(a);
+    }
     return CSI_OK;
 }
 
@@ -337,6 +374,11 @@ int update_state_impl(csi_handle *h, const DFields &f, cudaStream_t s)
     launch_fill_halo(c, g, p, f.u, 1, 0, 1);
     launch_mask_immersed(c, g, f.v, 0, 1);
     launch_fill_halo(c, g, p, f.v, 0, 1, 2);
+    if (h->thermo_on) {  // sea_ice_model.jl:386-389
+        launch_mask_immersed(c, g, h->thermo_f.mf_ice, 0, 0);
+        launch_mask_immersed(c, g, h->thermo_f.mf_snow, 0, 0);
+        launch_mask_immersed(c, g, h->thermo_f.mf_snowfall, 0, 0);
+    }
     if (h->nranks > 1) {
         const DArr arrs[5] = {f.h, f.a, f.u, f.v, f.hs};
         int rc = exchange_slab_halos(h, arrs, 5, g.Hy, s);
@@ -358,6 +400,7 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
         launch_tracer_tendencies(c, g, p, f);
         if ((rc = momentum_impl(h, f, dt, nsub, s))) return rc;
         launch_dynamic_step(c, g, f, f.h, f.a, f.hs, dt);
+        if (h->thermo_on) launch_thermodynamics(c, g, h->thermo_cfg, h->thermo_f, h->cfg.ice_density, dt);  // fe.jl:30
         return update_state_impl(h, f, s);
     }
     // cache_current_fields!  rk.jl:29-42
@@ -371,6 +414,7 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
         launch_tracer_tendencies(c, g, p, f);                      // rk.jl:84
         if ((rc = momentum_impl(h, f, dtau, nsub, s))) return rc;  // rk.jl:87
         launch_dynamic_step(c, g, f, f.hm, f.am, f.hsm, dtau);     // rk.jl:89
+        if (h->thermo_on) launch_thermodynamics(c, g, h->thermo_cfg, h->thermo_f, h->cfg.ice_density, dtau);  // rk.jl:91
         if ((rc = update_state_impl(h, f, s))) return rc;
     }
     return CSI_OK;
@@ -619,6 +663,36 @@ int csi_update_state(csi_handle *h, const csi_fields *f, csi_stream stream)
     int rc = convert_fields(h, f, NEED_TRACERS & ~0, &df);
     if (rc) return rc;
     return update_state_impl(h, df, (cudaStream_t)stream);
+}
+
+int csi_thermodynamic_time_step(csi_handle *h, const csi_thermo_config *cfg, const csi_thermo_fields *f, double dt, csi_stream stream)
+{
+    DThermoFields tf;
+    int rc = convert_thermo(h, cfg, f, &tf);
+    if (rc) return rc;
+    if (!(dt > 0)) return fail(h, CSI_ERR_ARG, "csi_thermodynamic_time_step: dt must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    Timed t(h, s);
+    LaunchCtx c{s, &h->launches};
+    launch_thermodynamics(c, h->g, *cfg, tf, h->cfg.ice_density, dt);
+    CSI_CUDA(h, cudaGetLastError());
+    return CSI_OK;
+}
+
+int csi_attach_thermodynamics(csi_handle *h, const csi_thermo_config *cfg, const csi_thermo_fields *f)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!cfg) {
+        h->thermo_on = false;
+        return CSI_OK;
+    }
+    DThermoFields tf;
+    int rc = convert_thermo(h, cfg, f, &tf);
+    if (rc) return rc;
+    h->thermo_cfg = *cfg;
+    h->thermo_f = tf;
+    h->thermo_on = true;
+    return CSI_OK;
 }
 
 int csi_fill_halos(csi_handle *h, const csi_array *a, int32_t loc_x, int32_t loc_y, int32_t which, csi_stream stream)

@@ -25,6 +25,7 @@ void launch_mask_immersed(const LaunchCtx &c, const DGrid &g, const DArr &a, int
 
 // ---- advection (csi_advection.cu) ------------------------------------------------------------
 void launch_tracer_tendencies(const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f);
+void launch_thermodynamics(const LaunchCtx &c, const DGrid &g, const csi_thermo_config &p, const DThermoFields &f, double rho_i, double dt);
 void launch_dynamic_step(const LaunchCtx &c, const DGrid &g, const DFields &f, const DArr &hn, const DArr &an, const DArr &hsn, double dt);
 
 // ---- reductions (csi_reduce.cu); results land in `scratch` (device), final value in out_dev ------

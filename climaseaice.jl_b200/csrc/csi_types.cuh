@@ -72,6 +72,11 @@ struct DFields {
     DArr hs, Ghs, hsm, fd_u, fd_v;
 };
 
+// csi_thermo_fields on the device, same member order
+struct DThermoFields {
+    DArr h, a, hs, Tu, Tus, S, hc, Qtop, Qbot, Sb, Tb, snowfall, rho_s, mf_ice, mf_snow, mf_snowfall;
+};
+
 // index window a kernel runs over (inclusive, 1-based reference indices)
 struct Range2 {
     int i0, i1, j0, j1;

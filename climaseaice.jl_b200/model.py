@@ -193,6 +193,84 @@ class ValueBoundaryCondition:
     value: float = 0.0
 
 
+# ---- thermodynamics (src/SeaIceThermodynamics) -------------------------------------------------------------------
+@dataclass
+class PhaseTransitions:
+    """PhaseTransitions(; density=917, heat_capacity=2000, liquid_density=999.8, liquid_heat_capacity=4186,
+    reference_latent_heat=334e3, reference_temperature=0, liquidus=LinearLiquidus(slope=0.054, T0=0))"""
+    density: float = 917.0
+    heat_capacity: float = 2000.0
+    liquid_density: float = 999.8
+    liquid_heat_capacity: float = 4186.0
+    reference_latent_heat: float = 334e3
+    reference_temperature: float = 0.0
+    liquidus_slope: float = 0.054
+    liquidus_freshwater_melting_temperature: float = 0.0
+
+
+@dataclass
+class MeltingConstrainedFluxBalance:
+    """Top temperature from the flux balance Q_x(T) = Q_i(T), capped by the melting temperature (secant solve)."""
+    tolerance: float = 1e-3      # RootSolvers SolutionTolerance default
+    maxiters: int = 10000        # RootSolvers find_zero default
+
+
+@dataclass
+class PrescribedTemperature:
+    temperature: object = 0.0    # number, or an array of parent shape (bottom only)
+
+
+@dataclass
+class IceWaterThermalEquilibrium:
+    salinity: object = 0.0       # number or Field
+
+
+@dataclass
+class ConductiveFlux:
+    conductivity: float = 2.0
+
+
+@dataclass
+class RadiativeEmission:
+    emissivity: float = 1.0
+    stefan_boltzmann_constant: float = 5.67e-8
+    reference_temperature: float = 273.15
+
+
+@dataclass
+class LinearHeatFlux:
+    """Q = coefficient * (T_top - temperature) [* aice]: the bulk sensible-heat FluxFunction of the reference's tests
+    (test/test_energy_conservation.jl:8-13), offered as a built-in because closures cannot cross the C ABI."""
+    coefficient: float = 0.0
+    temperature: float = 0.0
+    times_concentration: bool = True
+
+
+class SlabThermodynamics:
+    """SlabThermodynamics(grid; top_heat_boundary_condition=MeltingConstrainedFluxBalance(),
+    bottom_heat_boundary_condition=IceWaterThermalEquilibrium(), internal_heat_flux=ConductiveFlux(conductivity=2))
+    (slab_sea_ice_thermodynamics.jl:84-108)."""
+
+    def __init__(self, grid, top_surface_temperature=None, top_heat_boundary_condition=None,
+                 bottom_heat_boundary_condition=None, internal_heat_flux=None):
+        self.top = top_heat_boundary_condition or MeltingConstrainedFluxBalance()
+        self.bottom = bottom_heat_boundary_condition or IceWaterThermalEquilibrium()
+        self.internal_heat_flux = internal_heat_flux or ConductiveFlux(2.0)
+        self.top_surface_temperature = Field((Center, Center), grid)
+        if top_surface_temperature is not None:
+            self.top_surface_temperature.set(top_surface_temperature)
+        elif isinstance(self.top, PrescribedTemperature):
+            self.top_surface_temperature.set(self.top.temperature)
+
+
+def sea_ice_slab_thermodynamics(grid, **kw):
+    return SlabThermodynamics(grid, **kw)
+
+
+def snow_slab_thermodynamics(grid, conductivity=0.31, **kw):
+    return SlabThermodynamics(grid, internal_heat_flux=ConductiveFlux(conductivity), **kw)
+
+
 class SeaIceMomentumEquation:
     def __init__(self, grid, coriolis=None, rheology=None, top_momentum_stress=None, bottom_momentum_stress=None,
                  free_drift=None, solver=None, minimum_concentration=1e-3, minimum_mass=1.0):
@@ -230,11 +308,20 @@ class SeaIceModel:
 
     def __init__(self, grid, dynamics=None, advection=None, timestepper="SplitRungeKutta3", boundary_conditions=None,
                  ice_density=900.0, ice_thermodynamics=None, solver_impl="auto", immersed_mask=None,
-                 partition=None, immersed_drag=(0.0, 0.0), snow_thickness=False):
-        if ice_thermodynamics is not None:
-            raise NotImplementedError("thermodynamics is outside the hot path (SURVEY section 8f)")
+                 partition=None, immersed_drag=(0.0, 0.0), snow_thickness=False, snow_thermodynamics=None,
+                 top_heat_flux=None, bottom_heat_flux=0.0, snowfall=0.0, snow_density=330.0,
+                 ice_consolidation_thickness=0.05, ice_salinity=0.0, phase_transitions=None):
+        if dynamics is None and ice_thermodynamics is None:
+            raise ValueError("pass a SeaIceMomentumEquation as `dynamics` and/or SlabThermodynamics as `ice_thermodynamics`")
+        if snow_thermodynamics is not None and ice_thermodynamics is None:
+            raise ValueError("snow_thermodynamics needs ice_thermodynamics")
+        # a thermodynamics-only model keeps an (unused) momentum equation so that the field set stays uniform
+        self._no_dynamics = dynamics is None
         if dynamics is None:
-            raise ValueError("this drop-in accelerates the dynamics path: pass a SeaIceMomentumEquation")
+            dynamics = SeaIceMomentumEquation(grid)
+        snow_thickness = bool(snow_thickness) or snow_thermodynamics is not None  # sea_ice_model.jl:203
+        self.ice_thermodynamics, self.snow_thermodynamics = ice_thermodynamics, snow_thermodynamics
+        self.phase_transitions = phase_transitions or PhaseTransitions()
         self.grid, self.dynamics = grid, dynamics
         self.advection = advection
         self.timestepper = timestepper
@@ -270,6 +357,90 @@ class SeaIceModel:
         cfg = self._config()
         L.check(L.lib().csi_create(C.byref(cfg), C.byref(self._handle)))
         self._cfg = cfg
+        self._thermo = None
+        if ice_thermodynamics is not None:
+            self._setup_thermodynamics(top_heat_flux, bottom_heat_flux, snowfall, snow_density, ice_consolidation_thickness, ice_salinity)
+
+    # -- thermodynamics -> csi_thermo_config / csi_thermo_fields ----------------------------------
+    def _setup_thermodynamics(self, top_heat_flux, bottom_heat_flux, snowfall, snow_density, hc, salinity):
+        g, it, st, pt = self.grid, self.ice_thermodynamics, self.snow_thermodynamics, self.phase_transitions
+        cc = (Center, Center)
+        tc = L.csi_thermo_config()
+        for n in ("density", "heat_capacity", "liquid_density", "liquid_heat_capacity", "reference_latent_heat",
+                  "reference_temperature", "liquidus_slope", "liquidus_freshwater_melting_temperature"):
+            setattr(tc, n, getattr(pt, n))
+        kind = lambda bc: L.TOP_PRESCRIBED if isinstance(bc, PrescribedTemperature) else L.TOP_FLUX_BALANCE
+        tc.top_heat_bc = kind(it.top)
+        tc.snow_top_heat_bc = kind(st.top) if st is not None else L.TOP_FLUX_BALANCE
+        solver = next((bc for bc in ((st.top if st is not None else None), it.top) if isinstance(bc, MeltingConstrainedFluxBalance)),
+                      MeltingConstrainedFluxBalance())
+        tc.secant_tolerance, tc.secant_maxiters = solver.tolerance, solver.maxiters
+        tc.layered = 1 if st is not None else 0
+        tc.ice_conductivity = it.internal_heat_flux.conductivity
+        tc.snow_conductivity = st.internal_heat_flux.conductivity if st is not None else 0.31
+        arrays = {}
+
+        def scalar_or_field(value, name, attr):
+            if isinstance(value, Field):
+                arrays[name] = value
+            elif np.ndim(value) > 0:
+                arrays[name] = Field(cc, g, value)
+            else:
+                setattr(tc, attr, float(value))
+        if isinstance(it.bottom, PrescribedTemperature):
+            tc.bottom_heat_bc = L.BOTTOM_PRESCRIBED
+            scalar_or_field(it.bottom.temperature, "Tb", "bottom_temperature")
+        else:
+            tc.bottom_heat_bc = L.BOTTOM_EQUILIBRIUM
+            scalar_or_field(it.bottom.salinity, "Sb", "bottom_salinity")
+        # external top flux (sea_ice_model.jl:242-256): default 0, or the conductive flux itself for a bare-ice
+        # PrescribedTemperature top (no surface imbalance)
+        if top_heat_flux is None:
+            top_heat_flux = ("conductive",) if (st is None and isinstance(it.top, PrescribedTemperature)) else 0.0
+        terms = top_heat_flux if isinstance(top_heat_flux, (tuple, list)) else (top_heat_flux,)
+        if not 1 <= len(terms) <= 2:
+            raise NotImplementedError("top_heat_flux: one flux or a tuple of two")
+        tc.n_top_terms = len(terms)
+        for k, t in enumerate(terms):
+            if isinstance(t, RadiativeEmission):
+                tc.top_term_kind[k] = L.FLUX_RADIATIVE_EMISSION
+                tc.emissivity, tc.stefan_boltzmann_constant, tc.emission_reference_temperature = \
+                    t.emissivity, t.stefan_boltzmann_constant, t.reference_temperature
+            elif isinstance(t, LinearHeatFlux):
+                tc.top_term_kind[k] = L.FLUX_LINEAR
+                tc.linear_coefficient, tc.linear_temperature = t.coefficient, t.temperature
+                tc.linear_times_concentration = 1 if t.times_concentration else 0
+            elif isinstance(t, str) and t == "conductive":
+                tc.top_term_kind[k] = L.FLUX_CONDUCTIVE
+            elif isinstance(t, Field) or np.ndim(t) > 0:
+                tc.top_term_kind[k] = L.FLUX_ARRAY
+                arrays["Qtop"] = t if isinstance(t, Field) else Field(cc, g, t)
+            elif callable(t):
+                raise NotImplementedError("FluxFunction closures cannot cross the C ABI: use a number, an array, "
+                                          "RadiativeEmission or a tuple of two of them")
+            else:
+                tc.top_term_kind[k] = L.FLUX_CONST
+                tc.top_flux_const = float(t)
+        scalar_or_field(bottom_heat_flux, "Qbot", "bottom_flux_const")
+        scalar_or_field(snowfall, "snowfall", "snowfall")
+        scalar_or_field(snow_density, "rho_s", "snow_density")
+        scalar_or_field(hc, "hc", "ice_consolidation_thickness")
+        scalar_or_field(salinity, "S", "ice_salinity")
+        self.mass_fluxes = dict(ice=Field(cc, g), snow=Field(cc, g), intercepted_snowfall=Field(cc, g))
+        arrays.update(h=self.ice_thickness, a=self.ice_concentration, Tu=it.top_surface_temperature,
+                      mf_ice=self.mass_fluxes["ice"], mf_snow=self.mass_fluxes["snow"], mf_snowfall=self.mass_fluxes["intercepted_snowfall"])
+        if st is not None:
+            arrays.update(hs=self.snow_thickness, Tus=st.top_surface_temperature)
+        tf = L.csi_thermo_fields()
+        for n, fld in arrays.items():
+            setattr(tf, n, fld.as_csi())
+        self._thermo = (tc, tf, arrays)
+        L.check(L.lib().csi_attach_thermodynamics(self._handle, C.byref(tc), C.byref(tf)), self._handle)
+
+    def thermodynamic_time_step(self, dt):
+        """thermodynamic_time_step!(model, model.ice_thermodynamics, model.snow_thermodynamics, dt)"""
+        tc, tf, _ = self._thermo
+        L.check(L.lib().csi_thermodynamic_time_step(self._handle, C.byref(tc), C.byref(tf), float(dt), self._stream()), self._handle)
 
     # -- configuration -> csi_config ---------------------------------------------------------
     def _config(self):
@@ -400,9 +571,32 @@ class SeaIceModel:
 
     def time_step(self, dt):
         """time_step!(model, dt)"""
+        if self._no_dynamics:
+            return self._time_step_without_dynamics(dt)
         f = self.csi_fields()
         L.check(L.lib().csi_time_step(self._handle, C.byref(f), float(dt), 1 if self.iteration == 0 else 0, self._stream()),
                 self._handle)
+        self.iteration += 1
+        self.time += dt
+
+    def _time_step_without_dynamics(self, dt):
+        """time_step! with dynamics = nothing (fe.jl:13-34, rk.jl:81-94): advection with the model's (zero) velocities,
+        no momentum step, then the thermodynamic step; driven from the host through the per-stage entry points."""
+        if self.iteration == 0:
+            self.update_state()
+        if self.timestepper == "ForwardEuler":
+            self.compute_tracer_tendencies()
+            self.dynamic_time_step(dt)
+            self.thermodynamic_time_step(dt)
+            self.update_state()
+        else:
+            self.cache_current_fields()
+            for beta in (3, 2, 1):
+                dtau = dt / beta
+                self.compute_tracer_tendencies()
+                self.dynamic_time_step(dtau)
+                self.thermodynamic_time_step(dtau)
+                self.update_state()
         self.iteration += 1
         self.time += dt
 

@@ -192,6 +192,66 @@ int csi_comm_init(csi_handle *h, const uint8_t id128[128], int32_t rank, int32_t
  * DistributedComputations, used at src/sea_ice_model.jl:381-384, evp.jl:275-280) */
 int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream);
 
+/* ---- slab thermodynamics -----------------------------------------------
+ * thermodynamic_time_step!(model, ice_thermodynamics, snow_thermodynamics, dt)
+ *     src/SeaIceThermodynamics/thermodynamic_time_step.jl:6-59: one pointwise kernel per call, the bare-ice
+ *     `_ice_thermodynamic_time_step!` (:76-118) or the layered snow + ice `_layered_thermodynamic_time_step!`
+ *     (:132-291), with thermodynamic_tendency / ice_melt_freeze_tendency (slab_thermodynamics_tendencies.jl:30-135),
+ *     ice_volume_update, snow_ice_formation, ProportionalEvolution (:297-369), ConductiveFlux /
+ *     IceSnowConductiveFlux (slab_heat_and_tracer_fluxes.jl), PhaseTransitions / LinearLiquidus
+ *     (SeaIceThermodynamics.jl:22-167) and the heat boundary conditions (HeatBoundaryConditions/ *.jl).
+ * Julia closures cannot cross a C ABI, so the external top flux is a menu: up to two summed terms, each a constant,
+ * an array, RadiativeEmission, a linear bulk flux, or the conductive flux (the model's default for PrescribedTemperature,
+ * src/sea_ice_model.jl:244-252).  The surface-temperature solve restates RootSolvers.jl's SecantMethod. */
+enum { CSI_TOP_MELTING_CONSTRAINED_FLUX_BALANCE = 0, CSI_TOP_PRESCRIBED_TEMPERATURE = 1 };
+enum { CSI_BOTTOM_ICE_WATER_EQUILIBRIUM = 0, CSI_BOTTOM_PRESCRIBED_TEMPERATURE = 1 };
+/* CSI_FLUX_LINEAR: coefficient * (T_top - temperature), optionally times the concentration -- the bulk sensible-heat
+ * FluxFunction the reference's own tests use (test/test_energy_conservation.jl:8-13,103-110) */
+enum { CSI_FLUX_CONST = 0, CSI_FLUX_ARRAY = 1, CSI_FLUX_RADIATIVE_EMISSION = 2, CSI_FLUX_CONDUCTIVE = 3, CSI_FLUX_LINEAR = 4 };
+
+typedef struct {
+    /* PhaseTransitions(density=917, heat_capacity=2000, liquid_density=999.8, liquid_heat_capacity=4186,
+     * reference_latent_heat=334e3, reference_temperature=0, liquidus=LinearLiquidus(slope=0.054, T0=0)) */
+    double density, heat_capacity, liquid_density, liquid_heat_capacity, reference_latent_heat, reference_temperature;
+    double liquidus_freshwater_melting_temperature, liquidus_slope;
+    /* SlabThermodynamics(top_heat_boundary_condition, bottom_heat_boundary_condition, internal_heat_flux) of the ice
+     * slab and, when layered != 0, of the snow slab (snow_slab_thermodynamics: conductivity 0.31) */
+    int32_t top_heat_bc, snow_top_heat_bc; /* CSI_TOP_* */
+    int32_t bottom_heat_bc;                /* CSI_BOTTOM_* */
+    int32_t layered;                       /* 0: bare ice, 1: snow + ice */
+    double ice_conductivity, snow_conductivity;
+    double bottom_salinity, bottom_temperature; /* constants, used when csi_thermo_fields.Sb / .Tb are NULL */
+    /* model.external_heat_fluxes: top = term[0] (+ term[1]); bottom = Qbot array or the constant */
+    int32_t n_top_terms, top_term_kind[2], reserved_;
+    double top_flux_const, emissivity, stefan_boltzmann_constant, emission_reference_temperature;
+    double bottom_flux_const;
+    /* SeaIceModel keywords, each used when its array is NULL: snowfall = 0, snow_density = 330,
+     * ice_consolidation_thickness = 0.05, ice_salinity = 0 (src/sea_ice_model.jl:66-83) */
+    double snowfall, snow_density, ice_consolidation_thickness, ice_salinity;
+    /* RootSolvers.find_zero defaults: SolutionTolerance(1e-3), maxiters = 10 000 */
+    double secant_tolerance;
+    int32_t secant_maxiters, reserved2_;
+    double linear_coefficient, linear_temperature; /* CSI_FLUX_LINEAR */
+    int32_t linear_times_concentration, reserved3_;
+} csi_thermo_config;
+
+typedef struct {
+    csi_array h, a, hs;           /* ice_thickness, ice_concentration, snow_thickness (layered) -- all (c,c) */
+    csi_array Tu, Tus;            /* top_surface_temperature of the ice slab / of the snow slab */
+    csi_array S, hc;              /* ice salinity, ice_consolidation_thickness */
+    csi_array Qtop, Qbot;         /* external heat flux arrays */
+    csi_array Sb, Tb;             /* IceWaterThermalEquilibrium salinity / PrescribedTemperature at the bottom */
+    csi_array snowfall, rho_s;    /* snowfall (kg m^-2 s^-1), snow_density */
+    csi_array mf_ice, mf_snow, mf_snowfall; /* mass_fluxes.thermodynamics.ice / .snow, .intercepted_snowfall (outputs) */
+} csi_thermo_fields;
+
+int csi_thermodynamic_time_step(csi_handle *h, const csi_thermo_config *cfg, const csi_thermo_fields *f, double dt, csi_stream stream);
+/* Make the thermodynamics part of the model: csi_time_step then runs thermodynamic_time_step! after
+ * dynamic_time_step! in every stage (src/sea_ice_fe_step.jl:27-30, src/sea_ice_rk_substep.jl:89-91) and
+ * csi_update_state masks the three mass-flux diagnostics on immersed cells (src/sea_ice_model.jl:386-389).
+ * h, a (and hs) must be the arrays of the csi_fields passed to csi_time_step.  cfg == NULL detaches. */
+int csi_attach_thermodynamics(csi_handle *h, const csi_thermo_config *cfg, const csi_thermo_fields *f);
+
 /* Instrumentation: kernels launched by this handle so far; elapsed ms of the last device call
  * measured with CUDA events on its stream. */
 int64_t csi_launch_count(const csi_handle *h);

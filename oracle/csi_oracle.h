@@ -125,6 +125,49 @@ double csio_reconstruct_x(const csio_grid *g, int order, int bias, const csio_fi
 double csio_reconstruct_y(const csio_grid *g, int order, int bias, const csio_field *c, int i, int j);
 int csio_set_threads(int n);
 
+/* ---- slab thermodynamics (csi_oracle_thermo.c) ---- */
+enum { CSIO_TOP_MELTING_CONSTRAINED_FLUX_BALANCE = 0, CSIO_TOP_PRESCRIBED_TEMPERATURE = 1 };
+enum { CSIO_BOTTOM_ICE_WATER_EQUILIBRIUM = 0, CSIO_BOTTOM_PRESCRIBED_TEMPERATURE = 1 };
+enum { CSIO_FLUX_CONST = 0, CSIO_FLUX_ARRAY = 1, CSIO_FLUX_RADIATIVE_EMISSION = 2, CSIO_FLUX_CONDUCTIVE = 3, CSIO_FLUX_LINEAR = 4 };
+
+typedef struct {
+    /* PhaseTransitions + LinearLiquidus: SeaIceThermodynamics.jl:22-127 */
+    double density, heat_capacity, liquid_density, liquid_heat_capacity, reference_latent_heat, reference_temperature;
+    double liquidus_T0, liquidus_slope;
+    /* SlabThermodynamics: slab_sea_ice_thermodynamics.jl:18-108 */
+    int32_t top_bc, snow_top_bc;          /* CSIO_TOP_* of the ice slab / of the snow slab */
+    int32_t bottom_bc;                    /* CSIO_BOTTOM_* */
+    int32_t layered;                      /* 1: snow + ice kernel, 0: bare ice */
+    double ice_conductivity, snow_conductivity;
+    double bottom_salinity, bottom_temperature;  /* constants, used when Sb / Tb arrays are NULL */
+    /* external fluxes: top = term[0] (+ term[1]), bottom = array or constant */
+    int32_t n_top_terms, top_term_kind[2], pad_;
+    double top_flux_const, emissivity, stefan_boltzmann, emission_reference_temperature;
+    double bottom_flux_const;
+    /* model-level constants, each used when its array is NULL: sea_ice_model.jl:66-83 */
+    double snowfall, snow_density, consolidation_thickness, ice_salinity;
+    /* RootSolvers SecantMethod defaults [RS-recall] */
+    double secant_tol;
+    int32_t secant_maxiters, pad2_;
+    /* CSIO_FLUX_LINEAR: coefficient * (T - temperature) [* aice], the sensible-heat FluxFunction of
+     * test/test_energy_conservation.jl:8-13,103-110 */
+    double linear_coefficient, linear_temperature;
+    int32_t linear_times_concentration, pad3_;
+} csio_thermo_params;
+
+typedef struct {
+    csio_field h, a, hs;          /* ice thickness, concentration, snow thickness (layered) */
+    csio_field Tu, Tus;           /* top surface temperature of the ice slab / of the snow slab */
+    csio_field S, hc;             /* ice salinity, consolidation thickness */
+    csio_field Qtop, Qbot;        /* external heat flux arrays */
+    csio_field Sb, Tb;            /* bottom salinity / prescribed bottom temperature */
+    csio_field snowfall, rho_s;   /* snowfall, snow density */
+    csio_field mf_ice, mf_snow, mf_snowfall; /* mass_fluxes.thermodynamics.ice/.snow, .intercepted_snowfall */
+} csio_thermo_state;
+
+int csio_thermodynamic_time_step(const csio_grid *g, const csio_thermo_params *p, csio_thermo_state *s, double rho_ice, double dt);
+double csio_pow4(double x);
+
 #ifdef __cplusplus
 }
 #endif

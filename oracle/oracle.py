@@ -27,7 +27,7 @@ RK3, FE = 0, 1
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with gcc (oracle/Makefile)."""
-    srcs = [_HERE / "csi_oracle.c", _HERE / "csi_oracle_weno.c", _HERE / "csi_oracle.h"]
+    srcs = [_HERE / "csi_oracle.c", _HERE / "csi_oracle_weno.c", _HERE / "csi_oracle_thermo.c", _HERE / "csi_oracle.h"]
     if force or not _LIB_PATH.exists() or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH
@@ -93,6 +93,8 @@ def lib():
         L = C.CDLL(str(_LIB_PATH))
         L.csio_exp.restype = C.c_double
         L.csio_exp.argtypes = [C.c_double]
+        L.csio_pow4.restype = C.c_double
+        L.csio_pow4.argtypes = [C.c_double]
         L.csio_cell_advection_timescale.restype = C.c_double
         L.csio_reconstruct_x.restype = C.c_double
         L.csio_reconstruct_y.restype = C.c_double
@@ -234,6 +236,98 @@ class OracleModel:
         f = getattr(self.s, name)
         fn = lib().csio_reconstruct_x if axis == 0 else lib().csio_reconstruct_y
         return fn(C.byref(self.g), order, bias, C.byref(f), i, j)
+
+
+# ---- slab thermodynamics (csi_oracle_thermo.c) ---------------------------------------------------
+TOP_FLUX_BALANCE, TOP_PRESCRIBED = 0, 1
+BOTTOM_EQUILIBRIUM, BOTTOM_PRESCRIBED = 0, 1
+FLUX_CONST, FLUX_ARRAY, FLUX_RADIATIVE_EMISSION, FLUX_CONDUCTIVE, FLUX_LINEAR = 0, 1, 2, 3, 4
+
+
+class ThermoParams(C.Structure):
+    _fields_ = [
+        ("density", C.c_double), ("heat_capacity", C.c_double), ("liquid_density", C.c_double),
+        ("liquid_heat_capacity", C.c_double), ("reference_latent_heat", C.c_double), ("reference_temperature", C.c_double),
+        ("liquidus_T0", C.c_double), ("liquidus_slope", C.c_double),
+        ("top_bc", C.c_int32), ("snow_top_bc", C.c_int32), ("bottom_bc", C.c_int32), ("layered", C.c_int32),
+        ("ice_conductivity", C.c_double), ("snow_conductivity", C.c_double),
+        ("bottom_salinity", C.c_double), ("bottom_temperature", C.c_double),
+        ("n_top_terms", C.c_int32), ("top_term_kind", C.c_int32 * 2), ("pad_", C.c_int32),
+        ("top_flux_const", C.c_double), ("emissivity", C.c_double), ("stefan_boltzmann", C.c_double),
+        ("emission_reference_temperature", C.c_double), ("bottom_flux_const", C.c_double),
+        ("snowfall", C.c_double), ("snow_density", C.c_double), ("consolidation_thickness", C.c_double), ("ice_salinity", C.c_double),
+        ("secant_tol", C.c_double), ("secant_maxiters", C.c_int32), ("pad2_", C.c_int32),
+        ("linear_coefficient", C.c_double), ("linear_temperature", C.c_double),
+        ("linear_times_concentration", C.c_int32), ("pad3_", C.c_int32),
+    ]
+
+
+THERMO_FIELDS = ("h", "a", "hs", "Tu", "Tus", "S", "hc", "Qtop", "Qbot", "Sb", "Tb", "snowfall", "rho_s", "mf_ice", "mf_snow", "mf_snowfall")
+
+
+class ThermoState(C.Structure):
+    _fields_ = [(n, Field) for n in THERMO_FIELDS]
+
+
+# SeaIceModel / PhaseTransitions / SlabThermodynamics defaults (sea_ice_model.jl:66-83, SeaIceThermodynamics.jl:107-114,
+# slab_sea_ice_thermodynamics.jl:36-48,84-90); secant defaults are RootSolvers' [RS-recall]
+DEFAULT_THERMO = dict(
+    density=917.0, heat_capacity=2000.0, liquid_density=999.8, liquid_heat_capacity=4186.0, reference_latent_heat=334e3,
+    reference_temperature=0.0, liquidus_T0=0.0, liquidus_slope=0.054,
+    top_bc=TOP_FLUX_BALANCE, snow_top_bc=TOP_FLUX_BALANCE, bottom_bc=BOTTOM_EQUILIBRIUM, layered=0,
+    ice_conductivity=2.0, snow_conductivity=0.31, bottom_salinity=0.0, bottom_temperature=0.0,
+    n_top_terms=1, top_term_kind=(FLUX_CONST, FLUX_CONST), top_flux_const=0.0,
+    emissivity=1.0, stefan_boltzmann=5.67e-8, emission_reference_temperature=273.15, bottom_flux_const=0.0,
+    snowfall=0.0, snow_density=330.0, consolidation_thickness=0.05, ice_salinity=0.0,
+    secant_tol=1e-3, secant_maxiters=10000, linear_coefficient=0.0, linear_temperature=0.0, linear_times_concentration=0,
+)
+
+
+class ThermoOracle:
+    """Numpy copies of the thermodynamic fields of one (c,c)-located column set + the C oracle's step."""
+
+    def __init__(self, Nx, Ny, Hx, Hy, params=None, fields=None, rho_ice=900.0, shared=None):
+        """`shared`: name -> existing array used in place (e.g. h, a, hs of an OracleModel for a coupled step)."""
+        self.Nx, self.Ny, self.Hx, self.Hy = Nx, Ny, Hx, Hy
+        shared = shared or {}
+        prm = dict(DEFAULT_THERMO)
+        prm.update(params or {})
+        self.prm, self.rho_ice = prm, float(rho_ice)
+        self.g = Grid(Nx=Nx, Ny=Ny, Hx=Hx, Hy=Hy, topo_x=PERIODIC, topo_y=PERIODIC, dx=1.0, dy=1.0)
+        self.p = ThermoParams()
+        for k, v in prm.items():
+            if k == "top_term_kind":
+                self.p.top_term_kind[0], self.p.top_term_kind[1] = v
+            else:
+                setattr(self.p, k, v)
+        fields = fields or {}
+        shp = (Ny + 2 * Hy, Nx + 2 * Hx)
+        self.arr = {}
+        self.s = ThermoState()
+        always = ("h", "a", "Tu", "mf_ice", "mf_snow", "mf_snowfall") + (("hs", "Tus") if prm["layered"] else ())
+        for n in THERMO_FIELDS:
+            if n in shared:
+                a = shared[n]
+                assert a.dtype == np.float64 and a.shape == shp and a.flags["C_CONTIGUOUS"], n
+            elif fields.get(n) is not None:
+                a = np.ascontiguousarray(fields[n], dtype=np.float64).copy()
+                assert a.shape == shp, (n, a.shape, shp)
+            elif n in always:
+                a = np.zeros(shp)
+            else:
+                a = None
+            self.arr[n] = a
+            setattr(self.s, n, _as_field(a, Hx, Hy))
+
+    def interior(self, name):
+        return self.arr[name][self.Hy:self.Hy + self.Ny, self.Hx:self.Hx + self.Nx]
+
+    def step(self, dt):
+        lib().csio_thermodynamic_time_step(C.byref(self.g), C.byref(self.p), C.byref(self.s), C.c_double(self.rho_ice), C.c_double(dt))
+
+
+def pow4(x: float) -> float:
+    return lib().csio_pow4(float(x))
 
 
 def exp_cr(x: float) -> float:
