@@ -10,17 +10,15 @@ import torch
 
 from . import _lib as L
 from .model import (Bounded, FPlane, Field, LatitudeLongitudeGrid, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
-                    SplitExplicitSolver, StressBalanceFreeDrift, UpwindBiased, ValueBoundaryCondition, WENO)
+                    SlabThermodynamics, SplitExplicitSolver, StressBalanceFreeDrift, UpwindBiased, ValueBoundaryCondition, WENO)
 from .synthetic import LOC, Case
 
 
 def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearGrid:
     if case.latlon is not None:
-        if partitioned_y:
-            raise NotImplementedError("slab partitions of a LatitudeLongitudeGrid")
         return LatitudeLongitudeGrid(size=(case.Nx, case.Ny), longitude=case.latlon[0], latitude=case.latlon[1],
                                      halo=(case.Hx, case.Hy), topology=(case.topology[0], case.topology[1], "Flat"),
-                                     device=device, metrics=case.metrics())
+                                     device=device, metrics=case.metrics(), partitioned_y=partitioned_y)
     return RectilinearGrid(size=(case.Nx, case.Ny), x=(0, case.Lx), y=(0, case.Ly), halo=(case.Hx, case.Hy),
                            topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y)
 
@@ -58,8 +56,14 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
     if case.v_bc_value is not None:
         bcs["v"] = dict(west=ValueBoundaryCondition(case.v_bc_value), east=ValueBoundaryCondition(case.v_bc_value))
     adv = None if case.advection_order == 0 else (UpwindBiased(1) if case.advection_order == 1 else WENO(case.advection_order))
+    thermo = {}
+    if case.thermo is not None:   # coupled slab thermodynamics (bare ice): Tu / Qtop arrays + scalars
+        thermo = dict(ice_thermodynamics=SlabThermodynamics(grid, top_surface_temperature=F["Tu"]),
+                      top_heat_flux=Field((0, 0), grid, F["Qtop"]) if "Qtop" in F else None,
+                      bottom_heat_flux=case.thermo.get("bottom_heat_flux", 0.0), ice_salinity=case.thermo.get("ice_salinity", 0.0))
     m = SeaIceModel(grid, dynamics=dyn, advection=adv, timestepper=case.timestepper, boundary_conditions=bcs,
-                    solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag, snow_thickness="hs" in F)
+                    solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag,
+                    snow_thickness="hs" in F, **thermo)
     m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
     if "hs" in F:
         m.set(hs=F["hs"])

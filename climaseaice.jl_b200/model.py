@@ -77,8 +77,8 @@ class LatitudeLongitudeGrid(RectilinearGrid):
     """
 
     def __init__(self, size, longitude, latitude, halo=(3, 3), topology=(Bounded, Bounded, Flat), radius=6371e3, device=None,
-                 metrics=None):
-        super().__init__(size, longitude, latitude, halo=halo, topology=topology, device=device)
+                 metrics=None, partitioned_y=False):
+        super().__init__(size, longitude, latitude, halo=halo, topology=topology, device=device, partitioned_y=partitioned_y)
         self.radius = float(radius)
         if metrics is None:
             metrics = latitude_longitude_metrics(self.Nx, self.Ny, self.Hy, self.x, self.y, self.radius)

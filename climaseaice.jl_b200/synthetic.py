@@ -11,6 +11,7 @@ A `Case` is plain data -- sizes, physical settings and parent arrays (C-order (s
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -50,9 +51,14 @@ class Case:
     bottom_kind: str = "semi_implicit"   # "semi_implicit" (ue/ve or ocean_const = ocean velocity), "stress" (they hold tau), "none"
     free_drift: str | None = None        # None, "fields" (fields fd_u, fd_v) or "stress_balance"
     latlon: tuple | None = None          # ((lon0, lon1), (lat0, lat1)) in degrees: LatitudeLongitudeGrid; Lx, Ly = extents in degrees
+    metric_arrays: dict | None = None    # explicit j-indexed metric arrays (a slab's rows of the global grid's metrics)
+    thermo: dict | None = None           # slab thermodynamics on top of the dynamics: scalars bottom_heat_flux, ice_salinity;
+                                         # arrays Tu (initial top temperature) and Qtop (external top heat flux) live in `fields`
 
     def metrics(self):
         """j-indexed metric arrays of a lat-lon case (None on a RectilinearGrid)."""
+        if self.metric_arrays is not None:
+            return self.metric_arrays
         if self.latlon is None:
             return None
         return latitude_longitude_metrics(self.Nx, self.Ny, self.Hy, self.latlon[0], self.latlon[1])
@@ -80,7 +86,7 @@ class Case:
 
 
 LOC = dict(u=(1, 0), v=(0, 1), h=(0, 0), a=(0, 0), top_x=(1, 0), top_y=(0, 1), ue=(1, 0), ve=(0, 1), hs=(0, 0),
-           fd_u=(1, 0), fd_v=(0, 1))
+           fd_u=(1, 0), fd_v=(0, 1), Tu=(0, 0), Qtop=(0, 0))
 
 
 def _wrap_periodic(case: Case, arr, loc):
@@ -165,12 +171,12 @@ def anticyclone_case(N, H=7, seed=SEED, substeps=150, dt=120.0, advection_order=
 
 
 def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7, timestepper="SplitRungeKutta3",
-                topology=("Bounded", "Bounded")) -> Case:
+                topology=("Bounded", "Bounded"), lon=(0.0, 60.0), lat=(20.0, 70.0), Ny=None) -> Case:
     """A basin on a LatitudeLongitudeGrid (the grid of test/test_rheology_energy_budget.jl:18-24 and of the coupled
     ClimaOcean set-ups): lambda in (0, 60), phi in (20, 70), closed or zonally periodic, rotating wind stress,
     sheared ocean current, variable ice cover.  The metrics vary by a factor ~2.7 across the rows."""
-    lon, lat = (0.0, 60.0), (20.0, 70.0)
-    c = Case("latlon", N, N, H, H, tuple(topology), lon[1] - lon[0], lat[1] - lat[0], dt=dt, substeps=substeps,
+    Ny = N if Ny is None else Ny
+    c = Case("latlon", N, Ny, H, H, tuple(topology), lon[1] - lon[0], lat[1] - lat[0], dt=dt, substeps=substeps,
              advection_order=advection_order, timestepper=timestepper, latlon=(lon, lat),
              u_bc_value=0.0 if topology[1] == "Bounded" else None, v_bc_value=0.0 if topology[0] == "Bounded" else None)
     rng = np.random.default_rng(seed)
@@ -188,6 +194,24 @@ def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7,
     ve = 0.05 * np.sin(tp * fx(Xv))
     raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=ue, ve=ve, top_x=tx, top_y=ty)
     c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
+    return c
+
+
+def arctic_cap_case(Nx=192, Ny=48, H=7, seed=SEED, substeps=20, dt=600.0, timestepper="SplitRungeKutta3") -> Case:
+    """BASELINE config 5 in miniature: a zonally periodic lat-lon cap (lambda in (0, 360), phi in (60, 88); the metrics
+    shrink 14x towards the pole), EVP dynamics + WENO advection coupled to bare-ice slab thermodynamics with a
+    latitude-dependent surface heat flux (freezing near the pole, melting at the ice edge)."""
+    c = latlon_case(Nx, H=H, seed=seed, substeps=substeps, dt=dt, timestepper=timestepper, topology=("Periodic", "Bounded"),
+                    lon=(0.0, 360.0), lat=(60.0, 88.0), Ny=Ny)
+    c.name = "arctic-cap"
+    rng = np.random.default_rng(seed + 5)
+    X, Y = c.nodes(LOC["h"])
+    fy = Y / c.Ly
+    c.fields["Tu"] = -20.0 * fy - 2.0 + 0.1 * rng.uniform(-1, 1, X.shape)
+    c.fields["Qtop"] = 150.0 * (fy - 0.35) + 20.0 * np.sin(2 * np.pi * X / c.Lx)      # W m^-2, > 0: heat leaves the ice
+    c.thermo = dict(bottom_heat_flux=-4.0, ice_salinity=4.0)
+    for k in ("Tu", "Qtop"):
+        c.fields[k] = _wrap_periodic(c, np.ascontiguousarray(c.fields[k], dtype=np.float64), LOC[k])
     return c
 
 
@@ -264,10 +288,14 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
     """Rank-local y-slab (halo Hy) of a case whose x axis is anything and whose y axis is Periodic (halo rows =
     periodic images) or Bounded (halo rows = the global parent's rows where it has them, zeros beyond)."""
     assert case.Ny % nranks == 0
+    assert case.mask is None, "slabs of masked cases are not built here"
     ny = case.Ny // nranks
-    c = Case(case.name + f"-slab{rank}", case.Nx, ny, case.Hx, Hy, case.topology, case.Lx, case.Ly / nranks,
-             dt=case.dt, substeps=case.substeps, coriolis_f=case.coriolis_f, advection_order=case.advection_order,
-             timestepper=case.timestepper, u_bc_value=case.u_bc_value, v_bc_value=case.v_bc_value, rho_e=case.rho_e, Cd=case.Cd)
+    c = dataclasses.replace(case, name=case.name + f"-slab{rank}", Ny=ny, Hy=Hy, Ly=case.Ly / nranks, fields={}, metric_arrays=None)
+    if case.latlon is not None:
+        # the slab's rows of the GLOBAL grid's metrics (same expressions per global row index => same bits as on one rank);
+        # local row jl = 1-Hy .. ny+Hy+1 is global row rank*ny + jl
+        G = latitude_longitude_metrics(case.Nx, case.Ny, Hy, case.latlon[0], case.latlon[1])
+        c.metric_arrays = {k: np.ascontiguousarray(v[rank * ny:rank * ny + ny + 2 * Hy + 1]) for k, v in G.items()}
     j = np.arange(rank * ny - Hy, (rank + 1) * ny + Hy)          # 0-based global interior row of every slab row
     for k, arr in case.fields.items():
         if case.topology[1] == "Periodic":

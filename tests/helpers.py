@@ -72,3 +72,31 @@ def compare_model(model, oracle, case, names=("u", "v", "h", "a", "s11", "s22", 
             g, r = interior_of(g, case), interior_of(r, case)
         out[n] = (rel_err(g, r), bool(np.array_equal(g, r)))
     return out
+
+
+def thermo_oracle_from_case(case, o):
+    """The thermodynamics oracle of a coupled case (Case.thermo), working in place on the dynamics oracle's h, aice."""
+    F = case.fields
+    prm = dict(bottom_flux_const=case.thermo.get("bottom_heat_flux", 0.0), ice_salinity=case.thermo.get("ice_salinity", 0.0),
+               n_top_terms=1, top_term_kind=((O.FLUX_ARRAY if "Qtop" in F else O.FLUX_CONST), O.FLUX_CONST))
+    return O.ThermoOracle(case.Nx, case.Ny, case.Hx, case.Hy, params=prm, fields={k: F[k] for k in ("Tu", "Qtop") if k in F},
+                          shared=dict(h=o.arr["h"], a=o.arr["a"]), rho_ice=900.0)
+
+
+def coupled_oracle_step(o, t, dt):
+    """time_step!(model, dt) with dynamics and thermodynamics, stage by stage (fe.jl:13-34; rk.jl:29-94, beta = 3, 2, 1)."""
+    if o.iteration == 0:
+        o.update_state()
+    if o.prm["timestepper"] == O.FE:
+        stages = [dt]
+    else:
+        stages = [dt / 3, dt / 2, dt / 1]
+        for n in ("h", "a", "u", "v"):
+            o.arr[n + "m"][:] = o.arr[n]
+    for dtau in stages:
+        o.compute_tracer_tendencies()
+        o.time_step_momentum(dtau)
+        o.dynamic_time_step(dtau)
+        t.step(dtau)
+        o.update_state()
+    o.iteration += 1

@@ -17,7 +17,7 @@ import __graft_entry__ as entry  # noqa: E402
 entry.load_package()
 from climaseaice_b200 import nccl_unique_id  # noqa: E402
 from climaseaice_b200.driver import model_from_case  # noqa: E402
-from climaseaice_b200.synthetic import periodic_case, slab_of  # noqa: E402
+from climaseaice_b200.synthetic import arctic_cap_case, periodic_case, slab_of  # noqa: E402
 
 
 def main():
@@ -34,6 +34,8 @@ def main():
         case.u_bc_value = 0.0
         for k in ("v", "top_y", "ve"):
             case.fields[k] = np.ascontiguousarray(np.vstack([case.fields[k], case.fields[k][-1:]]))
+    if topo == "arctic":      # BASELINE config 5 in miniature: lat-lon cap, coupled thermodynamics, zonally periodic, walls in y
+        case = arctic_cap_case(96, 24 * world, H=7, substeps=10)
     Hy = max(2 * K + 3, 7)
     sl = slab_of(case, rank, world, Hy)
     m = model_from_case(sl, solver_impl=solver, partition=(rank, world, K), device=f"cuda:{local}")

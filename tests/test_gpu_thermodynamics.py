@@ -169,3 +169,24 @@ def test_thermodynamics_argument_errors():
     with pytest.raises(NotImplementedError, match="closures"):
         csi.SeaIceModel(m.grid, ice_thermodynamics=csi.SlabThermodynamics(m.grid), top_heat_flux=lambda *a: 0.0)
     m.close()
+
+
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_arctic_cap_config5_reduced(timestepper):
+    """BASELINE config 5 in miniature: coupled slab thermodynamics + EVP dynamics + WENO advection on a zonally periodic
+    lat-lon cap (general kernels: j-dependent metrics), against the staged oracle."""
+    from climaseaice_b200.synthetic import arctic_cap_case
+    from tests.helpers import coupled_oracle_step, thermo_oracle_from_case
+    case = arctic_cap_case(96, 32, H=5, substeps=12, timestepper=timestepper)
+    m = model_from_case(case)
+    o = oracle_from_case(case)
+    t = thermo_oracle_from_case(case, o)
+    for _ in range(2):
+        m.time_step(case.dt)
+        coupled_oracle_step(o, t, case.dt)
+    for n, (err, same) in compare_model(m, o, case).items():
+        assert same, (n, err)
+    assert_same(m, t, case, ("Tu", "mf_ice"))
+    mf = interior_of(m.mass_fluxes["ice"].numpy(), case)
+    assert (mf > 0).any() and (mf < 0).any()           # freezing near the pole, melting at the edge
+    m.close()
