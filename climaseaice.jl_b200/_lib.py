@@ -17,7 +17,7 @@ ABI_VERSION = 1
 PERIODIC, BOUNDED = 0, 1
 STRESS_NONE, STRESS_CONST, STRESS_FIELD, STRESS_SEMI_IMPLICIT = 0, 1, 2, 3
 REPLACEMENT_PRESSURE, ICE_STRENGTH = 0, 1
-CORIOLIS_NONE, CORIOLIS_FPLANE = 0, 1
+CORIOLIS_NONE, CORIOLIS_FPLANE, CORIOLIS_SPHERICAL = 0, 1, 2
 BC_DEFAULT, BC_VALUE = 0, 1
 RK3, FE = 0, 1
 SOLVER_AUTO, SOLVER_UNFUSED, SOLVER_FUSED = 0, 1, 2
@@ -63,6 +63,7 @@ class csi_config(C.Structure):
         ("immersed_drag_u", C.c_double), ("immersed_drag_v", C.c_double),
         ("metric_kind", C.c_int32), ("reserved2_", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
         ("free_drift_kind", C.c_int32), ("reserved3_", C.c_int32), ("top_rho_e", C.c_double), ("top_Cd", C.c_double),
+        ("coriolis_f_ff", C.POINTER(C.c_double)),
     ]
 
 

@@ -81,6 +81,7 @@ struct csi_handle {
     double *out_dev = nullptr;
     uint8_t *mask_dev = nullptr;
     double *met_dev = nullptr;
+    double *fff_dev = nullptr;
     std::vector<uint8_t> mask_host;
     FusedPlan *fused = nullptr;
     bool fused_failed = false;
@@ -487,6 +488,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         }
     }
     if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
+    if (cfg->coriolis_kind < CSI_CORIOLIS_NONE || cfg->coriolis_kind > CSI_CORIOLIS_SPHERICAL) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad coriolis_kind");
+    if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL && !cfg->coriolis_f_ff) return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_CORIOLIS_SPHERICAL needs coriolis_f_ff");
     for (int kind : {cfg->top_stress_kind, cfg->bottom_stress_kind})
         if (kind < CSI_STRESS_NONE || kind > CSI_STRESS_SEMI_IMPLICIT) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad stress kind");
     if (cfg->free_drift_kind < CSI_FD_NONE || cfg->free_drift_kind > CSI_FD_STRESS_BALANCE) return fail(nullptr, CSI_ERR_ARG, "csi_create: bad free_drift_kind");
@@ -555,6 +558,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     p.pad2_ = 0;
     p.top_rho = cfg->top_rho_e;
     p.top_Cd = cfg->top_Cd;
+    p.fff = nullptr;
     cudaError_t e;
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
         delete h;
@@ -581,6 +585,13 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         g.metL = L;
         for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;  // the caller's arrays are not retained
     }
+    if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) {
+        const int L = cfg->Ny + 2 * cfg->Hy + 1;
+        if ((e = cudaMalloc(&h->fff_dev, sizeof(double) * L)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(coriolis)"); }
+        cudaMemcpy(h->fff_dev, cfg->coriolis_f_ff, sizeof(double) * L, cudaMemcpyDefault);
+        p.fff = h->fff_dev;
+        h->cfg.coriolis_f_ff = nullptr;
+    }
     h->mirror.assign(NFIELDS, nullptr);
     h->mirror_n.assign(NFIELDS, 0);
     *out = h;
@@ -599,6 +610,7 @@ int csi_destroy(csi_handle *h)
     if (h->out_dev) cudaFree(h->out_dev);
     if (h->mask_dev) cudaFree(h->mask_dev);
     if (h->met_dev) cudaFree(h->met_dev);
+    if (h->fff_dev) cudaFree(h->fff_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -258,18 +258,43 @@ __device__ __forceinline__ double free_drift_v(const DParams &p, const DFields &
     return Ud - (t == 0 ? t : ty / sqrt(Cdrag * t));
 }
 
+// ---- Coriolis [OCN-recall]: FPlane, or HydrostaticSphericalCoriolis with the EnstrophyConserving scheme ------
+//   x_f_cross_U = -Iy^c(f^ff) * Ix^f(Iy^c(dx^cf v)) / dx^fc ;  y_f_cross_U = +Ix^c(f^ff) * Iy^f(Ix^c(dy^fc u)) / dy^cf
+__device__ __forceinline__ double x_f_cross_U(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
+{
+    if (p.cor == CSI_CORIOLIS_NONE) return 0.0;
+    if (p.cor == CSI_CORIOLIS_SPHERICAL) {
+        auto dxv = [&](int a, int b) { return (dxcf(g, b) * at(f.v, a, b) + dxcf(g, b + 1) * at(f.v, a, b + 1)) / 2; };
+        const double fbar = (__ldg(p.fff + (j - 1 + g.Hy)) + __ldg(p.fff + (j + g.Hy))) / 2;
+        return -fbar * ((dxv(i - 1, j) + dxv(i, j)) / 2) / dxfc(g, j);
+    }
+    auto vv = [&](int a, int b) { return at(f.v, a, b); };
+    return -p.f * avg_fc(vv, i, j);
+}
+__device__ __forceinline__ double y_f_cross_U(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
+{
+    if (p.cor == CSI_CORIOLIS_NONE) return 0.0;
+    if (p.cor == CSI_CORIOLIS_SPHERICAL) {
+        auto dyu = [&](int a, int b) { return (dyfc(g, b) * at(f.u, a, b) + dyfc(g, b) * at(f.u, a + 1, b)) / 2; };
+        const double fj = __ldg(p.fff + (j - 1 + g.Hy));
+        const double fbar = (fj + fj) / 2;
+        return fbar * ((dyu(i, j - 1) + dyu(i, j)) / 2) / dycf(g, j);
+    }
+    auto uu = [&](int a, int b) { return at(f.u, a, b); };
+    return p.f * avg_cf(uu, i, j);
+}
+
 // ---- _u_velocity_step! at one face: se:197-229 with mt:11-41, evp:384,391-395 -------------------
 __device__ __forceinline__ void u_step_node(const DGrid &g, const DParams &p, const DFields &f, double dt, int i, int j)
 {
     auto mm = [&](int a, int b) { return ice_mass(p, f, a, b); };
-    auto vv = [&](int a, int b) { return at(f.v, a, b); };
     const double mi = (mm(i, j) + mm(i - 1, j)) / 2;
     const double ai = (at(f.a, i, j) + at(f.a, i - 1, j)) / 2;
     const double abar = (at(f.alpha, i, j) + at(f.alpha, i - 1, j)) / 2;
     const double dtau = dt / abar;
     const double cbot = implicit_tx(p, f, BOT, i, j), ctop = implicit_tx(p, f, TOP, i, j);  // implicit_tx_coefficient
     const double tbot = explicit_tx(p, f, BOT, i, j, cbot), ttop = explicit_tx(p, f, TOP, i, j, ctop);
-    const double xcross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : -p.f * avg_fc(vv, i, j);
+    const double xcross = x_f_cross_U(g, p, f, i, j);
     const double rheo = (at(f.un, i, j) - at(f.u, i, j)) / dtau / abar;
     double Gu = -xcross - ttop / mi * ai + tbot / mi * ai + div_sigma_1j(g, f, i, j) / mi + immersed_div_sigma_1j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gu = mi <= 0 ? 0.0 : Gu;
@@ -287,14 +312,13 @@ __device__ __forceinline__ void u_step_node(const DGrid &g, const DParams &p, co
 __device__ __forceinline__ void v_step_node(const DGrid &g, const DParams &p, const DFields &f, double dt, int i, int j)
 {
     auto mm = [&](int a, int b) { return ice_mass(p, f, a, b); };
-    auto uu = [&](int a, int b) { return at(f.u, a, b); };
     const double mi = (mm(i, j) + mm(i, j - 1)) / 2;
     const double ai = (at(f.a, i, j) + at(f.a, i, j - 1)) / 2;
     const double abar = (at(f.alpha, i, j) + at(f.alpha, i, j - 1)) / 2;
     const double dtau = dt / abar;
     const double cbot = implicit_ty(p, f, BOT, i, j), ctop = implicit_ty(p, f, TOP, i, j);
     const double tbot = explicit_ty(p, f, BOT, i, j, cbot), ttop = explicit_ty(p, f, TOP, i, j, ctop);
-    const double ycross = p.cor == CSI_CORIOLIS_NONE ? 0.0 : p.f * avg_cf(uu, i, j);
+    const double ycross = y_f_cross_U(g, p, f, i, j);
     const double rheo = (at(f.vn, i, j) - at(f.v, i, j)) / dtau / abar;
     double Gv = -ycross - ttop / mi * ai + tbot / mi * ai + div_sigma_2j(g, f, i, j) / mi + immersed_div_sigma_2j(g, p, f, i, j) / mi + (0.0 + rheo);
     Gv = mi <= 0 ? 0.0 : Gv;

@@ -807,6 +807,7 @@ static EncodeTiledFn get_encode()
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
     if (g.met) { snprintf(why, nwhy, "j-dependent grid metrics (general kernels only)"); return 0; }
+    if (p.cor == CSI_CORIOLIS_SPHERICAL) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis (general kernels only)"); return 0; }
     if (p.fd_kind != CSI_FD_NONE) { snprintf(why, nwhy, "free-drift velocities (general kernels only)"); return 0; }
     if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT) { snprintf(why, nwhy, "SemiImplicitStress on top (general kernels only)"); return 0; }
     if (p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD) { snprintf(why, nwhy, "prescribed bottom stress (general kernels only)"); return 0; }

@@ -64,6 +64,7 @@ struct DParams {
     double imm_u, imm_v;  // immersed linear-drag flux BC coefficients (0 = none)
     int fd_kind, pad2_;   // free drift: CSI_FD_NONE / FIELDS / STRESS_BALANCE
     double top_rho, top_Cd;  // top SemiImplicitStress (u_e, v_e = top_x/top_y arrays or ttx/tty constants)
+    const double *fff;       // HydrostaticSphericalCoriolis: f at (Face, Face) per row (device), row j at [j-1+Hy]
 };
 
 struct DFields {

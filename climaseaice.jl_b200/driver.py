@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .model import (Bounded, FPlane, Field, LatitudeLongitudeGrid, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
+from .model import (Bounded, FPlane, Field, HydrostaticSphericalCoriolis, LatitudeLongitudeGrid, Periodic, RectilinearGrid, SeaIceModel, SeaIceMomentumEquation, SemiImplicitStress,
                     SlabThermodynamics, SplitExplicitSolver, StressBalanceFreeDrift, UpwindBiased, ValueBoundaryCondition, WENO)
 from .synthetic import LOC, Case
 
@@ -46,8 +46,12 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
         free_drift = dict(u=fld("fd_u"), v=fld("fd_v"))
     elif case.free_drift == "stress_balance":
         free_drift = StressBalanceFreeDrift()
+    if case.f_ff() is not None:
+        coriolis = HydrostaticSphericalCoriolis(case.rotation_rate, f_ff_override=case.f_ff())
+    else:
+        coriolis = FPlane(case.coriolis_f) if case.coriolis_f is not None else None
     dyn = SeaIceMomentumEquation(grid,
-                                 coriolis=FPlane(case.coriolis_f) if case.coriolis_f is not None else None,
+                                 coriolis=coriolis,
                                  top_momentum_stress=top, bottom_momentum_stress=bottom, free_drift=free_drift,
                                  solver=SplitExplicitSolver(substeps=case.substeps))
     bcs = {}

@@ -21,3 +21,10 @@ def latitude_longitude_metrics(Nx, Ny, Hy, longitude, latitude, radius=6371e3):
     dy = np.full_like(dxc, R * np.deg2rad(dp))
     azc, azf = R * R * dl * (np.sin(phif_n) - np.sin(phif)), R * R * dl * (np.sin(phic) - np.sin(phic_s))
     return dict(dxcc=dxc, dxfc=dxc, dxcf=dxf, dxff=dxf, dycc=dy, dyfc=dy, dycf=dy, dyff=dy, azcc=azc, azfc=azc, azcf=azf, azff=azf)
+
+
+def spherical_coriolis_f_ff(Ny, Hy, latitude, rotation_rate=7.292115e-5):
+    """f at (Face, Face) = 2 Omega sin(phi_f) per row (HydrostaticSphericalCoriolis), row j at [j - 1 + Hy]."""
+    dp = (latitude[1] - latitude[0]) / Ny
+    j = np.arange(1 - Hy, Ny + Hy + 2)
+    return np.ascontiguousarray(2 * rotation_rate * np.sin(np.deg2rad(latitude[0] + (j - 1) * dp)))

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .metrics import METRIC_NAMES, latitude_longitude_metrics
+from .metrics import METRIC_NAMES, latitude_longitude_metrics, spherical_coriolis_f_ff
 
 Periodic, Bounded, Flat = "Periodic", "Bounded", "Flat"
 Center, Face = 0, 1
@@ -176,6 +176,19 @@ class StressBalanceFreeDrift:
 @dataclass
 class FPlane:
     f: float = 1e-4
+
+
+@dataclass
+class HydrostaticSphericalCoriolis:
+    """HydrostaticSphericalCoriolis(; rotation_rate = Omega_Earth), EnstrophyConserving scheme, on a LatitudeLongitudeGrid:
+    f at (Face, Face) = 2 Omega sin(phi_f)."""
+    rotation_rate: float = 7.292115e-5
+    f_ff_override: object = None   # explicit per-row values (a slab's rows of the global grid's f)
+
+    def f_ff(self, grid):
+        if self.f_ff_override is not None:
+            return np.ascontiguousarray(self.f_ff_override, dtype=np.float64)
+        return spherical_coriolis_f_ff(grid.Ny, grid.Hy, grid.y, self.rotation_rate)
 
 
 @dataclass
@@ -468,8 +481,17 @@ class SeaIceModel:
         cfg.substeps = d.solver.substeps
         cfg.minimum_mass, cfg.minimum_concentration = d.minimum_mass, d.minimum_concentration
         cfg.ice_density = self.sea_ice_density
-        cfg.coriolis_kind = L.CORIOLIS_FPLANE if d.coriolis is not None else L.CORIOLIS_NONE
-        cfg.coriolis_f = d.coriolis.f if d.coriolis is not None else 0.0
+        if isinstance(d.coriolis, HydrostaticSphericalCoriolis):
+            if not isinstance(g, LatitudeLongitudeGrid):
+                raise ValueError("HydrostaticSphericalCoriolis needs a LatitudeLongitudeGrid")
+            cfg.coriolis_kind = L.CORIOLIS_SPHERICAL
+            self._f_ff = d.coriolis.f_ff(g)
+            if self._f_ff.shape != (g.Ny + 2 * g.Hy + 1,):
+                raise ValueError("coriolis f_ff: expected Ny + 2 Hy + 1 entries")
+            cfg.coriolis_f_ff = self._f_ff.ctypes.data_as(C.POINTER(C.c_double))
+        else:
+            cfg.coriolis_kind = L.CORIOLIS_FPLANE if d.coriolis is not None else L.CORIOLIS_NONE
+            cfg.coriolis_f = d.coriolis.f if d.coriolis is not None else 0.0
         # either stress: nothing | (u=Number, v=Number) | (u=Field, v=Field) | SemiImplicitStress   (ext.jl:8-40,84-146)
         def kind_of(st):
             if st is None:

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .metrics import latitude_longitude_metrics
+from .metrics import latitude_longitude_metrics, spherical_coriolis_f_ff
 
 SEED = 20260417
 
@@ -51,6 +51,7 @@ class Case:
     bottom_kind: str = "semi_implicit"   # "semi_implicit" (ue/ve or ocean_const = ocean velocity), "stress" (they hold tau), "none"
     free_drift: str | None = None        # None, "fields" (fields fd_u, fd_v) or "stress_balance"
     latlon: tuple | None = None          # ((lon0, lon1), (lat0, lat1)) in degrees: LatitudeLongitudeGrid; Lx, Ly = extents in degrees
+    rotation_rate: float | None = None   # lat-lon only: HydrostaticSphericalCoriolis(rotation_rate) instead of FPlane(coriolis_f)
     metric_arrays: dict | None = None    # explicit j-indexed metric arrays (a slab's rows of the global grid's metrics)
     thermo: dict | None = None           # slab thermodynamics on top of the dynamics: scalars bottom_heat_flux, ice_salinity;
                                          # arrays Tu (initial top temperature) and Qtop (external top heat flux) live in `fields`
@@ -58,10 +59,18 @@ class Case:
     def metrics(self):
         """j-indexed metric arrays of a lat-lon case (None on a RectilinearGrid)."""
         if self.metric_arrays is not None:
-            return self.metric_arrays
+            return {k: v for k, v in self.metric_arrays.items() if k != "f_ff"}
         if self.latlon is None:
             return None
         return latitude_longitude_metrics(self.Nx, self.Ny, self.Hy, self.latlon[0], self.latlon[1])
+
+    def f_ff(self):
+        """Per-row Coriolis parameter at (Face, Face) of a spherical-Coriolis case (None otherwise)."""
+        if self.rotation_rate is None or self.latlon is None:
+            return None
+        if self.metric_arrays is not None and "f_ff" in self.metric_arrays:
+            return self.metric_arrays["f_ff"]
+        return spherical_coriolis_f_ff(self.Ny, self.Hy, self.latlon[1], self.rotation_rate)
 
     @property
     def dx(self):
@@ -199,11 +208,12 @@ def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7,
 
 def arctic_cap_case(Nx=192, Ny=48, H=7, seed=SEED, substeps=20, dt=600.0, timestepper="SplitRungeKutta3") -> Case:
     """BASELINE config 5 in miniature: a zonally periodic lat-lon cap (lambda in (0, 360), phi in (60, 88); the metrics
-    shrink 14x towards the pole), EVP dynamics + WENO advection coupled to bare-ice slab thermodynamics with a
+    shrink 14x towards the pole), HydrostaticSphericalCoriolis, EVP dynamics + WENO advection coupled to bare-ice slab thermodynamics with a
     latitude-dependent surface heat flux (freezing near the pole, melting at the ice edge)."""
     c = latlon_case(Nx, H=H, seed=seed, substeps=substeps, dt=dt, timestepper=timestepper, topology=("Periodic", "Bounded"),
                     lon=(0.0, 360.0), lat=(60.0, 88.0), Ny=Ny)
     c.name = "arctic-cap"
+    c.rotation_rate = 7.292115e-5       # HydrostaticSphericalCoriolis
     rng = np.random.default_rng(seed + 5)
     X, Y = c.nodes(LOC["h"])
     fy = Y / c.Ly
@@ -295,6 +305,8 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
         # the slab's rows of the GLOBAL grid's metrics (same expressions per global row index => same bits as on one rank);
         # local row jl = 1-Hy .. ny+Hy+1 is global row rank*ny + jl
         G = latitude_longitude_metrics(case.Nx, case.Ny, Hy, case.latlon[0], case.latlon[1])
+        if case.rotation_rate is not None:
+            G["f_ff"] = spherical_coriolis_f_ff(case.Ny, Hy, case.latlon[1], case.rotation_rate)
         c.metric_arrays = {k: np.ascontiguousarray(v[rank * ny:rank * ny + ny + 2 * Hy + 1]) for k, v in G.items()}
     j = np.arange(rank * ny - Hy, (rank + 1) * ny + Hy)          # 0-based global interior row of every slab row
     for k, arr in case.fields.items():

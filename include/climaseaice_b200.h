@@ -42,7 +42,9 @@ typedef struct {
 enum { CSI_PERIODIC = 0, CSI_BOUNDED = 1 };
 enum { CSI_STRESS_NONE = 0, CSI_STRESS_CONST = 1, CSI_STRESS_FIELD = 2, CSI_STRESS_SEMI_IMPLICIT = 3 };
 enum { CSI_REPLACEMENT_PRESSURE = 0, CSI_ICE_STRENGTH = 1 };
-enum { CSI_CORIOLIS_NONE = 0, CSI_CORIOLIS_FPLANE = 1 };
+/* SPHERICAL: Oceananigans' HydrostaticSphericalCoriolis (EnstrophyConserving scheme) on a LatitudeLongitudeGrid;
+ * f at (Face, Face) is passed per row in csi_config.coriolis_f_ff */
+enum { CSI_CORIOLIS_NONE = 0, CSI_CORIOLIS_FPLANE = 1, CSI_CORIOLIS_SPHERICAL = 2 };
 enum { CSI_BC_DEFAULT = 0, CSI_BC_VALUE = 1 };
 /* free_drift of SeaIceMomentumEquation (src/SeaIceDynamics/stress_balance_free_drift.jl:61-129): nothing, a (u=, v=)
  * pair of arrays, or StressBalanceFreeDrift (closed form from the model's own stresses, exactly one of which must be
@@ -122,6 +124,9 @@ typedef struct {
      * its u_e, v_e are csi_fields.top_x/top_y, or the constants top_tau_x/top_tau_y when those are NULL.  Likewise the
      * BOTTOM stress may be CSI_STRESS_CONST (ue_const, ve_const hold tau) or CSI_STRESS_FIELD (ue, ve hold tau). */
     double top_rho_e, top_Cd;
+    /* CSI_CORIOLIS_SPHERICAL: f^ffa = 2 Omega sin(phi^f) per row, Ny + 2*Hy + 1 doubles, row j at [j - 1 + Hy] (host
+     * array, copied at csi_create); evaluated by the host with Oceananigans' own f^ffa */
+    const double *coriolis_f_ff;
 } csi_config;
 
 /* The arrays the hot path touches.  Unused ones may have ptr == NULL. */

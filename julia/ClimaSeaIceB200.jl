@@ -60,6 +60,7 @@ Base.@kwdef struct CsiConfig
     metrics :: NTuple{12, Ptr{Float64}} = ntuple(_ -> Ptr{Float64}(C_NULL), 12)
     free_drift_kind :: Int32 = 0; reserved3_ :: Int32 = 0     # 0 nothing, 1 (u=, v=) arrays, 2 StressBalanceFreeDrift
     top_rho_e :: Float64 = 1.3; top_Cd :: Float64 = 1.2e-3    # SemiImplicitStress as the top stress
+    coriolis_f_ff :: Ptr{Float64} = C_NULL                     # HydrostaticSphericalCoriolis: fᶠᶠᵃ per row (coriolis_kind = 2)
 end
 
 # LatitudeLongitudeGrid: the twelve j-indexed metric vectors csi_config.metrics takes (metric_kind = 1), each

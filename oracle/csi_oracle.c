@@ -378,15 +378,31 @@ static inline double free_drift_v(P p, const csio_state *s, int i, int j)
     return Ud - (t == 0 ? t : ty / sqrt(Cdrag * t));
 }
 
-/* Coriolis [OCN-recall]: x_f_cross_U(FPlane) = -f * Ixy^fc(v); y_f_cross_U = +f * Ixy^cf(u) */
-static inline double x_f_cross_U(P p, const csio_state *s, int i, int j)
+/* Coriolis [OCN-recall].
+ *   FPlane:  x_f_cross_U = -f * Ixy^fc(v);  y_f_cross_U = +f * Ixy^cf(u)
+ *   HydrostaticSphericalCoriolis, EnstrophyConserving scheme (f^ffa = 2 Omega sin(phi^f), supplied per row):
+ *     x_f_cross_U = -Iy^c(f^ff) * Ix^f(Iy^c(dx^cf * v)) / dx^fc
+ *     y_f_cross_U = +Ix^c(f^ff) * Iy^f(Ix^c(dy^fc * u)) / dy^cf
+ *   (the active-cell-weighted variant differs from it only next to immersed cells and is not restated) */
+#define FFF(J_) (p->f_ff[(J_)-1 + g->Hy])
+static inline double x_f_cross_U(G g, P p, const csio_state *s, int i, int j)
 {
     if (p->coriolis_kind == CSIO_CORIOLIS_NONE) return 0.0;
+    if (p->coriolis_kind == CSIO_CORIOLIS_SPHERICAL) {
+#define DXV(I_, J_) ((dxcf(g, (I_), (J_)) * VV((I_), (J_)) + dxcf(g, (I_), (J_) + 1) * VV((I_), (J_) + 1)) / 2)
+        double fbar = (FFF(j) + FFF(j + 1)) / 2;
+        return -fbar * ((DXV(i - 1, j) + DXV(i, j)) / 2) / dxfc(g, i, j);
+    }
     return -p->f * IXY_FC(VV, i, j);
 }
-static inline double y_f_cross_U(P p, const csio_state *s, int i, int j)
+static inline double y_f_cross_U(G g, P p, const csio_state *s, int i, int j)
 {
     if (p->coriolis_kind == CSIO_CORIOLIS_NONE) return 0.0;
+    if (p->coriolis_kind == CSIO_CORIOLIS_SPHERICAL) {
+#define DYU(I_, J_) ((dyfc(g, (I_), (J_)) * UU((I_), (J_)) + dyfc(g, (I_) + 1, (J_)) * UU((I_) + 1, (J_))) / 2)
+        double fbar = (FFF(j) + FFF(j)) / 2;
+        return fbar * ((DYU(i, j - 1) + DYU(i, j)) / 2) / dycf(g, i, j);
+    }
     return p->f * IXY_CF(UU, i, j);
 }
 
@@ -430,7 +446,7 @@ static inline double u_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double mi = (MM(i, j) + MM(i - 1, j)) / 2;
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->un, i, j) - F(s->u, i, j)) / dtau / ((AL(i, j) + AL(i - 1, j)) / 2);
-    double Gu = -x_f_cross_U(p, s, i, j) - explicit_tx(p, s, TOP, i, j) / mi * ai + explicit_tx(p, s, BOT, i, j) / mi * ai +
+    double Gu = -x_f_cross_U(g, p, s, i, j) - explicit_tx(p, s, TOP, i, j) / mi * ai + explicit_tx(p, s, BOT, i, j) / mi * ai +
                 div_sigma_1j(g, s, i, j) / mi + immersed_div_sigma_1j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gu;
 }
@@ -440,7 +456,7 @@ static inline double v_velocity_tendency(G g, P p, const csio_state *s, int i, i
     double mi = (MM(i, j) + MM(i, j - 1)) / 2;
     double user_forcing = 0.0;
     double rheology_forcing = (F(s->vn, i, j) - F(s->v, i, j)) / dtau / ((AL(i, j) + AL(i, j - 1)) / 2);
-    double Gv = -y_f_cross_U(p, s, i, j) - explicit_ty(p, s, TOP, i, j) / mi * ai + explicit_ty(p, s, BOT, i, j) / mi * ai +
+    double Gv = -y_f_cross_U(g, p, s, i, j) - explicit_ty(p, s, TOP, i, j) / mi * ai + explicit_ty(p, s, BOT, i, j) / mi * ai +
                 div_sigma_2j(g, s, i, j) / mi + immersed_div_sigma_2j(g, p, s, i, j) / mi + (user_forcing + rheology_forcing);
     return mi <= 0 ? 0.0 : Gv;
 }

@@ -56,7 +56,7 @@ typedef struct {
 /* external stress kinds: sea_ice_external_stress.jl:8-27,176-202 */
 enum { CSIO_STRESS_NONE = 0, CSIO_STRESS_CONST = 1, CSIO_STRESS_FIELD = 2, CSIO_STRESS_SEMI_IMPLICIT = 3 };
 enum { CSIO_REPLACEMENT_PRESSURE = 0, CSIO_ICE_STRENGTH = 1 };
-enum { CSIO_CORIOLIS_NONE = 0, CSIO_CORIOLIS_FPLANE = 1 };
+enum { CSIO_CORIOLIS_NONE = 0, CSIO_CORIOLIS_FPLANE = 1, CSIO_CORIOLIS_SPHERICAL = 2 };
 enum { CSIO_BC_DEFAULT = 0, CSIO_BC_VALUE = 1 };
 enum { CSIO_RK3 = 0, CSIO_FE = 1 };
 enum { CSIO_FD_NONE = 0, CSIO_FD_FIELDS = 1, CSIO_FD_STRESS_BALANCE = 2 };
@@ -94,6 +94,9 @@ typedef struct {
     /* top SemiImplicitStress (top_kind == SEMI_IMPLICIT): u_e, v_e = top_x/top_y arrays or top_tx/top_ty constants.
      * Likewise bot_kind may be CONST / FIELD, the stress then being ue/ve (arrays) or ue_c/ve_c (constants). */
     double top_rho, top_Cd;
+    /* HydrostaticSphericalCoriolis (coriolis_kind == SPHERICAL): f at (Face, Face) = 2 Omega sin(phi_f), j-indexed like the
+     * grid metrics (entry for row j at [j-1+Hy], length Ny+2Hy+1) */
+    const double *f_ff;
 } csio_params;
 
 typedef struct {

@@ -63,7 +63,7 @@ class Params(C.Structure):
         ("advection_order", C.c_int32), ("timestepper", C.c_int32),
         ("imm_drag_u", C.c_double), ("imm_drag_v", C.c_double),
         ("free_drift_kind", C.c_int32), ("pad3_", C.c_int32), ("fd_u", Field), ("fd_v", Field),
-        ("top_rho", C.c_double), ("top_Cd", C.c_double),
+        ("top_rho", C.c_double), ("top_Cd", C.c_double), ("f_ff", C.POINTER(C.c_double)),
     ]
 
 
@@ -172,7 +172,13 @@ class OracleModel:
             self.g.mask = m.ctypes.data_as(C.POINTER(C.c_uint8))
         self.p = Params()
         for k, v in prm.items():
-            setattr(self.p, k, v)
+            if k == "f_ff":   # HydrostaticSphericalCoriolis: j-indexed f at (Face, Face)
+                v = np.ascontiguousarray(v, dtype=np.float64)
+                assert v.shape == (Ny + 2 * Hy + 1,)
+                self._keep.append(v)
+                self.p.f_ff = v.ctypes.data_as(C.POINTER(C.c_double))
+            else:
+                setattr(self.p, k, v)
         for n in ("top_x", "top_y", "ue", "ve", "fd_u", "fd_v"):
             setattr(self.p, n, _as_field(self.arr[n], Hx, Hy))
         self.s = State()

@@ -14,6 +14,8 @@ def oracle_params(case) -> dict:
              timestepper=O.RK3 if case.timestepper == "SplitRungeKutta3" else O.FE,
              coriolis_kind=0 if case.coriolis_f is None else 1, f=case.coriolis_f or 0.0,
              rho_e=case.rho_e, Cd=case.Cd, top_rho=case.top_rho_Cd[0], top_Cd=case.top_rho_Cd[1])
+    if case.f_ff() is not None:
+        p.update(coriolis_kind=2, f_ff=case.f_ff())
     has_top = "top_x" in F or bool(case.top_const)
     if case.top_kind == "semi_implicit":
         p.update(top_kind=O.STRESS_SEMI_IMPLICIT)

@@ -399,3 +399,20 @@ def test_stress_balance_free_drift_argument_errors():
     with pytest.raises(RuntimeError, match="free-drift"):
         mf.time_step(mc.dt)
     mf.close()
+
+
+def test_hydrostatic_spherical_coriolis_on_latlon_grid():
+    """HydrostaticSphericalCoriolis (EnstrophyConserving, f^ff = 2 Omega sin(phi_f) per row) on the lat-lon basin."""
+    from climaseaice_b200.synthetic import latlon_case
+    case = latlon_case(48, substeps=20, topology=("Periodic", "Bounded"))
+    m0 = model_from_case(case)                      # FPlane(1e-4), for contrast
+    case.rotation_rate = 7.292115e-5
+    m = model_from_case(case)
+    o = oracle_from_case(case)
+    assert o.prm["coriolis_kind"] == 2
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt); m0.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    u, u0 = interior_of(m.all_fields()["u"].numpy(), case), interior_of(m0.all_fields()["u"].numpy(), case)
+    assert np.abs(u - u0).max() > 1e-6               # f varies with latitude: differs from the f-plane run
+    m.close(); m0.close()
