@@ -83,6 +83,7 @@ struct csi_handle {
     double *met_dev = nullptr;
     double *fff_dev = nullptr;
     std::vector<uint8_t> mask_host;
+    std::vector<double> met_host, fff_host;
     FusedPlan *fused = nullptr;
     bool fused_failed = false;
     // device mirrors for the *_host entry points, in csi_fields member order
@@ -530,6 +531,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.met = nullptr;
     g.metL = 0;
     g.pad_ = 0;
+    g.met_host = nullptr;
+    g.fff_host = nullptr;
     DParams &p = h->p;
     p.Pstar = cfg->ice_compressive_strength;
     p.C = cfg->ice_compaction_hardening;
@@ -583,6 +586,9 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         for (int k = 0; k < 12; k++) cudaMemcpy(h->met_dev + (size_t)k * L, cfg->metrics[k], sizeof(double) * L, cudaMemcpyDefault);
         g.met = h->met_dev;
         g.metL = L;
+        h->met_host.resize((size_t)12 * L);
+        for (int k = 0; k < 12; k++) std::copy(cfg->metrics[k], cfg->metrics[k] + L, h->met_host.begin() + (size_t)k * L);
+        g.met_host = h->met_host.data();
         for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;  // the caller's arrays are not retained
     }
     if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) {
@@ -590,6 +596,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         if ((e = cudaMalloc(&h->fff_dev, sizeof(double) * L)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(coriolis)"); }
         cudaMemcpy(h->fff_dev, cfg->coriolis_f_ff, sizeof(double) * L, cudaMemcpyDefault);
         p.fff = h->fff_dev;
+        h->fff_host.assign(cfg->coriolis_f_ff, cfg->coriolis_f_ff + L);
+        g.fff_host = h->fff_host.data();
         h->cfg.coriolis_f_ff = nullptr;
     }
     h->mirror.assign(NFIELDS, nullptr);

@@ -89,6 +89,41 @@ struct Params {
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     double *base;         // internal allocation
     const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
+    const double *met;    // j-dependent metrics (lat-lon grids): MC_N columns of `rows` doubles, or NULL on a regular grid
+};
+
+// columns of the per-row metric table (internal row = j - 1 + oy): the twelve metrics, the squares the SBP operators use,
+// the correctly rounded reciprocals of every metric that appears as a divisor, and f at (Face, Face)
+enum { MC_DXCC = 0, MC_DXFC, MC_DXCF, MC_DXFF, MC_DYCC, MC_DYFC, MC_DYCF, MC_DYFF, MC_AZCC, MC_AZFC, MC_AZCF, MC_AZFF,
+       MC_DXCC2, MC_DYCC2, MC_DXFF2, MC_DYFF2, MC_RDXFC, MC_RDXCF, MC_RDYFC, MC_RDYCF, MC_RAZCC, MC_RAZFC, MC_RAZCF, MC_RAZFF,
+       MC_FFF, MC_N };
+
+// Metric<false>: the regular grid's constants (kernel parameters); Metric<true>: the row's own values, warp-uniform
+// read-only loads that stay in L1.  r is the reference row index j.
+template <bool MET>
+struct Metric {
+    const Params &p;
+    __device__ __forceinline__ double ld(int col, int r) const
+    {
+        const int row = min(max(r - 1 + p.oy, 0), p.rows - 1);
+        return __ldg(p.met + (size_t)col * p.rows + row);
+    }
+#define CSI_MET(name, col, regular) \
+    __device__ __forceinline__ double name(int r) const { return MET ? ld(col, r) : (regular); }
+    CSI_MET(dxcc, MC_DXCC, p.dx) CSI_MET(dxfc, MC_DXFC, p.dx) CSI_MET(dxcf, MC_DXCF, p.dx) CSI_MET(dxff, MC_DXFF, p.dx)
+    CSI_MET(dycc, MC_DYCC, p.dy) CSI_MET(dyfc, MC_DYFC, p.dy) CSI_MET(dycf, MC_DYCF, p.dy) CSI_MET(dyff, MC_DYFF, p.dy)
+    CSI_MET(azcc, MC_AZCC, p.az) CSI_MET(azfc, MC_AZFC, p.az) CSI_MET(azcf, MC_AZCF, p.az) CSI_MET(azff, MC_AZFF, p.az)
+    CSI_MET(dxcc2, MC_DXCC2, p.dx2) CSI_MET(dycc2, MC_DYCC2, p.dy2) CSI_MET(dxff2, MC_DXFF2, p.dx2) CSI_MET(dyff2, MC_DYFF2, p.dy2)
+    CSI_MET(rdxfc, MC_RDXFC, p.rdx) CSI_MET(rdxcf, MC_RDXCF, p.rdx) CSI_MET(rdyfc, MC_RDYFC, p.rdy) CSI_MET(rdycf, MC_RDYCF, p.rdy)
+    CSI_MET(razcc, MC_RAZCC, p.raz) CSI_MET(razfc, MC_RAZFC, p.raz) CSI_MET(razcf, MC_RAZCF, p.raz) CSI_MET(razff, MC_RAZFF, p.raz)
+    CSI_MET(fff, MC_FFF, p.f)
+#undef CSI_MET
+};
+
+// the metric factors of one velocity node's stress divergence (isd:39-51): d = a (sD1 - sD0) / 2,
+// tt = (t2hi sT1 - t2lo sT0) / td / 2, SS = (s2hi s12hi - s2lo s12lo) / sd, all over az
+struct NodeMetric {
+    double a, t2hi, t2lo, td, rtd, s2hi, s2lo, sd, rsd, az, raz;
 };
 
 
@@ -234,8 +269,8 @@ struct MathSlow {
 
 // u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
 template <bool GEN, class M>
-__device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
-                                         double uold, double vbar, double ue, double vebar, double ttop, double un, double sD1, double sD0,
+__device__ __forceinline__ double u_node(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
+                                         double uold, double vbar, double xcross, double ue, double vebar, double ttop, double un, double sD1, double sD0,
                                          double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
 {
     const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
@@ -247,12 +282,11 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
         coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
         tbot = coef * ue;
     }
-    const double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : -p.f * vbar;
     const double rheo = mm.divn(mm.div(un - uold, dtau), Ra);
-    const double d = p.dy * (sD1 - sD0) / 2;
-    const double tt = mm.divc(p.dy2 * sT1 - p.dy2 * sT0, p.dy, p.rdy) / 2;
-    const double SS = mm.divc(p.dx2 * s12hi - p.dx2 * s12lo, p.dx, p.rdx);
-    const double dsig = mm.divc(d + tt + SS, p.az, p.raz);
+    const double d = nm.a * (sD1 - sD0) / 2;
+    const double tt = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd) / 2;
+    const double SS = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig = mm.divc(d + tt + SS, nm.az, nm.raz);
     double G = -xcross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
     G = mi <= 0 ? 0.0 : G;
     double tau = mm.divn(coef - 0.0, Rm) * ai;
@@ -263,8 +297,8 @@ __device__ __forceinline__ double u_node(M &mm, const Params &p, bool active, do
 }
 // v at (i, r): se:231-264, mt:44-74, ext:183-202, isd:46-51, evp:385,397-401.  *0 = row r-1.
 template <bool GEN, class M>
-__device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
-                                         double vold, double ubar, double ve, double uebar, double ttop, double vn, double sD1, double sD0,
+__device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
+                                         double vold, double ubar, double ycross, double ve, double uebar, double ttop, double vn, double sD1, double sD0,
                                          double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
 {
     const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
@@ -276,12 +310,11 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, bool active, do
         coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
         tbot = coef * ve;
     }
-    const double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : p.f * ubar;
     const double rheo = mm.divn(mm.div(vn - vold, dtau), Ra);
-    const double d = p.dx * (sD1 - sD0) / 2;
-    const double tt = mm.divc(-(p.dx2 * sT1 - p.dx2 * sT0), p.dx, p.rdx) / 2;
-    const double SS = mm.divc(p.dy2 * s12hi - p.dy2 * s12lo, p.dy, p.rdy);
-    const double dsig = mm.divc(d + tt + SS, p.az, p.raz);
+    const double d = nm.a * (sD1 - sD0) / 2;
+    const double tt = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd) / 2;
+    const double SS = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig = mm.divc(d + tt + SS, nm.az, nm.raz);
     double G = -ycross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
     G = mi <= 0 ? 0.0 : G;
     double tau = mm.divn(coef - 0.0, Rm) * ai;
@@ -308,10 +341,12 @@ struct TileCtx {
 // windows; global stores happen only when the pass is clean (the SLOW pass always is).
 // GEN = false compiles the common configuration (SemiImplicitStress with velocity arrays, wind-stress
 // arrays, FPlane, ReplacementPressure) without its run-time switches.
-template <bool VFIRST, bool AUX, bool GEN, class M>
+// MET: j-dependent metrics (lat-lon grid) read from the per-row table instead of the regular grid's constants.
+template <bool VFIRST, bool AUX, bool GEN, bool MET, class M>
 __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc)
 {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const Metric<MET> mt{p};
     const size_t plane = (size_t)p.pitch * p.rows;
     const bool use_ue = GEN ? p.use_ue != 0 : true, use_top = GEN ? p.use_top != 0 : true;
     // ---- TMA: tile + halo of every stencil field; u, v first (phase A starts on them) ----
@@ -381,22 +416,25 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     mbar_wait(&bar[0], parity);
     for (int n = tid; n < SXD * SYD; n += NT) {
         const int sx = n % SXD - 1, sy = n / SXD - 1;
+        const int r = tc.J0 - 1 + sy;  // reference row of the node
         double *b = sm + n;  // = &S(0, sx, sy)
         const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0);
         if (sx < BX && sy < BY) {
             const double u10 = SB(b, A_U, 1, 0), v01 = SB(b, A_V, 0, 1);
-            const double D = mm.divc((p.dy * u10 - p.dy * u00) + (p.dx * v01 - p.dx * v00), p.az, p.raz);
-            const double T = mm.divc(p.dy2 * (mm.divc(u10, p.dy, p.rdy) - mm.divc(u00, p.dy, p.rdy)) -
-                                         p.dx2 * (mm.divc(v01, p.dx, p.rdx) - mm.divc(v00, p.dx, p.rdx)),
-                                     p.az, p.raz);
+            const double dyf = mt.dyfc(r), rdyf = mt.rdyfc(r), dxf0 = mt.dxcf(r), dxf1 = mt.dxcf(r + 1), az = mt.azcc(r), raz = mt.razcc(r);
+            const double D = mm.divc((dyf * u10 - dyf * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
+            const double T = mm.divc(mt.dycc2(r) * (mm.divc(u10, dyf, rdyf) - mm.divc(u00, dyf, rdyf)) -
+                                         mt.dxcc2(r) * (mm.divc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc(v00, dxf0, mt.rdxcf(r))),
+                                     az, raz);
             SB(b, A_E11, 0, 0) = (D + T) / 2;
             SB(b, A_E22, 0, 0) = (D - T) / 2;
         }
         if (sx >= 0 && sy >= 0) {
             const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
-            const double Sh = mm.divc(p.dx2 * (mm.divc(u00, p.dx, p.rdx) - mm.divc(u0m, p.dx, p.rdx)) +
-                                          p.dy2 * (mm.divc(v00, p.dy, p.rdy) - mm.divc(vm0, p.dy, p.rdy)),
-                                      p.az, p.raz);
+            const double dyc = mt.dycf(r), rdyc = mt.rdycf(r);
+            const double Sh = mm.divc(mt.dxff2(r) * (mm.divc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
+                                          mt.dyff2(r) * (mm.divc(v00, dyc, rdyc) - mm.divc(vm0, dyc, rdyc)),
+                                      mt.azff(r), mt.razff(r));
             SB(b, A_E12, 0, 0) = Sh / 2;
         }
     }
@@ -409,6 +447,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll UNROLL_B
     for (int q = 0; q < 2; q++) {
         const int sx = lane, sy = wrp + 8 * q;
+        const int rB = tc.J0 - 1 + sy;
         double *b = &S(0, sx, sy);
         const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
         const double e12c = ((e12f + SB(b, A_E12, 1, 0)) / 2 + (SB(b, A_E12, 0, 1) + SB(b, A_E12, 1, 1)) / 2) / 2;
@@ -429,10 +468,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double s12n = 2 * ef * e12f;
         const double mc = SB(b, A_H, 0, 0);
         const double mf = ((SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) / 2 + (SB(b, A_H, -1, 0) + mc) / 2) / 2;
-        double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), p.az, p.raz);
+        double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
         g2c = (g2c != g2c) ? p.amax2 : g2c;
         const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
-        double g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), p.az, p.raz);
+        double g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(rB), mt.razff(rB));
         g2f = (g2f != g2f) ? p.amax2 : g2f;
         const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
         const NodeRecip Rg = mm.recip(gc);
@@ -456,6 +495,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const bool wall_active = !(p.bounded_x && (i <= 1 || i > p.Nx));
         const double *b = &S(0, sx, sy);
         const double vbar = ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
+        double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : -p.f * vbar;
+        if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc
+            const double dx0 = mt.dxcf(r), dx1 = mt.dxcf(r + 1);
+            const double gm = (dx0 * SB(b, VS, -1, 0) + dx1 * SB(b, VS, -1, 1)) / 2, g0 = (dx0 * SB(b, VS, 0, 0) + dx1 * SB(b, VS, 0, 1)) / 2;
+            const double fbar = (mt.fff(r) + mt.fff(r + 1)) / 2;
+            xcross = mm.divc(-fbar * ((gm + g0) / 2), mt.dxfc(r), mt.rdxfc(r));
+        }
         double ue = p.ue_c, vebar = ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
         if (use_ue) {
             ue = SB(b, A_UE, 0, 0);
@@ -477,13 +523,15 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         double imm = 0.0;
         if (has_imm) {
             const double bc = (-p.imm_u) * uold;
-            const double qW = 0.0 * (p.dy * 1.0), qE = 0.0 * (p.dy * 1.0);
-            const double qS = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (p.dx * 1.0);
-            const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (p.dx * 1.0);
-            imm = mm.divc(qE - qW + qN - qS, p.az * 1.0, p.raz);
+            const double qW = 0.0 * (mt.dycc(r) * 1.0), qE = 0.0 * (mt.dycc(r) * 1.0);
+            const double qS = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dxff(r) * 1.0);
+            const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (mt.dxff(r + 1) * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, mt.azfc(r) * 1.0, mt.razfc(r));
         }
-        const double val = u_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, -1, 0), uold, vbar, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        const double dyc2 = mt.dycc2(r), dyf = mt.dyfc(r);
+        const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
+        const double val = u_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
+                                       SB(b, A_AL, -1, 0), uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : uold;
     };
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
@@ -492,6 +540,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const bool wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
         const double *b = &S(0, sx, sy);
         const double ubar = ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
+        double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : p.f * ubar;
+        if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf
+            const double dy0 = mt.dyfc(r - 1), dy1 = mt.dyfc(r);
+            const double gm = (dy0 * SB(b, US, 0, -1) + dy0 * SB(b, US, 1, -1)) / 2, g0 = (dy1 * SB(b, US, 0, 0) + dy1 * SB(b, US, 1, 0)) / 2;
+            const double fj = mt.fff(r), fbar = (fj + fj) / 2;
+            ycross = mm.divc(fbar * ((gm + g0) / 2), mt.dycf(r), mt.rdycf(r));
+        }
         double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
         if (use_ue) {
             ve = SB(b, A_VE, 0, 0);
@@ -512,13 +567,15 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         double imm = 0.0;
         if (has_imm) {  // isd:84-101, -C*v on west/east immersed faces
             const double bc = (-p.imm_v) * vold;
-            const double qW = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (p.dy * 1.0);
-            const double qE = ((FLG(sx + 1, sy) & 2) ? bc : 0.0) * (p.dy * 1.0);
-            const double qS = 0.0 * (p.dx * 1.0), qN = 0.0 * (p.dx * 1.0);
-            imm = mm.divc(qE - qW + qN - qS, p.az * 1.0, p.raz);
+            const double qW = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dyff(r) * 1.0);
+            const double qE = ((FLG(sx + 1, sy) & 2) ? bc : 0.0) * (mt.dyff(r) * 1.0);
+            const double qS = 0.0 * (mt.dxcc(r - 1) * 1.0), qN = 0.0 * (mt.dxcc(r) * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, mt.azcf(r) * 1.0, mt.razcf(r));
         }
-        const double val = v_node<GEN>(mm, p, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, 0, -1), vold, ubar, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        const double dyf2 = mt.dyff2(r), dxf = mt.dxcf(r);
+        const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
+        const double val = v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                       SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
     };
 
@@ -567,16 +624,18 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // over the full parent extent, so corners hold images of the wall cells)
         if (is_u && ((p.wall_s && r == 1) || (p.wall_n && r == p.Ny))) {
             const int ix = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
-            const double wv = r == 1 ? (p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (p.dy / 2)) * (-p.dy) : val)
-                                     : (p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (p.dy / 2)) * p.dy : val);
+            const double Dw = r == 1 ? mt.dyff(1) : mt.dyff(p.Ny + 1);  // Delta y at (Face, Face) on the wall
+            const double wv = r == 1 ? (p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (Dw / 2)) * (-Dw) : val)
+                                     : (p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (Dw / 2)) * Dw : val);
             double *w = r == 1 ? q - p.pitch : q + p.pitch;
             w[0] = wv;
             if (ix) w[ix] = wv;
         }
         if (!is_u && p.bounded_x && (i == 1 || i == p.Nx)) {
             const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
-            const double wv = i == 1 ? (p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (p.dx / 2)) * (-p.dx) : val)
-                                     : (p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (p.dx / 2)) * p.dx : val);
+            const double Dw = mt.dxff(r);
+            const double wv = i == 1 ? (p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (Dw / 2)) * (-Dw) : val)
+                                     : (p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (Dw / 2)) * Dw : val);
             double *w = i == 1 ? q - 1 : q + 1;
             w[0] = wv;
             if (iy) w[(ptrdiff_t)iy * p.pitch] = wv;
@@ -650,7 +709,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
 // alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
-template <bool VFIRST, bool AUX, bool GEN>
+template <bool VFIRST, bool AUX, bool GEN, bool MET>
 __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -668,11 +727,11 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tile_pass<VFIRST, AUX, GEN, MathFast>(sm, bar, 0, &tmap, p, tc)) {
+    if (tile_pass<VFIRST, AUX, GEN, MET, MathFast>(sm, bar, 0, &tmap, p, tc)) {
         // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, denormals ...):
         // reload the tile and redo it with plain IEEE operators
         __syncthreads();
-        tile_pass<VFIRST, AUX, GEN, MathSlow>(sm, bar, 1, &tmap, p, tc);
+        tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, 1, &tmap, p, tc);
     }
 }
 #undef S
@@ -778,6 +837,7 @@ __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 // ---- host side ----------------------------------------------------------------------------------
 struct FusedPlan {
     uint8_t *flags = nullptr;
+    double *met = nullptr;  // per-row metric table (lat-lon grids)
     fz::Params P;
     dim3 grid;
     int cur_set = 0;
@@ -806,12 +866,18 @@ static EncodeTiledFn get_encode()
 
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
-    if (g.met) { snprintf(why, nwhy, "j-dependent grid metrics (general kernels only)"); return 0; }
-    if (p.cor == CSI_CORIOLIS_SPHERICAL) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis (general kernels only)"); return 0; }
+    if (g.met) {
+        // every metric that appears as a divisor must qualify for the constant-division shortcut, on every row a tile can touch
+        if (!g.met_host) { snprintf(why, nwhy, "host copy of the grid metrics missing"); return 0; }
+        const int divisors[8] = {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF};
+        for (int k : divisors)
+            for (int q = 0; q < g.metL; q++)
+                if (!recip_is_safe(g.met_host[(size_t)k * g.metL + q])) { snprintf(why, nwhy, "a grid metric is not eligible for the constant-division shortcut"); return 0; }
+    } else if (p.cor == CSI_CORIOLIS_SPHERICAL) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
     if (p.fd_kind != CSI_FD_NONE) { snprintf(why, nwhy, "free-drift velocities (general kernels only)"); return 0; }
     if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT) { snprintf(why, nwhy, "SemiImplicitStress on top (general kernels only)"); return 0; }
     if (p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD) { snprintf(why, nwhy, "prescribed bottom stress (general kernels only)"); return 0; }
-    if (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az)) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
+    if (!g.met && (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az))) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
@@ -859,6 +925,34 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
         if (cudaMalloc(&pl->flags, fl.size()) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flags)"); cudaFree(pl->base); delete pl; return nullptr; }
         cudaMemcpy(pl->flags, fl.data(), fl.size(), cudaMemcpyHostToDevice);
     }
+    if (g.met_host) {
+        // per-row metric table in internal row coordinates: row rho holds reference row j = rho + 1 - oy
+        std::vector<double> tb((size_t)MC_N * pl->rows, 1.0);
+        auto src = [&](int which, int rho) {
+            const int q = rho - pl->oy + g.Hy;  // index of row j in the host arrays (j - 1 + Hy)
+            return (q >= 0 && q < g.metL) ? g.met_host[(size_t)which * g.metL + q] : 1.0;
+        };
+        for (int rho = 0; rho < pl->rows; rho++) {
+            auto put = [&](int col, double v) { tb[(size_t)col * pl->rows + rho] = v; };
+            for (int k = 0; k < 12; k++) put(MC_DXCC + k, src(k, rho));
+            put(MC_DXCC2, src(M_DXCC, rho) * src(M_DXCC, rho));
+            put(MC_DYCC2, src(M_DYCC, rho) * src(M_DYCC, rho));
+            put(MC_DXFF2, src(M_DXFF, rho) * src(M_DXFF, rho));
+            put(MC_DYFF2, src(M_DYFF, rho) * src(M_DYFF, rho));
+            put(MC_RDXFC, 1.0 / src(M_DXFC, rho));
+            put(MC_RDXCF, 1.0 / src(M_DXCF, rho));
+            put(MC_RDYFC, 1.0 / src(M_DYFC, rho));
+            put(MC_RDYCF, 1.0 / src(M_DYCF, rho));
+            put(MC_RAZCC, 1.0 / src(M_AZCC, rho));
+            put(MC_RAZFC, 1.0 / src(M_AZFC, rho));
+            put(MC_RAZCF, 1.0 / src(M_AZCF, rho));
+            put(MC_RAZFF, 1.0 / src(M_AZFF, rho));
+            const int q = rho - pl->oy + g.Hy;
+            put(MC_FFF, (g.fff_host && q >= 0 && q < g.metL) ? g.fff_host[q] : 0.0);
+        }
+        if (cudaMalloc(&pl->met, tb.size() * sizeof(double)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(metric table)"); cudaFree(pl->base); delete pl; return nullptr; }
+        cudaMemcpy(pl->met, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) { snprintf(err, nerr, "cuTensorMapEncodeTiled unavailable"); cudaFree(pl->base); delete pl; return nullptr; }
     cuuint64_t dims[3] = {(cuuint64_t)pl->pitch, (cuuint64_t)pl->rows, (cuuint64_t)NF};
@@ -876,25 +970,27 @@ void fused_destroy(FusedPlan *pl)
     if (!pl) return;
     if (pl->base) cudaFree(pl->base);
     if (pl->flags) cudaFree(pl->flags);
+    if (pl->met) cudaFree(pl->met);
     delete pl;
 }
 
-template <bool VFIRST, bool AUX, bool GEN> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
+template <bool VFIRST, bool AUX, bool GEN, bool MET> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN, MET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    k_evp_substep_fused<VFIRST, AUX, GEN><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
+    k_evp_substep_fused<VFIRST, AUX, GEN, MET><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
     return cudaGetLastError();
 }
-template <bool GEN> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
+// GEN x MET: the regular grid has a switch-free variant; lat-lon grids (MET) always keep the run-time switches
+template <bool GEN, bool MET> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
 {
-    if (vfirst) return aux ? launch_one<true, true, GEN>(pl, P, grid, s) : launch_one<true, false, GEN>(pl, P, grid, s);
-    return aux ? launch_one<false, true, GEN>(pl, P, grid, s) : launch_one<false, false, GEN>(pl, P, grid, s);
+    if (vfirst) return aux ? launch_one<true, true, GEN, MET>(pl, P, grid, s) : launch_one<true, false, GEN, MET>(pl, P, grid, s);
+    return aux ? launch_one<false, true, GEN, MET>(pl, P, grid, s) : launch_one<false, false, GEN, MET>(pl, P, grid, s);
 }
 
 int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, char *err, int nerr)
@@ -935,6 +1031,8 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.base = pl->base;
     P.flags = pl->flags;
+    P.met = pl->met;
+    if (pl->met) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }
 
     // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
     P.a0 = P.sx0 < P.vx0 ? P.sx0 : P.vx0;
@@ -979,8 +1077,10 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         const bool vfirst = (sub % 2) != 0;
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
-        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags;
-        const cudaError_t e = common ? launch_sub<false>(pl, P, grid, c.stream, vfirst, aux) : launch_sub<true>(pl, P, grid, c.stream, vfirst, aux);
+        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
+        const cudaError_t e = P.met    ? launch_sub<true, true>(pl, P, grid, c.stream, vfirst, aux)
+                              : common ? launch_sub<false, false>(pl, P, grid, c.stream, vfirst, aux)
+                                       : launch_sub<true, false>(pl, P, grid, c.stream, vfirst, aux);
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
         ++*c.launches;
         pl->cur_set ^= 1;

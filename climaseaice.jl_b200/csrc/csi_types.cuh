@@ -30,6 +30,8 @@ struct DGrid {
     // order dxcc dxfc dxcf dxff dycc dyfc dycf dyff azcc azfc azcf azff.  NULL on a regular RectilinearGrid.
     const double *met;
     int metL, pad_;
+    const double *met_host;  // host copies (plan construction only): the 12 x metL metrics, and f at (Face, Face) or NULL
+    const double *fff_host;
 };
 
 // grid metrics at row j (they do not depend on i on the supported grids)

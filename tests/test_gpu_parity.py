@@ -302,17 +302,19 @@ def test_coastline_config4_reduced(impl):
     m.close()
 
 
+@pytest.mark.parametrize("impl", ("unfused", "fused"))
 @pytest.mark.parametrize("topology", [("Bounded", "Bounded"), ("Periodic", "Bounded")])
 @pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
-def test_latitude_longitude_grid(topology, timestepper):
+def test_latitude_longitude_grid(impl, topology, timestepper):
     """j-dependent metrics (LatitudeLongitudeGrid, the grid of test/test_rheology_energy_budget.jl:18-24): every
     dx/dy/Az in the strain rates, the SBP stress divergence, the relaxation factors, the flux divergence, the value
-    BCs and the CFL reduction is the row's own.  The general kernels serve this grid ("auto" must route there)."""
+    BCs and the CFL reduction is the row's own -- in the general kernels and in the fused tile kernel, which reads a
+    per-row table of metrics and correctly rounded reciprocals."""
     from climaseaice_b200.synthetic import latlon_case
     case = latlon_case(48, substeps=20, topology=topology, timestepper=timestepper)
     met = case.metrics()
     assert met["dxcc"].max() / met["dxcc"].min() > 2          # the metrics really vary
-    m = model_from_case(case, solver_impl="auto")
+    m = model_from_case(case, solver_impl=impl)
     o = oracle_from_case(case)
     for _ in range(2):
         m.time_step(case.dt); o.time_step(case.dt)
@@ -325,13 +327,8 @@ def test_latitude_longitude_grid(topology, timestepper):
     m.close()
 
 
-def test_latitude_longitude_grid_rejects_fused_and_bad_metrics():
+def test_latitude_longitude_grid_rejects_bad_metrics():
     from climaseaice_b200.synthetic import latlon_case
-    case = latlon_case(32, substeps=4)
-    m = model_from_case(case, solver_impl="fused")
-    with pytest.raises(RuntimeError, match="j-dependent grid metrics"):
-        m.time_step(case.dt)
-    m.close()
     bad = latlon_case(32, substeps=4)
     met = bad.metrics()
     met["azff"][bad.Hy + 3] = 0.0
@@ -401,13 +398,14 @@ def test_stress_balance_free_drift_argument_errors():
     mf.close()
 
 
-def test_hydrostatic_spherical_coriolis_on_latlon_grid():
+@pytest.mark.parametrize("impl", ("unfused", "fused"))
+def test_hydrostatic_spherical_coriolis_on_latlon_grid(impl):
     """HydrostaticSphericalCoriolis (EnstrophyConserving, f^ff = 2 Omega sin(phi_f) per row) on the lat-lon basin."""
     from climaseaice_b200.synthetic import latlon_case
     case = latlon_case(48, substeps=20, topology=("Periodic", "Bounded"))
     m0 = model_from_case(case)                      # FPlane(1e-4), for contrast
     case.rotation_rate = 7.292115e-5
-    m = model_from_case(case)
+    m = model_from_case(case, solver_impl=impl)
     o = oracle_from_case(case)
     assert o.prm["coriolis_kind"] == 2
     for _ in range(2):

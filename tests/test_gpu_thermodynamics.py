@@ -171,14 +171,15 @@ def test_thermodynamics_argument_errors():
     m.close()
 
 
+@pytest.mark.parametrize("impl", ("unfused", "fused"))
 @pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
-def test_arctic_cap_config5_reduced(timestepper):
+def test_arctic_cap_config5_reduced(impl, timestepper):
     """BASELINE config 5 in miniature: coupled slab thermodynamics + EVP dynamics + WENO advection on a zonally periodic
     lat-lon cap (general kernels: j-dependent metrics), against the staged oracle."""
     from climaseaice_b200.synthetic import arctic_cap_case
     from tests.helpers import coupled_oracle_step, thermo_oracle_from_case
     case = arctic_cap_case(96, 32, H=5, substeps=12, timestepper=timestepper)
-    m = model_from_case(case)
+    m = model_from_case(case, solver_impl=impl)
     o = oracle_from_case(case)
     t = thermo_oracle_from_case(case, o)
     for _ in range(2):
