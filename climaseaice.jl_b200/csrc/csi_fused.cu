@@ -29,6 +29,7 @@
 // Algorithmic HBM traffic: 14 loads + 5 stores per cell-update (u, v, s11, s22, s12 r/w; h, aice,
 // P, un, vn, tau_x, tau_y, ue, ve read) = 152 B, 144 B by the SURVEY convention (P recomputable).
 #include <cuda.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -85,6 +86,9 @@ struct Params {
     double em2, Dmin, amin, amax, amax2, ca, rho_i, rhoCd, f, min_mass, min_conc;
     double ttx, tty, ue_c, ve_c;
     double imm_u, imm_v;  // immersed linear-drag flux BC (0 = none)
+    // power-of-two multiples used by the scaled expression tree of the FAST pass (all exact)
+    double dt2, dt4, f4, Dmin2, Dmin8, min_mass2, min_conc2, dx2d, dy2d;
+    int sq;               // regular grid with dx == dy: phase A divides every u, v once (u/dx serves both operators)
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     double *base;         // internal allocation
@@ -118,6 +122,8 @@ struct Metric {
     CSI_MET(razcc, MC_RAZCC, p.raz) CSI_MET(razfc, MC_RAZFC, p.raz) CSI_MET(razcf, MC_RAZCF, p.raz) CSI_MET(razff, MC_RAZFF, p.raz)
     CSI_MET(fff, MC_FFF, p.f)
 #undef CSI_MET
+    __device__ __forceinline__ double dxff2d(int r) const { return MET ? 2 * ld(MC_DXFF2, r) : p.dx2d; }  // 2 dx^2 (exact)
+    __device__ __forceinline__ double dyff2d(int r) const { return MET ? 2 * ld(MC_DYFF2, r) : p.dy2d; }
 };
 
 // the metric factors of one velocity node's stress divergence (isd:39-51): d = a (sD1 - sD0) / 2,
@@ -187,6 +193,7 @@ struct MathFast {
     //  * radicands: checked like quotients (a zero radicand -- ice exactly at rest -- is legitimate), plus a sign accumulator
     // With these windows the numerators x = q d stay in [2^-766, 2^770), far from where the exact
     // residual d q0 - x could underflow (2^-969) or anything could overflow.
+    static constexpr bool SCALED = true;  // tile_pass evaluates the power-of-two-scaled expression tree (see there)
     uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u;
     static constexpr uint32_t QLO = 0x200u << 21, QHI = (0x600u << 21) - 1u;
     static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;
@@ -211,9 +218,9 @@ struct MathFast {
         chkd(y);
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+        // one cubic step r (1 + e + e^2) takes the 2^-20 seed to below one ulp; Markstein's step then returns RN(1/y)
         double e = __fma_rn(-y, r, 1.0);
-        r = __fma_rn(r, e, r);
-        e = __fma_rn(-y, r, 1.0);
+        e = __fma_rn(e, e, e);
         r = __fma_rn(r, e, r);
         e = __fma_rn(-y, r, 1.0);
         return __fma_rn(r, e, r);
@@ -253,6 +260,8 @@ struct MathFast {
     }
 };
 struct MathSlow {
+    static constexpr bool SCALED = false;  // the reference's expression tree, operator for operator
+    __device__ __forceinline__ void chkq(double) {}
     __device__ __forceinline__ bool bad() const { return false; }
     __device__ __forceinline__ double divc(double x, double d, double) { return x / d; }
     __device__ __forceinline__ NodeRecip recip(double d)
@@ -321,6 +330,77 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetri
     tau = mi <= 0 ? 0.0 : tau;
     const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
     const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
+    return jl_mul_bool(active_ice ? vD : 0.0, active);
+}
+
+// ---- the scaled expression tree (FAST pass) -----------------------------------------------------
+// Multiplying or dividing by a power of two is exact and commutes with every IEEE rounding as long as nothing
+// leaves the normal range, so the FAST pass carries the reference's intermediate values times a known power of
+// two and never spends an FP64 issue slot on "/ 2", "2 *" or "4 *":
+//     strain rates   stored as 2 e11, 2 e22 (centres), 2 e12 (corners)
+//     4-point means  carried as sums: 8 e11f, 8 e22f, 4 Pf, 4 mf, 4 vbar, 4 ve_bar;  4 e12c = (sum of 2 e12) / 2
+//     2 Delta_c, 8 Delta_f, face sums 2 m_i, 2 aice_i, 2 alpha_bar, and 2 x the stress divergence
+// with the factors cancelling inside quotients (P_f / 2 Delta_f = 4 P_f / 8 Delta_f, tau / m_i * aice_i = tau / 2 m_i * 2 aice_i ...)
+// or absorbed by constants (2 dt, 4 dt, f / 4, 2 Delta_min, 8 Delta_min, 2 dx^2) and by explicit FMAs
+// (a + X / 2 = fma(X, 0.5, a): one rounding of the same real number).  Every result handed on is bit-identical to the
+// reference tree's.  The normal-range premise is what the windows of MathFast enforce: all quotients, radicands and
+// divisors are checked, the inputs u, v (phase A quotients), u_e, v_e (checked on arrival) are zero or at least
+// 2^-511 in magnitude, so sums and differences of them are zero or normal and halving them is exact; products that
+// could underflow (squares of strain rates) only feed checked radicands, where an addend below 2^-1022 cannot move
+// a sum of at least 2^-511.  A tile that leaves the windows is redone with the reference tree (MathSlow).
+template <bool GEN, class M>
+__device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
+                                           double al0, double uold, double sv, double xcross, double ue, double sve, double ttop, double un, double sD1,
+                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
+{
+    // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
+    const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
+    const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
+    const double dtau = mm.divn(p.dt2, Ra);  // dt / alpha_bar
+    double coef = 0.0, tbot = 0.0;
+    if (GEN ? p.sis != 0 : true) {
+        const double du = ue - uold, dv4 = sve - sv;
+        coef = p.rhoCd * mm.sqrt_(__fma_rn(dv4 * dv4, 0.0625, du * du));
+        tbot = coef * ue;
+    }
+    const double rheo2 = mm.divn(mm.div(un - uold, dtau), Ra);  // rheo / 2
+    const double d2 = nm.a * (sD1 - sD0);
+    const double tt2 = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
+    const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
+    double G = -xcross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    G = m2 <= 0 ? 0.0 : G;
+    double tau = mm.divn(coef - 0.0, Rm) * a2;
+    tau = m2 <= 0 ? 0.0 : tau;
+    const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
+    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+    return jl_mul_bool(active_ice ? uD : 0.0, active);
+}
+template <bool GEN, class M>
+__device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
+                                           double al0, double vold, double su, double ycross, double ve, double sue, double ttop, double vn, double sD1,
+                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
+{
+    const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
+    const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
+    const double dtau = mm.divn(p.dt2, Ra);
+    double coef = 0.0, tbot = 0.0;
+    if (GEN ? p.sis != 0 : true) {
+        const double dv = ve - vold, du4 = sue - su;
+        coef = p.rhoCd * mm.sqrt_(__fma_rn(du4 * du4, 0.0625, dv * dv));
+        tbot = coef * ve;
+    }
+    const double rheo2 = mm.divn(mm.div(vn - vold, dtau), Ra);
+    const double d2 = nm.a * (sD1 - sD0);
+    const double tt2 = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
+    const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
+    double G = -ycross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    G = m2 <= 0 ? 0.0 : G;
+    double tau = mm.divn(coef - 0.0, Rm) * a2;
+    tau = m2 <= 0 ? 0.0 : tau;
+    const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
+    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? vD : 0.0, active);
 }
 
@@ -414,6 +494,29 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) ----------------
     // e11, e22 on [-1, BX-1] x [-1, BY-1]; e12 on [0, BX] x [0, BY]; m everywhere (in place over h)
     mbar_wait(&bar[0], parity);
+    if (M::SCALED && !MET && p.sq) {
+        // regular grid with dx == dy: u / dx and v / dx serve both the tension and the shear operator; divide every
+        // u, v of the tile once (into the arrays phases B and C fill later) instead of eight times per node
+        double *qu = sm + A_AL * ASTRIDE, *qv = sm + A_W * ASTRIDE;
+        for (int n = tid; n < SXD * SYD; n += NT) {
+            qu[n] = mm.divc(sm[A_U * ASTRIDE + n], p.dx, p.rdx);
+            qv[n] = mm.divc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
+        }
+        __syncthreads();
+        for (int n = tid; n < SXD * SYD; n += NT) {
+            const int sx = n % SXD - 1, sy = n / SXD - 1;
+            double *b = sm + n;
+            const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0), qu00 = SB(b, A_AL, 0, 0), qv00 = SB(b, A_W, 0, 0);
+            if (sx < BX && sy < BY) {
+                const double D = mm.divc((p.dy * SB(b, A_U, 1, 0) - p.dy * u00) + (p.dx * SB(b, A_V, 0, 1) - p.dx * v00), p.az, p.raz);
+                const double T = mm.divc(p.dy2 * (SB(b, A_AL, 1, 0) - qu00) - p.dx2 * (SB(b, A_W, 0, 1) - qv00), p.az, p.raz);
+                SB(b, A_E11, 0, 0) = D + T;  // 2 e11
+                SB(b, A_E22, 0, 0) = D - T;  // 2 e22
+            }
+            if (sx >= 0 && sy >= 0)
+                SB(b, A_E12, 0, 0) = mm.divc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
+        }
+    } else
     for (int n = tid; n < SXD * SYD; n += NT) {
         const int sx = n % SXD - 1, sy = n / SXD - 1;
         const int r = tc.J0 - 1 + sy;  // reference row of the node
@@ -426,8 +529,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double T = mm.divc(mt.dycc2(r) * (mm.divc(u10, dyf, rdyf) - mm.divc(u00, dyf, rdyf)) -
                                          mt.dxcc2(r) * (mm.divc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc(v00, dxf0, mt.rdxcf(r))),
                                      az, raz);
-            SB(b, A_E11, 0, 0) = (D + T) / 2;
-            SB(b, A_E22, 0, 0) = (D - T) / 2;
+            SB(b, A_E11, 0, 0) = M::SCALED ? D + T : (D + T) / 2;
+            SB(b, A_E22, 0, 0) = M::SCALED ? D - T : (D - T) / 2;
         }
         if (sx >= 0 && sy >= 0) {
             const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
@@ -435,11 +538,17 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double Sh = mm.divc(mt.dxff2(r) * (mm.divc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
                                           mt.dyff2(r) * (mm.divc(v00, dyc, rdyc) - mm.divc(vm0, dyc, rdyc)),
                                       mt.azff(r), mt.razff(r));
-            SB(b, A_E12, 0, 0) = Sh / 2;
+            SB(b, A_E12, 0, 0) = M::SCALED ? Sh : Sh / 2;
         }
     }
     mbar_wait(&bar[1], parity);
-    for (int n = tid; n < SXD * SYD; n += NT) sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
+    for (int n = tid; n < SXD * SYD; n += NT) {
+        sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
+        if (M::SCALED && use_ue) {  // the scaled tree sums ocean velocities before halving: they must be zero or normal
+            mm.chkq(sm[A_UE * ASTRIDE + n]);
+            mm.chkq(sm[A_VE * ASTRIDE + n]);
+        }
+    }
     __syncthreads();
 
     // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
@@ -449,6 +558,34 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int sx = lane, sy = wrp + 8 * q;
         const int rB = tc.J0 - 1 + sy;
         double *b = &S(0, sx, sy);
+        double zc, zf, Dc, s11n, s22n, s12n, mc, mf, g2c, g2f;
+        if (M::SCALED) {
+            // a, bb = 2 e11c, 2 e22c; Sh = 2 e12f; c4 = 4 e12c; af, bf = 8 e11f, 8 e22f
+            const double a = SB(b, A_E11, 0, 0), bb = SB(b, A_E22, 0, 0), Sh = SB(b, A_E12, 0, 0);
+            const double c4 = ((Sh + SB(b, A_E12, 1, 0)) + (SB(b, A_E12, 0, 1) + SB(b, A_E12, 1, 1))) * 0.5;
+            const double af = (SB(b, A_E11, -1, -1) + SB(b, A_E11, 0, -1)) + (SB(b, A_E11, -1, 0) + a);
+            const double bf = (SB(b, A_E22, -1, -1) + SB(b, A_E22, 0, -1)) + (SB(b, A_E22, -1, 0) + bb);
+            const double dc2 = a + bb, df8 = af + bf, Sh8 = 8 * Sh;
+            const double sc2 = mm.sqrt_((a - bb) * (a - bb) + c4 * c4);        // 2 sc
+            const double sf8 = mm.sqrt_((af - bf) * (af - bf) + Sh8 * Sh8);    // 8 sf
+            const double Dc2 = jl_max(mm.sqrt_(dc2 * dc2 + sc2 * sc2 * p.em2), p.Dmin2);  // 2 Delta_c
+            const double Df8 = jl_max(mm.sqrt_(df8 * df8 + sf8 * sf8 * p.em2), p.Dmin8);  // 8 Delta_f
+            const double Pc = SB(b, A_P, 0, 0);
+            const double Pf4 = (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
+            zf = mm.div(Pf4, Df8);
+            zc = mm.div(Pc, Dc2);
+            const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.div(Pc * Dc2, Dc2 + p.Dmin2);
+            const double ec = zc * p.em2, ef = zf * p.em2;
+            const double X = (zc - ec) * dc2 - Pr;  // 2 ((zeta - eta)(e11 + e22) - Pr / 2)
+            s11n = __fma_rn(X, 0.5, ec * a);
+            s22n = __fma_rn(X, 0.5, ec * bb);
+            s12n = ef * Sh;
+            mc = SB(b, A_H, 0, 0);
+            mf = (SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) + (SB(b, A_H, -1, 0) + mc);  // 4 mf
+            g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
+            g2f = mm.divc(mm.div(zf * p.ca * p.dt4, mf), mt.azff(rB), mt.razff(rB));
+            Dc = AUX ? Dc2 * 0.5 : 0.0;
+        } else {
         const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
         const double e12c = ((e12f + SB(b, A_E12, 1, 0)) / 2 + (SB(b, A_E12, 0, 1) + SB(b, A_E12, 1, 1)) / 2) / 2;
         const double e11f = ((SB(b, A_E11, -1, -1) + SB(b, A_E11, 0, -1)) / 2 + (SB(b, A_E11, -1, 0) + e11c) / 2) / 2;
@@ -456,22 +593,24 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double dc = e11c + e22c, df = e11f + e22f;
         const double sc = mm.sqrt_((e11c - e22c) * (e11c - e22c) + 4 * (e12c * e12c));
         const double sf = mm.sqrt_((e11f - e22f) * (e11f - e22f) + 4 * (e12f * e12f));
-        const double Dc = jl_max(mm.sqrt_(dc * dc + sc * sc * p.em2), p.Dmin);
+        Dc = jl_max(mm.sqrt_(dc * dc + sc * sc * p.em2), p.Dmin);
         const double Df = jl_max(mm.sqrt_(df * df + sf * sf * p.em2), p.Dmin);
         const double Pc = SB(b, A_P, 0, 0);
         const double Pf = ((SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) / 2 + (SB(b, A_P, -1, 0) + Pc) / 2) / 2;
-        const double zf = mm.div(Pf, 2 * Df), zc = mm.div(Pc, 2 * Dc);
+        zf = mm.div(Pf, 2 * Df);
+        zc = mm.div(Pc, 2 * Dc);
         const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.div(Pc * Dc, Dc + p.Dmin);
         const double ec = zc * p.em2, ef = zf * p.em2;
-        const double s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
-        const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
-        const double s12n = 2 * ef * e12f;
-        const double mc = SB(b, A_H, 0, 0);
-        const double mf = ((SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) / 2 + (SB(b, A_H, -1, 0) + mc) / 2) / 2;
-        double g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
+        s11n = 2 * ec * e11c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+        s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
+        s12n = 2 * ef * e12f;
+        mc = SB(b, A_H, 0, 0);
+        mf = ((SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) / 2 + (SB(b, A_H, -1, 0) + mc) / 2) / 2;
+        g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
+        g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(rB), mt.razff(rB));
+        }
         g2c = (g2c != g2c) ? p.amax2 : g2c;
         const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
-        double g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(rB), mt.razff(rB));
         g2f = (g2f != g2f) ? p.amax2 : g2f;
         const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
         const NodeRecip Rg = mm.recip(gc);
@@ -494,18 +633,21 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
         const bool wall_active = !(p.bounded_x && (i <= 1 || i > p.Nx));
         const double *b = &S(0, sx, sy);
-        const double vbar = ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
-        double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : -p.f * vbar;
+        // reference tree: vbar; scaled tree: the plain sum 4 vbar (and f / 4)
+        const double vsum = (SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1));
+        const double vbar = M::SCALED ? vsum : ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
+        double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : (M::SCALED ? -p.f4 * vsum : -p.f * vbar);
         if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc
             const double dx0 = mt.dxcf(r), dx1 = mt.dxcf(r + 1);
             const double gm = (dx0 * SB(b, VS, -1, 0) + dx1 * SB(b, VS, -1, 1)) / 2, g0 = (dx0 * SB(b, VS, 0, 0) + dx1 * SB(b, VS, 0, 1)) / 2;
             const double fbar = (mt.fff(r) + mt.fff(r + 1)) / 2;
             xcross = mm.divc(-fbar * ((gm + g0) / 2), mt.dxfc(r), mt.rdxfc(r));
         }
-        double ue = p.ue_c, vebar = ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
+        double ue = p.ue_c, vebar = M::SCALED ? (p.ve_c + p.ve_c) + (p.ve_c + p.ve_c) : ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
         if (use_ue) {
             ue = SB(b, A_UE, 0, 0);
-            vebar = ((SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) / 2 + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1)) / 2) / 2;
+            vebar = M::SCALED ? (SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1))
+                              : ((SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) / 2 + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1)) / 2) / 2;
         }
         const double uold = SB(b, A_U, 0, 0);
         double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, -1, 0), b0 = SB(b, A_S22, -1, 0);
@@ -529,9 +671,16 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             imm = mm.divc(qE - qW + qN - qS, mt.azfc(r) * 1.0, mt.razfc(r));
         }
         const double dyc2 = mt.dycc2(r), dyf = mt.dyfc(r);
-        const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
-        const double val = u_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, -1, 0), uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        double val;
+        if (M::SCALED) {
+            const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2d(r + 1), mt.dxff2d(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
+            val = u_node_s<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+                                uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm);
+        } else {
+            const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
+            val = u_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+                              uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        }
         return upd ? val : uold;
     };
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
@@ -539,18 +688,20 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
         const bool wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
         const double *b = &S(0, sx, sy);
-        const double ubar = ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
-        double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : p.f * ubar;
+        const double usum = (SB(b, US, 0, -1) + SB(b, US, 1, -1)) + (SB(b, US, 0, 0) + SB(b, US, 1, 0));
+        const double ubar = M::SCALED ? usum : ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
+        double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : (M::SCALED ? p.f4 * usum : p.f * ubar);
         if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf
             const double dy0 = mt.dyfc(r - 1), dy1 = mt.dyfc(r);
             const double gm = (dy0 * SB(b, US, 0, -1) + dy0 * SB(b, US, 1, -1)) / 2, g0 = (dy1 * SB(b, US, 0, 0) + dy1 * SB(b, US, 1, 0)) / 2;
             const double fj = mt.fff(r), fbar = (fj + fj) / 2;
             ycross = mm.divc(fbar * ((gm + g0) / 2), mt.dycf(r), mt.rdycf(r));
         }
-        double ve = p.ve_c, uebar = ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
+        double ve = p.ve_c, uebar = M::SCALED ? (p.ue_c + p.ue_c) + (p.ue_c + p.ue_c) : ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
         if (use_ue) {
             ve = SB(b, A_VE, 0, 0);
-            uebar = ((SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) / 2 + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0)) / 2) / 2;
+            uebar = M::SCALED ? (SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0))
+                              : ((SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) / 2 + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0)) / 2) / 2;
         }
         const double vold = SB(b, A_V, 0, 0);
         double a1 = SB(b, A_S11, 0, 0), b1 = SB(b, A_S22, 0, 0), a0 = SB(b, A_S11, 0, -1), b0 = SB(b, A_S22, 0, -1);
@@ -572,10 +723,12 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double qS = 0.0 * (mt.dxcc(r - 1) * 1.0), qN = 0.0 * (mt.dxcc(r) * 1.0);
             imm = mm.divc(qE - qW + qN - qS, mt.azcf(r) * 1.0, mt.razcf(r));
         }
-        const double dyf2 = mt.dyff2(r), dxf = mt.dxcf(r);
+        const double dyf2 = M::SCALED ? mt.dyff2d(r) : mt.dyff2(r), dxf = mt.dxcf(r);
         const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
-        const double val = v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                       SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        const double val = M::SCALED ? v_node_s<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                                     SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm)
+                                     : v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                                   SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
     };
 
@@ -879,6 +1032,10 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     if (p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD) { snprintf(why, nwhy, "prescribed bottom stress (general kernels only)"); return 0; }
     if (!g.met && (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az))) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
+    // premises of the scaled expression tree (exact power-of-two scalings): thresholds and constants far inside the normal range
+    auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-100 && fabs(x) <= 1e100); };
+    if (!(p.min_conc >= 1e-100) || !(p.min_mass >= 1e-100) || !sane(p.f) || !sane(p.Dmin) || !sane(p.em2) || !sane(p.ca) || !sane(p.rho_e * p.Cd) ||
+        (!g.met && (!sane(g.dx) || !sane(g.dy)))) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
     return 1;
@@ -1029,6 +1186,9 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.ue_c = p.ue_c; P.ve_c = p.ve_c;
     P.imm_u = p.imm_u; P.imm_v = p.imm_v;
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
+    P.dt2 = 2 * dt; P.dt4 = 4 * dt; P.f4 = p.f * 0.25; P.Dmin2 = 2 * p.Dmin; P.Dmin8 = 8 * p.Dmin;
+    P.min_mass2 = 2 * p.min_mass; P.min_conc2 = 2 * p.min_conc; P.dx2d = 2 * P.dx2; P.dy2d = 2 * P.dy2;
+    P.sq = !pl->met && g.dx == g.dy;
     P.base = pl->base;
     P.flags = pl->flags;
     P.met = pl->met;
