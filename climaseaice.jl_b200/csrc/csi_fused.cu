@@ -232,7 +232,15 @@ struct MathFast {
         const double t = __fma_rn(d, q0, -x);
         return __fma_rn(-t, r, q0);
     }
+    // *_nc: quotients whose operands are bounded by checks already made (see the call sites): no window test
+    __device__ __forceinline__ double quot_nc(double x, double d, double r)
+    {
+        const double q0 = x * r;
+        const double t = __fma_rn(d, q0, -x);
+        return __fma_rn(-t, r, q0);
+    }
     __device__ __forceinline__ double divc(double x, double d, double r) { return quot(x, d, r); }
+    __device__ __forceinline__ double divc_nc(double x, double d, double r) { return quot_nc(x, d, r); }
     __device__ __forceinline__ NodeRecip recip(double d)
     {
         NodeRecip R;
@@ -241,13 +249,18 @@ struct MathFast {
         return R;
     }
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return quot(x, R.d, R.r); }
+    __device__ __forceinline__ double divn_nc(double x, const NodeRecip &R) { return quot_nc(x, R.d, R.r); }
     __device__ __forceinline__ double div(double x, double y) { return quot(x, y, rcp(y)); }
-    __device__ __forceinline__ double sqrt_(double x)
+    // CHK = false: the radicand is a checked quotient times a bounded constant; only its sign is still tested
+    template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x)
     {
-        chkq(x);
+        if (CHK) chkq(x);
         neg |= (uint32_t)__double2hiint(x);
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        // x = +0 gives y = +inf; clamped to 2^1023 the iteration below returns +0 without a select (-0, negative and NaN
+        // radicands are rejected by the windows)
+        y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), __double2loint(y));
         double g = x * y, h = 0.5 * y;
         double e = __fma_rn(-h, g, 0.5);
         g = __fma_rn(g, e, g);
@@ -255,15 +268,19 @@ struct MathFast {
         e = __fma_rn(-h, g, 0.5);
         g = __fma_rn(g, e, g);  // (h keeps its 2^-44 accuracy: enough for the correction term)
         const double d = __fma_rn(-g, g, x);
-        g = __fma_rn(d, h, g);
-        return x > 0.0 ? g : x;  // sqrt(+-0) = +-0
+        return __fma_rn(d, h, g);
     }
+    // max(s, c) for a square root s >= +0 (never NaN in a clean pass) and a constant c > 0
+    __device__ __forceinline__ double max_pos(double s, double c) { return s > c ? s : c; }
 };
 struct MathSlow {
     static constexpr bool SCALED = false;  // the reference's expression tree, operator for operator
     __device__ __forceinline__ void chkq(double) {}
     __device__ __forceinline__ bool bad() const { return false; }
     __device__ __forceinline__ double divc(double x, double d, double) { return x / d; }
+    __device__ __forceinline__ double divc_nc(double x, double d, double) { return x / d; }
+    __device__ __forceinline__ double divn_nc(double x, const NodeRecip &R) { return x / R.d; }
+    __device__ __forceinline__ double max_pos(double s, double c) { return jl_max(s, c); }
     __device__ __forceinline__ NodeRecip recip(double d)
     {
         NodeRecip R;
@@ -273,7 +290,7 @@ struct MathSlow {
     }
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return x / R.d; }
     __device__ __forceinline__ double div(double x, double y) { return x / y; }
-    __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
 // u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
@@ -356,22 +373,20 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
     const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
-    const double dtau = mm.divn(p.dt2, Ra);  // dt / alpha_bar
+    const double dtau = mm.divn_nc(p.dt2, Ra);  // dt / alpha_bar; alpha in [alpha-, alpha+]: nothing to check
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
         const double du = ue - uold, dv4 = sve - sv;
         coef = p.rhoCd * mm.sqrt_(__fma_rn(dv4 * dv4, 0.0625, du * du));
         tbot = coef * ue;
     }
-    const double rheo2 = mm.divn(mm.div(un - uold, dtau), Ra);  // rheo / 2
+    const double rheo2 = mm.divn_nc(mm.div(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
     const double d2 = nm.a * (sD1 - sD0);
     const double tt2 = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
-    double G = -xcross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    G = m2 <= 0 ? 0.0 : G;
-    double tau = mm.divn(coef - 0.0, Rm) * a2;
-    tau = m2 <= 0 ? 0.0 : tau;
+    const double G = -xcross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double tau = mm.divn(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
     const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? uD : 0.0, active);
@@ -383,22 +398,20 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
 {
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
     const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
-    const double dtau = mm.divn(p.dt2, Ra);
+    const double dtau = mm.divn_nc(p.dt2, Ra);
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
         const double dv = ve - vold, du4 = sue - su;
         coef = p.rhoCd * mm.sqrt_(__fma_rn(du4 * du4, 0.0625, dv * dv));
         tbot = coef * ve;
     }
-    const double rheo2 = mm.divn(mm.div(vn - vold, dtau), Ra);
+    const double rheo2 = mm.divn_nc(mm.div(vn - vold, dtau), Ra);
     const double d2 = nm.a * (sD1 - sD0);
     const double tt2 = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
-    double G = -ycross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    G = m2 <= 0 ? 0.0 : G;
-    double tau = mm.divn(coef - 0.0, Rm) * a2;
-    tau = m2 <= 0 ? 0.0 : tau;
+    const double G = -ycross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double tau = mm.divn(coef - 0.0, Rm) * a2;
     const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? vD : 0.0, active);
@@ -451,12 +464,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         mbar_expect_tx(&bar[1], (uint32_t)n * SXD * SYD * sizeof(double));
     }
     // global offsets of the nodes this thread updates in phases C and D (32-wide rows: lane = column)
-    // C: odd  -> v at sx = lane (0..30), sy = 1 + wrp + 8 q (<= 15);  even -> u at sx = lane + 1 (1..31), sy = wrp + 8 q (<= 14)
-    // D: sx = lane + 1 (1..30), sy = 1 + wrp + 8 q (<= 14)
-    const int c_sx = VFIRST ? lane : lane + 1, c_sy0 = VFIRST ? 1 + wrp : wrp;
-    const bool c_on[2] = {lane < OUTX + 1, lane < OUTX + 1 && c_sy0 + 8 <= (VFIRST ? OUTY + 1 : OUTY)};
-    const int d_sx = lane + 1, d_sy0 = 1 + wrp;
-    const bool d_on[2] = {lane < OUTX, lane < OUTX && d_sy0 + 8 <= OUTY};
+    // A warp owns two adjacent rows (q = 0, 1), so the pair sums of the 4-point means and the loads they need are shared.
+    // C: odd  -> v at sx = lane (0..30), sy = 1 + 2 wrp + q (<= 15);  even -> u at sx = lane + 1 (1..31), sy = 2 wrp + q (<= 14)
+    // D: sx = lane + 1 (1..30), sy = 1 + 2 wrp + q (<= 14)
+    const int c_sx = VFIRST ? lane : lane + 1, c_sy0 = VFIRST ? 1 + 2 * wrp : 2 * wrp;
+    const bool c_on[2] = {lane < OUTX + 1, lane < OUTX + 1 && c_sy0 + 1 <= (VFIRST ? OUTY + 1 : OUTY)};
+    const int d_sx = lane + 1, d_sy0 = 1 + 2 * wrp;
+    const bool d_on[2] = {lane < OUTX && d_sy0 <= OUTY, lane < OUTX && d_sy0 + 1 <= OUTY};
     auto goff = [&](int sx, int sy) {
         // clamped into the plane: edge tiles reach past the allocation (those nodes are never stored)
         const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
@@ -467,8 +481,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     size_t c_g[2], d_g[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        c_g[q] = goff(c_sx, c_sy0 + 8 * q);
-        d_g[q] = goff(d_sx, d_sy0 + 8 * q);
+        c_g[q] = goff(c_sx, c_sy0 + q);
+        d_g[q] = goff(d_sx, d_sy0 + q);
         // pull the pointwise inputs of phases C / D towards L2/L1 while the tile lands and A, B run
         if (c_on[q]) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gC1 + c_g[q]));
@@ -508,13 +522,14 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             double *b = sm + n;
             const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0), qu00 = SB(b, A_AL, 0, 0), qv00 = SB(b, A_W, 0, 0);
             if (sx < BX && sy < BY) {
-                const double D = mm.divc((p.dy * SB(b, A_U, 1, 0) - p.dy * u00) + (p.dx * SB(b, A_V, 0, 1) - p.dx * v00), p.az, p.raz);
-                const double T = mm.divc(p.dy2 * (SB(b, A_AL, 1, 0) - qu00) - p.dx2 * (SB(b, A_W, 0, 1) - qv00), p.az, p.raz);
+                // (the numerators are built from checked quotients and bounded metrics: no second window test)
+                const double D = mm.divc_nc((p.dy * SB(b, A_U, 1, 0) - p.dy * u00) + (p.dx * SB(b, A_V, 0, 1) - p.dx * v00), p.az, p.raz);
+                const double T = mm.divc_nc(p.dy2 * (SB(b, A_AL, 1, 0) - qu00) - p.dx2 * (SB(b, A_W, 0, 1) - qv00), p.az, p.raz);
                 SB(b, A_E11, 0, 0) = D + T;  // 2 e11
                 SB(b, A_E22, 0, 0) = D - T;  // 2 e22
             }
             if (sx >= 0 && sy >= 0)
-                SB(b, A_E12, 0, 0) = mm.divc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
+                SB(b, A_E12, 0, 0) = mm.divc_nc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
         }
     } else
     for (int n = tid; n < SXD * SYD; n += NT) {
@@ -525,8 +540,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if (sx < BX && sy < BY) {
             const double u10 = SB(b, A_U, 1, 0), v01 = SB(b, A_V, 0, 1);
             const double dyf = mt.dyfc(r), rdyf = mt.rdyfc(r), dxf0 = mt.dxcf(r), dxf1 = mt.dxcf(r + 1), az = mt.azcc(r), raz = mt.razcc(r);
-            const double D = mm.divc((dyf * u10 - dyf * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
-            const double T = mm.divc(mt.dycc2(r) * (mm.divc(u10, dyf, rdyf) - mm.divc(u00, dyf, rdyf)) -
+            const double D = mm.divc_nc((dyf * u10 - dyf * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
+            const double T = mm.divc_nc(mt.dycc2(r) * (mm.divc(u10, dyf, rdyf) - mm.divc(u00, dyf, rdyf)) -
                                          mt.dxcc2(r) * (mm.divc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc(v00, dxf0, mt.rdxcf(r))),
                                      az, raz);
             SB(b, A_E11, 0, 0) = M::SCALED ? D + T : (D + T) / 2;
@@ -535,7 +550,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if (sx >= 0 && sy >= 0) {
             const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
             const double dyc = mt.dycf(r), rdyc = mt.rdycf(r);
-            const double Sh = mm.divc(mt.dxff2(r) * (mm.divc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
+            const double Sh = mm.divc_nc(mt.dxff2(r) * (mm.divc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
                                           mt.dyff2(r) * (mm.divc(v00, dyc, rdyc) - mm.divc(vm0, dyc, rdyc)),
                                       mt.azff(r), mt.razff(r));
             SB(b, A_E12, 0, 0) = M::SCALED ? Sh : Sh / 2;
@@ -555,7 +570,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     double aux_zc[2], aux_zf[2], aux_Dc[2];
 #pragma unroll UNROLL_B
     for (int q = 0; q < 2; q++) {
-        const int sx = lane, sy = wrp + 8 * q;
+        const int sx = lane, sy = 2 * wrp + q;
         const int rB = tc.J0 - 1 + sy;
         double *b = &S(0, sx, sy);
         double zc, zf, Dc, s11n, s22n, s12n, mc, mf, g2c, g2f;
@@ -568,8 +583,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double dc2 = a + bb, df8 = af + bf, Sh8 = 8 * Sh;
             const double sc2 = mm.sqrt_((a - bb) * (a - bb) + c4 * c4);        // 2 sc
             const double sf8 = mm.sqrt_((af - bf) * (af - bf) + Sh8 * Sh8);    // 8 sf
-            const double Dc2 = jl_max(mm.sqrt_(dc2 * dc2 + sc2 * sc2 * p.em2), p.Dmin2);  // 2 Delta_c
-            const double Df8 = jl_max(mm.sqrt_(df8 * df8 + sf8 * sf8 * p.em2), p.Dmin8);  // 8 Delta_f
+            const double Dc2 = mm.max_pos(mm.sqrt_(dc2 * dc2 + sc2 * sc2 * p.em2), p.Dmin2);  // 2 Delta_c
+            const double Df8 = mm.max_pos(mm.sqrt_(df8 * df8 + sf8 * sf8 * p.em2), p.Dmin8);  // 8 Delta_f
             const double Pc = SB(b, A_P, 0, 0);
             const double Pf4 = (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
             zf = mm.div(Pf4, Df8);
@@ -582,8 +597,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             s12n = ef * Sh;
             mc = SB(b, A_H, 0, 0);
             mf = (SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) + (SB(b, A_H, -1, 0) + mc);  // 4 mf
-            g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
-            g2f = mm.divc(mm.div(zf * p.ca * p.dt4, mf), mt.azff(rB), mt.razff(rB));
+            g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
+            g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf), mt.azff(rB), mt.razff(rB));
             Dc = AUX ? Dc2 * 0.5 : 0.0;
         } else {
         const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
@@ -609,17 +624,18 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
         g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(rB), mt.razff(rB));
         }
-        g2c = (g2c != g2c) ? p.amax2 : g2c;
-        const double gc = jl_clamp(mm.sqrt_(g2c), p.amin, p.amax);
-        g2f = (g2f != g2f) ? p.amax2 : g2f;
-        const double gf = jl_clamp(mm.sqrt_(g2f), p.amin, p.amax);
+        // (a clean FAST pass has no NaN quotient and no mass <= 0: both would have left the windows)
+        if (!M::SCALED) g2c = (g2c != g2c) ? p.amax2 : g2c;
+        const double gc = jl_clamp(mm.template sqrt_<!M::SCALED>(g2c), p.amin, p.amax);
+        if (!M::SCALED) g2f = (g2f != g2f) ? p.amax2 : g2f;
+        const double gf = jl_clamp(mm.template sqrt_<!M::SCALED>(g2f), p.amin, p.amax);
         const NodeRecip Rg = mm.recip(gc);
         const double o11 = SB(b, A_S11, 0, 0), o22 = SB(b, A_S22, 0, 0), o12 = SB(b, A_S12, 0, 0);
         const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.div(s12n - o12, gf);
         // in place: each thread owns its node of the sigma arrays
-        SB(b, A_S11, 0, 0) = o11 + (mc > 0 ? d11 : 0.0);
-        SB(b, A_S22, 0, 0) = o22 + (mc > 0 ? d22 : 0.0);
-        SB(b, A_S12, 0, 0) = o12 + (mf > 0 ? d12 : 0.0);
+        SB(b, A_S11, 0, 0) = o11 + (M::SCALED || mc > 0 ? d11 : 0.0);
+        SB(b, A_S22, 0, 0) = o22 + (M::SCALED || mc > 0 ? d22 : 0.0);
+        SB(b, A_S12, 0, 0) = o12 + (M::SCALED || mf > 0 ? d12 : 0.0);
         SB(b, A_AL, 0, 0) = gc;
         aux_zc[q] = zc;
         aux_zf[q] = zf;
@@ -736,7 +752,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll UNROLL_CD
     for (int q = 0; q < 2; q++)
         if (c_on[q]) {
-            const int sy = c_sy0 + 8 * q;
+            const int sy = c_sy0 + q;
             const double n1 = __ldg(gC1 + c_g[q]), t1 = use_top ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
             S(A_W, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
         }
@@ -747,7 +763,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll UNROLL_CD
     for (int q = 0; q < 2; q++)
         if (d_on[q]) {
-            const int sy = d_sy0 + 8 * q;
+            const int sy = d_sy0 + q;
             const double n1 = __ldg(gD1 + d_g[q]), t1 = use_top ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
             w2[q] = VFIRST ? u_at(d_sx, sy, A_W, n1, t1) : v_at(d_sx, sy, A_W, n1, t1);
         }
@@ -805,7 +821,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             double *o = p.base + (size_t)(tc.J0 - 2 + p.oy) * p.pitch + (size_t)(tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                const int sx = lane, sy = wrp + 8 * q;
+                const int sx = lane, sy = 2 * wrp + q;
                 if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
                     double *g = o + (size_t)sy * p.pitch + sx;
                     g[(size_t)(tc.fout + 2) * plane] = S(A_S11, sx, sy);
@@ -819,7 +835,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                     }
                 }
                 if (d_on[q]) {
-                    const int dsy = d_sy0 + 8 * q;
+                    const int dsy = d_sy0 + q;
                     double *g = o + (size_t)dsy * p.pitch + d_sx;
                     g[(size_t)(tc.fout + (VFIRST ? 0 : 1)) * plane] = w2[q];
                     g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(A_W, d_sx, dsy);
@@ -831,7 +847,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         // stresses (and aux) of the node this thread updated in phase B
-        const int sx = lane, sy = wrp + 8 * q;
+        const int sx = lane, sy = 2 * wrp + q;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY && i >= p.sx0 && i <= p.sx1 && r >= p.sy0 && r <= p.sy1) {
             put(tc.fout + 2, i, r, S(A_S11, sx, sy));
@@ -846,7 +862,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         // velocities of the output cell this thread updated in phase D
         if (d_on[q]) {
-            const int dsy = d_sy0 + 8 * q;
+            const int dsy = d_sy0 + q;
             const int ui = tc.I0 - 1 + d_sx, ur = tc.J0 - 1 + dsy;
             if (VFIRST) {
                 put_vel(tc.fout + 0, ui, ur, w2[q], true);
@@ -1033,9 +1049,17 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     if (!g.met && (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az))) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
     // premises of the scaled expression tree (exact power-of-two scalings): thresholds and constants far inside the normal range
-    auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-100 && fabs(x) <= 1e100); };
-    if (!(p.min_conc >= 1e-100) || !(p.min_mass >= 1e-100) || !sane(p.f) || !sane(p.Dmin) || !sane(p.em2) || !sane(p.ca) || !sane(p.rho_e * p.Cd) ||
-        (!g.met && (!sane(g.dx) || !sane(g.dy)))) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
+    // (and the quotients left unchecked in the kernel -- by cell areas, by alpha -- stay far from over/underflow)
+    auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-30 && fabs(x) <= 1e30); };
+    bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && sane(p.Dmin) && sane(p.em2) &&
+              sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i);
+    if (!g.met) ok = ok && sane(g.dx) && sane(g.dy) && g.dx > 0 && g.dy > 0;
+    else
+        for (int k : {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF})
+            // rows whose results are kept: the interior and the wall ring; a slab's connected side uses its whole halo
+            for (int q = (g.conn_s ? 0 : g.Hy - 1); q < (g.conn_n ? g.metL : std::min(g.metL, g.Hy + g.Ny + 2)) && ok; q++)
+                ok = g.met_host[(size_t)k * g.metL + q] >= 1e-30 && g.met_host[(size_t)k * g.metL + q] <= 1e30;
+    if (!ok) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
     return 1;
