@@ -187,35 +187,57 @@ struct NodeRecip {
 };
 
 struct MathFast {
-    // Window accumulators on the high word of each checked double (exponent field = bits 30..20):
-    //  * quotients (any sign, zero allowed): g = hi << 1; qmx = max g, qmn = min (g - 1)  -> |q| in [2^-511, 2^513) or q == 0
-    //  * divisors  (positive, non-zero): dacc = umax(hi - DLO)  -> d in [2^-255, 2^257); zeros, negatives, NaN wrap high
+    // Window accumulators on the high word of each checked double (sign, 11 exponent bits, 20 significand bits):
+    //  * quotients (any sign, zero allowed) are tested two at a time on the top halves of their high words (sign, exponent,
+    //    4 significand bits), packed into one register with the signs masked off: per 16-bit lane qmx = max g,
+    //    qmn = min (g - 1) (VIMNMX.U16x2 / VIADDMNMX.U16x2)  -> |q| in [2^-511, 2^513) or g == 0.  A quotient waits in
+    //    `pend` for its partner; straight-line code resolves `have` at compile time.  (g == 0 is a zero or a magnitude
+    //    below 2^-1026, which no chain of checked operations starting from fields above 1e-150 can produce.)
+    //  * divisors  (positive, non-zero): dacc = umax(hi - DLO)  -> d in [2^-255, 2^257); zeros, negatives, NaN wrap high;
+    //    lo1 catches a low word of all ones (superset of "significand all ones", the exception of Markstein's theorem)
     //  * radicands: checked like quotients (a zero radicand -- ice exactly at rest -- is legitimate), plus a sign accumulator
     // With these windows the numerators x = q d stay in [2^-766, 2^770), far from where the exact
     // residual d q0 - x could underflow (2^-969) or anything could overflow.
     static constexpr bool SCALED = true;  // tile_pass evaluates the power-of-two-scaled expression tree (see there)
-    uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u;
-    static constexpr uint32_t QLO = 0x200u << 21, QHI = (0x600u << 21) - 1u;
+    uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u, pend = 0u;
+    bool have = false;
+    static constexpr uint32_t QLO = 0x2000u, QHI = 0x5fffu;  // per lane: exponent field in [0x200, 0x600)
     static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;
+    __device__ __forceinline__ void chk2(uint32_t hi_a, uint32_t hi_b)
+    {
+        const uint32_t g = __byte_perm(hi_a, hi_b, 0x7632) & 0x7fff7fffu;
+        qmx = __vmaxu2(qmx, g);
+        qmn = __viaddmin_u16x2(g, 0xffffffffu, qmn);  // g == 0 wraps to 0xffff and is ignored
+    }
     __device__ __forceinline__ void chkq(double q)
     {
 #ifdef CSI_EXPERIMENT_NOCHECK
         return;
 #endif
-        const uint32_t g = (uint32_t)__double2hiint(q) << 1;
-        qmx = max(qmx, g);
-        qmn = min(qmn, g - 1u);  // g == 0 (a zero) wraps to 0xffffffff and is ignored
+        const uint32_t hi = (uint32_t)__double2hiint(q);
+        if (have) chk2(pend, hi);
+        else pend = hi;
+        have = !have;
     }
     __device__ __forceinline__ void chkd(double d)
     {
         dacc = max(dacc, (uint32_t)__double2hiint(d) - DLO);
-        lo1 = min(lo1, (uint32_t)__double2loint(d) + 1u);  // 0 if the low word is all ones (superset of "significand all ones")
+        chklo(d);
     }
-    __device__ __forceinline__ bool bad() const { return (qmn < QLO - 1u) | (qmx > QHI) | (dacc > DSPAN) | ((neg >> 31) != 0u) | (lo1 == 0u); }
-
-    __device__ __forceinline__ double rcp(double y)
+    __device__ __forceinline__ void chklo(double d) { lo1 = min(lo1, (uint32_t)__double2loint(d) + 1u); }
+    __device__ __forceinline__ bool bad()
     {
-        chkd(y);
+        if (have) chk2(pend, 0u);
+        have = false;
+        const bool q_out = ((qmx & 0xffffu) > QHI) | ((qmx >> 16) > QHI) | ((qmn & 0xffffu) < QLO - 1u) | ((qmn >> 16) < QLO - 1u);
+        return q_out | (dacc > DSPAN) | ((neg >> 31) != 0u) | (lo1 == 0u);
+    }
+
+    // B = true: the divisor's range is known from earlier checks (see the call sites); only its low word is tested
+    template <bool B = false> __device__ __forceinline__ double rcp(double y)
+    {
+        if (B) chklo(y);
+        else chkd(y);
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
         // one cubic step r (1 + e + e^2) takes the 2^-20 seed to below one ulp; Markstein's step then returns RN(1/y)
@@ -241,16 +263,16 @@ struct MathFast {
     }
     __device__ __forceinline__ double divc(double x, double d, double r) { return quot(x, d, r); }
     __device__ __forceinline__ double divc_nc(double x, double d, double r) { return quot_nc(x, d, r); }
-    __device__ __forceinline__ NodeRecip recip(double d)
+    template <bool B = false> __device__ __forceinline__ NodeRecip recip(double d)
     {
         NodeRecip R;
         R.d = d;
-        R.r = rcp(d);
+        R.r = rcp<B>(d);
         return R;
     }
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return quot(x, R.d, R.r); }
     __device__ __forceinline__ double divn_nc(double x, const NodeRecip &R) { return quot_nc(x, R.d, R.r); }
-    __device__ __forceinline__ double div(double x, double y) { return quot(x, y, rcp(y)); }
+    template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return quot(x, y, rcp<B>(y)); }
     // CHK = false: the radicand is a checked quotient times a bounded constant; only its sign is still tested
     template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x)
     {
@@ -276,12 +298,12 @@ struct MathFast {
 struct MathSlow {
     static constexpr bool SCALED = false;  // the reference's expression tree, operator for operator
     __device__ __forceinline__ void chkq(double) {}
-    __device__ __forceinline__ bool bad() const { return false; }
+    __device__ __forceinline__ bool bad() { return false; }
     __device__ __forceinline__ double divc(double x, double d, double) { return x / d; }
     __device__ __forceinline__ double divc_nc(double x, double d, double) { return x / d; }
     __device__ __forceinline__ double divn_nc(double x, const NodeRecip &R) { return x / R.d; }
     __device__ __forceinline__ double max_pos(double s, double c) { return jl_max(s, c); }
-    __device__ __forceinline__ NodeRecip recip(double d)
+    template <bool B = false> __device__ __forceinline__ NodeRecip recip(double d)
     {
         NodeRecip R;
         R.d = d;
@@ -289,7 +311,7 @@ struct MathSlow {
         return R;
     }
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return x / R.d; }
-    __device__ __forceinline__ double div(double x, double y) { return x / y; }
+    template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return x / y; }
     template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
@@ -372,7 +394,7 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
 {
     // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
+    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(m2);
     const double dtau = mm.divn_nc(p.dt2, Ra);  // dt / alpha_bar; alpha in [alpha-, alpha+]: nothing to check
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -380,7 +402,7 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
         coef = p.rhoCd * mm.sqrt_(__fma_rn(dv4 * dv4, 0.0625, du * du));
         tbot = coef * ue;
     }
-    const double rheo2 = mm.divn_nc(mm.div(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
+    const double rheo2 = mm.divn_nc(mm.template div<true>(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
     const double d2 = nm.a * (sD1 - sD0);
     const double tt2 = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
@@ -397,7 +419,7 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
                                            double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
 {
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    const NodeRecip Ra = mm.recip(ab2), Rm = mm.recip(m2);
+    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(m2);
     const double dtau = mm.divn_nc(p.dt2, Ra);
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -405,7 +427,7 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
         coef = p.rhoCd * mm.sqrt_(__fma_rn(du4 * du4, 0.0625, dv * dv));
         tbot = coef * ve;
     }
-    const double rheo2 = mm.divn_nc(mm.div(vn - vold, dtau), Ra);
+    const double rheo2 = mm.divn_nc(mm.template div<true>(vn - vold, dtau), Ra);
     const double d2 = nm.a * (sD1 - sD0);
     const double tt2 = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
@@ -587,9 +609,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double Df8 = mm.max_pos(mm.sqrt_(df8 * df8 + sf8 * sf8 * p.em2), p.Dmin8);  // 8 Delta_f
             const double Pc = SB(b, A_P, 0, 0);
             const double Pf4 = (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
-            zf = mm.div(Pf4, Df8);
-            zc = mm.div(Pc, Dc2);
-            const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.div(Pc * Dc2, Dc2 + p.Dmin2);
+            // (Delta in [Delta_min, 2^257) follows from its checked radicand: divisor range tests only where unknown)
+            zf = mm.template div<true>(Pf4, Df8);
+            zc = mm.template div<true>(Pc, Dc2);
+            const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.template div<true>(Pc * Dc2, Dc2 + p.Dmin2);
             const double ec = zc * p.em2, ef = zf * p.em2;
             const double X = (zc - ec) * dc2 - Pr;  // 2 ((zeta - eta)(e11 + e22) - Pr / 2)
             s11n = __fma_rn(X, 0.5, ec * a);
@@ -629,9 +652,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double gc = jl_clamp(mm.template sqrt_<!M::SCALED>(g2c), p.amin, p.amax);
         if (!M::SCALED) g2f = (g2f != g2f) ? p.amax2 : g2f;
         const double gf = jl_clamp(mm.template sqrt_<!M::SCALED>(g2f), p.amin, p.amax);
-        const NodeRecip Rg = mm.recip(gc);
+        const NodeRecip Rg = mm.template recip<M::SCALED>(gc);  // gamma in [alpha-, alpha+]
         const double o11 = SB(b, A_S11, 0, 0), o22 = SB(b, A_S22, 0, 0), o12 = SB(b, A_S12, 0, 0);
-        const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.div(s12n - o12, gf);
+        const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.template div<M::SCALED>(s12n - o12, gf);
         // in place: each thread owns its node of the sigma arrays
         SB(b, A_S11, 0, 0) = o11 + (M::SCALED || mc > 0 ? d11 : 0.0);
         SB(b, A_S22, 0, 0) = o22 + (M::SCALED || mc > 0 ? d22 : 0.0);
@@ -1051,7 +1074,7 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     // premises of the scaled expression tree (exact power-of-two scalings): thresholds and constants far inside the normal range
     // (and the quotients left unchecked in the kernel -- by cell areas, by alpha -- stay far from over/underflow)
     auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-30 && fabs(x) <= 1e30); };
-    bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && sane(p.Dmin) && sane(p.em2) &&
+    bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && p.Dmin >= 1e-30 && p.Dmin <= 1e30 && sane(p.em2) &&
               sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i);
     if (!g.met) ok = ok && sane(g.dx) && sane(g.dy) && g.dx > 0 && g.dy > 0;
     else
@@ -1179,6 +1202,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     using namespace fz;
     Params &P = pl->P;
 
+    if (!(dt >= 1e-30 && dt <= 1e30)) { snprintf(err, nerr, "fused solver: time step outside [1e-30, 1e30]"); return CSI_ERR_ARG; }
     memset(&P, 0, sizeof P);
     P.Nx = g.Nx; P.Ny = g.Ny; P.pitch = pl->pitch; P.rows = pl->rows; P.oy = pl->oy;
     P.px = g.topo_x == CSI_PERIODIC;
