@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         if (NQ > 2) sh[NQ - 1][lj][li] = at(f.hs, gi, gj);
     }
     __syncthreads();
-    const bool bx = g.topo_x == CSI_BOUNDED, by_lo = g.topo_y == CSI_BOUNDED && !g.conn_s, by_hi = g.topo_y == CSI_BOUNDED && !g.conn_n;
+    const bool bx_lo = g.topo_x == CSI_BOUNDED && !g.conn_w, bx_hi = g.topo_x == CSI_BOUNDED && !g.conn_e, by_lo = g.topo_y == CSI_BOUNDED && !g.conn_s, by_hi = g.topo_y == CSI_BOUNDED && !g.conn_n;
     // x faces: (ATX+1) x ATY
     for (int t = tid; t < (ATX + 1) * ATY; t += ATX * ATY) {
         const int li = t % (ATX + 1), lj = t / (ATX + 1);
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx + 1 && j <= g.Ny) {
             const double U = at(f.u, min(i, f.u.sx - f.u.ox), j);
-            const int b = buffer_at(B, bx, bx, g.Nx, i);
+            const int b = buffer_at(B, bx_lo, bx_hi, g.Nx, i);
             const bool imm = g.mask && imm_peripheral_fc(g, i, j);
 #pragma unroll
             for (int q = 0; q < NQ; q++) {

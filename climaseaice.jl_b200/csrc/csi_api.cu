@@ -98,6 +98,9 @@ struct csi_handle {
     // slab partition
     void *comm = nullptr;
     int rank = 0, nranks = 1;
+    int Rx = 1, Ry = 1, rx = 0, ry = 0;  // 2-D partition: rank = ry * Rx + rx
+    double *xbuf = nullptr;              // packed west/east strips: [send_w | send_e | recv_w | recv_e]
+    size_t xbuf_each = 0;
     cudaStream_t comm_stream = nullptr;
 };
 
@@ -140,7 +143,8 @@ int check_array(csi_handle *h, const csi_array &a, const FieldInfo &fi, bool req
 {
     if (!a.ptr) return required ? fail(h, CSI_ERR_ARG, std::string("field '") + fi.name + "' is required but NULL") : CSI_OK;
     const csi_config &c = h->cfg;
-    const int ex = c.Nx + 2 * c.Hx + ((fi.lx && c.topo_x == CSI_BOUNDED) ? 1 : 0);
+    // Face fields carry N+1 points along a Bounded axis, except along a partitioned axis (the wall point lives in the halo)
+    const int ex = c.Nx + 2 * c.Hx + ((fi.lx && c.topo_x == CSI_BOUNDED && h->Rx == 1) ? 1 : 0);
     const int ey = c.Ny + 2 * c.Hy + ((fi.ly && c.topo_y == CSI_BOUNDED && h->nranks == 1) ? 1 : 0);
     if (a.nx_tot != ex || a.ny_tot != ey || a.off_x != c.Hx || a.off_y != c.Hy) {
         char buf[256];
@@ -250,6 +254,8 @@ Range2 velocity_range(const DGrid &g)
     Range2 r{1, g.Nx, 1, g.Ny};
     if (g.conn_s) r.j0 = -g.Hy + 2;
     if (g.conn_n) r.j1 = g.Ny + g.Hy - 1;
+    if (g.conn_w) r.i0 = -g.Hx + 2;
+    if (g.conn_e) r.i1 = g.Nx + g.Hx - 1;
     return r;
 }
 
@@ -422,16 +428,79 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
     return CSI_OK;
 }
 
-// Slab neighbours along y: send my first/last `width` interior rows, receive into the halos.
+// Packed west/east strips of a 2-D partition: `width` columns x every parent row of each array, array after array.
+// All rows, not 1..Ny: a y axis that is not partitioned has its halo rows filled locally BEFORE the exchange, and the
+// corners (x halo columns of those rows) must come from the neighbour's already filled rows; with a partitioned y axis
+// the row exchange that follows overwrites the corners anyway.
+__global__ void k_pack_x_strips(const DArr a, double *send_w, double *send_e, int Nx, int width)
+{
+    const int pj = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;  // parent row, column within the strip
+    if (pj >= a.sy) return;
+    const int j = pj + 1 - a.oy;
+    send_w[(size_t)pj * width + k] = at(a, 1 + k, j);               // interior columns 1..width
+    send_e[(size_t)pj * width + k] = at(a, Nx - width + 1 + k, j);  // interior columns Nx-width+1..Nx
+}
+__global__ void k_unpack_x_strips(DArr a, const double *recv_w, const double *recv_e, int Nx, int width, int do_w, int do_e)
+{
+    const int pj = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (pj >= a.sy) return;
+    const int j = pj + 1 - a.oy;
+    if (do_w) at(a, 1 - width + k, j) = recv_w[(size_t)pj * width + k];  // halo columns 1-width..0
+    if (do_e) at(a, Nx + 1 + k, j) = recv_e[(size_t)pj * width + k];      // halo columns Nx+1..Nx+width
+}
+
+// Distributed fill_halo_regions! of a partition Rx x Ry (rank = ry Rx + rx).  West/east first: strips of `width` columns
+// are packed, sent and unpacked; then south/north: `width` whole parent rows -- x halos included, which carries the
+// corners -- go zero-copy (rows are contiguous in the i-fastest layout).
 int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaStream_t s)
 {
     if (h->nranks <= 1) return CSI_OK;
     if (!h->comm) return fail(h, CSI_ERR_ARG, "csi_comm_init has not been called on this handle");
     NcclApi &api = nccl();
     const DGrid &g = h->g;
-    // conn_s / conn_n already encode the topology: a Bounded y axis has no wrap-around neighbour
-    const int south = g.conn_s ? (h->rank + h->nranks - 1) % h->nranks : -1;
-    const int north = g.conn_n ? (h->rank + 1) % h->nranks : -1;
+    // conn_* already encode the topology: a Bounded axis has no wrap-around neighbour
+    const int south = g.conn_s ? ((h->ry + h->Ry - 1) % h->Ry) * h->Rx + h->rx : -1;
+    const int north = g.conn_n ? ((h->ry + 1) % h->Ry) * h->Rx + h->rx : -1;
+    const int west = g.conn_w ? h->ry * h->Rx + (h->rx + h->Rx - 1) % h->Rx : -1;
+    const int east = g.conn_e ? h->ry * h->Rx + (h->rx + 1) % h->Rx : -1;
+    if (west >= 0 || east >= 0) {
+        const int wx = width > g.Hx ? g.Hx : width;
+        size_t total = 0;
+        for (int k = 0; k < n; k++)
+            if (arrs[k].p) total += (size_t)wx * arrs[k].sy;
+        if (h->xbuf_each < total) {
+            if (h->xbuf) cudaFree(h->xbuf);
+            h->xbuf = nullptr;
+            h->xbuf_each = 0;
+            CSI_CUDA(h, cudaMalloc(&h->xbuf, 4 * total * sizeof(double)));
+            h->xbuf_each = total;
+        }
+        double *send_w = h->xbuf, *send_e = h->xbuf + h->xbuf_each, *recv_w = h->xbuf + 2 * h->xbuf_each, *recv_e = h->xbuf + 3 * h->xbuf_each;
+        size_t off = 0;
+        for (int k = 0; k < n; k++) {
+            if (!arrs[k].p) continue;
+            k_pack_x_strips<<<dim3((arrs[k].sy + 127) / 128, wx), 128, 0, s>>>(arrs[k], send_w + off, send_e + off, g.Nx, wx);
+            ++h->launches;
+            off += (size_t)wx * arrs[k].sy;
+        }
+        api.GroupStart();
+        // same pairing rule as below when both neighbours are the same rank
+        if (west >= 0) api.Send(send_w, total, NCCL_FLOAT64, west, h->comm, s);
+        if (east >= 0) api.Recv(recv_e, total, NCCL_FLOAT64, east, h->comm, s);
+        if (east >= 0) api.Send(send_e, total, NCCL_FLOAT64, east, h->comm, s);
+        if (west >= 0) api.Recv(recv_w, total, NCCL_FLOAT64, west, h->comm, s);
+        int rc = api.GroupEnd();
+        if (rc != 0) return fail(h, 1000 + rc, std::string("ncclGroupEnd: ") + (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+        off = 0;
+        for (int k = 0; k < n; k++) {
+            if (!arrs[k].p) continue;
+            k_unpack_x_strips<<<dim3((arrs[k].sy + 127) / 128, wx), 128, 0, s>>>(arrs[k], recv_w + off, recv_e + off, g.Nx, wx, west >= 0, east >= 0);
+            ++h->launches;
+            off += (size_t)wx * arrs[k].sy;
+        }
+        CSI_CUDA(h, cudaGetLastError());
+    }
+    if (south < 0 && north < 0) return CSI_OK;
     if (width > g.Hy) width = g.Hy;
     api.GroupStart();
     for (int k = 0; k < n; k++) {
@@ -500,10 +569,14 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         if (ts && bs) return fail(nullptr, CSI_ERR_ARG, "csi_create: StressBalanceFreeDrift supports a SemiImplicitStress only for the top or the bottom stress, not both");
         if (!ts && !bs) return fail(nullptr, CSI_ERR_ARG, "csi_create: StressBalanceFreeDrift requires a SemiImplicitStress for either the top or the bottom stress");
     }
+    const int Rx = cfg->partition_x > 1 ? cfg->partition_x : 1;
     if (cfg->nranks > 1) {
         const int K = cfg->exchange_every > 0 ? cfg->exchange_every : cfg->substeps;
-        if (cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: slab partitions need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
-    }
+        if (cfg->nranks % Rx != 0) return fail(nullptr, CSI_ERR_ARG, "csi_create: nranks must be a multiple of partition_x");
+        if (cfg->nranks / Rx > 1 && cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: partitions along y need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
+        if (Rx > 1 && cfg->Hx < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: partitions along x need Hx >= 2*exchange_every + 3 (se.jl:55-56)");
+        if (Rx > 1 && cfg->immersed_mask) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: immersed masks with a partition along x");
+    } else if (Rx > 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: partition_x > 1 needs nranks > 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -522,9 +595,15 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     DGrid &g = h->g;
     g.Nx = cfg->Nx; g.Ny = cfg->Ny; g.Hx = cfg->Hx; g.Hy = cfg->Hy;
     g.topo_x = cfg->topo_x; g.topo_y = cfg->topo_y;
-    // slab partition along y: a side is "connected" when another rank owns the rows beyond it
-    g.conn_s = h->nranks > 1 && (cfg->topo_y == CSI_PERIODIC || h->rank > 0);
-    g.conn_n = h->nranks > 1 && (cfg->topo_y == CSI_PERIODIC || h->rank < h->nranks - 1);
+    // partition Rx x Ry, rank = ry * Rx + rx: a side is "connected" when another rank owns the cells beyond it
+    h->Rx = h->nranks > 1 ? Rx : 1;
+    h->Ry = h->nranks / h->Rx;
+    h->rx = h->rank % h->Rx;
+    h->ry = h->rank / h->Rx;
+    g.conn_s = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry > 0);
+    g.conn_n = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry < h->Ry - 1);
+    g.conn_w = h->Rx > 1 && (cfg->topo_x == CSI_PERIODIC || h->rx > 0);
+    g.conn_e = h->Rx > 1 && (cfg->topo_x == CSI_PERIODIC || h->rx < h->Rx - 1);
     g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
     g.mask = nullptr;
     g.mask_host = nullptr;
@@ -613,6 +692,7 @@ int csi_destroy(csi_handle *h)
     if (h->fused) fused_destroy(h->fused);
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     for (double *m : h->mirror) if (m) cudaFree(m);
+    if (h->xbuf) cudaFree(h->xbuf);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->scratch) cudaFree(h->scratch);
     if (h->out_dev) cudaFree(h->out_dev);

@@ -17,8 +17,8 @@ namespace csi {
 // ---- node activity (Oceananigans inactive_cell / peripheral_node) ----------------------------
 __device__ __forceinline__ bool outside_domain(const DGrid &g, int i, int j)
 {
-    // a slab's connected south / north side is a rank boundary, not a wall
-    return (g.topo_x == CSI_BOUNDED && (i < 1 || i > g.Nx)) ||
+    // a partition's connected side is a rank boundary, not a wall
+    return (g.topo_x == CSI_BOUNDED && ((i < 1 && !g.conn_w) || (i > g.Nx && !g.conn_e))) ||
            (g.topo_y == CSI_BOUNDED && ((j < 1 && !g.conn_s) || (j > g.Ny && !g.conn_n)));
 }
 __device__ __forceinline__ bool immersed_cell(const DGrid &g, int i, int j)

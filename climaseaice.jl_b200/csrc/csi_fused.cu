@@ -72,7 +72,8 @@ struct Params {
     int oy;              // internal row of j = 1 is (oy)
     int px, py;          // periodic images along x / y
     int bounded_x, bounded_y;
-    int wall_s, wall_n;  // physical walls of a Bounded y axis on this rank (a slab's connected side is not a wall)
+    int wall_s, wall_n;  // physical walls of a Bounded y axis on this rank (a partition's connected side is not a wall)
+    int wall_w, wall_e;  // likewise along x
     // store windows (reference indices, inclusive)
     int sx0, sx1, sy0, sy1;  // stresses
     int vx0, vx1, vy0, vy1;  // velocities
@@ -670,7 +671,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     auto u_at = [&](int sx, int sy, int VS, double un, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool wall_active = !(p.bounded_x && (i <= 1 || i > p.Nx));
+        const bool wall_active = !((p.wall_w && i <= 1) || (p.wall_e && i > p.Nx));
         const double *b = &S(0, sx, sy);
         // reference tree: vbar; scaled tree: the plain sum 4 vbar (and f / 4)
         const double vsum = (SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1));
@@ -823,7 +824,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             w[0] = wv;
             if (ix) w[ix] = wv;
         }
-        if (!is_u && p.bounded_x && (i == 1 || i == p.Nx)) {
+        if (!is_u && ((p.wall_w && i == 1) || (p.wall_e && i == p.Nx))) {
             const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
             const double Dw = mt.dxff(r);
             const double wv = i == 1 ? (p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (Dw / 2)) * (-Dw) : val)
@@ -839,7 +840,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int i_lo = tc.I0, i_hi = tc.I0 + OUTX - 1, r_lo = tc.J0, r_hi = tc.J0 + OUTY - 1;
         const bool inside = i_lo >= max(p.sx0, p.vx0) && i_hi <= min(p.sx1, p.vx1) && r_lo >= max(p.sy0, p.vy0) && r_hi <= min(p.sy1, p.vy1);
         const bool no_img = (!p.px || (i_lo > W && i_hi <= p.Nx - W)) && (!p.py || (r_lo > W && r_hi <= p.Ny - W));
-        const bool no_wall = (!p.bounded_x || (i_lo > 1 && i_hi < p.Nx)) && (!p.wall_s || r_lo > 1) && (!p.wall_n || r_hi < p.Ny);
+        const bool no_wall = (!p.wall_w || i_lo > 1) && (!p.wall_e || i_hi < p.Nx) && (!p.wall_s || r_lo > 1) && (!p.wall_n || r_hi < p.Ny);
         if (inside && no_img && no_wall) {
             double *o = p.base + (size_t)(tc.J0 - 2 + p.oy) * p.pitch + (size_t)(tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
 #pragma unroll
@@ -1003,7 +1004,7 @@ struct PackItem {
 };
 __global__ void k_pack(PackItem it, Params p, int w)
 {
-    // window: i in [1-w, Nx+w(+1)], j in [1-w', Ny+w'(+1)] clipped to the parent
+    // window: i in [1-w, Nx+w(+1)] (w = Hx on a partitioned x axis), j in [1-w', Ny+w'(+1)], clipped to the parent
     const int i = 1 - w + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 - p.oy + blockIdx.y;
     if (i > p.Nx + w + 1 || j > p.Ny + p.oy) return;
@@ -1095,7 +1096,9 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     pl->Nx = g.Nx;
     pl->Ny = g.Ny;
     pl->oy = (g.conn_s || g.conn_n) ? g.Hy : W + 1;
-    pl->pitch = ((OX + g.Nx + 1 + W + 1 + 15) / 16) * 16;
+    const int wx = (g.conn_w || g.conn_e) ? g.Hx : W;  // halo columns kept in the internal layout
+    if (wx > OX - 3) { snprintf(err, nerr, "fused solver: Hx = %d exceeds the internal x halo (%d)", g.Hx, OX - 3); delete pl; return nullptr; }
+    pl->pitch = ((OX + g.Nx + 1 + wx + 1 + 15) / 16) * 16;
     pl->rows = g.Ny + 2 * pl->oy + 1;
     const size_t bytes = (size_t)NF * pl->pitch * pl->rows * sizeof(double);
     cudaError_t e = cudaMalloc(&pl->base, bytes);
@@ -1106,7 +1109,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
         // node flags from the centre mask, with the reference's inactive_cell / immersed_peripheral_node logic
         const int msx = g.Nx + 2 * g.Hx, msy = g.Ny + 2 * g.Hy;
         auto outside = [&](int i, int j) {
-            return (g.topo_x == CSI_BOUNDED && (i < 1 || i > g.Nx)) || (g.topo_y == CSI_BOUNDED && ((j < 1 && !g.conn_s) || (j > g.Ny && !g.conn_n)));
+            return (g.topo_x == CSI_BOUNDED && ((i < 1 && !g.conn_w) || (i > g.Nx && !g.conn_e))) || (g.topo_y == CSI_BOUNDED && ((j < 1 && !g.conn_s) || (j > g.Ny && !g.conn_n)));
         };
         auto immersed = [&](int i, int j) {
             const int pi = std::min(std::max(i - 1 + g.Hx, 0), msx - 1), pj = std::min(std::max(j - 1 + g.Hy, 0), msy - 1);
@@ -1205,21 +1208,25 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     if (!(dt >= 1e-30 && dt <= 1e30)) { snprintf(err, nerr, "fused solver: time step outside [1e-30, 1e30]"); return CSI_ERR_ARG; }
     memset(&P, 0, sizeof P);
     P.Nx = g.Nx; P.Ny = g.Ny; P.pitch = pl->pitch; P.rows = pl->rows; P.oy = pl->oy;
-    P.px = g.topo_x == CSI_PERIODIC;
+    P.px = g.topo_x == CSI_PERIODIC && !g.conn_w && !g.conn_e;
     P.py = g.topo_y == CSI_PERIODIC && !g.conn_s && !g.conn_n;
     P.bounded_x = g.topo_x == CSI_BOUNDED;
     P.bounded_y = g.topo_y == CSI_BOUNDED;
     P.wall_s = P.bounded_y && !g.conn_s;
     P.wall_n = P.bounded_y && !g.conn_n;
+    P.wall_w = P.bounded_x && !g.conn_w;
+    P.wall_e = P.bounded_x && !g.conn_e;
     // stresses: interior for periodic axes, one extra ring on Bounded axes (boundary nodes of sigma12 and
     // the first halo cell, which the reference also evolves, evp.jl:145); slabs: the widened range
-    P.sx0 = P.bounded_x ? 0 : 1; P.sx1 = P.bounded_x ? g.Nx + 1 : g.Nx;
+    P.sx0 = P.wall_w ? 0 : 1; P.sx1 = P.wall_e ? g.Nx + 1 : g.Nx;
     P.sy0 = P.wall_s ? 0 : 1; P.sy1 = P.wall_n ? g.Ny + 1 : g.Ny;
     P.vx0 = 1; P.vx1 = g.Nx; P.vy0 = 1; P.vy1 = g.Ny;
     if (g.conn_s) { P.sy0 = -g.Hy + 2; P.vy0 = -g.Hy + 2; }
     if (g.conn_n) { P.sy1 = g.Ny + g.Hy - 1; P.vy1 = g.Ny + g.Hy - 1; }
+    if (g.conn_w) { P.sx0 = -g.Hx + 2; P.vx0 = -g.Hx + 2; }
+    if (g.conn_e) { P.sx1 = g.Nx + g.Hx - 1; P.vx1 = g.Nx + g.Hx - 1; }
     const int BIG = 1 << 29;
-    P.cx0 = P.px ? -BIG : 1; P.cx1 = P.px ? BIG : g.Nx;
+    P.cx0 = P.px ? -BIG : P.vx0; P.cx1 = P.px ? BIG : P.vx1;
     P.cy0 = P.py ? -BIG : P.vy0; P.cy1 = P.py ? BIG : P.vy1;
     P.use_top = p.top_kind == CSI_STRESS_FIELD;
     P.use_ue = f.ue.p != nullptr && p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
@@ -1250,7 +1257,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     dim3 grid((ncols + OUTX - 1) / OUTX, (nrows + OUTY - 1) / OUTY);
 
     // pack: caller parents -> internal layout (window includes W halo cells; evolving fields into both copies)
-    const int w = W;
+    const int w = (g.conn_w || g.conn_e) ? g.Hx : W;
     auto pack = [&](const DArr &a, int field, int dup, int lx, int ly) {
         PackItem it{a, field, dup, lx, ly};
         dim3 pg((g.Nx + 2 * w + 2 + 127) / 128, g.Ny + 2 * pl->oy);

@@ -34,21 +34,21 @@ __global__ void k_fill_y_periodic(DArr a, int Ny, int Hy)
     at(a, i, Ny + k) = at(a, i, k);
 }
 
-__global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val)
+__global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val, int do_west, int do_east)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (j > Ny) return;
     const double D = dxff(g, j);  // Delta x at (Face, Face) on the wall, as Oceananigans' left/right_gradient uses
     if (mode == FILL_NOFLUX) {
-        at(a, 0, j) = at(a, 1, j);
-        at(a, Nx + 1, j) = at(a, Nx, j);
+        if (do_west) at(a, 0, j) = at(a, 1, j);
+        if (do_east) at(a, Nx + 1, j) = at(a, Nx, j);
     } else if (mode == FILL_VALUE) {
         const double c1 = at(a, 1, j), cN = at(a, Nx, j);
-        at(a, 0, j) = c1 + ((c1 - val) / (D / 2)) * (-D);
-        at(a, Nx + 1, j) = cN + ((val - cN) / (D / 2)) * D;
+        if (do_west) at(a, 0, j) = c1 + ((c1 - val) / (D / 2)) * (-D);
+        if (do_east) at(a, Nx + 1, j) = cN + ((val - cN) / (D / 2)) * D;
     } else if (mode == FILL_IMPENETRABLE) {
-        at(a, 1, j) = 0.0;
-        at(a, Nx + 1, j) = 0.0;
+        if (do_west) at(a, 1, j) = 0.0;
+        if (do_east) at(a, Nx + 1, j) = 0.0;
     }
 }
 
@@ -74,7 +74,7 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
 {
     if (!a.p) return;
     const int T = 128;
-    if (g.topo_x == CSI_BOUNDED) {
+    if (g.topo_x == CSI_BOUNDED && !(g.conn_w && g.conn_e)) {
         int mode = FILL_NONE;
         double val = 0.0;
         if (lx == 0) {
@@ -84,7 +84,7 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             mode = FILL_IMPENETRABLE;
         }
         if (mode != FILL_NONE) {
-            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val);
+            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val, !g.conn_w, !g.conn_e);
             ++*c.launches;
         }
     }
@@ -102,7 +102,7 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             ++*c.launches;
         }
     }
-    if (g.topo_x == CSI_PERIODIC) {
+    if (g.topo_x == CSI_PERIODIC && !g.conn_w && !g.conn_e) {
         k_fill_x_periodic<<<dim3((a.sy + T - 1) / T, g.Hx), T, 0, c.stream>>>(a, g.Nx, g.Hx);
         ++*c.launches;
     }
@@ -120,7 +120,7 @@ __global__ void k_mask_immersed(DGrid g, DArr a, int lx, int ly)
     auto imm = [&](int ii, int jj) {
         const int sx = g.Nx + 2 * g.Hx, sy = g.Ny + 2 * g.Hy;
         const int pi = min(max(ii - 1 + g.Hx, 0), sx - 1), pj = min(max(jj - 1 + g.Hy, 0), sy - 1);
-        const bool out = (g.topo_x == CSI_BOUNDED && (ii < 1 || ii > g.Nx)) ||
+        const bool out = (g.topo_x == CSI_BOUNDED && ((ii < 1 && !g.conn_w) || (ii > g.Nx && !g.conn_e))) ||
                          (g.topo_y == CSI_BOUNDED && ((jj < 1 && !g.conn_s) || (jj > g.Ny && !g.conn_n)));
         return out || g.mask[(size_t)pi + (size_t)pj * sx] != 0;
     };

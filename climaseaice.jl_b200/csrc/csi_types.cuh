@@ -22,7 +22,8 @@ __device__ __forceinline__ double ld(const DArr &a, int i, int j)
 struct DGrid {
     int Nx, Ny, Hx, Hy;
     int topo_x, topo_y;     // CSI_PERIODIC / CSI_BOUNDED
-    int conn_s, conn_n;     // slab partition: south / north side is a rank boundary (halo exchanged)
+    int conn_s, conn_n;     // partition: south / north side is a rank boundary (halo exchanged)
+    int conn_w, conn_e;     // 2-D partition: west / east side is a rank boundary
     double dx, dy, az;      // regular rectilinear metrics; az = dx*dy
     const uint8_t *mask;    // optional immersed mask at centres (parent-shaped), device pointer
     const uint8_t *mask_host;  // the same mask in host memory (plan construction only)

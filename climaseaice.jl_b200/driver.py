@@ -14,17 +14,17 @@ from .model import (Bounded, FPlane, Field, HydrostaticSphericalCoriolis, Latitu
 from .synthetic import LOC, Case
 
 
-def grid_from_case(case: Case, device=None, partitioned_y=False) -> RectilinearGrid:
+def grid_from_case(case: Case, device=None, partitioned_y=False, partitioned_x=False) -> RectilinearGrid:
     if case.latlon is not None:
         return LatitudeLongitudeGrid(size=(case.Nx, case.Ny), longitude=case.latlon[0], latitude=case.latlon[1],
                                      halo=(case.Hx, case.Hy), topology=(case.topology[0], case.topology[1], "Flat"),
                                      device=device, metrics=case.metrics(), partitioned_y=partitioned_y)
     return RectilinearGrid(size=(case.Nx, case.Ny), x=(0, case.Lx), y=(0, case.Ly), halo=(case.Hx, case.Hy),
-                           topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y)
+                           topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y, partitioned_x=partitioned_x)
 
 
 def model_from_case(case: Case, solver_impl="auto", partition=None, device=None) -> SeaIceModel:
-    grid = grid_from_case(case, device, partitioned_y=partition is not None)
+    grid = grid_from_case(case, device, partitioned_y=partition is not None, partitioned_x=partition is not None and len(partition) > 3 and partition[3] > 1)
     F = case.fields
     oc = case.ocean_const or (0.0, 0.0)
     fld = lambda n: Field(LOC[n], grid, F[n])

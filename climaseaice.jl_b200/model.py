@@ -32,10 +32,11 @@ Center, Face = 0, 1
 class RectilinearGrid:
     """RectilinearGrid(size=(Nx, Ny), x=(x0, x1), y=(y0, y1), halo=(Hx, Hy), topology=(TX, TY, Flat))."""
 
-    def __init__(self, size, x, y, halo=(3, 3), topology=(Periodic, Periodic, Flat), device=None, partitioned_y=False):
-        # partitioned_y: this grid is a rank-local y-slab; Face fields then carry no extra row on a Bounded y axis
-        # (the wall row lives in the slab's halo), as with Oceananigans' Distributed grids
+    def __init__(self, size, x, y, halo=(3, 3), topology=(Periodic, Periodic, Flat), device=None, partitioned_y=False, partitioned_x=False):
+        # partitioned_y / partitioned_x: this grid is a rank-local block; Face fields then carry no extra row / column on a
+        # Bounded axis (the wall point lives in the block's halo), as with Oceananigans' Distributed grids
         self.partitioned_y = bool(partitioned_y)
+        self.partitioned_x = bool(partitioned_x)
         self.Nx, self.Ny = int(size[0]), int(size[1])
         self.Hx, self.Hy = int(halo[0]), int(halo[1])
         self.x, self.y = (float(x[0]), float(x[1])), (float(y[0]), float(y[1]))
@@ -53,7 +54,7 @@ class RectilinearGrid:
 
     def parent_shape(self, loc):
         """(sy, sx) of a field's parent: Face fields carry N+1 points along Bounded axes."""
-        sx = self.Nx + 2 * self.Hx + (1 if (loc[0] == Face and self.topology[0] == Bounded) else 0)
+        sx = self.Nx + 2 * self.Hx + (1 if (loc[0] == Face and self.topology[0] == Bounded and not self.partitioned_x) else 0)
         sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] == Bounded and not self.partitioned_y) else 0)
         return sy, sx
 
@@ -360,7 +361,7 @@ class SeaIceModel:
         bcs = boundary_conditions or {}
         self._u_bc = bcs.get("u", {})
         self._v_bc = bcs.get("v", {})
-        self.partition = partition  # (rank, nranks, exchange_every) for slab runs
+        self.partition = partition  # (rank, nranks, exchange_every[, Rx]): y-slabs, or Rx x (nranks / Rx) blocks with rank = ry * Rx + rx
         # ImmersedBoundaryCondition with the discrete-form flux -C*u (u: south/north) and -C*v (v: west/east), as in
         # examples/ice_advected_on_coastline.jl:91-98
         self.immersed_drag = (float(immersed_drag[0]), float(immersed_drag[1]))
@@ -522,7 +523,8 @@ class SeaIceModel:
         cfg.solver_impl = self._solver_impl
         cfg.immersed_drag_u, cfg.immersed_drag_v = self.immersed_drag
         if self.partition:
-            cfg.rank, cfg.nranks, cfg.exchange_every = self.partition
+            cfg.rank, cfg.nranks, cfg.exchange_every = self.partition[:3]
+            cfg.partition_x = int(self.partition[3]) if len(self.partition) > 3 else 0
         else:
             cfg.rank, cfg.nranks, cfg.exchange_every = 0, 1, 0
         return cfg
@@ -635,7 +637,7 @@ class SeaIceModel:
         return dict(zip(("sum_h_Az", "sum_a_Az", "sum_ha_Az", "max_abs_u", "max_abs_v"), out))
 
     def comm_init(self, unique_id: bytes):
-        rank, nranks, _ = self.partition
+        rank, nranks = self.partition[:2]
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         L.check(L.lib().csi_comm_init(self._handle, buf, rank, nranks), self._handle)
 

@@ -322,6 +322,30 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
     return c
 
 
+def block_of(case: Case, rank: int, Rx: int, Ry: int, Hx: int, Hy: int) -> Case:
+    """Rank-local block (halos Hx, Hy) of a Rx x Ry partition, rank = ry * Rx + rx, of a regular-grid case: the y-slab of
+    row ry, cut along x.  Halo columns are periodic images (Periodic x) or the global parent's columns (Bounded x)."""
+    assert case.Nx % Rx == 0 and case.latlon is None
+    rx, ry = rank % Rx, rank // Rx
+    sl = slab_of(case, ry, Ry, Hy)
+    if Rx == 1:
+        return sl
+    nx = case.Nx // Rx
+    c = dataclasses.replace(sl, name=case.name + f"-block{rx}.{ry}", Nx=nx, Hx=Hx, Lx=case.Lx / Rx, fields={})
+    i = np.arange(rx * nx - Hx, (rx + 1) * nx + Hx)               # 0-based global interior column of every block column
+    for k, arr in sl.fields.items():
+        if case.topology[0] == "Periodic":
+            interior = arr[:, case.Hx:case.Hx + case.Nx]
+            c.fields[k] = np.ascontiguousarray(interior[:, i % case.Nx])
+        else:
+            out = np.zeros((arr.shape[0], nx + 2 * Hx))
+            pi = i + case.Hx
+            ok = (pi >= 0) & (pi < arr.shape[1])
+            out[:, ok] = arr[:, pi[ok]]
+            c.fields[k] = out
+    return c
+
+
 def slab_rows(case: Case, rank: int, nranks: int):
     """Rows of the global parent array that rank's interior covers."""
     ny = case.Ny // nranks

@@ -103,10 +103,11 @@ typedef struct {
     double v_west_east_value;
     int32_t timestepper;        /* CSI_RK3 (":SplitRungeKutta3", default) or CSI_FE */
     int32_t solver_impl;        /* CSI_SOLVER_* : kernel formulation used by csi_evp_substeps */
-    /* slab partition along y (rank-local block; halos of connected sides are exchanged) */
+    /* partition (rank-local block; halos of connected sides are exchanged): slabs along y, or Rx x Ry blocks */
     int32_t rank, nranks;
     int32_t exchange_every;     /* K: substeps between halo exchanges (needs Hy >= 2K+3) */
-    int32_t reserved_;
+    int32_t partition_x;        /* Rx of a 2-D partition Rx x (nranks / Rx), rank = ry * Rx + rx; 0 or 1 = slabs along y
+                                   (needs Hx >= 2K+3; Face fields then carry no extra column on a Bounded x axis) */
     /* ImmersedBoundaryCondition of examples/ice_advected_on_coastline.jl:91-98: discrete-form flux -C*u on the
      * south/north immersed faces of u and -C*v on the west/east ones of v (isd.jl:57-123); 0 = none */
     double immersed_drag_u, immersed_drag_v;

@@ -54,7 +54,7 @@ Base.@kwdef struct CsiConfig
     v_west_east_bc :: Int32 = 0; advection_order :: Int32 = 7
     v_west_east_value :: Float64 = 0.0
     timestepper :: Int32 = 0; solver_impl :: Int32 = 0
-    rank :: Int32 = 0; nranks :: Int32 = 1; exchange_every :: Int32 = 0; reserved_ :: Int32 = 0
+    rank :: Int32 = 0; nranks :: Int32 = 1; exchange_every :: Int32 = 0; partition_x :: Int32 = 0
     immersed_drag_u :: Float64 = 0.0; immersed_drag_v :: Float64 = 0.0
     metric_kind :: Int32 = 0; reserved2_ :: Int32 = 0
     metrics :: NTuple{12, Ptr{Float64}} = ntuple(_ -> Ptr{Float64}(C_NULL), 12)

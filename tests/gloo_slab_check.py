@@ -13,7 +13,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 entry.load_package()
 from climaseaice_b200 import lib  # noqa: E402
-from climaseaice_b200.synthetic import periodic_case, slab_of  # noqa: E402
+from climaseaice_b200.synthetic import block_of, periodic_case, slab_of  # noqa: E402
 
 
 def main():
@@ -37,6 +37,20 @@ def main():
         recv = [torch.empty_like(first) for _ in range(world)]
         dist.all_gather(recv, first)
         ok &= np.array_equal(north.numpy(), recv[(rank + 1) % world].numpy())
+    # 2-D partition world x 1 (blocks along x, rank = rx): interiors tile the case, my east halo is the first Hx interior
+    # columns of the next rank (the packed strip csi_exchange_halos sends westwards)
+    bcase = periodic_case(16 * world, Ny=12, substeps=K)
+    bl = block_of(bcase, rank, world, 1, Hy, Hy)
+    for name, arr in bl.fields.items():
+        mine = torch.from_numpy(np.ascontiguousarray(arr[Hy:Hy + bl.Ny, Hy:Hy + bl.Nx]))
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        ok &= np.array_equal(torch.cat(parts, 1).numpy(), bcase.fields[name][bcase.Hy:bcase.Hy + bcase.Ny, bcase.Hx:bcase.Hx + bcase.Nx])
+        east = np.ascontiguousarray(arr[Hy:Hy + bl.Ny, Hy + bl.Nx:])
+        first = torch.from_numpy(np.ascontiguousarray(arr[Hy:Hy + bl.Ny, Hy:2 * Hy]))
+        recv = [torch.empty_like(first) for _ in range(world)]
+        dist.all_gather(recv, first)
+        ok &= np.array_equal(east, recv[(rank + 1) % world].numpy())
     flag = torch.tensor([0 if ok else 1])
     dist.all_reduce(flag)
     if rank == 0:

@@ -36,3 +36,25 @@ def test_two_gpus_equal_one_gpu(solver, K, topo):
     r = _torchrun(ROOT / "tests" / "multigpu_check.py", 2, solver, K, 2, topo)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU_OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 4, "bounded_x"), ("unfused", 3, "bounded_x")])
+def test_two_gpus_split_along_x_equal_one_gpu(solver, K, topo):
+    """Partition(2, 1): packed west/east strips instead of zero-copy rows (test/distributed_tests_utils.jl:60-62 runs (4,1))."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(ROOT / "tests" / "multigpu_check.py", 2, solver, K, 2, topo, 2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTIGPU_OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,K,topo", [("auto", 3, "periodic"), ("unfused", 3, "periodic"), ("auto", 3, "bounded_x")])
+def test_four_gpus_2x2_equal_one_gpu(solver, K, topo):
+    """Partition(2, 2): strips, rows and the corners the rows carry (test/distributed_tests_utils.jl:60-62 runs (2,2))."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    r = _torchrun(ROOT / "tests" / "multigpu_check.py", 4, solver, K, 2, topo, 2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTIGPU_OK" in r.stdout
