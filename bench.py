@@ -141,7 +141,14 @@ def run_reference(args):
     return 0
 
 
-def workload_config(ngpus):
+def workload_config(ngpus, Rx=1):
+    if ngpus > 1 and Rx > 1:
+        Ry = ngpus // Rx
+        return {"workload": f"doubly periodic EVP on 16384x{2048 * ngpus} (BASELINE config 3 at 8 GPUs = 16384^2), {Rx}x{Ry} blocks of "
+                            f"{16384 // Rx}x{2048 * ngpus // Ry} per GPU, NCCL halo exchange (packed west/east strips, zero-copy rows) every 4 substeps, "
+                            "150 substeps per step",
+                "grid": [16384, 2048 * ngpus], "per_gpu": [16384 // Rx, 2048 * ngpus // Ry], "partition": [Rx, Ry], "substeps": SUBSTEPS,
+                "exchange_every": 4, "l2_policy": "inputs larger than L2 (4.9 GB working set per GPU vs 126 MB)"}
     if ngpus == 1:
         return {"workload": "anticyclone EVP benchmark scaled to 4096x4096 (BASELINE config 2): Bounded x Bounded, H=7, dx=4 km, "
                             "FPlane f=1e-4, wind-stress arrays + SemiImplicitStress ocean drag, 150 substeps per step",
@@ -181,8 +188,12 @@ def run_gpu(args):
     else:
         # each rank builds only its own slab of the global periodic case (same seed => consistent fields)
         Hy = 2 * K + 3
-        case = periodic_slab_case(nx, ny, rank, ngpus, Hy)
-        model = model_from_case(case, solver_impl=args.solver, partition=(rank, ngpus, K), device=dev)
+        Rx = max(1, args.partition_x)
+        if ngpus % Rx:
+            raise SystemExit("bench.py: --partition-x must divide the number of GPUs")
+        Ry = ngpus // Rx
+        case = periodic_slab_case(nx // Rx, ny * ngpus // Ry, rank // Rx, Ry, Hy, rx=rank % Rx, Rx=Rx)
+        model = model_from_case(case, solver_impl=args.solver, partition=(rank, ngpus, K, Rx) if Rx > 1 else (rank, ngpus, K), device=dev)
         ids = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         model.comm_init(ids[0])
@@ -262,7 +273,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(ngpus) if not (args.nx or args.periodic) else {"workload": f"custom {case.name} {case.Nx}x{case.Ny} per GPU"},
+            "data": "synthetic", "config": workload_config(ngpus, max(1, args.partition_x)) if not (args.nx or args.periodic) else {"workload": f"custom {case.name} {case.Nx}x{case.Ny} per GPU"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "solver": args.solver,
             "full_time_step": {"ms": full_ms, "cell_updates_per_s": cells * ngpus * 3 * SUBSTEPS / (full_ms * 1e-3),
@@ -274,19 +285,20 @@ def run_gpu(args):
     return 0
 
 
-def periodic_slab_case(nx, ny_local, rank, nranks, Hy):
-    """Rank-local slab of the global doubly periodic case, generated without materialising the global arrays."""
+def periodic_slab_case(nx, ny_local, rank, nranks, Hy, rx=0, Rx=1):
+    """Rank-local slab (row `rank` of `nranks`; with Rx > 1 the block rx of that row, `nx` columns wide, halo Hy on both axes)
+    of the global doubly periodic case, generated without materialising the global arrays."""
     import numpy as np
     from climaseaice_b200.synthetic import Case, LOC
     Ny = ny_local * nranks
-    c = Case(f"periodic-slab{rank}", nx, ny_local, 7, Hy, ("Periodic", "Periodic"), nx * 4000.0, ny_local * 4000.0)
+    c = Case(f"periodic-slab{rank}.{rx}", nx, ny_local, Hy if Rx > 1 else 7, Hy, ("Periodic", "Periodic"), nx * 4000.0, ny_local * 4000.0)
     tp = 2 * np.pi
-    Lx, Ly = nx * 4000.0, Ny * 4000.0
-    rng = np.random.default_rng(20260417 + rank)
+    Lx, Ly = nx * Rx * 4000.0, Ny * 4000.0
+    rng = np.random.default_rng(20260417 + rank * Rx + rx)
 
     def nodes(loc):
         sy, sx = c.parent_shape(loc)
-        i = np.arange(sx) - c.Hx + 1
+        i = np.arange(sx) - c.Hx + 1 + rx * nx
         j = np.arange(sy) - c.Hy + 1 + rank * ny_local
         x = ((i - 1) if loc[0] else (i - 0.5)) * 4000.0
         y = ((j - 1) if loc[1] else (j - 0.5)) * 4000.0
@@ -343,6 +355,7 @@ def main():
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--periodic", action="store_true")
+    ap.add_argument("--partition-x", type=int, default=1, help="N > 1: Rx of an Rx x (N / Rx) block partition (default 1 = y-slabs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=2048)

@@ -61,7 +61,7 @@ class csi_config(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("exchange_every", C.c_int32), ("partition_x", C.c_int32),
         ("immersed_drag_u", C.c_double), ("immersed_drag_v", C.c_double),
-        ("metric_kind", C.c_int32), ("reserved2_", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
+        ("metric_kind", C.c_int32), ("serial_exchange", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
         ("free_drift_kind", C.c_int32), ("reserved3_", C.c_int32), ("top_rho_e", C.c_double), ("top_Cd", C.c_double),
         ("coriolis_f_ff", C.POINTER(C.c_double)),
     ]

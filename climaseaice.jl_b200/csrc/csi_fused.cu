@@ -92,6 +92,7 @@ struct Params {
     int sq;               // regular grid with dx == dy: phase A divides every u, v once (u/dx serves both operators)
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
+    int ty0;              // first tile row of this launch (a substep may be launched in row bands, see fused_steps)
     double *base;         // internal allocation
     const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
     const double *met;    // j-dependent metrics (lat-lon grids): MC_N columns of `rows` doubles, or NULL on a regular grid
@@ -911,7 +912,7 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
     const int y0 = p.sy0 < p.vy0 ? p.sy0 : p.vy0;
     TileCtx tc;
     tc.I0 = p.a0 + blockIdx.x * OUTX;
-    tc.J0 = y0 + blockIdx.y * OUTY;
+    tc.J0 = y0 + (blockIdx.y + p.ty0) * OUTY;
     tc.fin = p.in_set ? F_U1 : F_U0;
     tc.fout = p.out_set ? F_U1 : F_U0;
     if (threadIdx.x == 0) {
@@ -1280,11 +1281,19 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
 
 // `nsub` substeps starting at substep index `first_sub` (odd substeps update v first, se.jl:178-187);
 // `aux_last`: the last of them also writes alpha, zeta, Delta.
-int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool aux_last, char *err, int nerr)
+// `halo_ready` (slabs): an event recorded on another stream after the halo rows of the current copy have been received.
+// The first substep is then launched in row bands: the tile rows whose boxes stay inside rows 1..Ny go first and overlap
+// the exchange, the tile rows that read halo rows wait for the event.
+int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool aux_last, char *err, int nerr, cudaEvent_t halo_ready)
 {
     using namespace fz;
     Params &P = pl->P;
     const dim3 grid = pl->grid;
+    const int y0 = P.sy0 < P.vy0 ? P.sy0 : P.vy0;
+    // tile row t covers rows J0 = y0 + OUTY t ... and reads J0 - 2 .. J0 + OUTY + 1
+    int t_lo = 0, t_hi = (int)grid.y;  // interior band [t_lo, t_hi)
+    while (t_lo < (int)grid.y && y0 + OUTY * t_lo - 2 < 1) t_lo++;
+    while (t_hi > t_lo && y0 + OUTY * (t_hi - 1) + OUTY + 1 > P.Ny) t_hi--;
     for (int k = 0; k < nsub; k++) {
         const int sub = first_sub + k;
         P.in_set = pl->cur_set;
@@ -1293,11 +1302,26 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
         const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
-        const cudaError_t e = P.met    ? launch_sub<true, true>(pl, P, grid, c.stream, vfirst, aux)
-                              : common ? launch_sub<false, false>(pl, P, grid, c.stream, vfirst, aux)
-                                       : launch_sub<true, false>(pl, P, grid, c.stream, vfirst, aux);
+        auto band = [&](int t0, int t1) -> cudaError_t {
+            if (t1 <= t0) return cudaSuccess;
+            P.ty0 = t0;
+            const dim3 gb(grid.x, t1 - t0);
+            ++*c.launches;
+            return P.met    ? launch_sub<true, true>(pl, P, gb, c.stream, vfirst, aux)
+                   : common ? launch_sub<false, false>(pl, P, gb, c.stream, vfirst, aux)
+                            : launch_sub<true, false>(pl, P, gb, c.stream, vfirst, aux);
+        };
+        cudaError_t e;
+        if (k == 0 && halo_ready && t_hi > t_lo) {
+            e = band(t_lo, t_hi);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, halo_ready, 0);
+            if (e == cudaSuccess) e = band(0, t_lo);
+            if (e == cudaSuccess) e = band(t_hi, (int)grid.y);
+        } else {
+            if (k == 0 && halo_ready && (e = cudaStreamWaitEvent(c.stream, halo_ready, 0)) != cudaSuccess) { snprintf(err, nerr, "wait: %s", cudaGetErrorString(e)); return (int)e; }
+            e = band(0, (int)grid.y);
+        }
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
-        ++*c.launches;
         pl->cur_set ^= 1;
     }
     return 0;
@@ -1355,7 +1379,7 @@ int fused_run(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams &
 {
     int rc = fused_begin(pl, c, g, p, f, dt, err, nerr);
     if (rc) return rc;
-    if ((rc = fused_steps(pl, c, first_sub, nsub, true, err, nerr))) return rc;
+    if ((rc = fused_steps(pl, c, first_sub, nsub, true, err, nerr, nullptr))) return rc;
     return nsub > 0 ? fused_end(pl, c, f, err, nerr) : 0;
 }
 

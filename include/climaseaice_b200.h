@@ -116,7 +116,8 @@ typedef struct {
      * order dx{cc,fc,cf,ff}, dy{cc,fc,cf,ff}, Az{cc,fc,cf,ff} (Oceananigans' Delta-x/Delta-y/Az at the four
      * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above. */
     int32_t metric_kind;
-    int32_t reserved2_;
+    int32_t serial_exchange;    /* slabs + fused solver: 0 = the halo exchange between blocks of K substeps runs on its own stream
+                                   while the next substep's interior tiles compute (boundary tiles wait for it); 1 = on the compute stream */
     const double *metrics[12];
     /* free drift velocity of marginal ice (mass or concentration under the thresholds but above eps): CSI_FD_* */
     int32_t free_drift_kind;

@@ -56,7 +56,7 @@ Base.@kwdef struct CsiConfig
     timestepper :: Int32 = 0; solver_impl :: Int32 = 0
     rank :: Int32 = 0; nranks :: Int32 = 1; exchange_every :: Int32 = 0; partition_x :: Int32 = 0
     immersed_drag_u :: Float64 = 0.0; immersed_drag_v :: Float64 = 0.0
-    metric_kind :: Int32 = 0; reserved2_ :: Int32 = 0
+    metric_kind :: Int32 = 0; serial_exchange :: Int32 = 0
     metrics :: NTuple{12, Ptr{Float64}} = ntuple(_ -> Ptr{Float64}(C_NULL), 12)
     free_drift_kind :: Int32 = 0; reserved3_ :: Int32 = 0     # 0 nothing, 1 (u=, v=) arrays, 2 StressBalanceFreeDrift
     top_rho_e :: Float64 = 1.3; top_Cd :: Float64 = 1.2e-3    # SemiImplicitStress as the top stress
