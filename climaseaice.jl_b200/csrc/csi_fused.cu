@@ -93,6 +93,9 @@ struct Params {
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     int ty0;              // first tile row of this launch (a substep may be launched in row bands, see fused_steps)
+    // tile columns / rows (inclusive) whose cells all lie inside every store window, have no periodic image and no wall
+    // neighbour, and whose velocity nodes are all evolved: the vast majority; they skip the per-node edge tests
+    int it_x0, it_x1, it_y0, it_y1;
     double *base;         // internal allocation
     const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
     const double *met;    // j-dependent metrics (lat-lon grids): MC_N columns of `rows` doubles, or NULL on a regular grid
@@ -452,6 +455,7 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
 struct TileCtx {
     int I0, J0;  // reference index of the first velocity cell of the tile
     int fin, fout;
+    bool interior;  // see Params::it_x0
 };
 
 // All phases of one tile under one arithmetic policy.  Returns whether any thread left the policy's
@@ -495,18 +499,30 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     const bool c_on[2] = {lane < OUTX + 1, lane < OUTX + 1 && c_sy0 + 1 <= (VFIRST ? OUTY + 1 : OUTY)};
     const int d_sx = lane + 1, d_sy0 = 1 + 2 * wrp;
     const bool d_on[2] = {lane < OUTX && d_sy0 <= OUTY, lane < OUTX && d_sy0 + 1 <= OUTY};
-    auto goff = [&](int sx, int sy) {
+    // offsets inside one plane fit 32 bits (pitch x rows < 2^31 doubles is checked when the plan is built)
+    const int o00 = (tc.J0 - 2 + p.oy) * p.pitch + (tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
+    auto goff = [&](int sx, int sy) -> int {
         // clamped into the plane: edge tiles reach past the allocation (those nodes are never stored)
         const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
-        return (size_t)row * p.pitch + (size_t)col;
+        return row * p.pitch + col;
     };
     const double *gC1 = p.base + (size_t)(VFIRST ? F_VN : F_UN) * plane, *gC2 = p.base + (size_t)(VFIRST ? F_TY : F_TX) * plane;
     const double *gD1 = p.base + (size_t)(VFIRST ? F_UN : F_VN) * plane, *gD2 = p.base + (size_t)(VFIRST ? F_TX : F_TY) * plane;
-    size_t c_g[2], d_g[2];
+    int c_g[2], d_g[2];
+    if (tc.interior) {
+        c_g[0] = o00 + c_sy0 * p.pitch + c_sx;
+        d_g[0] = o00 + d_sy0 * p.pitch + d_sx;
+        c_g[1] = c_g[0] + p.pitch;
+        d_g[1] = d_g[0] + p.pitch;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            c_g[q] = goff(c_sx, c_sy0 + q);
+            d_g[q] = goff(d_sx, d_sy0 + q);
+        }
+    }
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        c_g[q] = goff(c_sx, c_sy0 + q);
-        d_g[q] = goff(d_sx, d_sy0 + q);
         // pull the pointwise inputs of phases C / D towards L2/L1 while the tile lands and A, B run
         if (c_on[q]) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gC1 + c_g[q]));
@@ -541,8 +557,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             qv[n] = mm.divc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
         }
         __syncthreads();
-        for (int n = tid; n < SXD * SYD; n += NT) {
-            const int sx = n % SXD - 1, sy = n / SXD - 1;
+        int sx = tid % SXD - 1, sy = tid / SXD - 1;  // node of n = tid; advanced by NT per iteration without dividing
+        for (int n = tid; n < SXD * SYD; n += NT, sx += NT % SXD, sy += NT / SXD) {
+            if (sx >= SXD - 1) { sx -= SXD; sy++; }
             double *b = sm + n;
             const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0), qu00 = SB(b, A_AL, 0, 0), qv00 = SB(b, A_W, 0, 0);
             if (sx < BX && sy < BY) {
@@ -671,8 +688,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
     auto u_at = [&](int sx, int sy, int VS, double un, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
-        const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool wall_active = !((p.wall_w && i <= 1) || (p.wall_e && i > p.Nx));
+        bool upd = true, wall_active = true;
+        if (!tc.interior) {
+            upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
+            wall_active = !((p.wall_w && i <= 1) || (p.wall_e && i > p.Nx));
+        }
         const double *b = &S(0, sx, sy);
         // reference tree: vbar; scaled tree: the plain sum 4 vbar (and f / 4)
         const double vsum = (SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1));
@@ -726,8 +746,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     };
     auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
-        const bool upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
-        const bool wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
+        bool upd = true, wall_active = true;
+        if (!tc.interior) {
+            upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
+            wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
+        }
         const double *b = &S(0, sx, sy);
         const double usum = (SB(b, US, 0, -1) + SB(b, US, 1, -1)) + (SB(b, US, 0, 0) + SB(b, US, 1, 0));
         const double ubar = M::SCALED ? usum : ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
@@ -838,17 +861,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // interior tiles (the vast majority): every output cell is inside all store windows and has no periodic
     // image or wall neighbour -> plain stores at one precomputed offset
     {
-        const int i_lo = tc.I0, i_hi = tc.I0 + OUTX - 1, r_lo = tc.J0, r_hi = tc.J0 + OUTY - 1;
-        const bool inside = i_lo >= max(p.sx0, p.vx0) && i_hi <= min(p.sx1, p.vx1) && r_lo >= max(p.sy0, p.vy0) && r_hi <= min(p.sy1, p.vy1);
-        const bool no_img = (!p.px || (i_lo > W && i_hi <= p.Nx - W)) && (!p.py || (r_lo > W && r_hi <= p.Ny - W));
-        const bool no_wall = (!p.wall_w || i_lo > 1) && (!p.wall_e || i_hi < p.Nx) && (!p.wall_s || r_lo > 1) && (!p.wall_n || r_hi < p.Ny);
-        if (inside && no_img && no_wall) {
-            double *o = p.base + (size_t)(tc.J0 - 2 + p.oy) * p.pitch + (size_t)(tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
+        if (tc.interior) {
+            double *o = p.base + o00 + 2 * wrp * p.pitch + lane;  // this thread's node (lane, 2 wrp)
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int sx = lane, sy = 2 * wrp + q;
                 if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
-                    double *g = o + (size_t)sy * p.pitch + sx;
+                    double *g = o + q * p.pitch;
                     g[(size_t)(tc.fout + 2) * plane] = S(A_S11, sx, sy);
                     g[(size_t)(tc.fout + 3) * plane] = S(A_S22, sx, sy);
                     g[(size_t)(tc.fout + 4) * plane] = S(A_S12, sx, sy);
@@ -861,7 +880,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                 }
                 if (d_on[q]) {
                     const int dsy = d_sy0 + q;
-                    double *g = o + (size_t)dsy * p.pitch + d_sx;
+                    double *g = o + (q + 1) * p.pitch + 1;  // node (lane + 1, 2 wrp + 1 + q)
                     g[(size_t)(tc.fout + (VFIRST ? 0 : 1)) * plane] = w2[q];
                     g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(A_W, d_sx, dsy);
                 }
@@ -915,6 +934,8 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
     tc.J0 = y0 + (blockIdx.y + p.ty0) * OUTY;
     tc.fin = p.in_set ? F_U1 : F_U0;
     tc.fout = p.out_set ? F_U1 : F_U0;
+    const int by = blockIdx.y + p.ty0;
+    tc.interior = (int)blockIdx.x >= p.it_x0 && (int)blockIdx.x <= p.it_x1 && by >= p.it_y0 && by <= p.it_y1;
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -1101,6 +1122,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     if (wx > OX - 3) { snprintf(err, nerr, "fused solver: Hx = %d exceeds the internal x halo (%d)", g.Hx, OX - 3); delete pl; return nullptr; }
     pl->pitch = ((OX + g.Nx + 1 + wx + 1 + 15) / 16) * 16;
     pl->rows = g.Ny + 2 * pl->oy + 1;
+    if ((double)pl->pitch * (double)pl->rows >= 2147483647.0) { snprintf(err, nerr, "fused solver: block too large for 32-bit in-plane offsets"); delete pl; return nullptr; }
     const size_t bytes = (size_t)NF * pl->pitch * pl->rows * sizeof(double);
     cudaError_t e = cudaMalloc(&pl->base, bytes);
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
@@ -1271,6 +1293,24 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     pack(f.un, F_UN, 0, 1, 0); pack(f.vn, F_VN, 0, 0, 1);
     if (P.use_top) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
     if (P.use_ue) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
+
+    // interior tile columns / rows: every test the edge code makes is trivially true (see Params::it_x0)
+    auto interior_range = [&](int ntiles, int first, int out, int s0, int s1, int v0, int v1, int c0, int c1, bool per, bool wall_lo, bool wall_hi, int N,
+                              int &lo, int &hi) {
+        lo = 1 << 30; hi = -1;
+        for (int k = 0; k < ntiles; k++) {
+            const int a = first + k * out, b = a + out - 1;  // output cells a..b; velocity nodes a-1..b+1 are computed
+            bool ok = a >= std::max(s0, v0) && b <= std::min(s1, v1);
+            ok = ok && (!per || (a > W && b <= N - W));
+            ok = ok && (!wall_lo || a - 1 > 1) && (!wall_hi || b + 1 < N);
+            ok = ok && a - 1 >= c0 && b + 1 <= c1;
+            if (ok) { lo = std::min(lo, k); hi = std::max(hi, k); }
+            else if (hi >= 0) break;  // keep the range contiguous
+        }
+    };
+    const int y0 = P.sy0 < P.vy0 ? P.sy0 : P.vy0;
+    interior_range((int)grid.x, P.a0, OUTX, P.sx0, P.sx1, P.vx0, P.vx1, P.cx0, P.cx1, P.px != 0, P.wall_w != 0, P.wall_e != 0, g.Nx, P.it_x0, P.it_x1);
+    interior_range((int)grid.y, y0, OUTY, P.sy0, P.sy1, P.vy0, P.vy1, P.cy0, P.cy1, P.py != 0, P.wall_s != 0, P.wall_n != 0, g.Ny, P.it_y0, P.it_y1);
 
     pl->grid = grid;
     pl->cur_set = 0;

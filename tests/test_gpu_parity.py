@@ -414,3 +414,38 @@ def test_hydrostatic_spherical_coriolis_on_latlon_grid(impl):
     u, u0 = interior_of(m.all_fields()["u"].numpy(), case), interior_of(m0.all_fields()["u"].numpy(), case)
     assert np.abs(u - u0).max() > 1e-6               # f varies with latitude: differs from the f-plane run
     m.close(); m0.close()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("nsub", [1, 4])
+def test_extreme_magnitudes_stay_bitwise(impl, nsub):
+    """Subnormal and near-underflow values in every input (u, v, ocean velocity, wind stress, h, aice, sigma): the fused
+    kernel's shortcut arithmetic (branch-free division / sqrt, power-of-two-scaled expression tree) is only valid inside
+    its exponent windows, so such tiles must be detected and redone with the IEEE operators -- same bits as the oracle."""
+    case = periodic_case(64, Ny=48, substeps=nsub, aice="mixed", timestepper="ForwardEuler")
+    F, H = case.fields, case.Hx
+
+    def patch(arr, j0, j1, i0, i1, val):
+        arr[H + j0:H + j1, H + i0:H + i1] = val
+
+    patch(F["u"], 5, 9, 5, 9, 4.9e-324)
+    patch(F["v"], 5, 9, 12, 16, -1e-310)
+    patch(F["u"], 12, 15, 5, 9, 3e-200)
+    patch(F["v"], 12, 15, 12, 16, 7e-160)
+    patch(F["ue"], 20, 24, 5, 9, 1e-309)
+    patch(F["ve"], 20, 24, 12, 16, -2e-308)
+    patch(F["top_x"], 10, 14, 30, 34, 1e-312)
+    patch(F["top_y"], 10, 14, 36, 40, -3e-250)
+    patch(F["h"], 30, 34, 5, 9, 1e-180)
+    patch(F["a"], 30, 34, 12, 16, 1e-200)
+    patch(F["h"], 36, 40, 20, 24, 1e-300)
+    patch(F["a"], 36, 40, 28, 32, 5e-324)
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    for name, (j0, i0, val) in dict(s11=(20, 40, 1e-320), s22=(24, 44, -3e-310), s12=(28, 48, 2e-200)).items():
+        patch(m.all_fields()[name].parent, j0, j0 + 3, i0, i0 + 3, val)
+        patch(o.arr[name], j0, j0 + 3, i0, i0 + 3, val)
+    m.update_state(); o.update_state()
+    m.time_step_momentum(case.dt); o.time_step_momentum(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "s11", "s22", "s12", "alpha", "P")))
+    m.close()
