@@ -54,6 +54,7 @@ constexpr int SXD = BX + 2, SYD = BY + 2;    // shared-memory tile = TMA box: ti
 #endif
 constexpr int UNROLL_B = CSI_UNROLL_B, UNROLL_CD = CSI_UNROLL_CD;
 constexpr int NT = 256;                       // threads per CTA
+constexpr int NIT = (SXD * SYD + NT - 1) / NT;  // sweeps of the CTA over the haloed tile
 constexpr int ASTRIDE = ((SXD * SYD * 8 + 127) / 128) * 128 / 8;  // doubles between shared arrays (TMA destinations are 128-byte aligned)
 constexpr int W = 3;             // halo ring kept valid in the internal layout
 constexpr int OX = 16;           // internal column of i = 1 (128-byte aligned)
@@ -154,12 +155,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680)  // suspend-time hint: sleep in the barrier unit instead of spinning through issue slots
         : "memory");
 }
 __device__ __forceinline__ void tma_load_row(double *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
@@ -552,13 +553,20 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // regular grid with dx == dy: u / dx and v / dx serve both the tension and the shear operator; divide every
         // u, v of the tile once (into the arrays phases B and C fill later) instead of eight times per node
         double *qu = sm + A_AL * ASTRIDE, *qv = sm + A_W * ASTRIDE;
-        for (int n = tid; n < SXD * SYD; n += NT) {
+        // (the element loops of this phase are unrolled: NIT - 1 full sweeps of the CTA and a partial one)
+#pragma unroll
+        for (int k = 0; k < NIT; k++) {
+            const int n = tid + k * NT;
+            if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
             qu[n] = mm.divc(sm[A_U * ASTRIDE + n], p.dx, p.rdx);
             qv[n] = mm.divc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
         }
         __syncthreads();
         int sx = tid % SXD - 1, sy = tid / SXD - 1;  // node of n = tid; advanced by NT per iteration without dividing
-        for (int n = tid; n < SXD * SYD; n += NT, sx += NT % SXD, sy += NT / SXD) {
+#pragma unroll
+        for (int k = 0; k < NIT; k++, sx += NT % SXD, sy += NT / SXD) {
+            const int n = tid + k * NT;
+            if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
             if (sx >= SXD - 1) { sx -= SXD; sy++; }
             double *b = sm + n;
             const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0), qu00 = SB(b, A_AL, 0, 0), qv00 = SB(b, A_W, 0, 0);
@@ -598,7 +606,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
     }
     mbar_wait(&bar[1], parity);
-    for (int n = tid; n < SXD * SYD; n += NT) {
+#pragma unroll
+    for (int k = 0; k < NIT; k++) {
+        const int n = tid + k * NT;
+        if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
         sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
         if (M::SCALED && use_ue) {  // the scaled tree sums ocean velocities before halving: they must be zero or normal
             mm.chkq(sm[A_UE * ASTRIDE + n]);
