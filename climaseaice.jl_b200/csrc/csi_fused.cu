@@ -43,7 +43,10 @@ namespace csi {
 
 namespace fz {
 
-constexpr int BX = 32, BY = 16;  // stress nodes per tile
+#ifndef CSI_TILE_BY
+#define CSI_TILE_BY 16
+#endif
+constexpr int BX = 32, BY = CSI_TILE_BY;  // stress nodes per tile (a warp owns two rows: BY = 2 x warps per CTA)
 constexpr int OUTX = BX - 2, OUTY = BY - 2;  // velocity cells per tile
 constexpr int SXD = BX + 2, SYD = BY + 2;    // shared-memory tile = TMA box: tile + 1 halo ring
 #ifndef CSI_UNROLL_B
@@ -53,7 +56,7 @@ constexpr int SXD = BX + 2, SYD = BY + 2;    // shared-memory tile = TMA box: ti
 #define CSI_UNROLL_CD 2
 #endif
 constexpr int UNROLL_B = CSI_UNROLL_B, UNROLL_CD = CSI_UNROLL_CD;
-constexpr int NT = 256;                       // threads per CTA
+constexpr int NT = 32 * (BY / 2);              // threads per CTA
 constexpr int NIT = (SXD * SYD + NT - 1) / NT;  // sweeps of the CTA over the haloed tile
 constexpr int ASTRIDE = ((SXD * SYD * 8 + 127) / 128) * 128 / 8;  // doubles between shared arrays (TMA destinations are 128-byte aligned)
 constexpr int W = 3;             // halo ring kept valid in the internal layout
@@ -525,6 +528,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         // pull the pointwise inputs of phases C / D towards L2/L1 while the tile lands and A, B run
+#ifndef CSI_EXPERIMENT_NO_PREFETCH
         if (c_on[q]) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gC1 + c_g[q]));
             if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gC2 + c_g[q]));
@@ -533,6 +537,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gD1 + d_g[q]));
             if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gD2 + d_g[q]));
         }
+#endif
     }
 
     // immersed-boundary node flags of the tile (bit 0: centre masked, 1: corner masked, 2: u face peripheral, 3: v face peripheral)
