@@ -103,6 +103,8 @@ struct Params {
     double *base;         // internal allocation
     const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
     const double *met;    // j-dependent metrics (lat-lon grids): MC_N columns of `rows` doubles, or NULL on a regular grid
+    int *invalid;         // device flag raised by k_pack when an input is neither zero nor in [2^-300, 2^300): the whole
+                          // stage then runs the IEEE pass (the FAST pass relies on validated inputs, see MathFast)
 };
 
 // columns of the per-row metric table (internal row = j - 1 + oy): the twelve metrics, the squares the SBP operators use,
@@ -199,18 +201,21 @@ struct MathFast {
     // Window accumulators on the high word of each checked double (sign, 11 exponent bits, 20 significand bits):
     //  * quotients (any sign, zero allowed) are tested two at a time on the top halves of their high words (sign, exponent,
     //    4 significand bits), packed into one register with the signs masked off: per 16-bit lane qmx = max g,
-    //    qmn = min (g - 1) (VIMNMX.U16x2 / VIADDMNMX.U16x2)  -> |q| in [2^-511, 2^513) or g == 0.  A quotient waits in
-    //    `pend` for its partner; straight-line code resolves `have` at compile time.  (g == 0 is a zero or a magnitude
-    //    below 2^-1026, which no chain of checked operations starting from fields above 1e-150 can produce.)
+    //    qmn = min (g - 1) (VIMNMX.U16x2 / VIADDMNMX.U16x2)  -> |q| in [2^-300, 2^300) or g == 0.  A quotient waits in
+    //    `pend` for its partner; straight-line code resolves `have` at compile time.  g == 0 is a zero -- or a magnitude
+    //    below 2^-1026, which cannot occur: the pack kernel admits only inputs that are zero or in [2^-300, 2^300)
+    //    (anything else sends the whole stage to the IEEE pass), checked quotients and radicands stay in that window,
+    //    sums and differences of such values are zero or at least 2^-352, and no expression of the step multiplies more
+    //    than two of them with constants from [1e-30, 1e30] (>= 2^-804).
     //  * divisors  (positive, non-zero): dacc = umax(hi - DLO)  -> d in [2^-255, 2^257); zeros, negatives, NaN wrap high;
     //    lo1 catches a low word of all ones (superset of "significand all ones", the exception of Markstein's theorem)
     //  * radicands: checked like quotients (a zero radicand -- ice exactly at rest -- is legitimate), plus a sign accumulator
-    // With these windows the numerators x = q d stay in [2^-766, 2^770), far from where the exact
+    // With these windows the numerators x = q d stay in [2^-555, 2^557), far from where the exact
     // residual d q0 - x could underflow (2^-969) or anything could overflow.
     static constexpr bool SCALED = true;  // tile_pass evaluates the power-of-two-scaled expression tree (see there)
     uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u, pend = 0u;
     bool have = false;
-    static constexpr uint32_t QLO = 0x2000u, QHI = 0x5fffu;  // per lane: exponent field in [0x200, 0x600)
+    static constexpr uint32_t QLO = 0x2d30u, QHI = 0x52afu;  // per lane: exponent field in [1023 - 300, 1023 + 300)
     static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;
     __device__ __forceinline__ void chk2(uint32_t hi_a, uint32_t hi_b)
     {
@@ -282,6 +287,7 @@ struct MathFast {
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return quot(x, R.d, R.r); }
     __device__ __forceinline__ double divn_nc(double x, const NodeRecip &R) { return quot_nc(x, R.d, R.r); }
     template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return quot(x, y, rcp<B>(y)); }
+    template <bool B = false> __device__ __forceinline__ double div_nc(double x, double y) { return quot_nc(x, y, rcp<B>(y)); }
     // CHK = false: the radicand is a checked quotient times a bounded constant; only its sign is still tested
     template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x)
     {
@@ -321,6 +327,7 @@ struct MathSlow {
     }
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return x / R.d; }
     template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return x / y; }
+    template <bool B = false> __device__ __forceinline__ double div_nc(double x, double y) { return x / y; }
     template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
@@ -416,8 +423,10 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     const double tt2 = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
-    const double G = -xcross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    const double tau = mm.divn(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
+    // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
+    // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
+    const double G = -xcross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
     const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? uD : 0.0, active);
@@ -441,8 +450,10 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
     const double tt2 = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
     const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
-    const double G = -ycross - mm.divn(ttop, Rm) * a2 + mm.divn(tbot, Rm) * a2 + mm.divn(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    const double tau = mm.divn(coef - 0.0, Rm) * a2;
+    // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
+    // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
+    const double G = -ycross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;
     const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? vD : 0.0, active);
@@ -563,8 +574,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         for (int k = 0; k < NIT; k++) {
             const int n = tid + k * NT;
             if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
-            qu[n] = mm.divc(sm[A_U * ASTRIDE + n], p.dx, p.rdx);
-            qv[n] = mm.divc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
+            // (u, v are validated inputs or checked quotients of the previous substep: zero or in [2^-300, 2^300))
+            qu[n] = mm.divc_nc(sm[A_U * ASTRIDE + n], p.dx, p.rdx);
+            qv[n] = mm.divc_nc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
         }
         __syncthreads();
         int sx = tid % SXD - 1, sy = tid / SXD - 1;  // node of n = tid; advanced by NT per iteration without dividing
@@ -616,10 +628,6 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int n = tid + k * NT;
         if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
         sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
-        if (M::SCALED && use_ue) {  // the scaled tree sums ocean velocities before halving: they must be zero or normal
-            mm.chkq(sm[A_UE * ASTRIDE + n]);
-            mm.chkq(sm[A_VE * ASTRIDE + n]);
-        }
     }
     __syncthreads();
 
@@ -645,9 +653,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double Pc = SB(b, A_P, 0, 0);
             const double Pf4 = (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
             // (Delta in [Delta_min, 2^257) follows from its checked radicand: divisor range tests only where unknown)
-            zf = mm.template div<true>(Pf4, Df8);
-            zc = mm.template div<true>(Pc, Dc2);
-            const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.template div<true>(Pc * Dc2, Dc2 + p.Dmin2);
+            // P is a validated input (zero or in [2^-300, 2^300)): these quotients cannot leave the normal range
+            zf = mm.template div_nc<true>(Pf4, Df8);
+            zc = mm.template div_nc<true>(Pc, Dc2);
+            const double Pr = (GEN && p.pform == CSI_ICE_STRENGTH) ? Pc : mm.template div_nc<true>(Pc * Dc2, Dc2 + p.Dmin2);
             const double ec = zc * p.em2, ef = zf * p.em2;
             const double X = (zc - ec) * dc2 - Pr;  // 2 ((zeta - eta)(e11 + e22) - Pr / 2)
             s11n = __fma_rn(X, 0.5, ec * a);
@@ -958,12 +967,16 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tile_pass<VFIRST, AUX, GEN, MET, MathFast>(sm, bar, 0, &tmap, p, tc)) {
-        // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, denormals ...):
-        // reload the tile and redo it with plain IEEE operators
-        __syncthreads();
-        tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, 1, &tmap, p, tc);
+    // an input outside the validated range (flag raised by k_pack) sends every tile of the stage to the IEEE pass
+    const bool fast_ok = *p.invalid == 0;
+    bool redo = true;
+    if (fast_ok) {
+        redo = tile_pass<VFIRST, AUX, GEN, MET, MathFast>(sm, bar, 0, &tmap, p, tc);
+        // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, a quotient out of range ...):
+        // reload the tile and redo it with plain IEEE operators and the reference's expression tree
+        if (redo) __syncthreads();
     }
+    if (redo) tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, fast_ok ? 1 : 0, &tmap, p, tc);
 }
 #undef S
 #undef SB
@@ -1053,6 +1066,10 @@ __global__ void k_pack(PackItem it, Params p, int w)
     const size_t off = (size_t)(j - 1 + p.oy) * p.pitch + (size_t)(i - 1 + OX);
     p.base[(size_t)it.field * plane + off] = val;
     if (it.dup) p.base[(size_t)(it.field + 5) * plane + off] = val;
+    // input validation for the FAST pass: zero, or magnitude in [2^-300, 2^300) (NaN, Inf, subnormals and extremes fail)
+    const uint32_t hi = (uint32_t)__double2hiint(val) & 0x7fffffffu, e = hi >> 20;
+    const bool zero = (hi | (uint32_t)__double2loint(val)) == 0u;
+    if (!zero && (e < 1023u - 300u || e >= 1023u + 300u)) atomicOr(p.invalid, 1);
 }
 __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 {
@@ -1069,6 +1086,7 @@ __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 struct FusedPlan {
     uint8_t *flags = nullptr;
     double *met = nullptr;  // per-row metric table (lat-lon grids)
+    int *invalid = nullptr; // device flag: an input of the current stage is outside the validated range
     fz::Params P;
     dim3 grid;
     int cur_set = 0;
@@ -1113,14 +1131,15 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     // premises of the scaled expression tree (exact power-of-two scalings): thresholds and constants far inside the normal range
     // (and the quotients left unchecked in the kernel -- by cell areas, by alpha -- stay far from over/underflow)
     auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-30 && fabs(x) <= 1e30); };
+    auto sane_len = [](double x) { return x >= 1e-6 && x <= 1e12; };  // grid spacings in metres (areas: the square)
     bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && p.Dmin >= 1e-30 && p.Dmin <= 1e30 && sane(p.em2) &&
               sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i);
-    if (!g.met) ok = ok && sane(g.dx) && sane(g.dy) && g.dx > 0 && g.dy > 0;
+    if (!g.met) ok = ok && sane_len(g.dx) && sane_len(g.dy);
     else
         for (int k : {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF})
             // rows whose results are kept: the interior and the wall ring; a slab's connected side uses its whole halo
             for (int q = (g.conn_s ? 0 : g.Hy - 1); q < (g.conn_n ? g.metL : std::min(g.metL, g.Hy + g.Ny + 2)) && ok; q++)
-                ok = g.met_host[(size_t)k * g.metL + q] >= 1e-30 && g.met_host[(size_t)k * g.metL + q] <= 1e30;
+                ok = k >= M_AZCC ? (g.met_host[(size_t)k * g.metL + q] >= 1e-12 && g.met_host[(size_t)k * g.metL + q] <= 1e24) : sane_len(g.met_host[(size_t)k * g.metL + q]);
     if (!ok) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
@@ -1143,6 +1162,8 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     cudaError_t e = cudaMalloc(&pl->base, bytes);
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
     cudaMemset(pl->base, 0, bytes);
+    if (cudaMalloc(&pl->invalid, sizeof(int)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flag)"); cudaFree(pl->base); delete pl; return nullptr; }
+    cudaMemset(pl->invalid, 0, sizeof(int));
     cudaDeviceSynchronize();  // the plan may be used next from a non-blocking stream
     if (g.mask_host) {
         // node flags from the centre mask, with the reference's inactive_cell / immersed_peripheral_node logic
@@ -1217,6 +1238,7 @@ void fused_destroy(FusedPlan *pl)
     if (pl->base) cudaFree(pl->base);
     if (pl->flags) cudaFree(pl->flags);
     if (pl->met) cudaFree(pl->met);
+    if (pl->invalid) cudaFree(pl->invalid);
     delete pl;
 }
 
@@ -1286,6 +1308,8 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.base = pl->base;
     P.flags = pl->flags;
     P.met = pl->met;
+    P.invalid = pl->invalid;
+    cudaMemsetAsync(pl->invalid, 0, sizeof(int), c.stream);  // re-validated by the pack kernels below
     if (pl->met) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }
 
     // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)

