@@ -1001,6 +1001,18 @@ int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, 
 
 int64_t csi_launch_count(const csi_handle *h) { return h ? h->launches : 0; }
 
+int csi_fused_stats(const csi_handle *h, int64_t out3[3])
+{
+    if (!h || !out3) return CSI_ERR_ARG;
+    out3[0] = out3[1] = out3[2] = 0;
+    if (!h->fused) return CSI_OK;
+    long long v[3];
+    cudaSetDevice(h->cfg.device);
+    fused_stats(h->fused, v);
+    for (int k = 0; k < 3; k++) out3[k] = v[k];
+    return CSI_OK;
+}
+
 double csi_last_elapsed_ms(const csi_handle *h)
 {
     if (!h || !h->timed) return 0.0;

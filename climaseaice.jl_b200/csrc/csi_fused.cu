@@ -976,7 +976,10 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
         // reload the tile and redo it with plain IEEE operators and the reference's expression tree
         if (redo) __syncthreads();
     }
-    if (redo) tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, fast_ok ? 1 : 0, &tmap, p, tc);
+    if (redo) {
+        if (threadIdx.x == 0) atomicAdd(p.invalid + 1, 1);  // diagnostics: tiles that took the IEEE pass
+        tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, fast_ok ? 1 : 0, &tmap, p, tc);
+    }
 }
 #undef S
 #undef SB
@@ -1162,8 +1165,8 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     cudaError_t e = cudaMalloc(&pl->base, bytes);
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
     cudaMemset(pl->base, 0, bytes);
-    if (cudaMalloc(&pl->invalid, sizeof(int)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flag)"); cudaFree(pl->base); delete pl; return nullptr; }
-    cudaMemset(pl->invalid, 0, sizeof(int));
+    if (cudaMalloc(&pl->invalid, 2 * sizeof(int)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flag)"); cudaFree(pl->base); delete pl; return nullptr; }
+    cudaMemset(pl->invalid, 0, 2 * sizeof(int));
     cudaDeviceSynchronize();  // the plan may be used next from a non-blocking stream
     if (g.mask_host) {
         // node flags from the centre mask, with the reference's inactive_cell / immersed_peripheral_node logic
@@ -1309,7 +1312,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.flags = pl->flags;
     P.met = pl->met;
     P.invalid = pl->invalid;
-    cudaMemsetAsync(pl->invalid, 0, sizeof(int), c.stream);  // re-validated by the pack kernels below
+    cudaMemsetAsync(pl->invalid, 0, 2 * sizeof(int), c.stream);  // re-validated by the pack kernels below; tile counter reset
     if (pl->met) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }
 
     // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
@@ -1405,6 +1408,18 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         pl->cur_set ^= 1;
     }
     return 0;
+}
+
+// diagnostics of the last stage: out[0] = inputs failed validation (whole stage on the IEEE pass), out[1] = tile passes
+// redone with the IEEE operators, out[2] = tiles per substep.  Synchronises the device.
+void fused_stats(const FusedPlan *pl, long long out[3])
+{
+    int v[2] = {0, 0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(v, pl->invalid, sizeof v, cudaMemcpyDeviceToHost);
+    out[0] = v[0];
+    out[1] = v[1];
+    out[2] = (long long)pl->grid.x * pl->grid.y;
 }
 
 // views of the current copy of the evolving fields (u, v, s11, s22, s12) in the internal layout,

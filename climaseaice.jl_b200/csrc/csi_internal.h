@@ -44,6 +44,7 @@ int fused_run(FusedPlan *, const LaunchCtx &c, const DGrid &g, const DParams &p,
 int fused_begin(FusedPlan *, const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f, double dt, char *err, int nerr);
 int fused_steps(FusedPlan *, const LaunchCtx &c, int first_sub, int nsub, bool aux_last, char *err, int nerr, cudaEvent_t halo_ready);
 void fused_views(const FusedPlan *, DArr out[5]);
+void fused_stats(const FusedPlan *, long long out[3]);
 int fused_end(FusedPlan *, const LaunchCtx &c, const DFields &f, char *err, int nerr);
 
 namespace fz {

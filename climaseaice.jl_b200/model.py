@@ -641,6 +641,12 @@ class SeaIceModel:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         L.check(L.lib().csi_comm_init(self._handle, buf, rank, nranks), self._handle)
 
+    def fused_stats(self):
+        """(inputs_failed_validation, tile passes redone with the IEEE operators, tiles per substep) of the last momentum solve."""
+        out = (C.c_int64 * 3)()
+        L.check(L.lib().csi_fused_stats(self._handle, out), self._handle)
+        return tuple(out)
+
     @property
     def launch_count(self):
         return L.lib().csi_launch_count(self._handle)

@@ -262,6 +262,10 @@ int csi_attach_thermodynamics(csi_handle *h, const csi_thermo_config *cfg, const
 /* Instrumentation: kernels launched by this handle so far; elapsed ms of the last device call
  * measured with CUDA events on its stream. */
 int64_t csi_launch_count(const csi_handle *h);
+/* Diagnostics of the fused solver's last momentum solve (synchronises the device): out[0] != 0 if an input failed the
+ * range validation (whole stage on the IEEE pass), out[1] = tile passes redone with the IEEE operators, out[2] = tiles
+ * per substep.  All zero when the general kernels ran. */
+int csi_fused_stats(const csi_handle *h, int64_t out3[3]);
 double csi_last_elapsed_ms(const csi_handle *h);
 
 /* Launches the dominant kernel of csi_evp_substeps (the fused substep kernel, or the stress kernel of

@@ -448,4 +448,32 @@ def test_extreme_magnitudes_stay_bitwise(impl, nsub):
     m.update_state(); o.update_state()
     m.time_step_momentum(case.dt); o.time_step_momentum(case.dt)
     _assert_parity(compare_model(m, o, case, names=("u", "v", "s11", "s22", "s12", "alpha", "P")))
+    if impl == "auto":
+        assert m.fused_stats()[0] == 1   # subnormal inputs fail the validation: the whole stage takes the IEEE pass
+    m.close()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_out_of_window_intermediates_fall_back_per_tile(impl):
+    """Inputs inside the validated range [2^-300, 2^300) whose *intermediates* leave the kernel's windows (squares of
+    1e-89 strain rates underflow the radicand window, 1e81 strain rates overflow it): only the tiles concerned are
+    redone with the IEEE operators; everything stays bitwise equal to the oracle."""
+    case = periodic_case(96, Ny=64, substeps=3, aice="ones", timestepper="ForwardEuler")
+    F, H = case.fields, case.Hx
+    rng = np.random.default_rng(7)
+    F["u"][H + 6:H + 14, H + 6:H + 14] = 1e-85 * rng.uniform(0.5, 1.0, (8, 8))
+    F["v"][H + 6:H + 14, H + 20:H + 28] = -3e-88 * rng.uniform(0.5, 1.0, (8, 8))
+    F["u"][H + 40:H + 46, H + 60:H + 66] = 1e85 * rng.uniform(0.5, 1.0, (6, 6))
+    F["v"][H + 40:H + 46, H + 70:H + 76] = -2e84 * rng.uniform(0.5, 1.0, (6, 6))
+    F["ue"][H + 24:H + 30, H + 40:H + 46] = 1e-80
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    m.update_state(); o.update_state()
+    m.time_step_momentum(case.dt); o.time_step_momentum(case.dt)
+    res = compare_model(m, o, case, names=("u", "v", "s11", "s22", "s12", "alpha"))
+    for n, (err, same) in res.items():
+        assert same, (n, err)
+    if impl == "auto":
+        invalid, redone, tiles = m.fused_stats()
+        assert invalid == 0 and 0 < redone < 3 * tiles, (invalid, redone, tiles)   # the tiles concerned, not the whole stage
     m.close()
