@@ -289,10 +289,11 @@ struct MathFast {
     template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return quot(x, y, rcp<B>(y)); }
     template <bool B = false> __device__ __forceinline__ double div_nc(double x, double y) { return quot_nc(x, y, rcp<B>(y)); }
     // CHK = false: the radicand is a checked quotient times a bounded constant; only its sign is still tested
-    template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x)
+    // SGN = false: the radicand is a sum of squares (never negative, never -0)
+    template <bool CHK = true, bool SGN = true> __device__ __forceinline__ double sqrt_(double x)
     {
         if (CHK) chkq(x);
-        neg |= (uint32_t)__double2hiint(x);
+        if (SGN) neg |= (uint32_t)__double2hiint(x);
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
         // x = +0 gives y = +inf; clamped to 2^1023 the iteration below returns +0 without a select (-0, negative and NaN
@@ -328,7 +329,7 @@ struct MathSlow {
     __device__ __forceinline__ double divn(double x, const NodeRecip &R) { return x / R.d; }
     template <bool B = false> __device__ __forceinline__ double div(double x, double y) { return x / y; }
     template <bool B = false> __device__ __forceinline__ double div_nc(double x, double y) { return x / y; }
-    template <bool CHK = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    template <bool CHK = true, bool SGN = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
 // u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
@@ -415,14 +416,17 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
         const double du = ue - uold, dv4 = sve - sv;
-        coef = p.rhoCd * mm.sqrt_(__fma_rn(dv4 * dv4, 0.0625, du * du));
+        // du, dv4: differences of validated inputs and checked quotients (zero or >= 2^-352, < 2^303): the squares stay normal
+        coef = p.rhoCd * mm.template sqrt_<false, false>(__fma_rn(dv4 * dv4, 0.0625, du * du));
         tbot = coef * ue;
     }
-    const double rheo2 = mm.divn_nc(mm.template div<true>(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
+    const double rheo2 = mm.divn_nc(mm.template div_nc<true>(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
     const double d2 = nm.a * (sD1 - sD0);
-    const double tt2 = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
-    const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
-    const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
+    // sigma = validated input + checked increments (zero or >= 2^-352, < 2^310): the stress divergence needs no test;
+    // whatever it adds up to, the velocity quotient below is tested
+    const double tt2 = mm.divc_nc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
+    const double SS2 = mm.divc_nc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
     // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
     // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
     const double G = -xcross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
@@ -442,14 +446,14 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
         const double dv = ve - vold, du4 = sue - su;
-        coef = p.rhoCd * mm.sqrt_(__fma_rn(du4 * du4, 0.0625, dv * dv));
+        coef = p.rhoCd * mm.template sqrt_<false, false>(__fma_rn(du4 * du4, 0.0625, dv * dv));
         tbot = coef * ve;
     }
-    const double rheo2 = mm.divn_nc(mm.template div<true>(vn - vold, dtau), Ra);
+    const double rheo2 = mm.divn_nc(mm.template div_nc<true>(vn - vold, dtau), Ra);
     const double d2 = nm.a * (sD1 - sD0);
-    const double tt2 = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
-    const double SS2 = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
-    const double dsig2 = mm.divc(d2 + tt2 + SS2, nm.az, nm.raz);
+    const double tt2 = mm.divc_nc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
+    const double SS2 = mm.divc_nc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
+    const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
     // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
     // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
     const double G = -ycross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
