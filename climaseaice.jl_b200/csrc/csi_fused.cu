@@ -399,11 +399,14 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetri
 // with the factors cancelling inside quotients (P_f / 2 Delta_f = 4 P_f / 8 Delta_f, tau / m_i * aice_i = tau / 2 m_i * 2 aice_i ...)
 // or absorbed by constants (2 dt, 4 dt, f / 4, 2 Delta_min, 8 Delta_min, 2 dx^2) and by explicit FMAs
 // (a + X / 2 = fma(X, 0.5, a): one rounding of the same real number).  Every result handed on is bit-identical to the
-// reference tree's.  The normal-range premise is what the windows of MathFast enforce: all quotients, radicands and
-// divisors are checked, the inputs u, v (phase A quotients), u_e, v_e (checked on arrival) are zero or at least
-// 2^-511 in magnitude, so sums and differences of them are zero or normal and halving them is exact; products that
-// could underflow (squares of strain rates) only feed checked radicands, where an addend below 2^-1022 cannot move
-// a sum of at least 2^-511.  A tile that leaves the windows is redone with the reference tree (MathSlow).
+// reference tree's.  The normal-range premise rests on an induction over the substeps: the pack kernels admit only inputs
+// that are zero or in [2^-300, 2^300) (else the whole stage takes the IEEE pass); the quantities that carry the state
+// forward -- the stress increments, the new velocities -- are window-tested quotients, so u, v, sigma stay zero or in
+// [2^-352, 2^311); sums and differences of such values are zero or normal and halving them is exact; a quotient whose
+// operands are bounded this way (by a cell area, by alpha, by the face mass after its range test, of a validated input)
+// cannot leave the normal range and is not tested again; products that could underflow (squares of strain rates) only
+// feed tested radicands, where an addend below 2^-1022 cannot move a sum of at least 2^-300.  A tile that leaves the
+// windows is redone with the reference tree (MathSlow).
 template <bool GEN, class M>
 __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
                                            double al0, double uold, double sv, double xcross, double ue, double sve, double ttop, double un, double sD1,
