@@ -102,7 +102,9 @@ struct Params {
     int it_x0, it_x1, it_y0, it_y1;
     double *base;         // internal allocation
     const uint8_t *flags; // immersed-boundary node flags in the internal layout (rows x pitch bytes), or NULL
-    const double *met;    // j-dependent metrics (lat-lon grids): MC_N columns of `rows` doubles, or NULL on a regular grid
+    const double *met;    // j-dependent metrics (lat-lon grids), or NULL on a regular grid: one record of MC_N doubles per row,
+                          // the pointer pre-offset so that the record of reference row j starts at met[j * MC_N]; MET_PAD padding
+                          // records on either side, so that no tile needs a clamp
     int *invalid;         // device flag raised by k_pack when an input is neither zero nor in [2^-300, 2^300): the whole
                           // stage then runs the IEEE pass (the FAST pass relies on validated inputs, see MathFast)
 };
@@ -112,6 +114,7 @@ struct Params {
 enum { MC_DXCC = 0, MC_DXFC, MC_DXCF, MC_DXFF, MC_DYCC, MC_DYFC, MC_DYCF, MC_DYFF, MC_AZCC, MC_AZFC, MC_AZCF, MC_AZFF,
        MC_DXCC2, MC_DYCC2, MC_DXFF2, MC_DYFF2, MC_RDXFC, MC_RDXCF, MC_RDYFC, MC_RDYCF, MC_RAZCC, MC_RAZFC, MC_RAZCF, MC_RAZFF,
        MC_FFF, MC_N };
+constexpr int MET_PAD = 40;  // padding records of the metric table (>= tile height + halos beyond either end)
 
 // Metric<false>: the regular grid's constants (kernel parameters); Metric<true>: the row's own values, warp-uniform
 // read-only loads that stay in L1.  r is the reference row index j.
@@ -120,8 +123,7 @@ struct Metric {
     const Params &p;
     __device__ __forceinline__ double ld(int col, int r) const
     {
-        const int row = min(max(r - 1 + p.oy, 0), p.rows - 1);
-        return __ldg(p.met + (size_t)col * p.rows + row);
+        return __ldg(p.met + r * MC_N + col);
     }
 #define CSI_MET(name, col, regular) \
     __device__ __forceinline__ double name(int r) const { return MET ? ld(col, r) : (regular); }
@@ -604,9 +606,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             if (sx >= 0 && sy >= 0)
                 SB(b, A_E12, 0, 0) = mm.divc_nc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
         }
-    } else
-    for (int n = tid; n < SXD * SYD; n += NT) {
-        const int sx = n % SXD - 1, sy = n / SXD - 1;
+    } else {
+    int sx = tid % SXD - 1, sy = tid / SXD - 1;
+#pragma unroll
+    for (int k = 0; k < NIT; k++, sx += NT % SXD, sy += NT / SXD) {
+        const int n = tid + k * NT;
+        if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
+        if (sx >= SXD - 1) { sx -= SXD; sy++; }
         const int r = tc.J0 - 1 + sy;  // reference row of the node
         double *b = sm + n;  // = &S(0, sx, sy)
         const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0);
@@ -614,8 +620,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double u10 = SB(b, A_U, 1, 0), v01 = SB(b, A_V, 0, 1);
             const double dyf = mt.dyfc(r), rdyf = mt.rdyfc(r), dxf0 = mt.dxcf(r), dxf1 = mt.dxcf(r + 1), az = mt.azcc(r), raz = mt.razcc(r);
             const double D = mm.divc_nc((dyf * u10 - dyf * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
-            const double T = mm.divc_nc(mt.dycc2(r) * (mm.divc(u10, dyf, rdyf) - mm.divc(u00, dyf, rdyf)) -
-                                         mt.dxcc2(r) * (mm.divc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc(v00, dxf0, mt.rdxcf(r))),
+            // (u, v are validated inputs or tested quotients of the previous substep: no window test on u / metric)
+            const double T = mm.divc_nc(mt.dycc2(r) * (mm.divc_nc(u10, dyf, rdyf) - mm.divc_nc(u00, dyf, rdyf)) -
+                                         mt.dxcc2(r) * (mm.divc_nc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc_nc(v00, dxf0, mt.rdxcf(r))),
                                      az, raz);
             SB(b, A_E11, 0, 0) = M::SCALED ? D + T : (D + T) / 2;
             SB(b, A_E22, 0, 0) = M::SCALED ? D - T : (D - T) / 2;
@@ -623,11 +630,12 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if (sx >= 0 && sy >= 0) {
             const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
             const double dyc = mt.dycf(r), rdyc = mt.rdycf(r);
-            const double Sh = mm.divc_nc(mt.dxff2(r) * (mm.divc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
-                                          mt.dyff2(r) * (mm.divc(v00, dyc, rdyc) - mm.divc(vm0, dyc, rdyc)),
+            const double Sh = mm.divc_nc(mt.dxff2(r) * (mm.divc_nc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc_nc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
+                                          mt.dyff2(r) * (mm.divc_nc(v00, dyc, rdyc) - mm.divc_nc(vm0, dyc, rdyc)),
                                       mt.azff(r), mt.razff(r));
             SB(b, A_E12, 0, 0) = M::SCALED ? Sh : Sh / 2;
         }
+    }
     }
     mbar_wait(&bar[1], parity);
 #pragma unroll
@@ -671,6 +679,12 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             s12n = ef * Sh;
             mc = SB(b, A_H, 0, 0);
             mf = (SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) + (SB(b, A_H, -1, 0) + mc);  // 4 mf
+            if (!tc.interior) {
+                // nodes beyond a wall's ring of stress nodes (the caller's deeper halo holds no ice there) are computed but
+                // never stored nor read by a stored cell: give them a harmless mass instead of failing the tile's divisor test
+                const int i = tc.I0 - 1 + sx;
+                if ((p.wall_w && i < p.sx0) || (p.wall_e && i > p.sx1) || (p.wall_s && rB < p.sy0) || (p.wall_n && rB > p.sy1)) { mc = 1.0; mf = 4.0; }
+            }
             g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
             g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf), mt.azff(rB), mt.razff(rB));
             Dc = AUX ? Dc2 * 0.5 : 0.0;
@@ -767,7 +781,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         double val;
         if (M::SCALED) {
             const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2d(r + 1), mt.dxff2d(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
-            val = u_node_s<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+            // (a node that is not evolved returns its old value whatever is computed: harmless masses keep it from failing the tile)
+            const double m1 = upd ? SB(b, A_H, 0, 0) : 1.0, m0 = upd ? SB(b, A_H, -1, 0) : 1.0;
+            val = u_node_s<GEN>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
                                 uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm);
         } else {
             const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
@@ -821,7 +837,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         const double dyf2 = M::SCALED ? mt.dyff2d(r) : mt.dyff2(r), dxf = mt.dxcf(r);
         const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
-        const double val = M::SCALED ? v_node_s<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+        const double val = M::SCALED ? v_node_s<GEN>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
                                                      SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm)
                                      : v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
                                                    SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
@@ -1204,13 +1220,13 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     }
     if (g.met_host) {
         // per-row metric table in internal row coordinates: row rho holds reference row j = rho + 1 - oy
-        std::vector<double> tb((size_t)MC_N * pl->rows, 1.0);
+        std::vector<double> tb((size_t)MC_N * (pl->rows + 2 * MET_PAD), 1.0);
         auto src = [&](int which, int rho) {
             const int q = rho - pl->oy + g.Hy;  // index of row j in the host arrays (j - 1 + Hy)
             return (q >= 0 && q < g.metL) ? g.met_host[(size_t)which * g.metL + q] : 1.0;
         };
         for (int rho = 0; rho < pl->rows; rho++) {
-            auto put = [&](int col, double v) { tb[(size_t)col * pl->rows + rho] = v; };
+            auto put = [&](int col, double v) { tb[(size_t)(rho + MET_PAD) * MC_N + col] = v; };
             for (int k = 0; k < 12; k++) put(MC_DXCC + k, src(k, rho));
             put(MC_DXCC2, src(M_DXCC, rho) * src(M_DXCC, rho));
             put(MC_DYCC2, src(M_DYCC, rho) * src(M_DYCC, rho));
@@ -1317,7 +1333,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.sq = !pl->met && g.dx == g.dy;
     P.base = pl->base;
     P.flags = pl->flags;
-    P.met = pl->met;
+    P.met = pl->met ? pl->met + (size_t)(MET_PAD - 1 + pl->oy) * MC_N : nullptr;  // record of row j at met[j * MC_N]
     P.invalid = pl->invalid;
     cudaMemsetAsync(pl->invalid, 0, 2 * sizeof(int), c.stream);  // re-validated by the pack kernels below; tile counter reset
     if (pl->met) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }

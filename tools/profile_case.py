@@ -23,4 +23,4 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 ev0.record(); m.time_step_momentum(case.dt, nsub); ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1)
 cells = case.Nx * case.Ny
-print(f"{case.name} {case.Nx}x{case.Ny} {solver}: {ms:.3f} ms for {nsub} substeps -> {ms/nsub:.4f} ms/substep, {cells*nsub/ms/1e6:.3f} G cell-updates/s")
+print(f"{case.name} {case.Nx}x{case.Ny} {solver}: {ms:.3f} ms for {nsub} substeps -> {ms/nsub:.4f} ms/substep, {cells*nsub/ms/1e6:.3f} G cell-updates/s, fused stats (invalid, tile passes redone, tiles) = {m.fused_stats()}")
