@@ -93,6 +93,7 @@ struct Params {
     double imm_u, imm_v;  // immersed linear-drag flux BC (0 = none)
     // power-of-two multiples used by the scaled expression tree of the FAST pass (all exact)
     double dt2, dt4, f4, Dmin2, Dmin8, min_mass2, min_conc2, dx2d, dy2d;
+    double gnan;          // clamp(sqrt(alpha+^2), alpha-, alpha+): the reference's gamma where its gamma^2 is NaN (0 / 0 in open water)
     int sq;               // regular grid with dx == dy: phase A divides every u, v once (u/dx serves both operators)
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
@@ -416,7 +417,10 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
 {
     // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(m2);
+    // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
+    // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
+    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
     const double dtau = mm.divn_nc(p.dt2, Ra);  // dt / alpha_bar; alpha in [alpha-, alpha+]: nothing to check
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -437,7 +441,6 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     const double G = -xcross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
     const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
     const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
-    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? uD : 0.0, active);
 }
 template <bool GEN, class M>
@@ -446,7 +449,10 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
                                            double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
 {
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(m2);
+    // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
+    // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
+    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
     const double dtau = mm.divn_nc(p.dt2, Ra);
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -464,7 +470,6 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
     const double G = -ycross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
     const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;
     const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
-    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     return jl_mul_bool(active_ice ? vD : 0.0, active);
 }
 
@@ -654,6 +659,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int rB = tc.J0 - 1 + sy;
         double *b = &S(0, sx, sy);
         double zc, zf, Dc, s11n, s22n, s12n, mc, mf, g2c, g2f;
+        bool mc0 = false, mf0 = false;
         if (M::SCALED) {
             // a, bb = 2 e11c, 2 e22c; Sh = 2 e12f; c4 = 4 e12c; af, bf = 8 e11f, 8 e22f
             const double a = SB(b, A_E11, 0, 0), bb = SB(b, A_E22, 0, 0), Sh = SB(b, A_E12, 0, 0);
@@ -685,8 +691,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                 const int i = tc.I0 - 1 + sx;
                 if ((p.wall_w && i < p.sx0) || (p.wall_e && i > p.sx1) || (p.wall_s && rB < p.sy0) || (p.wall_n && rB > p.sy1)) { mc = 1.0; mf = 4.0; }
             }
-            g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
-            g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf), mt.azff(rB), mt.razff(rB));
+            // open water (mass exactly 0, P >= 0): the reference divides by zero -- zeta / 0 = +inf, or NaN when zeta = 0 too, which
+            // it replaces by alpha+^2 -- and clamps the result to alpha+ (p.gnan when it came from the NaN branch), and it
+            // leaves sigma alone.  Same values here without dividing by zero, so open water does not send the tile to the IEEE pass.
+            mc0 = mc == 0.0 && Pc >= 0.0;
+            mf0 = mf == 0.0 && Pf4 >= 0.0;
+            g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc0 ? 1.0 : mc), mt.azcc(rB), mt.razcc(rB));
+            g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf0 ? 4.0 : mf), mt.azff(rB), mt.razff(rB));
             Dc = AUX ? Dc2 * 0.5 : 0.0;
         } else {
         const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
@@ -714,16 +725,20 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         // (a clean FAST pass has no NaN quotient and no mass <= 0: both would have left the windows)
         if (!M::SCALED) g2c = (g2c != g2c) ? p.amax2 : g2c;
-        const double gc = jl_clamp(mm.template sqrt_<!M::SCALED>(g2c), p.amin, p.amax);
+        double gc = jl_clamp(mm.template sqrt_<!M::SCALED>(g2c), p.amin, p.amax);
         if (!M::SCALED) g2f = (g2f != g2f) ? p.amax2 : g2f;
-        const double gf = jl_clamp(mm.template sqrt_<!M::SCALED>(g2f), p.amin, p.amax);
+        double gf = jl_clamp(mm.template sqrt_<!M::SCALED>(g2f), p.amin, p.amax);
+        if (M::SCALED) {
+            gc = mc0 ? (zc == 0.0 ? p.gnan : p.amax) : gc;
+            gf = mf0 ? (zf == 0.0 ? p.gnan : p.amax) : gf;
+        }
         const NodeRecip Rg = mm.template recip<M::SCALED>(gc);  // gamma in [alpha-, alpha+]
         const double o11 = SB(b, A_S11, 0, 0), o22 = SB(b, A_S22, 0, 0), o12 = SB(b, A_S12, 0, 0);
         const double d11 = mm.divn(s11n - o11, Rg), d22 = mm.divn(s22n - o22, Rg), d12 = mm.template div<M::SCALED>(s12n - o12, gf);
         // in place: each thread owns its node of the sigma arrays
-        SB(b, A_S11, 0, 0) = o11 + (M::SCALED || mc > 0 ? d11 : 0.0);
-        SB(b, A_S22, 0, 0) = o22 + (M::SCALED || mc > 0 ? d22 : 0.0);
-        SB(b, A_S12, 0, 0) = o12 + (M::SCALED || mf > 0 ? d12 : 0.0);
+        SB(b, A_S11, 0, 0) = o11 + ((M::SCALED ? !mc0 : mc > 0) ? d11 : 0.0);
+        SB(b, A_S22, 0, 0) = o22 + ((M::SCALED ? !mc0 : mc > 0) ? d22 : 0.0);
+        SB(b, A_S12, 0, 0) = o12 + ((M::SCALED ? !mf0 : mf > 0) ? d12 : 0.0);
         SB(b, A_AL, 0, 0) = gc;
         aux_zc[q] = zc;
         aux_zf[q] = zf;
@@ -1330,6 +1345,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.pform = p.pform; P.cor = p.cor; P.sis = p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.dt2 = 2 * dt; P.dt4 = 4 * dt; P.f4 = p.f * 0.25; P.Dmin2 = 2 * p.Dmin; P.Dmin8 = 8 * p.Dmin;
     P.min_mass2 = 2 * p.min_mass; P.min_conc2 = 2 * p.min_conc; P.dx2d = 2 * P.dx2; P.dy2d = 2 * P.dy2;
+    P.gnan = jl_clamp(sqrt(P.amax2), p.amin, p.amax);
     P.sq = !pl->met && g.dx == g.dy;
     P.base = pl->base;
     P.flags = pl->flags;
