@@ -11,7 +11,7 @@
 //     30 x 14 cells inside.  One elected thread issues one `cp.async.bulk.tensor` per stencil field
 //     (u, v, h, aice, P, s11, s22, s12, ue, ve): a 34 x 18 box = tile + halo, landing in shared
 //     memory, completion on an mbarrier.  Then four phases, separated by block barriers:
-//       A  strain rates e11, e22, e12 and ice mass on the haloed tile      (evp:360-375)
+//       A  strain rates e11, e22, e12 and ice mass on the haloed tile      (evp:360-375); on square grids u/dx, v/dx first
 //       B  viscosities, replacement pressure, stress relaxation, alpha     (evp:236-354)
 //       C  first velocity component on the tile + 1 ring                   (se:197-264)
 //       D  second velocity component on the output cells
@@ -22,9 +22,12 @@
 //   * The five evolving fields are double buffered in HBM (read set A, write set B), so there is
 //     no hazard between CTAs; the owner of a cell also stores its periodic images / wall values,
 //     which replaces the two halo-fill launches per substep.
-//   * Arithmetic keeps the reference's Float64 expression trees (compiled with -fmad=false) and
-//     uses the bit-exact FAST policy below; a tile whose operands leave the FAST windows is
-//     recomputed with plain IEEE operators.
+//   * Arithmetic is bit-exact (compiled with -fmad=false).  The FAST pass uses branch-free, correctly rounded
+//     division / reciprocal / square root built from FMAs and a power-of-two-scaled form of the reference's expression
+//     trees (see MathFast and the comment above u_node_s); its premises are enforced by range validation of all inputs
+//     once per stage (k_pack) and by window tests on the quotients and radicands that carry the state forward.  A tile
+//     whose operands leave the windows is recomputed with plain IEEE operators and the reference's own trees (MathSlow);
+//     csi_fused_stats reports how often that happened.
 //
 // Algorithmic HBM traffic: 14 loads + 5 stores per cell-update (u, v, s11, s22, s12 r/w; h, aice,
 // P, un, vn, tau_x, tau_y, ue, ve read) = 152 B, 144 B by the SURVEY convention (P recomputable).
@@ -1111,6 +1114,9 @@ __global__ void k_pack(PackItem it, Params p, int w)
     const uint32_t hi = (uint32_t)__double2hiint(val) & 0x7fffffffu, e = hi >> 20;
     const bool zero = (hi | (uint32_t)__double2loint(val)) == 0u;
     if (!zero && (e < 1023u - 300u || e >= 1023u + 300u)) atomicOr(p.invalid, 1);
+    // thickness and concentration must not carry a sign bit (not even -0): the open-water shortcut of phase B reads a mass
+    // of exactly +0 as "the reference divides by +0 here"
+    if ((it.field == F_H || it.field == F_A) && __double2hiint(val) < 0) atomicOr(p.invalid, 1);
 }
 __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 {
@@ -1174,7 +1180,7 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-30 && fabs(x) <= 1e30); };
     auto sane_len = [](double x) { return x >= 1e-6 && x <= 1e12; };  // grid spacings in metres (areas: the square)
     bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && p.Dmin >= 1e-30 && p.Dmin <= 1e30 && sane(p.em2) &&
-              sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i);
+              sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i) && p.rho_i > 0;
     if (!g.met) ok = ok && sane_len(g.dx) && sane_len(g.dy);
     else
         for (int k : {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF})
