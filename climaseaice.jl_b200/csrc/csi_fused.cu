@@ -761,8 +761,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // reference tree: vbar; scaled tree: the plain sum 4 vbar (and f / 4)
         const double vsum = (SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1));
         const double vbar = M::SCALED ? vsum : ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
-        double xcross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : (M::SCALED ? -p.f4 * vsum : -p.f * vbar);
-        if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc
+        // (the switch-free variants: FPlane on regular grids, HydrostaticSphericalCoriolis on lat-lon grids)
+        double xcross = ((GEN && p.cor == CSI_CORIOLIS_NONE) || (MET && !GEN)) ? 0.0 : (M::SCALED ? -p.f4 * vsum : -p.f * vbar);
+        if (MET && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc
             const double dx0 = mt.dxcf(r), dx1 = mt.dxcf(r + 1);
             const double gm = (dx0 * SB(b, VS, -1, 0) + dx1 * SB(b, VS, -1, 1)) / 2, g0 = (dx0 * SB(b, VS, 0, 0) + dx1 * SB(b, VS, 0, 1)) / 2;
             const double fbar = (mt.fff(r) + mt.fff(r + 1)) / 2;
@@ -820,8 +821,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double *b = &S(0, sx, sy);
         const double usum = (SB(b, US, 0, -1) + SB(b, US, 1, -1)) + (SB(b, US, 0, 0) + SB(b, US, 1, 0));
         const double ubar = M::SCALED ? usum : ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
-        double ycross = (GEN && p.cor == CSI_CORIOLIS_NONE) ? 0.0 : (M::SCALED ? p.f4 * usum : p.f * ubar);
-        if (MET && p.cor == CSI_CORIOLIS_SPHERICAL) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf
+        double ycross = ((GEN && p.cor == CSI_CORIOLIS_NONE) || (MET && !GEN)) ? 0.0 : (M::SCALED ? p.f4 * usum : p.f * ubar);
+        if (MET && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf
             const double dy0 = mt.dyfc(r - 1), dy1 = mt.dyfc(r);
             const double gm = (dy0 * SB(b, US, 0, -1) + dy0 * SB(b, US, 1, -1)) / 2, g0 = (dy1 * SB(b, US, 0, 0) + dy1 * SB(b, US, 1, 0)) / 2;
             const double fj = mt.fff(r), fbar = (fj + fj) / 2;
@@ -1430,14 +1431,14 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
         const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
+        const bool common_met = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
         auto band = [&](int t0, int t1) -> cudaError_t {
             if (t1 <= t0) return cudaSuccess;
             P.ty0 = t0;
             const dim3 gb(grid.x, t1 - t0);
             ++*c.launches;
-            return P.met    ? launch_sub<true, true>(pl, P, gb, c.stream, vfirst, aux)
-                   : common ? launch_sub<false, false>(pl, P, gb, c.stream, vfirst, aux)
-                            : launch_sub<true, false>(pl, P, gb, c.stream, vfirst, aux);
+            if (P.met) return common_met ? launch_sub<false, true>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, true>(pl, P, gb, c.stream, vfirst, aux);
+            return common ? launch_sub<false, false>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, false>(pl, P, gb, c.stream, vfirst, aux);
         };
         cudaError_t e;
         if (k == 0 && halo_ready && t_hi > t_lo) {
