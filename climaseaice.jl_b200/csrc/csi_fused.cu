@@ -747,6 +747,15 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         aux_zf[q] = zf;
         aux_Dc[q] = Dc;
     }
+    // the pointwise inputs of phase C are requested before the barrier, so their L2 latency overlaps the wait
+#ifndef CSI_EXPERIMENT_LATE_LDG
+    double cn[2], ct[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        cn[q] = c_on[q] ? __ldg(gC1 + c_g[q]) : 0.0;
+        ct[q] = (c_on[q] && use_top) ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
+    }
+#endif
     __syncthreads();
 
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
@@ -868,9 +877,21 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     for (int q = 0; q < 2; q++)
         if (c_on[q]) {
             const int sy = c_sy0 + q;
+#ifdef CSI_EXPERIMENT_LATE_LDG
             const double n1 = __ldg(gC1 + c_g[q]), t1 = use_top ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
+#else
+            const double n1 = cn[q], t1 = ct[q];
+#endif
             S(A_W, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
         }
+#ifndef CSI_EXPERIMENT_LATE_LDG
+    double dn[2], dtt[2];  // likewise for phase D
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        dn[q] = d_on[q] ? __ldg(gD1 + d_g[q]) : 0.0;
+        dtt[q] = (d_on[q] && use_top) ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
+    }
+#endif
     __syncthreads();
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
@@ -879,7 +900,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     for (int q = 0; q < 2; q++)
         if (d_on[q]) {
             const int sy = d_sy0 + q;
+#ifdef CSI_EXPERIMENT_LATE_LDG
             const double n1 = __ldg(gD1 + d_g[q]), t1 = use_top ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
+#else
+            const double n1 = dn[q], t1 = dtt[q];
+#endif
             w2[q] = VFIRST ? u_at(d_sx, sy, A_W, n1, t1) : v_at(d_sx, sy, A_W, n1, t1);
         }
 
