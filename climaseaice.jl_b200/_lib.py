@@ -21,7 +21,7 @@ CORIOLIS_NONE, CORIOLIS_FPLANE, CORIOLIS_SPHERICAL = 0, 1, 2
 BC_DEFAULT, BC_VALUE = 0, 1
 RK3, FE = 0, 1
 SOLVER_AUTO, SOLVER_UNFUSED, SOLVER_FUSED = 0, 1, 2
-METRIC_REGULAR, METRIC_J = 0, 1
+METRIC_REGULAR, METRIC_J, METRIC_IJ = 0, 1, 2
 FD_NONE, FD_FIELDS, FD_STRESS_BALANCE = 0, 1, 2
 
 ERRORS = {-1: "CSI_ERR_ARG", -2: "CSI_ERR_SHAPE", -3: "CSI_ERR_UNSUPPORTED", -4: "CSI_ERR_NO_DEVICE", -5: "CSI_ERR_NCCL_MISSING"}

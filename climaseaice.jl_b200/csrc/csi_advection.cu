@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH][li + AH - 1], 1, U > 0);
-                const double fl = (dyfc(g, j) * 1.0) * U * ct;
+                const double fl = (dyfc(g, i, j) * 1.0) * U * ct;
                 fx[q][lj][li] = imm ? 0.0 : fl;
             }
         }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
                 const double ct = weno::face_value_dyn(b, &sh[q][lj + AH - 1][li + AH], SX, V > 0);
-                const double fl = (dxcf(g, j) * 1.0) * V * ct;
+                const double fl = (dxcf(g, i, j) * 1.0) * V * ct;
                 fy[q][lj][li] = imm ? 0.0 : fl;
             }
         }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
     __syncthreads();
     const int li = threadIdx.x, lj = threadIdx.y, i = i0 + li, j = j0 + lj;
     if (i <= g.Nx && j <= g.Ny) {
-        const double V = azcc(g, j) * 1.0;
+        const double V = azcc(g, i, j) * 1.0;
         at(f.Gh, i, j) = -(1 / V * ((fx[0][lj][li + 1] - fx[0][lj][li]) + (fy[0][lj + 1][li] - fy[0][lj][li])));
         at(f.Ga, i, j) = -(1 / V * ((fx[1][lj][li + 1] - fx[1][lj][li]) + (fy[1][lj + 1][li] - fy[1][lj][li])));
         if (NQ > 2) at(f.Ghs, i, j) = -(1 / V * ((fx[NQ - 1][lj][li + 1] - fx[NQ - 1][lj][li]) + (fy[NQ - 1][lj + 1][li] - fy[NQ - 1][lj][li])));

@@ -562,7 +562,21 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     if (cfg->Hx < B || cfg->Hy < B) return fail(nullptr, CSI_ERR_ARG, "csi_create: halo smaller than the advection stencil");
     if ((cfg->topo_x != CSI_PERIODIC && cfg->topo_x != CSI_BOUNDED) || (cfg->topo_y != CSI_PERIODIC && cfg->topo_y != CSI_BOUNDED))
         return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED");
-    if (cfg->metric_kind != CSI_METRIC_REGULAR && cfg->metric_kind != CSI_METRIC_J) return fail(nullptr, CSI_ERR_ARG, "csi_create: metric_kind must be CSI_METRIC_REGULAR or CSI_METRIC_J");
+    if (cfg->metric_kind != CSI_METRIC_REGULAR && cfg->metric_kind != CSI_METRIC_J && cfg->metric_kind != CSI_METRIC_IJ)
+        return fail(nullptr, CSI_ERR_ARG, "csi_create: metric_kind must be CSI_METRIC_REGULAR, CSI_METRIC_J or CSI_METRIC_IJ");
+    if (cfg->metric_kind == CSI_METRIC_IJ) {
+        const int L = cfg->Ny + 2 * cfg->Hy + 1, Wd = cfg->Nx + 2 * cfg->Hx + 1;
+        if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: HydrostaticSphericalCoriolis with two-dimensional metrics");
+        if (cfg->nranks > 1) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: partitions with two-dimensional metrics");
+        for (int k = 0; k < 12; k++) {
+            if (!cfg->metrics[k]) return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_METRIC_IJ needs all 12 metric arrays");
+            // cells the stencils touch: i = 0 .. Nx+2, j = 0 .. Ny+2
+            for (int j = 0; j <= cfg->Ny + 2; j++)
+                for (int i = 0; i <= cfg->Nx + 2; i++)
+                    if (j - 1 + cfg->Hy < L && i - 1 + cfg->Hx < Wd && !(cfg->metrics[k][(size_t)(j - 1 + cfg->Hy) * Wd + (i - 1 + cfg->Hx)] > 0))
+                        return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive");
+        }
+    }
     if (cfg->metric_kind == CSI_METRIC_REGULAR && (!(cfg->dx > 0) || !(cfg->dy > 0))) return fail(nullptr, CSI_ERR_ARG, "csi_create: dx, dy must be positive");
     if (cfg->metric_kind == CSI_METRIC_J) {
         const int L = cfg->Ny + 2 * cfg->Hy + 1;
@@ -625,7 +639,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.mask_host = nullptr;
     g.met = nullptr;
     g.metL = 0;
-    g.pad_ = 0;
+    g.metW = 0;
     g.met_host = nullptr;
     g.fff_host = nullptr;
     DParams &p = h->p;
@@ -685,6 +699,16 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         for (int k = 0; k < 12; k++) std::copy(cfg->metrics[k], cfg->metrics[k] + L, h->met_host.begin() + (size_t)k * L);
         g.met_host = h->met_host.data();
         for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;  // the caller's arrays are not retained
+    }
+    if (cfg->metric_kind == CSI_METRIC_IJ) {  // orthogonal curvilinear grid: twelve (Ny+2Hy+1) x (Nx+2Hx+1) arrays, i fastest
+        const int L = cfg->Ny + 2 * cfg->Hy + 1, Wd = cfg->Nx + 2 * cfg->Hx + 1;
+        const size_t n = (size_t)L * Wd;
+        if ((e = cudaMalloc(&h->met_dev, sizeof(double) * 12 * n)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(metrics)"); }
+        for (int k = 0; k < 12; k++) cudaMemcpy(h->met_dev + (size_t)k * n, cfg->metrics[k], sizeof(double) * n, cudaMemcpyDefault);
+        g.met = h->met_dev;
+        g.metL = L;
+        g.metW = Wd;
+        for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;
     }
     if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) {
         const int L = cfg->Ny + 2 * cfg->Hy + 1;

@@ -56,19 +56,19 @@ template <class Fn> __device__ __forceinline__ double avg_cf(Fn q, int i, int j)
 // ---- strain rates: evp:360-375 (metrics: scalars on a RectilinearGrid, functions of j on a lat-lon grid) ----
 __device__ __forceinline__ double eps_D(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    return ((dyfc(g, j) * at(u, i + 1, j) - dyfc(g, j) * at(u, i, j)) + (dxcf(g, j + 1) * at(v, i, j + 1) - dxcf(g, j) * at(v, i, j))) / azcc(g, j);
+    return ((dyfc(g, i + 1, j) * at(u, i + 1, j) - dyfc(g, i, j) * at(u, i, j)) + (dxcf(g, i, j + 1) * at(v, i, j + 1) - dxcf(g, i, j) * at(v, i, j))) / azcc(g, i, j);
 }
 __device__ __forceinline__ double eps_T(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    const double dy = dycc(g, j), dx = dxcc(g, j);
-    return (dy * dy * (at(u, i + 1, j) / dyfc(g, j) - at(u, i, j) / dyfc(g, j)) - dx * dx * (at(v, i, j + 1) / dxcf(g, j + 1) - at(v, i, j) / dxcf(g, j))) /
-           azcc(g, j);
+    const double dy = dycc(g, i, j), dx = dxcc(g, i, j);
+    return (dy * dy * (at(u, i + 1, j) / dyfc(g, i + 1, j) - at(u, i, j) / dyfc(g, i, j)) - dx * dx * (at(v, i, j + 1) / dxcf(g, i, j + 1) - at(v, i, j) / dxcf(g, i, j))) /
+           azcc(g, i, j);
 }
 __device__ __forceinline__ double eps_S(const DGrid &g, const DArr &u, const DArr &v, int i, int j)
 {
-    const double dx = dxff(g, j), dy = dyff(g, j);
-    return (dx * dx * (at(u, i, j) / dxfc(g, j) - at(u, i, j - 1) / dxfc(g, j - 1)) + dy * dy * (at(v, i, j) / dycf(g, j) - at(v, i - 1, j) / dycf(g, j))) /
-           azff(g, j);
+    const double dx = dxff(g, i, j), dy = dyff(g, i, j);
+    return (dx * dx * (at(u, i, j) / dxfc(g, i, j) - at(u, i, j - 1) / dxfc(g, i, j - 1)) + dy * dy * (at(v, i, j) / dycf(g, i, j) - at(v, i - 1, j) / dycf(g, i - 1, j))) /
+           azff(g, i, j);
 }
 __device__ __forceinline__ double strain_xx(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) + eps_T(g, u, v, i, j)) / 2; }
 __device__ __forceinline__ double strain_yy(const DGrid &g, const DArr &u, const DArr &v, int i, int j) { return (eps_D(g, u, v, i, j) - eps_T(g, u, v, i, j)) / 2; }
@@ -107,10 +107,10 @@ __device__ __forceinline__ void evp_stress_node(const DGrid &g, const DParams &p
     const double s22n = 2 * ec * e22c + ((zc - ec) * (e11c + e22c) - Pr / 2);
     const double s12n = 2 * ef * e12f;
     const double mc = mm(i, j), mf = avg_ff(mm, i, j);
-    double g2c = zc * p.ca * dt / mc / azcc(g, j);
+    double g2c = zc * p.ca * dt / mc / azcc(g, i, j);
     g2c = (g2c != g2c) ? p.amax * p.amax : g2c;
     const double gc = jl_clamp(sqrt(g2c), p.amin, p.amax);
-    double g2f = zf * p.ca * dt / mf / azff(g, j);
+    double g2f = zf * p.ca * dt / mf / azff(g, i, j);
     g2f = (g2f != g2f) ? p.amax * p.amax : g2f;
     const double gf = jl_clamp(sqrt(g2f), p.amin, p.amax);
     const double d11 = (s11n - at(f.s11, i, j)) / gc;
@@ -129,17 +129,17 @@ __device__ __forceinline__ double sigD(const DGrid &g, const DFields &f, int i, 
 __device__ __forceinline__ double sigT(const DGrid &g, const DFields &f, int i, int j) { return stress_cc(g, f.s11, i, j) - stress_cc(g, f.s22, i, j); }
 __device__ __forceinline__ double div_sigma_1j(const DGrid &g, const DFields &f, int i, int j)
 {
-    const double d = dyfc(g, j) * (sigD(g, f, i, j) - sigD(g, f, i - 1, j)) / 2;
-    const double t = (dycc(g, j) * dycc(g, j) * sigT(g, f, i, j) - dycc(g, j) * dycc(g, j) * sigT(g, f, i - 1, j)) / dyfc(g, j) / 2;
-    const double S = (dxff(g, j + 1) * dxff(g, j + 1) * stress_ff(g, f.s12, i, j + 1) - dxff(g, j) * dxff(g, j) * stress_ff(g, f.s12, i, j)) / dxfc(g, j);
-    return (d + t + S) / azfc(g, j);
+    const double d = dyfc(g, i, j) * (sigD(g, f, i, j) - sigD(g, f, i - 1, j)) / 2;
+    const double t = (dycc(g, i, j) * dycc(g, i, j) * sigT(g, f, i, j) - dycc(g, i - 1, j) * dycc(g, i - 1, j) * sigT(g, f, i - 1, j)) / dyfc(g, i, j) / 2;
+    const double S = (dxff(g, i, j + 1) * dxff(g, i, j + 1) * stress_ff(g, f.s12, i, j + 1) - dxff(g, i, j) * dxff(g, i, j) * stress_ff(g, f.s12, i, j)) / dxfc(g, i, j);
+    return (d + t + S) / azfc(g, i, j);
 }
 __device__ __forceinline__ double div_sigma_2j(const DGrid &g, const DFields &f, int i, int j)
 {
-    const double d = dxcf(g, j) * (sigD(g, f, i, j) - sigD(g, f, i, j - 1)) / 2;
-    const double t = -(dxcc(g, j) * dxcc(g, j) * sigT(g, f, i, j) - dxcc(g, j - 1) * dxcc(g, j - 1) * sigT(g, f, i, j - 1)) / dxcf(g, j) / 2;
-    const double S = (dyff(g, j) * dyff(g, j) * stress_ff(g, f.s12, i + 1, j) - dyff(g, j) * dyff(g, j) * stress_ff(g, f.s12, i, j)) / dycf(g, j);
-    return (d + t + S) / azcf(g, j);
+    const double d = dxcf(g, i, j) * (sigD(g, f, i, j) - sigD(g, f, i, j - 1)) / 2;
+    const double t = -(dxcc(g, i, j) * dxcc(g, i, j) * sigT(g, f, i, j) - dxcc(g, i, j - 1) * dxcc(g, i, j - 1) * sigT(g, f, i, j - 1)) / dxcf(g, i, j) / 2;
+    const double S = (dyff(g, i + 1, j) * dyff(g, i + 1, j) * stress_ff(g, f.s12, i + 1, j) - dyff(g, i, j) * dyff(g, i, j) * stress_ff(g, f.s12, i, j)) / dycf(g, i, j);
+    return (d + t + S) / azcf(g, i, j);
 }
 
 // ---- immersed stress divergence: isd:57-123 with the linear-drag FluxBoundaryCondition -C*u (coastline example) ----
@@ -147,19 +147,19 @@ __device__ __forceinline__ double immersed_div_sigma_1j(const DGrid &g, const DP
 {
     if (!g.mask || p.imm_u == 0.0) return 0.0;
     const double bc = (-p.imm_u) * at(f.u, i, j);
-    const double qW = 0.0 * (dycc(g, j) * 1.0), qE = 0.0 * (dycc(g, j) * 1.0);
-    const double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dxff(g, j) * 1.0);
-    const double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (dxff(g, j + 1) * 1.0);
-    return (qE - qW + qN - qS) / (azfc(g, j) * 1.0);
+    const double qW = 0.0 * (dycc(g, i - 1, j) * 1.0), qE = 0.0 * (dycc(g, i, j) * 1.0);
+    const double qS = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dxff(g, i, j) * 1.0);
+    const double qN = (imm_peripheral_ff(g, i, j + 1) ? bc : 0.0) * (dxff(g, i, j + 1) * 1.0);
+    return (qE - qW + qN - qS) / (azfc(g, i, j) * 1.0);
 }
 __device__ __forceinline__ double immersed_div_sigma_2j(const DGrid &g, const DParams &p, const DFields &f, int i, int j)
 {
     if (!g.mask || p.imm_v == 0.0) return 0.0;
     const double bc = (-p.imm_v) * at(f.v, i, j);
-    const double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dyff(g, j) * 1.0);
-    const double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (dyff(g, j) * 1.0);
-    const double qS = 0.0 * (dxcc(g, j - 1) * 1.0), qN = 0.0 * (dxcc(g, j) * 1.0);
-    return (qE - qW + qN - qS) / (azcf(g, j) * 1.0);
+    const double qW = (imm_peripheral_ff(g, i, j) ? -bc : 0.0) * (dyff(g, i, j) * 1.0);
+    const double qE = (imm_peripheral_ff(g, i + 1, j) ? bc : 0.0) * (dyff(g, i + 1, j) * 1.0);
+    const double qS = 0.0 * (dxcc(g, i, j - 1) * 1.0), qN = 0.0 * (dxcc(g, i, j) * 1.0);
+    return (qE - qW + qN - qS) / (azcf(g, i, j) * 1.0);
 }
 
 // ---- external stresses: ext:8-40,176-210 -----------------------------------------------------------
@@ -264,9 +264,9 @@ __device__ __forceinline__ double x_f_cross_U(const DGrid &g, const DParams &p, 
 {
     if (p.cor == CSI_CORIOLIS_NONE) return 0.0;
     if (p.cor == CSI_CORIOLIS_SPHERICAL) {
-        auto dxv = [&](int a, int b) { return (dxcf(g, b) * at(f.v, a, b) + dxcf(g, b + 1) * at(f.v, a, b + 1)) / 2; };
+        auto dxv = [&](int a, int b) { return (dxcf(g, a, b) * at(f.v, a, b) + dxcf(g, a, b + 1) * at(f.v, a, b + 1)) / 2; };
         const double fbar = (__ldg(p.fff + (j - 1 + g.Hy)) + __ldg(p.fff + (j + g.Hy))) / 2;
-        return -fbar * ((dxv(i - 1, j) + dxv(i, j)) / 2) / dxfc(g, j);
+        return -fbar * ((dxv(i - 1, j) + dxv(i, j)) / 2) / dxfc(g, i, j);
     }
     auto vv = [&](int a, int b) { return at(f.v, a, b); };
     return -p.f * avg_fc(vv, i, j);
@@ -275,10 +275,10 @@ __device__ __forceinline__ double y_f_cross_U(const DGrid &g, const DParams &p, 
 {
     if (p.cor == CSI_CORIOLIS_NONE) return 0.0;
     if (p.cor == CSI_CORIOLIS_SPHERICAL) {
-        auto dyu = [&](int a, int b) { return (dyfc(g, b) * at(f.u, a, b) + dyfc(g, b) * at(f.u, a + 1, b)) / 2; };
+        auto dyu = [&](int a, int b) { return (dyfc(g, a, b) * at(f.u, a, b) + dyfc(g, a + 1, b) * at(f.u, a + 1, b)) / 2; };
         const double fj = __ldg(p.fff + (j - 1 + g.Hy));
         const double fbar = (fj + fj) / 2;
-        return fbar * ((dyu(i, j - 1) + dyu(i, j)) / 2) / dycf(g, j);
+        return fbar * ((dyu(i, j - 1) + dyu(i, j)) / 2) / dycf(g, i, j);
     }
     auto uu = [&](int a, int b) { return at(f.u, a, b); };
     return p.f * avg_cf(uu, i, j);

@@ -38,14 +38,14 @@ __global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, doub
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (j > Ny) return;
-    const double D = dxff(g, j);  // Delta x at (Face, Face) on the wall, as Oceananigans' left/right_gradient uses
+    const double Dw = dxff(g, 1, j), De = dxff(g, Nx + 1, j);  // Delta x at (Face, Face) on the walls, as Oceananigans' left/right_gradient uses
     if (mode == FILL_NOFLUX) {
         if (do_west) at(a, 0, j) = at(a, 1, j);
         if (do_east) at(a, Nx + 1, j) = at(a, Nx, j);
     } else if (mode == FILL_VALUE) {
         const double c1 = at(a, 1, j), cN = at(a, Nx, j);
-        if (do_west) at(a, 0, j) = c1 + ((c1 - val) / (D / 2)) * (-D);
-        if (do_east) at(a, Nx + 1, j) = cN + ((val - cN) / (D / 2)) * D;
+        if (do_west) at(a, 0, j) = c1 + ((c1 - val) / (Dw / 2)) * (-Dw);
+        if (do_east) at(a, Nx + 1, j) = cN + ((val - cN) / (De / 2)) * De;
     } else if (mode == FILL_IMPENETRABLE) {
         if (do_west) at(a, 1, j) = 0.0;
         if (do_east) at(a, Nx + 1, j) = 0.0;
@@ -56,7 +56,7 @@ __global__ void k_fill_y_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, doub
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > Nx) return;
-    const double Ds = dyff(g, 1), Dn = dyff(g, Ny + 1);
+    const double Ds = dyff(g, i, 1), Dn = dyff(g, i, Ny + 1);
     if (mode == FILL_NOFLUX) {
         if (do_south) at(a, i, 0) = at(a, i, 1);
         if (do_north) at(a, i, Ny + 1) = at(a, i, Ny);

@@ -69,12 +69,12 @@ __global__ void __launch_bounds__(RT) k_reduce_pass1(const __grid_constant__ DGr
             const double h = f.h.p ? at(f.h, i, j) : 0.0, c = f.a.p ? at(f.a, i, j) : 0.0;
             const double u = at(f.u, i, j), v = at(f.v, i, j);
             Acc b;
-            b.s0 = h * azcc(g, j);
-            b.s1 = c * azcc(g, j);
-            b.s2 = h * c * azcc(g, j);
+            b.s0 = h * azcc(g, i, j);
+            b.s1 = c * azcc(g, i, j);
+            b.s2 = h * c * azcc(g, i, j);
             b.m0 = fabs(u);
             b.m1 = fabs(v);
-            b.tmin = 1 / (fabs(u) / dxfc(g, j) + fabs(v) / dycf(g, j));
+            b.tmin = 1 / (fabs(u) / dxfc(g, i, j) + fabs(v) / dycf(g, i, j));
             a = acc_merge(a, b);
         }
     a = block_reduce(a);

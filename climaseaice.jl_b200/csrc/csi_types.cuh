@@ -30,29 +30,29 @@ struct DGrid {
     // j-dependent metrics (LatitudeLongitudeGrid): 12 arrays of metL doubles, entry for index j at [j-1+Hy];
     // order dxcc dxfc dxcf dxff dycc dyfc dycf dyff azcc azfc azcf azff.  NULL on a regular RectilinearGrid.
     const double *met;
-    int metL, pad_;
+    int metL, metW;         // rows of the metric arrays; columns per row (0: the metrics depend on j only)
     const double *met_host;  // host copies (plan construction only): the 12 x metL metrics, and f at (Face, Face) or NULL
     const double *fff_host;
 };
 
-// grid metrics at row j (they do not depend on i on the supported grids)
+// grid metrics at (i, j): constants on a RectilinearGrid, functions of j on a LatitudeLongitudeGrid (metW == 0), full 2-D
+// arrays on an orthogonal curvilinear grid (metW = Nx + 2 Hx + 1 columns per row, entry (i, j) at [(j-1+Hy) metW + (i-1+Hx)])
 enum { M_DXCC = 0, M_DXFC, M_DXCF, M_DXFF, M_DYCC, M_DYFC, M_DYCF, M_DYFF, M_AZCC, M_AZFC, M_AZCF, M_AZFF };
-__device__ __forceinline__ double metric(const DGrid &g, int which, int j, double regular)
+__device__ __forceinline__ double metric(const DGrid &g, int which, int i, int j, double regular)
 {
-    return g.met ? __ldg(g.met + (size_t)which * g.metL + (j - 1 + g.Hy)) : regular;
+    if (!g.met) return regular;
+    if (g.metW) {
+        const int pi = min(max(i - 1 + g.Hx, 0), g.metW - 1);
+        return __ldg(g.met + ((size_t)which * g.metL + (j - 1 + g.Hy)) * g.metW + pi);
+    }
+    return __ldg(g.met + (size_t)which * g.metL + (j - 1 + g.Hy));
 }
-__device__ __forceinline__ double dxcc(const DGrid &g, int j) { return metric(g, M_DXCC, j, g.dx); }
-__device__ __forceinline__ double dxfc(const DGrid &g, int j) { return metric(g, M_DXFC, j, g.dx); }
-__device__ __forceinline__ double dxcf(const DGrid &g, int j) { return metric(g, M_DXCF, j, g.dx); }
-__device__ __forceinline__ double dxff(const DGrid &g, int j) { return metric(g, M_DXFF, j, g.dx); }
-__device__ __forceinline__ double dycc(const DGrid &g, int j) { return metric(g, M_DYCC, j, g.dy); }
-__device__ __forceinline__ double dyfc(const DGrid &g, int j) { return metric(g, M_DYFC, j, g.dy); }
-__device__ __forceinline__ double dycf(const DGrid &g, int j) { return metric(g, M_DYCF, j, g.dy); }
-__device__ __forceinline__ double dyff(const DGrid &g, int j) { return metric(g, M_DYFF, j, g.dy); }
-__device__ __forceinline__ double azcc(const DGrid &g, int j) { return metric(g, M_AZCC, j, g.az); }
-__device__ __forceinline__ double azfc(const DGrid &g, int j) { return metric(g, M_AZFC, j, g.az); }
-__device__ __forceinline__ double azcf(const DGrid &g, int j) { return metric(g, M_AZCF, j, g.az); }
-__device__ __forceinline__ double azff(const DGrid &g, int j) { return metric(g, M_AZFF, j, g.az); }
+#define CSI_METRIC_FN(name, which, regular) \
+    __device__ __forceinline__ double name(const DGrid &g, int i, int j) { return metric(g, which, i, j, regular); }
+CSI_METRIC_FN(dxcc, M_DXCC, g.dx) CSI_METRIC_FN(dxfc, M_DXFC, g.dx) CSI_METRIC_FN(dxcf, M_DXCF, g.dx) CSI_METRIC_FN(dxff, M_DXFF, g.dx)
+CSI_METRIC_FN(dycc, M_DYCC, g.dy) CSI_METRIC_FN(dyfc, M_DYFC, g.dy) CSI_METRIC_FN(dycf, M_DYCF, g.dy) CSI_METRIC_FN(dyff, M_DYFF, g.dy)
+CSI_METRIC_FN(azcc, M_AZCC, g.az) CSI_METRIC_FN(azfc, M_AZFC, g.az) CSI_METRIC_FN(azcf, M_AZCF, g.az) CSI_METRIC_FN(azff, M_AZFF, g.az)
+#undef CSI_METRIC_FN
 
 struct DParams {
     double Pstar, C, em2, Dmin, amin, amax, ca;

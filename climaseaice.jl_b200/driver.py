@@ -15,6 +15,10 @@ from .synthetic import LOC, Case
 
 
 def grid_from_case(case: Case, device=None, partitioned_y=False, partitioned_x=False) -> RectilinearGrid:
+    if case.metric_arrays is not None and next(iter(case.metric_arrays.values())).ndim == 2:   # orthogonal curvilinear grid
+        from .model import OrthogonalSphericalShellGrid
+        return OrthogonalSphericalShellGrid(size=(case.Nx, case.Ny), metrics=case.metric_arrays, halo=(case.Hx, case.Hy),
+                                            topology=(case.topology[0], case.topology[1], "Flat"), device=device)
     if case.latlon is not None:
         return LatitudeLongitudeGrid(size=(case.Nx, case.Ny), longitude=case.latlon[0], latitude=case.latlon[1],
                                      halo=(case.Hx, case.Hy), topology=(case.topology[0], case.topology[1], "Flat"),

@@ -91,6 +91,24 @@ class LatitudeLongitudeGrid(RectilinearGrid):
             self.metrics[n] = a
 
 
+class OrthogonalSphericalShellGrid(RectilinearGrid):
+    """Orthogonal curvilinear grid given by its metrics (Oceananigans' OrthogonalSphericalShellGrid family: rotated,
+    stretched or conformally mapped meshes; no fold): `metrics[name]` is a (Ny + 2Hy + 1) x (Nx + 2Hx + 1) array with the
+    value at index (i, j) -- halos included -- stored at [j - 1 + Hy, i - 1 + Hx], for the twelve names of METRIC_NAMES
+    (dx, dy, Az at the four horizontal locations), i.e. what Oceananigans' `Δxᶜᶜᵃ` ... `Azᶠᶠᵃ` return.  `nodes()` are index
+    coordinates.  Runs on the general (per-kernel) solver formulation."""
+
+    def __init__(self, size, metrics, halo=(3, 3), topology=(Bounded, Bounded, Flat), device=None):
+        super().__init__(size, (0.0, float(size[0])), (0.0, float(size[1])), halo=halo, topology=topology, device=device)
+        self.metrics = {}
+        shp = (self.Ny + 2 * self.Hy + 1, self.Nx + 2 * self.Hx + 1)
+        for n in METRIC_NAMES:
+            a = np.ascontiguousarray(metrics[n], dtype=np.float64).copy()
+            if a.shape != shp:
+                raise ValueError(f"metric {n}: expected shape {shp}, got {a.shape}")
+            self.metrics[n] = a
+
+
 class Field:
     """Oceananigans-layout field: a dense (sy, sx) float64 parent (i fastest) with halos, on the GPU."""
 
@@ -466,8 +484,8 @@ class SeaIceModel:
         cfg.Nx, cfg.Ny, cfg.Hx, cfg.Hy = g.Nx, g.Ny, g.Hx, g.Hy
         cfg.topo_x, cfg.topo_y = g.topo_codes
         cfg.dx, cfg.dy = g.dx, g.dy
-        if isinstance(g, LatitudeLongitudeGrid):
-            cfg.metric_kind = L.METRIC_J
+        if isinstance(g, (LatitudeLongitudeGrid, OrthogonalSphericalShellGrid)):
+            cfg.metric_kind = L.METRIC_J if isinstance(g, LatitudeLongitudeGrid) else L.METRIC_IJ
             for k, n in enumerate(METRIC_NAMES):
                 cfg.metrics[k] = g.metrics[n].ctypes.data_as(C.POINTER(C.c_double))
         cfg.immersed_mask = self._mask.ctypes.data if self._mask is not None else None

@@ -206,6 +206,41 @@ def latlon_case(N=96, H=4, seed=SEED, substeps=150, dt=600.0, advection_order=7,
     return c
 
 
+def curvilinear_case(N=72, Ny=56, H=4, seed=SEED, substeps=20, dt=600.0, advection_order=7, timestepper="SplitRungeKutta3",
+                     topology=("Bounded", "Bounded")) -> Case:
+    """An orthogonal curvilinear mesh given by two-dimensional metrics (the layout of Oceananigans' OrthogonalSphericalShellGrid,
+    e.g. one panel of a rotated or stretched mesh): spacings vary smoothly by +-25 % in both directions; the areas are the
+    products of the local spacings at each of the four locations.  Fields as in latlon_case."""
+    c = Case("curvilinear", N, Ny, H, H, tuple(topology), float(N), float(Ny), dt=dt, substeps=substeps,
+             advection_order=advection_order, timestepper=timestepper,
+             u_bc_value=0.0 if topology[1] == "Bounded" else None, v_bc_value=0.0 if topology[0] == "Bounded" else None)
+    tp = 2 * np.pi
+    i = np.arange(1 - H, N + H + 2)[None, :].astype(np.float64)
+    j = np.arange(1 - H, Ny + H + 2)[:, None].astype(np.float64)
+
+    def spacing(x, y, base, phase):   # x, y: index coordinates of the location (periodic in the periodic directions)
+        return base * (1.0 + 0.15 * np.sin(tp * x / N + phase) + 0.10 * np.cos(tp * y / Ny - phase))
+
+    xc, xf, yc, yf = i - 0.5, i - 1.0, j - 0.5, j - 1.0
+    M = {}
+    for name, (x, y) in dict(cc=(xc, yc), fc=(xf, yc), cf=(xc, yf), ff=(xf, yf)).items():
+        M["dx" + name] = spacing(x, y, 4000.0, 0.3) + 0 * (x + y)
+        M["dy" + name] = spacing(x, y, 3000.0, 1.1) + 0 * (x + y)
+        M["az" + name] = M["dx" + name] * M["dy" + name]
+    c.metric_arrays = {k: np.ascontiguousarray(v) for k, v in M.items()}
+    rng = np.random.default_rng(seed)
+    X, Y = c.nodes(LOC["h"])
+    Xu, Yu = c.nodes(LOC["u"])
+    Xv, Yv = c.nodes(LOC["v"])
+    fx, fy = (lambda x: x / c.Lx), (lambda y: y / c.Ly)
+    h = 0.5 + 0.2 * np.sin(tp * fx(X)) * np.cos(tp * fy(Y)) + 1e-3 * rng.uniform(-1, 1, X.shape)
+    a = np.clip(0.95 + 0.05 * np.cos(2 * tp * fx(X)) - 0.3 * (fy(Y) < 0.15), 0.0, 1.0)
+    raw = dict(h=h, a=a, u=np.zeros_like(Xu), v=np.zeros_like(Xv), ue=0.05 * np.sin(tp * fy(Yu)), ve=0.05 * np.sin(tp * fx(Xv)),
+               top_x=0.1 * np.cos(tp * fy(Yu)), top_y=0.1 * np.sin(tp * fx(Xv)))
+    c.fields = {k: _wrap_periodic(c, np.ascontiguousarray(vv, dtype=np.float64), LOC[k]) for k, vv in raw.items()}
+    return c
+
+
 def arctic_cap_case(Nx=192, Ny=48, H=7, seed=SEED, substeps=20, dt=600.0, timestepper="SplitRungeKutta3") -> Case:
     """BASELINE config 5 in miniature: a zonally periodic lat-lon cap (lambda in (0, 360), phi in (60, 88); the metrics
     shrink 14x towards the pole), HydrostaticSphericalCoriolis, EVP dynamics + WENO advection coupled to bare-ice slab thermodynamics with a

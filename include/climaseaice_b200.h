@@ -114,7 +114,10 @@ typedef struct {
     /* LatitudeLongitudeGrid (or any grid whose metrics depend on j only): metric_kind = CSI_METRIC_J and
      * metrics[k] -> host array of Ny + 2*Hy + 1 doubles, the value at index j stored at [j - 1 + Hy], in the
      * order dx{cc,fc,cf,ff}, dy{cc,fc,cf,ff}, Az{cc,fc,cf,ff} (Oceananigans' Delta-x/Delta-y/Az at the four
-     * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above. */
+     * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above.
+     * CSI_METRIC_IJ (orthogonal curvilinear grids: OrthogonalSphericalShellGrid, rotated or stretched meshes): the same
+     * twelve metrics as two-dimensional host arrays of (Ny + 2*Hy + 1) rows x (Nx + 2*Hx + 1) columns, i fastest, the value
+     * at (i, j) stored at [(j - 1 + Hy) * (Nx + 2*Hx + 1) + (i - 1 + Hx)]; general kernels only, one rank, no fold. */
     int32_t metric_kind;
     int32_t serial_exchange;    /* slabs + fused solver: 0 = the halo exchange between blocks of K substeps runs on its own stream
                                    while the next substep's interior tiles compute (boundary tiles wait for it); 1 = on the compute stream */
@@ -146,7 +149,7 @@ typedef struct {
     csi_array fd_u, fd_v;           /* free-drift velocities (f,c) (c,f) when free_drift_kind = CSI_FD_FIELDS */
 } csi_fields;
 
-enum { CSI_METRIC_REGULAR = 0, CSI_METRIC_J = 1 };
+enum { CSI_METRIC_REGULAR = 0, CSI_METRIC_J = 1, CSI_METRIC_IJ = 2 };
 
 int csi_version(void);
 const char *csi_last_error(const csi_handle *h); /* h may be NULL: last error of csi_create */

@@ -56,19 +56,21 @@ double csio_exp(double x) { return (double)expq((__float128)x); }
  * Grid metrics [OCN-recall]: regular RectilinearGrid (all spacings scalar, Az = dx*dy) or j-indexed
  * arrays (LatitudeLongitudeGrid).
  * ------------------------------------------------------------------------------------------- */
-#define MJ(a) (g->a[j - 1 + g->Hy])
-static inline double dxcc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dxcc) : g->dx; }
-static inline double dxfc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dxfc) : g->dx; }
-static inline double dxcf(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dxcf) : g->dx; }
-static inline double dxff(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dxff) : g->dx; }
-static inline double dycc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dycc) : g->dy; }
-static inline double dyfc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dyfc) : g->dy; }
-static inline double dycf(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dycf) : g->dy; }
-static inline double dyff(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(dyff) : g->dy; }
-static inline double azcc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(azcc) : g->dx * g->dy; }
-static inline double azfc(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(azfc) : g->dx * g->dy; }
-static inline double azcf(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(azcf) : g->dx * g->dy; }
-static inline double azff(G g, int i, int j) { (void)i; return g->metric_kind ? MJ(azff) : g->dx * g->dy; }
+/* CSIO_JMETRIC: a[j-1+Hy]; CSIO_IJMETRIC: two-dimensional arrays, metW columns per row, entry (i, j) at [(j-1+Hy) metW + (i-1+Hx)] */
+#define MJ(a) (g->metric_kind == CSIO_IJMETRIC ? g->a[(size_t)(j - 1 + g->Hy) * g->metW + (size_t)(i - 1 + g->Hx < 0 ? 0 : (i - 1 + g->Hx >= g->metW ? g->metW - 1 : i - 1 + g->Hx))] \
+                                               : g->a[j - 1 + g->Hy])
+static inline double dxcc(G g, int i, int j) { return g->metric_kind ? MJ(dxcc) : g->dx; }
+static inline double dxfc(G g, int i, int j) { return g->metric_kind ? MJ(dxfc) : g->dx; }
+static inline double dxcf(G g, int i, int j) { return g->metric_kind ? MJ(dxcf) : g->dx; }
+static inline double dxff(G g, int i, int j) { return g->metric_kind ? MJ(dxff) : g->dx; }
+static inline double dycc(G g, int i, int j) { return g->metric_kind ? MJ(dycc) : g->dy; }
+static inline double dyfc(G g, int i, int j) { return g->metric_kind ? MJ(dyfc) : g->dy; }
+static inline double dycf(G g, int i, int j) { return g->metric_kind ? MJ(dycf) : g->dy; }
+static inline double dyff(G g, int i, int j) { return g->metric_kind ? MJ(dyff) : g->dy; }
+static inline double azcc(G g, int i, int j) { return g->metric_kind ? MJ(azcc) : g->dx * g->dy; }
+static inline double azfc(G g, int i, int j) { return g->metric_kind ? MJ(azfc) : g->dx * g->dy; }
+static inline double azcf(G g, int i, int j) { return g->metric_kind ? MJ(azcf) : g->dx * g->dy; }
+static inline double azff(G g, int i, int j) { return g->metric_kind ? MJ(azff) : g->dx * g->dy; }
 /* Flat z: dz = 1, so Ax = dy*1, Ay = dx*1, V = Az*1 */
 static inline double axfcc(G g, int i, int j) { return dyfc(g, i, j) * 1.0; }
 static inline double aycfc(G g, int i, int j) { return dxcf(g, i, j) * 1.0; }

@@ -37,13 +37,13 @@ typedef struct {
 } csio_field;
 
 enum { CSIO_PERIODIC = 0, CSIO_BOUNDED = 1 };
-enum { CSIO_REGULAR = 0, CSIO_JMETRIC = 1 };
+enum { CSIO_REGULAR = 0, CSIO_JMETRIC = 1, CSIO_IJMETRIC = 2 };
 
 typedef struct {
     int32_t Nx, Ny, Hx, Hy;
     int32_t topo_x, topo_y;  /* CSIO_PERIODIC / CSIO_BOUNDED */
-    int32_t metric_kind;     /* CSIO_REGULAR: dx,dy scalars; CSIO_JMETRIC: j-indexed arrays (lat-lon) */
-    int32_t pad_;
+    int32_t metric_kind;     /* CSIO_REGULAR: dx,dy scalars; CSIO_JMETRIC: j-indexed arrays (lat-lon); CSIO_IJMETRIC: 2-D arrays */
+    int32_t metW;            /* CSIO_IJMETRIC: columns per row of the metric arrays (Nx + 2 Hx + 1) */
     double dx, dy;
     /* j-indexed metrics, entry for index j at arr[j-1+Hy], length Ny+2Hy+1 (CSIO_JMETRIC only) */
     const double *dxcc, *dxfc, *dxcf, *dxff;

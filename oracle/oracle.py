@@ -40,7 +40,7 @@ class Field(C.Structure):
 class Grid(C.Structure):
     _fields_ = [
         ("Nx", C.c_int32), ("Ny", C.c_int32), ("Hx", C.c_int32), ("Hy", C.c_int32),
-        ("topo_x", C.c_int32), ("topo_y", C.c_int32), ("metric_kind", C.c_int32), ("pad_", C.c_int32),
+        ("topo_x", C.c_int32), ("topo_y", C.c_int32), ("metric_kind", C.c_int32), ("metW", C.c_int32),
         ("dx", C.c_double), ("dy", C.c_double),
     ] + [(n, C.POINTER(C.c_double)) for n in
          ("dxcc", "dxfc", "dxcf", "dxff", "dycc", "dyfc", "dycf", "dyff", "azcc", "azfc", "azcf", "azff")] + [
@@ -159,10 +159,13 @@ class OracleModel:
         self.g = Grid(Nx=Nx, Ny=Ny, Hx=Hx, Hy=Hy, topo_x=self.topo[0], topo_y=self.topo[1], dx=dx, dy=dy)
         self._keep = []
         if metrics is not None:
-            self.g.metric_kind = 1
+            two_d = next(iter(metrics.values())).ndim == 2   # orthogonal curvilinear grid: (Ny+2Hy+1) x (Nx+2Hx+1) arrays
+            self.g.metric_kind = 2 if two_d else 1
+            if two_d:
+                self.g.metW = Nx + 2 * Hx + 1
             for k, v in metrics.items():
                 v = np.ascontiguousarray(v, dtype=np.float64)
-                assert v.shape == (Ny + 2 * Hy + 1,), (k, v.shape)
+                assert v.shape == ((Ny + 2 * Hy + 1, Nx + 2 * Hx + 1) if two_d else (Ny + 2 * Hy + 1,)), (k, v.shape)
                 self._keep.append(v)
                 setattr(self.g, k, v.ctypes.data_as(C.POINTER(C.c_double)))
         if mask is not None:

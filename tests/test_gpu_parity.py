@@ -327,6 +327,33 @@ def test_latitude_longitude_grid(impl, topology, timestepper):
     m.close()
 
 
+@pytest.mark.parametrize("topology", [("Bounded", "Bounded"), ("Periodic", "Bounded"), ("Periodic", "Periodic")])
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_two_dimensional_metrics(topology, timestepper):
+    """Metrics that depend on i and j (CSI_METRIC_IJ: orthogonal curvilinear grids, the metric layout of Oceananigans'
+    OrthogonalSphericalShellGrid family): every dx/dy/Az of the strain rates, the stress divergence, the relaxation
+    factors, the flux divergence, the value BCs and the reductions is taken at the
+    (i, j) the reference's operators name.  General kernels; the fused kernel declines such grids."""
+    from climaseaice_b200.synthetic import curvilinear_case
+    case = curvilinear_case(72, 56, substeps=20, topology=topology, timestepper=timestepper)
+    met = case.metrics()
+    assert met["dxcc"].max() / met["dxcc"].min() > 1.5 and np.ptp(met["dxcc"], axis=1).max() > 100.0   # they vary along i too
+    m = model_from_case(case, solver_impl="auto")
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "delta")))
+    assert np.abs(interior_of(m.all_fields()["u"].numpy(), case)).max() > 1e-4
+    assert m.fused_stats() == (0, 0, 0)                      # the general kernels ran
+    assert m.cell_advection_timescale() == pytest.approx(o.cell_advection_timescale(), rel=1e-15)
+    d = m.diagnostics()
+    az = met["azcc"][case.Hy:case.Hy + case.Ny, case.Hx:case.Hx + case.Nx]
+    assert d["sum_h_Az"] == pytest.approx((o.interior("h") * az).sum(), rel=1e-13)
+    with pytest.raises(RuntimeError, match="two-dimensional metrics"):
+        model_from_case(case, solver_impl="fused").time_step(case.dt)
+    m.close()
+
+
 def test_latitude_longitude_grid_rejects_bad_metrics():
     from climaseaice_b200.synthetic import latlon_case
     bad = latlon_case(32, substeps=4)

@@ -52,6 +52,25 @@ def test_energy_budget_adjoint_identity(N):
     assert imb(Wn) < 1e-6 * imb(Wo)   # :123
 
 
+def test_energy_budget_adjoint_identity_two_dimensional_metrics():
+    """The same summation-by-parts identity (test/test_rheology_energy_budget.jl:50-124) with metrics that depend on i and j
+    (orthogonal curvilinear grid): it holds only if the strain rates and the stress divergence take every metric at
+    matching (i, j) -- the pairing of evp.jl:360-375 with ice_stress_divergence.jl:39-51."""
+    from climaseaice_b200.synthetic import curvilinear_case
+    N, Ny, H = 36, 28, 4
+    c = curvilinear_case(N, Ny, H=H)
+    m = O.OracleModel(N, Ny, H, H, topo=(O.BOUNDED, O.BOUNDED), metrics=c.metrics())
+    rng = np.random.default_rng(3)
+    for name in ("u", "v", "s11", "s22", "s12"):
+        a = m.arr[name]
+        a[:] = 0
+        a[H + 2:H + Ny - 2, H + 2:H + N - 2] = rng.uniform(-1, 1, (Ny - 4, N - 4))   # compact support: no boundary terms
+    Wn, Wo, D = m.stress_power_budget()
+    imb = lambda W: abs(W + D) / max(abs(W), abs(D))
+    assert imb(Wn) < 1e-12
+    assert imb(Wo) > 1e-3
+
+
 def test_semi_implicit_ocean_drag_bounds():
     """test/test_time_stepping.jl:56-80: 8x8 periodic, substeps=10, 20 steps of 60 s from rest."""
     N, H, uo = 8, 4, 0.1
