@@ -74,6 +74,16 @@ function metric_vectors(grid)
     return vecs, ntuple(k -> pointer(vecs[k]), 12)
 end
 
+# Orthogonal curvilinear grids (OrthogonalSphericalShellGrid without a fold): the same twelve metrics as two-dimensional
+# arrays (metric_kind = 2), (Nx + 2Hx + 1) x (Ny + 2Hy + 1) column-major = i fastest, index (i, j) at [i + Hx, j + Hy].
+function metric_arrays(grid)
+    Nx, Ny, _ = size(grid); Hx, Hy, _ = halo_size(grid)
+    ops = (Δxᶜᶜᶜ, Δxᶠᶜᶜ, Δxᶜᶠᶜ, Δxᶠᶠᶜ, Δyᶜᶜᶜ, Δyᶠᶜᶜ, Δyᶜᶠᶜ, Δyᶠᶠᶜ, Azᶜᶜᶜ, Azᶠᶜᶜ, Azᶜᶠᶜ, Azᶠᶠᶜ)
+    cpu = on_architecture(CPU(), grid)
+    arrs = [Float64[op(i, j, 1, cpu) for i in 1-Hx:Nx+Hx+1, j in 1-Hy:Ny+Hy+1] for op in ops]
+    return arrs, ntuple(k -> pointer(arrs[k]), 12)
+end
+
 # csi_fields: 29 csi_array in header order
 const FIELD_ORDER = (:u, :v, :h, :a, :s11, :s22, :s12, :zeta_f, :zeta_c, :delta, :alpha, :un, :vn, :P,
                      :top_x, :top_y, :ue, :ve, :Gh, :Ga, :hm, :am, :um, :vm, :hs, :Ghs, :hsm, :fd_u, :fd_v)
@@ -95,11 +105,12 @@ function create(model::SeaIceModel)
     dyn, r = model.dynamics, model.dynamics.rheology
     Nx, Ny, _ = size(grid); Hx, Hy, _ = halo_size(grid); TX, TY, _ = topology(grid)
     bottom = dyn.external_momentum_stresses.bottom
-    regular = grid isa RectilinearGrid      # else: LatitudeLongitudeGrid, metrics depend on j
-    vecs, metrics = regular ? (nothing, ntuple(_ -> Ptr{Float64}(C_NULL), 12)) : metric_vectors(grid)
+    regular = grid isa RectilinearGrid      # else: LatitudeLongitudeGrid (metrics depend on j) or an orthogonal curvilinear grid
+    latlon = grid isa LatitudeLongitudeGrid
+    vecs, metrics = regular ? (nothing, ntuple(_ -> Ptr{Float64}(C_NULL), 12)) : (latlon ? metric_vectors(grid) : metric_arrays(grid))
     cfg = CsiConfig(; Nx, Ny, Hx, Hy, topo_x = topo_code(TX), topo_y = topo_code(TY),
                     dx = regular ? grid.Δxᶜᵃᵃ : 0.0, dy = regular ? grid.Δyᵃᶜᵃ : 0.0, device = CUDA.deviceid(),
-                    metric_kind = regular ? 0 : 1, metrics,
+                    metric_kind = regular ? 0 : (latlon ? 1 : 2), metrics,
                     ice_compressive_strength = r.ice_compressive_strength, ice_compaction_hardening = r.ice_compaction_hardening,
                     yield_curve_eccentricity = r.yield_curve_eccentricity, minimum_plastic_stress = r.minimum_plastic_stress,
                     min_relaxation_parameter = r.min_relaxation_parameter, max_relaxation_parameter = r.max_relaxation_parameter,
