@@ -120,14 +120,18 @@ enum { MC_DXCC = 0, MC_DXFC, MC_DXCF, MC_DXFF, MC_DYCC, MC_DYFC, MC_DYCF, MC_DYF
        MC_FFF, MC_N };
 constexpr int MET_PAD = 40;  // padding records of the metric table (>= tile height + halos beyond either end)
 
-// Metric<false>: the regular grid's constants (kernel parameters); Metric<true>: the row's own values, warp-uniform
-// read-only loads that stay in L1.  r is the reference row index j.
+// Metric<false>: the regular grid's constants (kernel parameters); Metric<true>: the row's own values, read from the
+// records of the tile's rows staged in shared memory (warp-uniform, conflict-free broadcasts).  r is the reference row index j.
+constexpr int MET_ROWS = BY + 5;  // rows J0 - 3 .. J0 + BY + 1: every row a tile's stencils and wall cells name
+static_assert(MET_ROWS * MC_N <= SXD * SYD, "the staged metric records must fit the shared-memory array they borrow");
 template <bool MET>
 struct Metric {
     const Params &p;
+    const double *smt;  // staged records (MET only): row r at smt[(r - rbase) * MC_N]
+    int rbase;
     __device__ __forceinline__ double ld(int col, int r) const
     {
-        return __ldg(p.met + r * MC_N + col);
+        return smt[(r - rbase) * MC_N + col];
     }
 #define CSI_MET(name, col, regular) \
     __device__ __forceinline__ double name(int r) const { return MET ? ld(col, r) : (regular); }
@@ -499,7 +503,15 @@ template <bool VFIRST, bool AUX, bool GEN, bool MET, class M>
 __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc)
 {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const Metric<MET> mt{p};
+    // lat-lon variant: the first-velocity array W shares the slot of e11 (dead after phase B) and W's own slot holds the
+    // metric records of the tile's rows, copied once per pass from the per-row table
+    constexpr int AW = MET ? A_E11 : A_W;
+    const Metric<MET> mt{p, sm + A_W * ASTRIDE, tc.J0 - 3};
+    if (MET) {
+        const double *src = p.met + (tc.J0 - 3) * MC_N;
+        for (int n = tid; n < MET_ROWS * MC_N; n += NT) sm[A_W * ASTRIDE + n] = __ldg(src + n);
+        __syncthreads();
+    }
     const size_t plane = (size_t)p.pitch * p.rows;
     const bool use_ue = GEN ? p.use_ue != 0 : true, use_top = GEN ? p.use_top != 0 : true;
     // ---- TMA: tile + halo of every stencil field; u, v first (phase A starts on them) ----
@@ -882,7 +894,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #else
             const double n1 = cn[q], t1 = ct[q];
 #endif
-            S(A_W, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
+            S(AW, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
         }
 #ifndef CSI_EXPERIMENT_LATE_LDG
     double dn[2], dtt[2];  // likewise for phase D
@@ -905,7 +917,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #else
             const double n1 = dn[q], t1 = dtt[q];
 #endif
-            w2[q] = VFIRST ? u_at(d_sx, sy, A_W, n1, t1) : v_at(d_sx, sy, A_W, n1, t1);
+            w2[q] = VFIRST ? u_at(d_sx, sy, AW, n1, t1) : v_at(d_sx, sy, AW, n1, t1);
         }
 
     const bool bad = __syncthreads_or(mm.bad());
@@ -974,7 +986,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                     const int dsy = d_sy0 + q;
                     double *g = o + (q + 1) * p.pitch + 1;  // node (lane + 1, 2 wrp + 1 + q)
                     g[(size_t)(tc.fout + (VFIRST ? 0 : 1)) * plane] = w2[q];
-                    g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(A_W, d_sx, dsy);
+                    g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(AW, d_sx, dsy);
                 }
             }
             return false;
@@ -1002,10 +1014,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const int ui = tc.I0 - 1 + d_sx, ur = tc.J0 - 1 + dsy;
             if (VFIRST) {
                 put_vel(tc.fout + 0, ui, ur, w2[q], true);
-                put_vel(tc.fout + 1, ui, ur, S(A_W, d_sx, dsy), false);
+                put_vel(tc.fout + 1, ui, ur, S(AW, d_sx, dsy), false);
             } else {
                 put_vel(tc.fout + 1, ui, ur, w2[q], false);
-                put_vel(tc.fout + 0, ui, ur, S(A_W, d_sx, dsy), true);
+                put_vel(tc.fout + 0, ui, ur, S(AW, d_sx, dsy), true);
             }
         }
     }
