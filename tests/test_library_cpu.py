@@ -112,3 +112,26 @@ def test_synthetic_cases_are_deterministic_and_periodic():
     assert c.fields["u"].shape == (16 + 14, 16 + 15) and c.fields["v"].shape == (16 + 15, 16 + 14)
     s = slab_of(periodic_case(16, Ny=32), 1, 2, 9)
     assert s.fields["h"].shape == (16 + 18, 16 + 14)
+
+
+def test_bench_block_generator_is_consistent_across_ranks():
+    """bench.py builds each rank's block of the global doubly periodic case without the global arrays: the analytic fields
+    of neighbouring blocks must agree where a block's halo overlaps its neighbour's interior (2 x 2 partition, rank = ry Rx + rx)."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import __graft_entry__ as entry
+    entry.load_package()
+    nx, ny, H, Rx, Ry = 24, 16, 5, 2, 2
+    blocks = {(rx, ry): bench.periodic_slab_case(nx, ny, ry, Ry, H, rx=rx, Rx=Rx) for rx in range(Rx) for ry in range(Ry)}
+    for name in ("u", "v", "ue", "ve", "top_x", "top_y"):
+        for (rx, ry), c in blocks.items():
+            a = c.fields[name]
+            assert a.shape == (ny + 2 * H, nx + 2 * H)
+            east = blocks[((rx + 1) % Rx, ry)].fields[name]
+            north = blocks[(rx, (ry + 1) % Ry)].fields[name]
+            # my east halo columns = the first H interior columns of the block to the east (periodic wrap: the fields are periodic)
+            assert np.allclose(a[H:H + ny, H + nx:], east[H:H + ny, H:2 * H], rtol=0, atol=1e-15)
+            assert np.allclose(a[H + ny:, H:H + nx], north[H:2 * H, H:H + nx], rtol=0, atol=1e-15)
