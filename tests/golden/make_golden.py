@@ -14,13 +14,15 @@ sys.path.insert(0, str(ROOT))
 import __graft_entry__ as entry  # noqa: E402
 
 entry.load_package()
-from climaseaice_b200.synthetic import anticyclone_case, periodic_case  # noqa: E402
+from climaseaice_b200.synthetic import anticyclone_case, curvilinear_case, latlon_case, periodic_case  # noqa: E402
 from tests.helpers import oracle_from_case  # noqa: E402
 
 CASES = {
     "periodic_24x20_rk3_weno7": lambda: periodic_case(24, Ny=20, substeps=12, aice="mixed"),
     "anticyclone_20_rk3_weno7": lambda: anticyclone_case(20, substeps=12),
     "periodic_18x22_fe_weno5": lambda: periodic_case(18, Ny=22, substeps=9, aice="mixed", advection_order=5, timestepper="ForwardEuler"),
+    "latlon_48_rk3_weno7": lambda: latlon_case(48, substeps=20, topology=("Periodic", "Bounded")),          # j-dependent metrics
+    "curvilinear_72x56_rk3_weno7": lambda: curvilinear_case(72, 56, substeps=20),                            # (i, j)-dependent metrics
 }
 FIELDS = ("u", "v", "h", "a", "s11", "s22", "s12", "alpha")
 
