@@ -10,8 +10,8 @@ finalize) over one synthetic batch.  N = 1: BASELINE config 2, the anticyclone c
 16384 x 2048 per GPU (16384^2 at N = 8), NCCL halo exchange every K substeps; weak scaling.
 `value`  : cell-updates/s with inputs resident in HBM, CUDA events, max over ranks.
 `e2e`    : the same metric through the host-buffer C-ABI call (pinned host arrays, H2D + D2H inside).
-`roofline`: dominant kernel, algorithmic bytes (144 B per cell-update fused / see DESIGN.md) over
-            its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`roofline`: dominant kernel, algorithmic bytes (144 B per cell-update fused / see DESIGN.md) over its average launch
+            duration in the timed region (CUDA events), against MEASURED_PEAKS.json hbm_gbs; `*_alone`: the kernel in a burst.
 `cpu_baseline`: the CPU oracle (C restatement of the reference's KernelAbstractions-CPU path; the
             Julia original cannot run in this image) on all host cores, bounded sample.
 """
@@ -227,14 +227,21 @@ def run_gpu(args):
     ms_per_step = ms / args.steps
     value = cells * ngpus * SUBSTEPS / (ms_per_step * 1e-3)
 
-    # dominant kernel, timed alone with CUDA events on its stream
-    kern_ms, kern_name, kern_bytes = time_dominant_kernel(model, cells)
+    # dominant kernel: its average launch duration over the timed region (CUDA events on its stream).  The fused solver
+    # launches it once per substep, so that is the region's time over the launches -- an upper bound, the region also holds
+    # the stage's pack / unpack / init kernels (about 1 %) and, for N > 1, the halo exchange.  The same kernel launched
+    # alone in a short burst (higher clock, no power cap yet) is reported beside it.
+    kern_alone_ms, kern_name, kern_bytes = time_dominant_kernel(model, cells)
+    if kern_name == "k_evp_substep_fused":
+        kern_ms, kern_src = ms_per_step / SUBSTEPS, "timed region / launches (includes the stage's pack, unpack and init kernels, about 1 %)"
+    else:
+        kern_ms, kern_src = kern_alone_ms, "kernel launched alone between CUDA events (several kernels per substep)"
     peak, peak_src = peaks()
     achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": traffic_from_profile(kern_name), "launch_ms": kern_ms,
+                "peak_source": peak_src, "traffic": traffic_from_profile(kern_name), "launch_ms": kern_ms, "launch_ms_source": kern_src,
                 "algorithmic_bytes_per_launch": kern_bytes,
-                "whole_substep_GBps_at_144B": BYTES_PER_CELL_FUSED * cells * SUBSTEPS / (ms_per_step * 1e-3) / 1e9}
+                "launch_ms_alone": kern_alone_ms, "achieved_alone": kern_bytes / (kern_alone_ms * 1e-3) / 1e9 if kern_alone_ms > 0 else None}
 
     # full model step (3 RK stages incl. advection), reported beside the headline
     barrier()
