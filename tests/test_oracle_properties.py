@@ -279,3 +279,20 @@ def test_snow_is_advected_and_clipped_with_the_ice():
     o2.time_step(case2.dt)
     assert np.all(o2.interior("hs")[o2.interior("a") <= 0] == 0.0)
     assert (o2.interior("a") <= 0).any()
+
+
+def test_one_ulp_of_input_exceeds_the_tolerance_after_one_step():
+    """The intrinsic-sensitivity yardstick of SURVEY 8(d): one ulp added to ONE thickness value changes u, v, sigma by
+    more than north_star's 1e-12 after a single time_step! (3 stages x 150 substeps) -- by 6e-12 on the smooth periodic
+    case and by 5e-3 on the anticyclone case, whose plastic regime amplifies round-off exponentially.  Hence the library
+    reproduces the oracle's operation sequence bit for bit instead of aiming at a tolerance."""
+    for make, floor in ((lambda: periodic_case(32, substeps=150, aice="ones"), 1e-12), (lambda: anticyclone_case(32, substeps=150), 1e-6)):
+        case = make()
+        a, b = oracle_from_case(case), oracle_from_case(case)
+        H = case.Hx
+        b.arr["h"][H + 10, H + 12] = np.nextafter(b.arr["h"][H + 10, H + 12], 10.0)
+        a.time_step(case.dt)
+        b.time_step(case.dt)
+        rel = lambda n: np.abs(a.arr[n] - b.arr[n]).max() / np.abs(a.arr[n]).max()
+        assert rel("u") > floor and rel("s11") > floor, (case.name, rel("u"), rel("s11"))
+        assert rel("h") < 1e-13          # the perturbation itself stays one ulp in h
