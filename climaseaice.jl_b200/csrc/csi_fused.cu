@@ -67,7 +67,26 @@ constexpr int OX = 16;           // internal column of i = 1 (128-byte aligned)
 
 // internal field indices
 enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, F_S12_1,
-       F_H, F_A, F_P, F_UN, F_VN, F_TX, F_TY, F_UE, F_VE, F_ALPHA, F_ZC, F_ZF, F_DELTA, NF };
+       F_H, F_A, F_P, F_UN, F_VN, F_TX, F_TY, F_UE, F_VE, F_ALPHA, F_ZC, F_ZF, F_DELTA,
+       // stage constants written once per stage by k_prep (see there): ice mass, and the top-stress term of the velocity
+       // tendencies (tau_top / m_i * aice_i at u and v nodes)
+       F_M, F_T1X, F_T1Y,
+       // optional stage constants (compile-time switches CSI_PRE_*): reciprocals of the face-mass sums at u / v nodes (with the
+       // marginal-ice decision folded in), of the centre mass and of the corner mass sum, the corner sum of P, and the
+       // 4-point sums of the ocean velocity at u / v nodes
+       F_RM2U, F_RM2V, F_RMC, F_RMF, F_PF4, F_SVE, F_SUE, NF };
+#ifndef CSI_PRE_RM2
+#define CSI_PRE_RM2 0
+#endif
+#ifndef CSI_PRE_RMC
+#define CSI_PRE_RMC 0
+#endif
+#ifndef CSI_PRE_PF4
+#define CSI_PRE_PF4 0
+#endif
+#ifndef CSI_PRE_SVE
+#define CSI_PRE_SVE 0
+#endif
 // shared-memory arrays (each SXD x SYD doubles)
 enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E22, A_E12, A_AL, A_W, NARR };
 
@@ -101,6 +120,14 @@ struct Params {
     int pform, cor, sis;
     int in_set, out_set;  // 0 / 1: which copy of the evolving fields is read / written
     int ty0;              // first tile row of this launch (a substep may be launched in row bands, see fused_steps)
+    // planes of this launch (set per substep by fused_steps): the pointwise inputs of the first (c) / second (d) velocity
+    // phase -- previous-stage velocity, precomputed top-stress term (FAST pass), raw top stress (IEEE pass) -- and the outputs
+    const double *g_cn, *g_ct1, *g_ctt, *g_dn, *g_dt1, *g_dtt;
+    const double *g_rmc, *g_rmf, *g_pf4;  // reciprocal centre mass / corner mass sum, corner sum of P (CSI_PRE_RMC, CSI_PRE_PF4)
+    const double *g_crm, *g_drm;          // reciprocal face-mass sums of the first / second velocity component (CSI_PRE_RM2)
+    const double *g_cue, *g_csv, *g_due, *g_dsv;  // ocean velocity at the node and the 4-point sum of the other component (CSI_PRE_SVE)
+    double *o_c, *o_d, *o_s11, *o_s22, *o_s12;  // first / second velocity component, stresses
+    int use_t1;           // a top stress exists (field or constant): the FAST pass reads its precomputed term
     // tile columns / rows (inclusive) whose cells all lie inside every store window, have no periodic image and no wall
     // neighbour, and whose velocity nodes are all evolved: the vast majority; they skip the per-node edge tests
     int it_x0, it_x1, it_y0, it_y1;
@@ -186,6 +213,11 @@ __device__ __forceinline__ void tma_load_row(double *dst, const CUtensorMap *map
                  : "memory");
 }
 
+// L2 prefetch of one box (the pointwise inputs of the velocity phases: one instruction of the elected thread per field)
+__device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *map, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -226,7 +258,7 @@ struct MathFast {
     uint32_t qmn = 0xffffffffu, qmx = 0u, lo1 = 0xffffffffu, dacc = 0u, neg = 0u, pend = 0u;
     bool have = false;
     static constexpr uint32_t QLO = 0x2d30u, QHI = 0x52afu;  // per lane: exponent field in [1023 - 300, 1023 + 300)
-    static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;
+    static constexpr uint32_t DLO = 0x300u << 20, DSPAN = (0x200u << 20) - 1u;  // (public: k_prep applies the same test)
     __device__ __forceinline__ void chk2(uint32_t hi_a, uint32_t hi_b)
     {
         const uint32_t g = __byte_perm(hi_a, hi_b, 0x7632) & 0x7fff7fffu;
@@ -419,15 +451,25 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetri
 // windows is redone with the reference tree (MathSlow).
 template <bool GEN, class M>
 __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
-                                           double al0, double uold, double sv, double xcross, double ue, double sve, double ttop, double un, double sD1,
-                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
+                                           double al0, double uold, double sv, double xcross, double ue, double sve, double t1, double un, double sD1,
+                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2, double rm)
 {
     // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
     // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
     // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
+#if CSI_PRE_RM2
+    // rm: the reciprocal of the face-mass sum from k_prep -- -1 for marginal ice / open water, +inf where the divisor
+    // would have failed the range test (the poisoned quotients then fail the window test of the velocity quotient)
+    const bool active_ice = rm > 0.0;
+    NodeRecip Rm;
+    Rm.d = active_ice ? m2 : 1.0;
+    Rm.r = active_ice ? rm : 1.0;
+    const NodeRecip Ra = mm.template recip<true>(ab2);
+#else
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
+#endif
     const double dtau = mm.divn_nc(p.dt2, Ra);  // dt / alpha_bar; alpha in [alpha-, alpha+]: nothing to check
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -445,21 +487,30 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
     // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
     // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
-    const double G = -xcross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    // t1 = tau_top / m_i * aice_i: a stage constant, computed once per stage by k_prep with these very operations
+    const double G = -xcross - t1 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
     const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
     const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
     return jl_mul_bool(active_ice ? uD : 0.0, active);
 }
 template <bool GEN, class M>
 __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
-                                           double al0, double vold, double su, double ycross, double ve, double sue, double ttop, double vn, double sD1,
-                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2)
+                                           double al0, double vold, double su, double ycross, double ve, double sue, double t1, double vn, double sD1,
+                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2, double rm)
 {
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
     // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
     // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
+#if CSI_PRE_RM2
+    const bool active_ice = rm > 0.0;
+    NodeRecip Rm;
+    Rm.d = active_ice ? m2 : 1.0;
+    Rm.r = active_ice ? rm : 1.0;
+    const NodeRecip Ra = mm.template recip<true>(ab2);
+#else
     const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
     const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
+#endif
     const double dtau = mm.divn_nc(p.dt2, Ra);
     double coef = 0.0, tbot = 0.0;
     if (GEN ? p.sis != 0 : true) {
@@ -474,7 +525,7 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
     const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
     // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
     // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
-    const double G = -ycross - mm.divn_nc(ttop, Rm) * a2 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double G = -ycross - t1 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
     const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;
     const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
     return jl_mul_bool(active_ice ? vD : 0.0, active);
@@ -488,10 +539,13 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
 #define S(a, sx, sy) (sm[(a) * ASTRIDE + ((sy) + 1) * SXD + ((sx) + 1)])
 #define SB(b, a, dx, dy) ((b)[(a) * ASTRIDE + (dy) * SXD + (dx)])
 
+// pointwise inputs of one velocity node: previous-stage velocity, top-stress term, and the optional stage constants
+struct Pt {
+    double n, t, rm, ue, sv;
+};
 struct TileCtx {
     int I0, J0;  // reference index of the first velocity cell of the tile
     int fin, fout;
-    bool interior;  // see Params::it_x0
 };
 
 // All phases of one tile under one arithmetic policy.  Returns whether any thread left the policy's
@@ -499,8 +553,10 @@ struct TileCtx {
 // GEN = false compiles the common configuration (SemiImplicitStress with velocity arrays, wind-stress
 // arrays, FPlane, ReplacementPressure) without its run-time switches.
 // MET: j-dependent metrics (lat-lon grid) read from the per-row table instead of the regular grid's constants.
-template <bool VFIRST, bool AUX, bool GEN, bool MET, class M>
-__device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc)
+// INTERIOR: the tile lies inside every store window, has no periodic image, wall neighbour or unevolved node (Params::it_x0):
+// its instantiation carries none of the per-node edge logic.
+template <bool VFIRST, bool AUX, bool GEN, bool MET, class M, bool INTERIOR>
+__device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc, int inv)
 {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     // lat-lon variant: the first-velocity array W shares the slot of e11 (dead after phase B) and W's own slot holds the
@@ -522,18 +578,34 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         ld(A_V, tc.fin + 1, &bar[0]);
         mbar_expect_tx(&bar[0], 2u * SXD * SYD * sizeof(double));
         int n = 6;
-        ld(A_H, F_H, &bar[1]);
+        ld(A_H, F_M, &bar[1]);  // ice mass (k_prep): the array is called A_H for historical reasons
         ld(A_A, F_A, &bar[1]);
         ld(A_P, F_P, &bar[1]);
         ld(A_S11, tc.fin + 2, &bar[1]);
         ld(A_S22, tc.fin + 3, &bar[1]);
         ld(A_S12, tc.fin + 4, &bar[1]);
-        if (use_ue) {
+        if (use_ue && !(M::SCALED && CSI_PRE_SVE)) {
             ld(A_UE, F_UE, &bar[1]);
             ld(A_VE, F_VE, &bar[1]);
             n += 2;
         }
         mbar_expect_tx(&bar[1], (uint32_t)n * SXD * SYD * sizeof(double));
+#ifndef CSI_EXPERIMENT_NO_PREFETCH
+        // pull the pointwise inputs of phases C / D towards L2 while the tile lands and A, B run
+        tma_prefetch_box(tmap, x, y, F_UN);
+        tma_prefetch_box(tmap, x, y, F_VN);
+        if (M::SCALED ? (GEN ? p.use_t1 != 0 : true) : use_top) {
+            tma_prefetch_box(tmap, x, y, M::SCALED ? F_T1X : F_TX);
+            tma_prefetch_box(tmap, x, y, M::SCALED ? F_T1Y : F_TY);
+        }
+        if (M::SCALED && CSI_PRE_RMC) { tma_prefetch_box(tmap, x, y, F_RMC); tma_prefetch_box(tmap, x, y, F_RMF); }
+        if (M::SCALED && CSI_PRE_PF4) tma_prefetch_box(tmap, x, y, F_PF4);
+        if (M::SCALED && CSI_PRE_RM2) { tma_prefetch_box(tmap, x, y, F_RM2U); tma_prefetch_box(tmap, x, y, F_RM2V); }
+        if (M::SCALED && CSI_PRE_SVE && use_ue) {
+            tma_prefetch_box(tmap, x, y, F_UE); tma_prefetch_box(tmap, x, y, F_VE);
+            tma_prefetch_box(tmap, x, y, F_SUE); tma_prefetch_box(tmap, x, y, F_SVE);
+        }
+#endif
     }
     // global offsets of the nodes this thread updates in phases C and D (32-wide rows: lane = column)
     // A warp owns two adjacent rows (q = 0, 1), so the pair sums of the 4-point means and the loads they need are shared.
@@ -550,10 +622,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
         return row * p.pitch + col;
     };
-    const double *gC1 = p.base + (size_t)(VFIRST ? F_VN : F_UN) * plane, *gC2 = p.base + (size_t)(VFIRST ? F_TY : F_TX) * plane;
-    const double *gD1 = p.base + (size_t)(VFIRST ? F_UN : F_VN) * plane, *gD2 = p.base + (size_t)(VFIRST ? F_TX : F_TY) * plane;
-    int c_g[2], d_g[2];
-    if (tc.interior) {
+    // previous-stage velocity and top-stress input of the two velocity phases: the FAST pass reads the precomputed term
+    // tau_top / m_i * aice_i (k_prep), the IEEE pass the raw stress
+    const double *gC1 = p.g_cn, *gC2 = M::SCALED ? p.g_ct1 : p.g_ctt;
+    const double *gD1 = p.g_dn, *gD2 = M::SCALED ? p.g_dt1 : p.g_dtt;
+    const bool use_t = M::SCALED ? (GEN ? p.use_t1 != 0 : true) : use_top;
+    uint32_t c_g[2], d_g[2];
+    if (INTERIOR) {
         c_g[0] = o00 + c_sy0 * p.pitch + c_sx;
         d_g[0] = o00 + d_sy0 * p.pitch + d_sx;
         c_g[1] = c_g[0] + p.pitch;
@@ -564,20 +639,6 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             c_g[q] = goff(c_sx, c_sy0 + q);
             d_g[q] = goff(d_sx, d_sy0 + q);
         }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        // pull the pointwise inputs of phases C / D towards L2/L1 while the tile lands and A, B run
-#ifndef CSI_EXPERIMENT_NO_PREFETCH
-        if (c_on[q]) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gC1 + c_g[q]));
-            if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gC2 + c_g[q]));
-        }
-        if (d_on[q]) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gD1 + d_g[q]));
-            if (use_top) asm volatile("prefetch.global.L2 [%0];" ::"l"(gD2 + d_g[q]));
-        }
-#endif
     }
 
     // immersed-boundary node flags of the tile (bit 0: centre masked, 1: corner masked, 2: u face peripheral, 3: v face peripheral)
@@ -608,23 +669,21 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             qv[n] = mm.divc_nc(sm[A_V * ASTRIDE + n], p.dx, p.rdx);
         }
         __syncthreads();
-        int sx = tid % SXD - 1, sy = tid / SXD - 1;  // node of n = tid; advanced by NT per iteration without dividing
+        // Every element of the haloed tile gets all three strain rates, without edge tests: e11, e22 of the last column / row
+        // and e12 of the first ones are built from neighbours outside the tile (whatever the adjacent shared memory holds),
+        // are never read by phase B, and these unchecked operators raise no window flag
 #pragma unroll
-        for (int k = 0; k < NIT; k++, sx += NT % SXD, sy += NT / SXD) {
+        for (int k = 0; k < NIT; k++) {
             const int n = tid + k * NT;
             if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
-            if (sx >= SXD - 1) { sx -= SXD; sy++; }
             double *b = sm + n;
             const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0), qu00 = SB(b, A_AL, 0, 0), qv00 = SB(b, A_W, 0, 0);
-            if (sx < BX && sy < BY) {
-                // (the numerators are built from checked quotients and bounded metrics: no second window test)
-                const double D = mm.divc_nc((p.dy * SB(b, A_U, 1, 0) - p.dy * u00) + (p.dx * SB(b, A_V, 0, 1) - p.dx * v00), p.az, p.raz);
-                const double T = mm.divc_nc(p.dy2 * (SB(b, A_AL, 1, 0) - qu00) - p.dx2 * (SB(b, A_W, 0, 1) - qv00), p.az, p.raz);
-                SB(b, A_E11, 0, 0) = D + T;  // 2 e11
-                SB(b, A_E22, 0, 0) = D - T;  // 2 e22
-            }
-            if (sx >= 0 && sy >= 0)
-                SB(b, A_E12, 0, 0) = mm.divc_nc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
+            // (the numerators are built from checked quotients and bounded metrics: no second window test)
+            const double D = mm.divc_nc((p.dy * SB(b, A_U, 1, 0) - p.dy * u00) + (p.dx * SB(b, A_V, 0, 1) - p.dx * v00), p.az, p.raz);
+            const double T = mm.divc_nc(p.dy2 * (SB(b, A_AL, 1, 0) - qu00) - p.dx2 * (SB(b, A_W, 0, 1) - qv00), p.az, p.raz);
+            SB(b, A_E11, 0, 0) = D + T;  // 2 e11
+            SB(b, A_E22, 0, 0) = D - T;  // 2 e22
+            SB(b, A_E12, 0, 0) = mm.divc_nc(p.dx2 * (qu00 - SB(b, A_AL, 0, -1)) + p.dy2 * (qv00 - SB(b, A_W, -1, 0)), p.az, p.raz);  // 2 e12
         }
     } else {
     int sx = tid % SXD - 1, sy = tid / SXD - 1;
@@ -657,17 +716,21 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
     }
     }
-    mbar_wait(&bar[1], parity);
-#pragma unroll
-    for (int k = 0; k < NIT; k++) {
-        const int n = tid + k * NT;
-        if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
-        sm[A_H * ASTRIDE + n] = sm[A_H * ASTRIDE + n] * p.rho_i * sm[A_A * ASTRIDE + n];  // h -> m
-    }
     __syncthreads();
+    mbar_wait(&bar[1], parity);  // (the ice mass m = h rho aice arrives precomputed: k_prep)
 
     // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
     double aux_zc[2], aux_zf[2], aux_Dc[2];
+    constexpr bool PRE_RMC = M::SCALED && CSI_PRE_RMC, PRE_PF4 = M::SCALED && CSI_PRE_PF4;
+    double b_rmc[2] = {0.0, 0.0}, b_rmf[2] = {0.0, 0.0}, b_pf4[2] = {0.0, 0.0};
+    if (PRE_RMC || PRE_PF4) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint32_t g = INTERIOR ? (uint32_t)(o00 + (2 * wrp + q) * p.pitch + lane) : (uint32_t)goff(lane, 2 * wrp + q);
+            if (PRE_RMC) { b_rmc[q] = __ldg(p.g_rmc + g); b_rmf[q] = __ldg(p.g_rmf + g); }
+            if (PRE_PF4) b_pf4[q] = __ldg(p.g_pf4 + g);
+        }
+    }
 #pragma unroll UNROLL_B
     for (int q = 0; q < 2; q++) {
         const int sx = lane, sy = 2 * wrp + q;
@@ -687,7 +750,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double Dc2 = mm.max_pos(mm.sqrt_(dc2 * dc2 + sc2 * sc2 * p.em2), p.Dmin2);  // 2 Delta_c
             const double Df8 = mm.max_pos(mm.sqrt_(df8 * df8 + sf8 * sf8 * p.em2), p.Dmin8);  // 8 Delta_f
             const double Pc = SB(b, A_P, 0, 0);
-            const double Pf4 = (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
+            const double Pf4 = PRE_PF4 ? b_pf4[q] : (SB(b, A_P, -1, -1) + SB(b, A_P, 0, -1)) + (SB(b, A_P, -1, 0) + Pc);
             // (Delta in [Delta_min, 2^257) follows from its checked radicand: divisor range tests only where unknown)
             // P is a validated input (zero or in [2^-300, 2^300)): these quotients cannot leave the normal range
             zf = mm.template div_nc<true>(Pf4, Df8);
@@ -700,19 +763,29 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             s12n = ef * Sh;
             mc = SB(b, A_H, 0, 0);
             mf = (SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) + (SB(b, A_H, -1, 0) + mc);  // 4 mf
-            if (!tc.interior) {
+            if (!INTERIOR) {
                 // nodes beyond a wall's ring of stress nodes (the caller's deeper halo holds no ice there) are computed but
                 // never stored nor read by a stored cell: give them a harmless mass instead of failing the tile's divisor test
                 const int i = tc.I0 - 1 + sx;
-                if ((p.wall_w && i < p.sx0) || (p.wall_e && i > p.sx1) || (p.wall_s && rB < p.sy0) || (p.wall_n && rB > p.sy1)) { mc = 1.0; mf = 4.0; }
+                if ((p.wall_w && i < p.sx0) || (p.wall_e && i > p.sx1) || (p.wall_s && rB < p.sy0) || (p.wall_n && rB > p.sy1)) {
+                    mc = 1.0; mf = 4.0;
+                    b_rmc[q] = 1.0; b_rmf[q] = 0.25;
+                }
             }
             // open water (mass exactly 0, P >= 0): the reference divides by zero -- zeta / 0 = +inf, or NaN when zeta = 0 too, which
             // it replaces by alpha+^2 -- and clamps the result to alpha+ (p.gnan when it came from the NaN branch), and it
             // leaves sigma alone.  Same values here without dividing by zero, so open water does not send the tile to the IEEE pass.
             mc0 = mc == 0.0 && Pc >= 0.0;
             mf0 = mf == 0.0 && Pf4 >= 0.0;
-            g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc0 ? 1.0 : mc), mt.azcc(rB), mt.razcc(rB));
-            g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf0 ? 4.0 : mf), mt.azff(rB), mt.razff(rB));
+            if (PRE_RMC) {
+                // reciprocals from k_prep: 1 resp. 1/4 in open water, +inf where the divisor would have failed its range test
+                // (the quotient then fails its window test)
+                g2c = mm.divc_nc(mm.divc(zc * p.ca * p.dt, mc0 ? 1.0 : mc, b_rmc[q]), mt.azcc(rB), mt.razcc(rB));
+                g2f = mm.divc_nc(mm.divc(zf * p.ca * p.dt4, mf0 ? 4.0 : mf, b_rmf[q]), mt.azff(rB), mt.razff(rB));
+            } else {
+                g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc0 ? 1.0 : mc), mt.azcc(rB), mt.razcc(rB));
+                g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf0 ? 4.0 : mf), mt.azff(rB), mt.razff(rB));
+            }
             Dc = AUX ? Dc2 * 0.5 : 0.0;
         } else {
         const double e11c = SB(b, A_E11, 0, 0), e22c = SB(b, A_E22, 0, 0), e12f = SB(b, A_E12, 0, 0);
@@ -760,21 +833,27 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         aux_Dc[q] = Dc;
     }
     // the pointwise inputs of phase C are requested before the barrier, so their L2 latency overlaps the wait
-#ifndef CSI_EXPERIMENT_LATE_LDG
-    double cn[2], ct[2];
+    constexpr bool PRE_SVE = M::SCALED && CSI_PRE_SVE, PRE_RM2 = M::SCALED && CSI_PRE_RM2;
+    auto load_pt = [&](bool on, uint32_t g, const double *gn, const double *gt, const double *grm, const double *gue, const double *gsv, double tconst) {
+        Pt pt;
+        pt.n = on ? __ldg(gn + g) : 0.0;
+        pt.t = (on && use_t) ? __ldg(gt + g) : (M::SCALED ? 0.0 : tconst);
+        pt.rm = (PRE_RM2 && on) ? __ldg(grm + g) : 1.0;
+        pt.ue = (PRE_SVE && on && use_ue) ? __ldg(gue + g) : 0.0;
+        pt.sv = (PRE_SVE && on && use_ue) ? __ldg(gsv + g) : 0.0;
+        return pt;
+    };
+    Pt cpt[2];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        cn[q] = c_on[q] ? __ldg(gC1 + c_g[q]) : 0.0;
-        ct[q] = (c_on[q] && use_top) ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
-    }
-#endif
+    for (int q = 0; q < 2; q++) cpt[q] = load_pt(c_on[q], c_g[q], gC1, gC2, p.g_crm, p.g_cue, p.g_csv, VFIRST ? p.tty : p.ttx);
     __syncthreads();
 
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
-    auto u_at = [&](int sx, int sy, int VS, double un, double ttop) -> double {
+    auto u_at = [&](int sx, int sy, int VS, const Pt &pt) -> double {
+        const double un = pt.n, ttop = pt.t;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         bool upd = true, wall_active = true;
-        if (!tc.interior) {
+        if (!INTERIOR) {
             upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
             wall_active = !((p.wall_w && i <= 1) || (p.wall_e && i > p.Nx));
         }
@@ -791,7 +870,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             xcross = mm.divc(-fbar * ((gm + g0) / 2), mt.dxfc(r), mt.rdxfc(r));
         }
         double ue = p.ue_c, vebar = M::SCALED ? (p.ve_c + p.ve_c) + (p.ve_c + p.ve_c) : ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
-        if (use_ue) {
+        if (PRE_SVE && use_ue) {
+            ue = pt.ue;
+            vebar = pt.sv;
+        } else if (use_ue) {
             ue = SB(b, A_UE, 0, 0);
             vebar = M::SCALED ? (SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1))
                               : ((SB(b, A_VE, -1, 0) + SB(b, A_VE, 0, 0)) / 2 + (SB(b, A_VE, -1, 1) + SB(b, A_VE, 0, 1)) / 2) / 2;
@@ -824,7 +906,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             // (a node that is not evolved returns its old value whatever is computed: harmless masses keep it from failing the tile)
             const double m1 = upd ? SB(b, A_H, 0, 0) : 1.0, m0 = upd ? SB(b, A_H, -1, 0) : 1.0;
             val = u_node_s<GEN>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
-                                uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm);
+                                uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5);
         } else {
             const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
             val = u_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
@@ -832,10 +914,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         return upd ? val : uold;
     };
-    auto v_at = [&](int sx, int sy, int US, double vn, double ttop) -> double {
+    auto v_at = [&](int sx, int sy, int US, const Pt &pt) -> double {
+        const double vn = pt.n, ttop = pt.t;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
         bool upd = true, wall_active = true;
-        if (!tc.interior) {
+        if (!INTERIOR) {
             upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
             wall_active = !((p.wall_s && r <= 1) || (p.wall_n && r > p.Ny));
         }
@@ -850,7 +933,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             ycross = mm.divc(fbar * ((gm + g0) / 2), mt.dycf(r), mt.rdycf(r));
         }
         double ve = p.ve_c, uebar = M::SCALED ? (p.ue_c + p.ue_c) + (p.ue_c + p.ue_c) : ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
-        if (use_ue) {
+        if (PRE_SVE && use_ue) {
+            ve = pt.ue;
+            uebar = pt.sv;
+        } else if (use_ue) {
             ve = SB(b, A_VE, 0, 0);
             uebar = M::SCALED ? (SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0))
                               : ((SB(b, A_UE, 0, -1) + SB(b, A_UE, 1, -1)) / 2 + (SB(b, A_UE, 0, 0) + SB(b, A_UE, 1, 0)) / 2) / 2;
@@ -878,7 +964,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double dyf2 = M::SCALED ? mt.dyff2d(r) : mt.dyff2(r), dxf = mt.dxcf(r);
         const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
         const double val = M::SCALED ? v_node_s<GEN>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                                     SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm)
+                                                     SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
                                      : v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
                                                    SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
@@ -889,21 +975,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     for (int q = 0; q < 2; q++)
         if (c_on[q]) {
             const int sy = c_sy0 + q;
-#ifdef CSI_EXPERIMENT_LATE_LDG
-            const double n1 = __ldg(gC1 + c_g[q]), t1 = use_top ? __ldg(gC2 + c_g[q]) : (VFIRST ? p.tty : p.ttx);
-#else
-            const double n1 = cn[q], t1 = ct[q];
-#endif
-            S(AW, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, n1, t1) : u_at(c_sx, sy, A_V, n1, t1);
+            S(AW, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, cpt[q]) : u_at(c_sx, sy, A_V, cpt[q]);
         }
-#ifndef CSI_EXPERIMENT_LATE_LDG
-    double dn[2], dtt[2];  // likewise for phase D
+    Pt dpt[2];  // likewise for phase D
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        dn[q] = d_on[q] ? __ldg(gD1 + d_g[q]) : 0.0;
-        dtt[q] = (d_on[q] && use_top) ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
-    }
-#endif
+    for (int q = 0; q < 2; q++) dpt[q] = load_pt(d_on[q], d_g[q], gD1, gD2, p.g_drm, p.g_due, p.g_dsv, VFIRST ? p.ttx : p.tty);
     __syncthreads();
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
@@ -912,15 +988,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     for (int q = 0; q < 2; q++)
         if (d_on[q]) {
             const int sy = d_sy0 + q;
-#ifdef CSI_EXPERIMENT_LATE_LDG
-            const double n1 = __ldg(gD1 + d_g[q]), t1 = use_top ? __ldg(gD2 + d_g[q]) : (VFIRST ? p.ttx : p.tty);
-#else
-            const double n1 = dn[q], t1 = dtt[q];
-#endif
-            w2[q] = VFIRST ? u_at(d_sx, sy, AW, n1, t1) : v_at(d_sx, sy, AW, n1, t1);
+            w2[q] = VFIRST ? u_at(d_sx, sy, AW, dpt[q]) : v_at(d_sx, sy, AW, dpt[q]);
         }
 
-    const bool bad = __syncthreads_or(mm.bad());
+    const bool bad = __syncthreads_or(mm.bad() | (inv != 0));
     if (bad) return true;
 
     // ---------------- stores: home cell + periodic images + wall cells ----------------------------------
@@ -965,28 +1036,28 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // interior tiles (the vast majority): every output cell is inside all store windows and has no periodic
     // image or wall neighbour -> plain stores at one precomputed offset
     {
-        if (tc.interior) {
-            double *o = p.base + o00 + 2 * wrp * p.pitch + lane;  // this thread's node (lane, 2 wrp)
+        if (INTERIOR) {
+            // one 32-bit in-plane offset per node and the plane pointers of this launch (kernel parameters): one address
+            // instruction per store
+            uint32_t so = (uint32_t)(o00 + 2 * wrp * p.pitch + lane);  // this thread's node (lane, 2 wrp)
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
+            for (int q = 0; q < 2; q++, so += (uint32_t)p.pitch) {
                 const int sx = lane, sy = 2 * wrp + q;
                 if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
-                    double *g = o + q * p.pitch;
-                    g[(size_t)(tc.fout + 2) * plane] = S(A_S11, sx, sy);
-                    g[(size_t)(tc.fout + 3) * plane] = S(A_S22, sx, sy);
-                    g[(size_t)(tc.fout + 4) * plane] = S(A_S12, sx, sy);
+                    p.o_s11[so] = S(A_S11, sx, sy);
+                    p.o_s22[so] = S(A_S22, sx, sy);
+                    p.o_s12[so] = S(A_S12, sx, sy);
                     if (AUX) {
+                        double *g = p.base + so;
                         g[(size_t)F_ALPHA * plane] = S(A_AL, sx, sy);
                         g[(size_t)F_ZC * plane] = aux_zc[q];
                         g[(size_t)F_ZF * plane] = aux_zf[q];
                         g[(size_t)F_DELTA * plane] = aux_Dc[q];
                     }
                 }
-                if (d_on[q]) {
-                    const int dsy = d_sy0 + q;
-                    double *g = o + (q + 1) * p.pitch + 1;  // node (lane + 1, 2 wrp + 1 + q)
-                    g[(size_t)(tc.fout + (VFIRST ? 0 : 1)) * plane] = w2[q];
-                    g[(size_t)(tc.fout + (VFIRST ? 1 : 0)) * plane] = S(AW, d_sx, dsy);
+                if (d_on[q]) {  // node (lane + 1, 2 wrp + 1 + q): the offset the pointwise inputs of phase D were read at
+                    p.o_d[d_g[q]] = w2[q];
+                    p.o_c[d_g[q]] = S(AW, d_sx, d_sy0 + q);
                 }
             }
             return false;
@@ -1039,25 +1110,25 @@ __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const 
     tc.fin = p.in_set ? F_U1 : F_U0;
     tc.fout = p.out_set ? F_U1 : F_U0;
     const int by = blockIdx.y + p.ty0;
-    tc.interior = (int)blockIdx.x >= p.it_x0 && (int)blockIdx.x <= p.it_x1 && by >= p.it_y0 && by <= p.it_y1;
+    const bool interior = (int)blockIdx.x >= p.it_x0 && (int)blockIdx.x <= p.it_x1 && by >= p.it_y0 && by <= p.it_y1;
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // an input outside the validated range (flag raised by k_pack) sends every tile of the stage to the IEEE pass
-    const bool fast_ok = *p.invalid == 0;
-    bool redo = true;
-    if (fast_ok) {
-        redo = tile_pass<VFIRST, AUX, GEN, MET, MathFast>(sm, bar, 0, &tmap, p, tc);
-        // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, a quotient out of range ...):
-        // reload the tile and redo it with plain IEEE operators and the reference's expression tree
-        if (redo) __syncthreads();
-    }
+    // an input outside the validated range (flag raised by k_pack / k_prep) sends every tile of the stage to the IEEE pass.
+    // The flag is requested here and consumed where the FAST pass decides whether it may store (no stall on its latency;
+    // a pass over unvalidated inputs computes garbage and stores nothing)
+    const int inv = *p.invalid;
+    const bool redo = interior ? tile_pass<VFIRST, AUX, GEN, MET, MathFast, true>(sm, bar, 0, &tmap, p, tc, inv)
+                               : tile_pass<VFIRST, AUX, GEN, MET, MathFast, false>(sm, bar, 0, &tmap, p, tc, inv);
+    // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, a quotient out of range ...):
+    // reload the tile and redo it with plain IEEE operators and the reference's expression tree
     if (redo) {
+        __syncthreads();
         if (threadIdx.x == 0) atomicAdd(p.invalid + 1, 1);  // diagnostics: tiles that took the IEEE pass
-        tile_pass<VFIRST, AUX, GEN, MET, MathSlow>(sm, bar, fast_ok ? 1 : 0, &tmap, p, tc);
+        tile_pass<VFIRST, AUX, GEN, MET, MathSlow, false>(sm, bar, 1, &tmap, p, tc, 0);
     }
 }
 #undef S
@@ -1155,6 +1226,77 @@ __global__ void k_pack(PackItem it, Params p, int w)
     // thickness and concentration must not carry a sign bit (not even -0): the open-water shortcut of phase B reads a mass
     // of exactly +0 as "the reference divides by +0 here"
     if ((it.field == F_H || it.field == F_A) && __double2hiint(val) < 0) atomicOr(p.invalid, 1);
+}
+// Stage constants of the substep loop, written once per time_step_momentum! (h, aice, tau_top do not change inside it):
+//   F_M    m = h rho aice at every node (ClimaSeaIce.jl:42; the reference recomputes it at every use)
+//   F_T1X  the top-stress term of the u tendency, tau_x / m_i * aice_i (mt:33, ext:176-181) in the FAST pass's scaled form
+//          (tau_x / 2 m_i') * 2 aice_i with m_i' the harmless mass of marginal nodes -- the very operations u_node_s used to
+//          repeat every substep, so the bits are the same; F_T1Y likewise for v.
+// The IEEE pass keeps reading the raw stress.
+__global__ void k_prep(Params p, int top_const)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= p.pitch) return;
+    const size_t plane = (size_t)p.pitch * p.rows, o = (size_t)r * p.pitch + c;
+    const double *H = p.base + (size_t)F_H * plane, *A = p.base + (size_t)F_A * plane;
+    const double a11 = A[o];
+    const double m11 = H[o] * p.rho_i * a11;
+    p.base[(size_t)F_M * plane + o] = m11;
+    // a divisor the FAST pass may use with a stored reciprocal: inside the range window of MathFast::chkd, low word not all ones
+    auto safe = [](double d) {
+        return (uint32_t)__double2hiint(d) - MathFast::DLO <= MathFast::DSPAN && (uint32_t)__double2loint(d) != 0xffffffffu;
+    };
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const bool west = c >= 1, south = r >= 1;
+    const double m01 = west ? H[o - 1] * p.rho_i * A[o - 1] : 0.0, m10 = south ? H[o - p.pitch] * p.rho_i * A[o - p.pitch] : 0.0;
+    double t1x = 0.0, t1y = 0.0, rmu = -1.0, rmv = -1.0;
+    if (west) {
+        const double m2 = m11 + m01, a2 = a11 + A[o - 1];
+        const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+        const double tt = !p.use_t1 ? 0.0 : (top_const ? p.ttx : p.base[(size_t)F_TX * plane + o]);
+        t1x = (tt / (active_ice ? m2 : 1.0)) * a2;
+        rmu = active_ice ? (safe(m2) ? 1.0 / m2 : inf) : -1.0;
+    }
+    if (south) {
+        const double m2 = m11 + m10, a2 = a11 + A[o - p.pitch];
+        const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+        const double tt = !p.use_t1 ? 0.0 : (top_const ? p.tty : p.base[(size_t)F_TY * plane + o]);
+        t1y = (tt / (active_ice ? m2 : 1.0)) * a2;
+        rmv = active_ice ? (safe(m2) ? 1.0 / m2 : inf) : -1.0;
+    }
+    if (p.use_t1) {
+        p.base[(size_t)F_T1X * plane + o] = t1x;
+        p.base[(size_t)F_T1Y * plane + o] = t1y;
+    }
+#if CSI_PRE_RM2
+    p.base[(size_t)F_RM2U * plane + o] = rmu;
+    p.base[(size_t)F_RM2V * plane + o] = rmv;
+#endif
+#if CSI_PRE_RMC || CSI_PRE_PF4
+    {
+        const double *Pp = p.base + (size_t)F_P * plane;
+        const double Pc = Pp[o];
+        double mf4 = 0.0, Pf4 = 0.0;
+        if (west && south) {
+            const double m00 = H[o - p.pitch - 1] * p.rho_i * A[o - p.pitch - 1];
+            mf4 = (m00 + m10) + (m01 + m11);
+            Pf4 = (Pp[o - p.pitch - 1] + Pp[o - p.pitch]) + (Pp[o - 1] + Pc);
+        }
+        // open water (mass exactly 0, P >= 0): the kernel divides by the harmless 1 resp. 4 (see phase B)
+        p.base[(size_t)F_RMC * plane + o] = (m11 == 0.0 && Pc >= 0.0) ? 1.0 : (safe(m11) ? 1.0 / m11 : inf);
+        p.base[(size_t)F_RMF * plane + o] = (mf4 == 0.0 && Pf4 >= 0.0) ? 0.25 : (safe(mf4) ? 1.0 / mf4 : inf);
+        p.base[(size_t)F_PF4 * plane + o] = Pf4;
+    }
+#endif
+#if CSI_PRE_SVE
+    if (p.use_ue) {
+        const double *UE = p.base + (size_t)F_UE * plane, *VE = p.base + (size_t)F_VE * plane;
+        const bool north = r + 1 < p.rows, east = c + 1 < p.pitch;
+        // 4 v_e-bar at the u node (i, j): (i-1, j) + (i, j) + (i-1, j+1) + (i, j+1); 4 u_e-bar at the v node: (i, j-1) + (i+1, j-1) + (i, j) + (i+1, j)
+        p.base[(size_t)F_SVE * plane + o] = (west && north) ? (VE[o - 1] + VE[o]) + (VE[o + p.pitch - 1] + VE[o + p.pitch]) : 0.0;
+        p.base[(size_t)F_SUE * plane + o] = (south && east) ? (UE[o - p.pitch] + UE[o - p.pitch + 1]) + (UE[o] + UE[o + 1]) : 0.0;
+    }
+#endif
 }
 __global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
 {
@@ -1376,6 +1518,7 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.cx0 = P.px ? -BIG : P.vx0; P.cx1 = P.px ? BIG : P.vx1;
     P.cy0 = P.py ? -BIG : P.vy0; P.cy1 = P.py ? BIG : P.vy1;
     P.use_top = p.top_kind == CSI_STRESS_FIELD;
+    P.use_t1 = p.top_kind == CSI_STRESS_FIELD || p.top_kind == CSI_STRESS_CONST;
     P.use_ue = f.ue.p != nullptr && p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
     P.u_sn_bc = p.u_sn_bc; P.v_we_bc = p.v_we_bc; P.u_sn_val = p.u_sn_val; P.v_we_val = p.v_we_val;
     P.dt = dt;
@@ -1420,6 +1563,9 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     pack(f.un, F_UN, 0, 1, 0); pack(f.vn, F_VN, 0, 0, 1);
     if (P.use_top) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
     if (P.use_ue) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
+    // stage constants of the substep loop (ice mass, top-stress terms)
+    k_prep<<<dim3((pl->pitch + 127) / 128, pl->rows), 128, 0, c.stream>>>(P, p.top_kind == CSI_STRESS_CONST);
+    ++*c.launches;
 
     // interior tile columns / rows: every test the edge code makes is trivially true (see Params::it_x0)
     auto interior_range = [&](int ntiles, int first, int out, int s0, int s1, int v0, int v1, int c0, int c1, bool per, bool wall_lo, bool wall_hi, int N,
@@ -1466,6 +1612,19 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         P.in_set = pl->cur_set;
         P.out_set = pl->cur_set ^ 1;
         const bool vfirst = (sub % 2) != 0;
+        {
+            const size_t plane = (size_t)P.pitch * P.rows;
+            auto at = [&](int f) { return P.base + (size_t)f * plane; };
+            const int fo = P.out_set ? F_U1 : F_U0;
+            P.g_cn = at(vfirst ? F_VN : F_UN); P.g_ct1 = at(vfirst ? F_T1Y : F_T1X); P.g_ctt = at(vfirst ? F_TY : F_TX);
+            P.g_dn = at(vfirst ? F_UN : F_VN); P.g_dt1 = at(vfirst ? F_T1X : F_T1Y); P.g_dtt = at(vfirst ? F_TX : F_TY);
+            P.o_c = at(fo + (vfirst ? 1 : 0)); P.o_d = at(fo + (vfirst ? 0 : 1));
+            P.o_s11 = at(fo + 2); P.o_s22 = at(fo + 3); P.o_s12 = at(fo + 4);
+            P.g_crm = at(vfirst ? F_RM2V : F_RM2U); P.g_drm = at(vfirst ? F_RM2U : F_RM2V);
+            P.g_cue = at(vfirst ? F_VE : F_UE); P.g_csv = at(vfirst ? F_SUE : F_SVE);
+            P.g_due = at(vfirst ? F_UE : F_VE); P.g_dsv = at(vfirst ? F_SVE : F_SUE);
+            P.g_rmc = at(F_RMC); P.g_rmf = at(F_RMF); P.g_pf4 = at(F_PF4);
+        }
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
         const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
