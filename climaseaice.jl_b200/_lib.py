@@ -117,7 +117,7 @@ EXPORTS = (
     "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
     "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
     "csi_evp_substeps_host", "csi_last_transfer_bytes", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count", "csi_fused_stats",
-    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_thermodynamic_time_step", "csi_attach_thermodynamics", "csi_selftest_math", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
+    "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_thermodynamic_time_step", "csi_attach_thermodynamics", "csi_selftest_math", "csi_measure_fp64_rate", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
 )
 
 _lib = None
@@ -163,6 +163,7 @@ def lib():
     L.csi_time_dominant_kernel.argtypes = [H, C.POINTER(csi_fields), C.c_double, C.c_int32, C.POINTER(C.c_double), C.c_char_p,
                                            C.POINTER(C.c_int32), C.c_void_p]
     L.csi_selftest_math.argtypes = [C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+    L.csi_measure_fp64_rate.argtypes = [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.csi_host_exp.restype = C.c_double
     L.csi_host_exp.argtypes = [C.c_double]
     L.csi_host_div_by_const.restype = C.c_double

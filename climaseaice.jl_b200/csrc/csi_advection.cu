@@ -118,6 +118,19 @@ __device__ __forceinline__ int buffer_at(int B, bool wall_lo, bool wall_hi, int 
     return b < 1 ? 1 : b;
 }
 
+// ImmersedBoundaryGrid: a scheme of buffer b is used at a face only if none of the 2b cells of its left- and right-biased
+// stencils (face-b .. face+b-1 along the stencil direction) is inactive, else the next lower order is tried (Oceananigans'
+// near_*_immersed_boundary_biased + buffer_scheme chain, call site src/sea_ice_advection.jl:51-58); first order is never tested
+template <bool XDIR> __device__ __forceinline__ int buffer_immersed(const DGrid &g, int b0, int i, int j)
+{
+    for (int b = b0; b >= 2; b--) {
+        bool bad = false;
+        for (int c = -b; c <= b - 1; c++) bad = bad || (XDIR ? inactive_cell(g, i + c, j) : inactive_cell(g, i, j + c));
+        if (!bad) return b;
+    }
+    return 1;
+}
+
 static constexpr int ATX = 32, ATY = 8, AH = 4;  // tile and the widest stencil halo (WENO7)
 
 // G^n.h = -div(U h), G^n.aice = -div(U aice) and, with snow (NQ = 3), G^n.hs = -div(U hs)  (tracer_tendency:27-52)
@@ -149,7 +162,8 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx + 1 && j <= g.Ny) {
             const double U = at(f.u, min(i, f.u.sx - f.u.ox), j);
-            const int b = buffer_at(B, bx_lo, bx_hi, g.Nx, i);
+            int b = buffer_at(B, bx_lo, bx_hi, g.Nx, i);
+            if (g.mask) b = buffer_immersed<true>(g, b, i, j);
             const bool imm = g.mask && imm_peripheral_fc(g, i, j);
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
@@ -165,7 +179,8 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx && j <= g.Ny + 1) {
             const double V = at(f.v, i, min(j, f.v.sy - f.v.oy));
-            const int b = buffer_at(B, by_lo, by_hi, g.Ny, j);
+            int b = buffer_at(B, by_lo, by_hi, g.Ny, j);
+            if (g.mask) b = buffer_immersed<false>(g, b, i, j);
             const bool imm = g.mask && imm_peripheral_cf(g, i, j);
 #pragma unroll
             for (int q = 0; q < NQ; q++) {

@@ -31,6 +31,7 @@ struct NcclApi {
     int (*CommDestroy)(void *) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -54,6 +55,7 @@ NcclApi &nccl()
             CSI_SYM(CommDestroy, "ncclCommDestroy");
             CSI_SYM(Send, "ncclSend");
             CSI_SYM(Recv, "ncclRecv");
+            CSI_SYM(AllReduce, "ncclAllReduce");
             CSI_SYM(GroupStart, "ncclGroupStart");
             CSI_SYM(GroupEnd, "ncclGroupEnd");
             CSI_SYM(GetErrorString, "ncclGetErrorString");
@@ -63,7 +65,7 @@ NcclApi &nccl()
     }
     return api;
 }
-const int NCCL_FLOAT64 = 8;
+const int NCCL_FLOAT64 = 8, NCCL_INT32 = 2, NCCL_MIN = 3;
 
 }  // namespace
 
@@ -86,6 +88,8 @@ struct csi_handle {
     std::vector<double> met_host, fff_host;
     FusedPlan *fused = nullptr;
     bool fused_failed = false;
+    int solver_agreed = 0;  // partitions: 0 = not yet agreed, 1 = every rank runs the fused solver, 2 = every rank the general kernels
+    int *agree_dev = nullptr;
     // device mirrors for the *_host entry points, in csi_fields member order
     std::vector<double *> mirror;
     std::vector<size_t> mirror_n;
@@ -295,20 +299,48 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
     }
 
     bool use_fused = false;
+    std::string why_not;
     if (h->cfg.solver_impl != CSI_SOLVER_UNFUSED && !h->fused_failed) {
         char why[256] = {0};
         use_fused = fused_supported(g, p, f, why, sizeof why) != 0;
-        if (!use_fused && h->cfg.solver_impl == CSI_SOLVER_FUSED) return fail(h, CSI_ERR_UNSUPPORTED, std::string("fused solver: ") + why);
+        if (!use_fused) why_not = std::string("fused solver: ") + why;
+        if (!use_fused && h->cfg.solver_impl == CSI_SOLVER_FUSED && h->nranks == 1) return fail(h, CSI_ERR_UNSUPPORTED, why_not);
+    }
+    if (use_fused && !h->fused) {
+        char err[256] = {0};
+        h->fused = fused_create(g, p, err, sizeof err);
+        if (!h->fused) {
+            h->fused_failed = true;
+            use_fused = false;
+            why_not = std::string("fused_create: ") + err;
+            if (h->nranks == 1) return fail(h, 1, why_not);
+        }
+    }
+    if (h->nranks > 1 && h->cfg.solver_impl != CSI_SOLVER_UNFUSED) {
+        // Every rank of a partition must take the same path: the two solvers exchange different buffers (internal planes vs
+        // the caller's parents), and a rank that fell back or failed alone would leave its neighbours blocked in NCCL.  The
+        // choice depends on rank-local data (metric rows, device memory), so it is agreed once: min over the ranks.
+        if (h->solver_agreed == 0) {
+            if (!h->comm) return fail(h, CSI_ERR_ARG, "csi_comm_init has not been called on this handle");
+            NcclApi &api = nccl();
+            if (!api.AllReduce) return fail(h, CSI_ERR_NCCL_MISSING, "ncclAllReduce missing");
+            if (!h->agree_dev) CSI_CUDA(h, cudaMalloc(&h->agree_dev, sizeof(int)));
+            int mine = use_fused ? 1 : 0;
+            CSI_CUDA(h, cudaMemcpyAsync(h->agree_dev, &mine, sizeof(int), cudaMemcpyHostToDevice, s));
+            int nrc = api.AllReduce(h->agree_dev, h->agree_dev, 1, NCCL_INT32, NCCL_MIN, h->comm, s);
+            if (nrc != 0) return fail(h, 1000 + nrc, "ncclAllReduce (solver agreement) failed");
+            int all = 0;
+            CSI_CUDA(h, cudaMemcpyAsync(&all, h->agree_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CSI_CUDA(h, cudaStreamSynchronize(s));
+            h->solver_agreed = all ? 1 : 2;
+            if (!all && use_fused) why_not = "fused solver: another rank of the partition cannot run it";
+        }
+        use_fused = h->solver_agreed == 1;
+        // (collectively: every rank returns here when any rank cannot run an explicitly requested fused solver)
+        if (!use_fused && h->cfg.solver_impl == CSI_SOLVER_FUSED) return fail(h, CSI_ERR_UNSUPPORTED, why_not.empty() ? "fused solver unavailable on this partition" : why_not);
     }
     if (use_fused) {
         char err[256] = {0};
-        if (!h->fused) {
-            h->fused = fused_create(g, p, err, sizeof err);
-            if (!h->fused) {
-                h->fused_failed = true;
-                return fail(h, 1, std::string("fused_create: ") + err);
-            }
-        }
         // pack -> blocks of K substeps with a slab halo exchange of the internal (double-buffered) fields
         // in between -> unpack.  K = exchange_every (halo Hy >= 2K+3, se.jl:55-56); one block when serial.
         int rc = fused_begin(h->fused, c, g, p, f, dt, err, sizeof err);
@@ -733,6 +765,7 @@ int csi_destroy(csi_handle *h)
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     for (double *m : h->mirror) if (m) cudaFree(m);
     if (h->xbuf) cudaFree(h->xbuf);
+    if (h->agree_dev) cudaFree(h->agree_dev);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);

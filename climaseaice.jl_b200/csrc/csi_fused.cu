@@ -835,12 +835,12 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // the pointwise inputs of phase C are requested before the barrier, so their L2 latency overlaps the wait
     constexpr bool PRE_SVE = M::SCALED && CSI_PRE_SVE, PRE_RM2 = M::SCALED && CSI_PRE_RM2;
     auto load_pt = [&](bool on, uint32_t g, const double *gn, const double *gt, const double *grm, const double *gue, const double *gsv, double tconst) {
-        Pt pt;
+        Pt pt;  // (members a configuration does not use stay unset and cost nothing)
         pt.n = on ? __ldg(gn + g) : 0.0;
         pt.t = (on && use_t) ? __ldg(gt + g) : (M::SCALED ? 0.0 : tconst);
-        pt.rm = (PRE_RM2 && on) ? __ldg(grm + g) : 1.0;
-        pt.ue = (PRE_SVE && on && use_ue) ? __ldg(gue + g) : 0.0;
-        pt.sv = (PRE_SVE && on && use_ue) ? __ldg(gsv + g) : 0.0;
+        if (PRE_RM2) pt.rm = on ? __ldg(grm + g) : 1.0;
+        if (PRE_SVE) pt.ue = (on && use_ue) ? __ldg(gue + g) : 0.0;
+        if (PRE_SVE) pt.sv = (on && use_ue) ? __ldg(gsv + g) : 0.0;
         return pt;
     };
     Pt cpt[2];
@@ -1473,11 +1473,14 @@ void fused_destroy(FusedPlan *pl)
 template <bool VFIRST, bool AUX, bool GEN, bool MET> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
-    static bool attr = false;
-    if (!attr) {
+    // the attribute is per device (a process may hold handles on several devices through csi_config.device)
+    static bool attr[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN, MET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     k_evp_substep_fused<VFIRST, AUX, GEN, MET><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
     return cudaGetLastError();

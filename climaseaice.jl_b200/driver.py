@@ -82,9 +82,11 @@ class HostStepper:
     """Drives csi_time_step_host / csi_evp_substeps_host on pinned host arrays: every call uploads
     the inputs, runs on the GPU and downloads the results (the end-to-end figure of bench.py)."""
 
-    def __init__(self, case: Case, solver_impl="auto", device_index=0):
+    def __init__(self, case: Case, solver_impl="auto", device_index=0, partition=None, unique_id=None):
         self.case = case
-        self.model = model_from_case(case, solver_impl=solver_impl, device=f"cuda:{device_index}")
+        self.model = model_from_case(case, solver_impl=solver_impl, device=f"cuda:{device_index}", partition=partition)
+        if partition is not None:   # one rank of a partition: host blocks with halos, NCCL exchange inside the call
+            self.model.comm_init(unique_id)
         self.host = {}
         for n, fld in self.model.all_fields().items():
             t = torch.empty(fld.parent.shape, dtype=torch.float64).pin_memory()

@@ -284,6 +284,11 @@ int csi_time_dominant_kernel(csi_handle *h, const csi_fields *f, double dt_stage
  * fast windows}.  A correct build returns zeros in out5[0..3]. */
 int csi_selftest_math(int64_t samples, uint64_t seed, int32_t exponent_span, uint64_t *out5);
 
+/* Device microbenchmark behind bench.py's FP64 roofline: thread-level FP64 FMA instructions per second of `device`
+ * (eight independent chains per thread, full occupancy), as a burst (best short launch) and sustained over the second half
+ * of `seconds` of back-to-back launches (power-capped clock).  Instrumentation only. */
+int csi_measure_fp64_rate(int32_t device, double seconds, double *burst_fma_per_s, double *sustained_fma_per_s);
+
 /* Host-side helpers exported for CPU tests (no GPU needed). */
 double csi_host_exp(double x);                       /* the correctly rounded exp used for ice_strength */
 double csi_host_div_by_const(double x, double c);    /* the Markstein constant-division used in the kernels */

@@ -92,8 +92,26 @@ static double weno_from_cells(int B, const double *q)
     return out;
 }
 
-/* Order reduction next to Bounded walls ([OCN-recall], confidence L): the buffer at face i is
- * min(B, i-1, N+1-i), at least 1, so no stencil leaves the interior cells. */
+/* Order reduction ([OCN-recall], confidence M).  Bounded walls: the buffer at face i is min(B, i-1, N+1-i), at least 1,
+ * so no stencil leaves the interior cells (Oceananigans `outside_biased_halo`: the full-order stencil is used where
+ * i >= B+1 and i <= N+1-B, else the scheme's `buffer_scheme`, recursively: 7 -> 5 -> 3 -> first-order upwind).
+ * ImmersedBoundaryGrid (g->mask): the same chain, driven by `near_x_immersed_boundary_biased` -- a scheme of buffer b is
+ * used at face i only if none of the 2b cells i-b .. i+b-1 (the union of the left- and the right-biased stencil) is
+ * inactive (immersed, or outside a Bounded domain), else its buffer_scheme is tried; the first-order scheme (b = 1) is
+ * never tested.  Call site: /root/reference/src/sea_ice_advection.jl:51-58 (`_advective_tracer_flux_x/y` on the grid of
+ * /root/reference/examples/ice_advected_on_coastline.jl:54-55). */
+static int cell_inactive(const csio_grid *g, int i, int j)
+{
+    if ((g->topo_x == CSIO_BOUNDED && (i < 1 || i > g->Nx)) || (g->topo_y == CSIO_BOUNDED && (j < 1 || j > g->Ny))) return 1;
+    if (!g->mask) return 0;
+    int sx = g->Nx + 2 * g->Hx, sy = g->Ny + 2 * g->Hy;
+    int pi = i - 1 + g->Hx, pj = j - 1 + g->Hy;
+    if (pi < 0) pi = 0;
+    if (pj < 0) pj = 0;
+    if (pi >= sx) pi = sx - 1;
+    if (pj >= sy) pj = sy - 1;
+    return g->mask[(size_t)pi + (size_t)pj * (size_t)sx] != 0;
+}
 static int buffer_at(int B, int topo, int N, int i)
 {
     if (topo != CSIO_BOUNDED) return B;
@@ -102,12 +120,23 @@ static int buffer_at(int B, int topo, int N, int i)
     if (N + 1 - i < b) b = N + 1 - i;
     return b < 1 ? 1 : b;
 }
+/* dir = 0: x face (i, j), stencil along i; dir = 1: y face, stencil along j */
+static int buffer_immersed(const csio_grid *g, int B, int dir, int i, int j)
+{
+    for (int b = B; b >= 2; b--) {
+        int bad = 0;
+        for (int c = -b; c <= b - 1 && !bad; c++) bad = dir == 0 ? cell_inactive(g, i + c, j) : cell_inactive(g, i, j + c);
+        if (!bad) return b;
+    }
+    return 1;
+}
 
 static int order_to_buffer(int order) { return order <= 1 ? 1 : (order + 1) / 2; }
 
 double csio_reconstruct_x(const csio_grid *g, int order, int bias, const csio_field *c, int i, int j)
 {
     int B = buffer_at(order_to_buffer(order), g->topo_x, g->Nx, i);
+    if (g->mask) B = buffer_immersed(g, B, 0, i, j);
     double q[7];
     for (int n = 0; n < 2 * B - 1; n++) q[n] = bias == 0 ? F(*c, i - B + n, j) : F(*c, i + B - 1 - n, j);
     return weno_from_cells(B, q);
@@ -116,6 +145,7 @@ double csio_reconstruct_x(const csio_grid *g, int order, int bias, const csio_fi
 double csio_reconstruct_y(const csio_grid *g, int order, int bias, const csio_field *c, int i, int j)
 {
     int B = buffer_at(order_to_buffer(order), g->topo_y, g->Ny, j);
+    if (g->mask) B = buffer_immersed(g, B, 1, i, j);
     double q[7];
     for (int n = 0; n < 2 * B - 1; n++) q[n] = bias == 0 ? F(*c, i, j - B + n) : F(*c, i, j + B - 1 - n);
     return weno_from_cells(B, q);

@@ -46,8 +46,9 @@ def test_full_rk3_step_periodic(impl):
     o = oracle_from_case(case)
     m.time_step(case.dt); o.time_step(case.dt)
     _assert_parity(compare_model(m, o, case))
-    # halos of the prognostic fields are periodic images after update_state!
-    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a"), interior_only=False))
+    # halos of the prognostic fields are periodic images after update_state!, those of the stresses after
+    # finalize_rheology! (evp:275-280)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "s11", "s22", "s12"), interior_only=False))
     m.close()
 
 
@@ -142,6 +143,53 @@ def test_full_size_properties_4096():
         assert torch.equal(fa, fb), n
     after = a.diagnostics()
     assert abs(after["sum_h_Az"] - before["sum_h_Az"]) / before["sum_h_Az"] < 1e-12
+    a.close(); b.close()
+
+
+def _assert_same_bits(a, b, case, names=("u", "v", "s11", "s22", "s12", "alpha", "zeta_c", "zeta_f", "delta")):
+    """Interior plus the first halo ring (everything an interior stencil can read).  Deeper halo cells of the stresses on a
+    Bounded axis are scratch: the general kernels run the stress update over the extended window like the reference's launch
+    (evp:145-167), the tile kernel stores the ring the velocity stencils read; no boundary condition ever fills them."""
+    for n in names:
+        fa, fb = a.all_fields()[n].parent, b.all_fields()[n].parent
+        assert torch.isfinite(fa).all(), n
+        if n in ("u", "v"):
+            assert torch.equal(fa, fb), n
+        else:
+            r = 1 if n in ("s11", "s22", "s12") else 0   # alpha, zeta, Delta are diagnostics: no halo fill, interior only
+            sl = (slice(case.Hy - r, case.Hy + case.Ny + r), slice(case.Hx - r, case.Hx + case.Nx + r))   # j, i in [1 - r, N + r]
+            assert torch.equal(fa[sl], fb[sl]), n
+
+
+def test_bench_configuration_2_fused_equals_general_kernels():
+    """The configuration bench.py times at N = 1 -- BASELINE config 2, the Bounded anticyclone case at 4096^2, one
+    time_step_momentum! of 150 substeps -- is too large for the oracle; the general kernels (one thread per node, the
+    reference's launch structure, themselves compared with the oracle at small sizes) and the fused tile kernel must agree
+    bit for bit on every output, halos included."""
+    case = anticyclone_case(4096)
+    a = model_from_case(case, solver_impl="unfused")
+    b = model_from_case(case, solver_impl="fused")
+    for m in (a, b):
+        m.update_state()
+        m.time_step_momentum(120.0, 150)
+    _assert_same_bits(a, b, case)
+    inv, redone, tiles = b.fused_stats()
+    assert inv == 0 and tiles > 0 and redone < 0.01 * 150 * tiles   # the FAST pass did the work
+    assert float(b.all_fields()["u"].parent.abs().max()) > 1e-3
+    a.close(); b.close()
+
+
+def test_bench_configuration_3_block_fused_equals_general_kernels():
+    """The per-GPU block of BASELINE config 3 that bench.py times at N > 1 (16384 x 2048, doubly periodic, 150 substeps),
+    here as one periodic domain on one GPU: fused tile kernel == general kernels, bit for bit."""
+    case = periodic_case(16384, Ny=2048, substeps=150, aice="mixed")
+    a = model_from_case(case, solver_impl="unfused")
+    b = model_from_case(case, solver_impl="fused")
+    for m in (a, b):
+        m.update_state()
+        m.time_step_momentum(120.0, 150)
+    _assert_same_bits(a, b, case)
+    assert b.fused_stats()[0] == 0 and b.fused_stats()[2] > 0
     a.close(); b.close()
 
 
@@ -252,11 +300,11 @@ def test_shape_errors_are_reported():
     m.close()
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", ("unfused", "auto", "fused"))
 def test_immersed_mask(impl):
     """Immersed-boundary land mask (BASELINE config 4 ingredients: masked stresses isd:16-24, peripheral-node
-    velocity mask se:226,261, zero flux through immersed faces, mask_immersed_field_xy! in update_state!).
-    Masks run on the unfused kernels; solver_impl='auto' must pick them and give the same answer."""
+    velocity mask se:226,261, zero flux through immersed faces, mask_immersed_field_xy! in update_state!): in the
+    general kernels and inside the fused tile kernel (node flags in shared memory), which 'auto' must pick."""
     case = periodic_case(40, Ny=36, substeps=9, aice="mixed")
     X, Y = case.nodes((0, 0))
     sy, sx = case.parent_shape((0, 0))
@@ -282,10 +330,11 @@ def test_immersed_mask(impl):
     _assert_parity(compare_model(m, o, case))
     inside = mask[case.Hy:-case.Hy, case.Hx:-case.Hx].astype(bool)
     assert np.all(interior_of(m.all_fields()["h"].numpy(), case)[inside] == 0)   # land stays ice free
+    assert (m.fused_stats()[2] > 0) == (impl != "unfused")   # the tile kernel really ran (tiles per substep)
     m.close()
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", ("unfused", "auto", "fused"))
 def test_coastline_config4_reduced(impl):
     """BASELINE config 4 (examples/ice_advected_on_coastline.jl) at reduced size: Periodic x Bounded, immersed
     triangular coast, uniform wind, ocean at rest, wall BCs and the linear immersed drag flux BC."""
@@ -299,6 +348,7 @@ def test_coastline_config4_reduced(impl):
     _assert_parity(compare_model(m, o, case))
     u = interior_of(m.all_fields()["u"].numpy(), case)
     assert np.abs(u).max() > 1e-4          # the wind moved the ice
+    assert (m.fused_stats()[2] > 0) == (impl != "unfused")
     m.close()
 
 

@@ -296,3 +296,63 @@ def test_one_ulp_of_input_exceeds_the_tolerance_after_one_step():
         rel = lambda n: np.abs(a.arr[n] - b.arr[n]).max() / np.abs(a.arr[n]).max()
         assert rel("u") > floor and rel("s11") > floor, (case.name, rel("u"), rel("s11"))
         assert rel("h") < 1e-13          # the perturbation itself stays one ulp in h
+
+
+def _masked_model(order=7):
+    """A periodic 24 x 20 oracle with an immersed island and a smooth positive tracer."""
+    N, Ny, H = 24, 20, 7
+    sy, sx = Ny + 2 * H, N + 2 * H
+    mask = np.zeros((sy, sx), dtype=np.uint8)
+    mask[H + 8:H + 12, H + 10:H + 14] = 1          # cells i = 11..14, j = 9..12
+    m = O.OracleModel(N, Ny, H, H, dx=1.0, dy=1.0, params=dict(advection_order=order), mask=mask)
+    return m, mask, N, Ny, H
+
+
+def test_weno_order_is_reduced_next_to_immersed_cells():
+    """Oceananigans' ImmersedBoundaryGrid reconstruction (call site src/sea_ice_advection.jl:51-58, grid of
+    examples/ice_advected_on_coastline.jl:54-55): no stencil may read an immersed cell.  Poison the masked cells with a huge
+    value: every face value that is used (faces that are not immersed-peripheral) must stay within the range of the active data,
+    for both biases and both directions, and far from the island the full-order value is unchanged."""
+    for order in (3, 5, 7):
+        m, mask, N, Ny, H = _masked_model(order)
+        X = np.arange(N + 2 * H)[None, :] - H + 0.5
+        Y = np.arange(Ny + 2 * H)[:, None] - H + 0.5
+        smooth = 1.0 + 0.1 * np.sin(2 * np.pi * X / N) * np.cos(2 * np.pi * Y / Ny)
+        m.arr["h"][:] = smooth
+        clean = {(d, b, i, j): m.reconstruct(d, "h", order, b, i, j) for d in (0, 1) for b in (0, 1) for i in range(1, N + 1) for j in range(1, Ny + 1)}
+        m.arr["h"][mask.astype(bool)] = 1e30
+        lo, hi = smooth.min() - 0.05, smooth.max() + 0.05
+        changed = 0
+        for (d, b, i, j), ref in clean.items():
+            # a face between an active and an immersed cell (or two immersed cells) carries no flux: skip it
+            c0 = mask[H + j - 1 - (1 if d == 1 else 0), H + i - 1 - (1 if d == 0 else 0)]
+            c1 = mask[H + j - 1, H + i - 1]
+            if c0 or c1:
+                continue
+            got = m.reconstruct(d, "h", order, b, i, j)
+            assert lo <= got <= hi, (order, d, b, i, j, got)
+            changed += got != ref
+        assert changed == 0    # poisoning cells no stencil may read changes nothing
+
+
+def test_constant_state_is_preserved_along_a_coast():
+    """With order reduction no reconstruction mixes the masked zeros into the ice next to the island: a uniform tracer advected by
+    a uniform flow keeps zero tendency away from the coast faces, and one oracle step keeps h uniform on cells whose four faces
+    are all active."""
+    m, mask, N, Ny, H = _masked_model(7)
+    m.arr["h"][:] = 1.0
+    m.arr["a"][:] = 1.0
+    m.arr["h"][mask.astype(bool)] = 0.0
+    m.arr["a"][mask.astype(bool)] = 0.0
+    m.arr["u"][:] = 0.3
+    m.arr["v"][:] = -0.2
+    m.compute_tracer_tendencies()
+    G = m.interior("Gh")
+    mk = mask[H:-H, H:-H].astype(bool)
+    near = np.zeros_like(mk)
+    for dj, di in ((0, 0), (0, 1), (0, -1), (1, 0), (-1, 0)):
+        near |= np.roll(np.roll(mk, dj, axis=0), di, axis=1)
+    # uniform flow, uniform tracer, every stencil on active cells: no divergence beyond the round-off of the WENO weights
+    # (a stencil reading the island's zeros would give O(0.1))
+    assert np.abs(G[~near]).max() < 1e-14
+    assert np.isfinite(G).all()

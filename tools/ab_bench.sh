@@ -7,7 +7,7 @@ for spec in "$@"; do
     unset CSI_PF_DIST
     for kv in ${envs//,/ }; do export "$kv"; done
     if [ "$v" = "base" ]; then unset CSI_B200_LIB; else export CSI_B200_LIB="$PWD/$v"; fi
-    python bench.py --steps ${AB_STEPS:-3} --warmup 3 --no-e2e --no-cpu ${AB_ARGS} > /tmp/ab.json 2> /tmp/ab.err || { echo "== $spec FAILED"; tail -5 /tmp/ab.err; continue; }
+    python bench.py --steps ${AB_STEPS:-3} --warmup 3 --no-e2e --no-cpu --no-configs ${AB_ARGS} > /tmp/ab.json 2> /tmp/ab.err || { echo "== $spec FAILED"; tail -5 /tmp/ab.err; continue; }
     python - "$spec" <<'EOF'
 import json, sys
 d = json.loads(open('/tmp/ab.json').read().strip().splitlines()[-1])
