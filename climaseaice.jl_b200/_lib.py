@@ -116,7 +116,7 @@ EXPORTS = (
     "csi_version", "csi_last_error", "csi_create", "csi_destroy", "csi_evp_substeps",
     "csi_compute_tracer_tendencies", "csi_dynamic_time_step", "csi_cache_current_fields", "csi_update_state",
     "csi_fill_halos", "csi_time_step", "csi_cell_advection_timescale", "csi_diagnostics", "csi_time_step_host",
-    "csi_evp_substeps_host", "csi_last_transfer_bytes", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_launch_count", "csi_fused_stats",
+    "csi_evp_substeps_host", "csi_last_transfer_bytes", "csi_nccl_unique_id", "csi_comm_init", "csi_exchange_halos", "csi_exchange_halos_async", "csi_wait_halos", "csi_launch_count", "csi_fused_stats",
     "csi_last_elapsed_ms", "csi_time_dominant_kernel", "csi_thermodynamic_time_step", "csi_attach_thermodynamics", "csi_selftest_math", "csi_measure_fp64_rate", "csi_host_exp", "csi_host_div_by_const", "csi_host_halo_width",
 )
 

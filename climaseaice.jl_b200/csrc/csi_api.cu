@@ -107,6 +107,9 @@ struct csi_handle {
     size_t xbuf_each = 0;
     cudaStream_t comm_stream = nullptr;  // halo exchanges overlapped with interior tiles (slabs, fused solver)
     cudaEvent_t ev_block = nullptr, ev_halo = nullptr;
+    // asynchronous exchange (fill_halo_regions!(...; async = true) + synchronize_communication!, evp:204-206,275-280)
+    cudaEvent_t ev_async_in = nullptr, ev_async_done = nullptr;
+    bool halo_pending = false;
 };
 
 namespace {
@@ -266,12 +269,50 @@ Range2 velocity_range(const DGrid &g)
 
 int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaStream_t s);
 
-// time_step_momentum!  (se.jl:103-195)
-int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStream_t s)
+int ensure_comm_stream(csi_handle *h)
+{
+    if (!h->comm_stream) {
+        CSI_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming));
+        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_async_in, cudaEventDisableTiming));
+        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_async_done, cudaEventDisableTiming));
+    }
+    return CSI_OK;
+}
+// fill_halo_regions!(fields; async = true): the exchange is ordered behind everything already on `s` and runs on the
+// handle's communication stream; `s` does not wait for it.  wait_halos = synchronize_communication! (stream-ordered).
+int exchange_halos_async(csi_handle *h, const DArr *arrs, int n, int width, cudaStream_t s)
+{
+    if (h->nranks <= 1) return CSI_OK;
+    int rc = ensure_comm_stream(h);
+    if (rc) return rc;
+    CSI_CUDA(h, cudaEventRecord(h->ev_async_in, s));
+    CSI_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_async_in, 0));
+    if ((rc = exchange_slab_halos(h, arrs, n, width, h->comm_stream))) return rc;
+    CSI_CUDA(h, cudaEventRecord(h->ev_async_done, h->comm_stream));
+    h->halo_pending = true;
+    return CSI_OK;
+}
+int wait_halos(csi_handle *h, cudaStream_t s)
+{
+    if (!h->halo_pending) return CSI_OK;
+    CSI_CUDA(h, cudaStreamWaitEvent(s, h->ev_async_done, 0));
+    h->halo_pending = false;
+    return CSI_OK;
+}
+
+// time_step_momentum!  (se.jl:103-195).  defer_sigma: the stress halo exchange of finalize_rheology! is left in flight
+// (evp:275-280, async = true); the next momentum step -- or the caller, through wait_halos -- synchronises it (evp:204-206)
+int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStream_t s, bool defer_sigma = false)
 {
     LaunchCtx c{s, &h->launches};
     const DGrid &g = h->g;
     const DParams &p = h->p;
+    {
+        int rc = wait_halos(h, s);  // synchronize_communication!(fields.sigma*)  evp:204-206
+        if (rc) return rc;
+    }
     if (h->cfg.timestepper == CSI_RK3 && f.um.p && f.vm.p) {  // reset_velocities!  se.jl:87-93
         int rc = copy_parent(h, f.u, f.um, s);
         if (rc) return rc;
@@ -356,11 +397,7 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
                 // interior tile rows do not wait for it (north_star: halo exchange overlapped with interior compute)
                 const bool overlap = h->Rx == 1 && !h->cfg.serial_exchange;
                 if (overlap) {
-                    if (!h->comm_stream) {
-                        CSI_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-                        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming));
-                        CSI_CUDA(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
-                    }
+                    if ((rc = ensure_comm_stream(h))) return rc;
                     CSI_CUDA(h, cudaEventRecord(h->ev_block, s));
                     CSI_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_block, 0));
                     if ((rc = exchange_slab_halos(h, views, 5, g.Hy, h->comm_stream))) return rc;
@@ -405,7 +442,9 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
     launch_fill_halo(c, g, p, f.s22, 0, 0, 0);
     if (h->nranks > 1) {
         const DArr arrs[3] = {f.s11, f.s12, f.s22};
-        int rc = exchange_slab_halos(h, arrs, 3, g.Hy, s);
+        // (slabs only: the rows go zero-copy; the packed strips of a 2-D partition share one staging buffer with the
+        // exchanges that follow on the compute stream)
+        int rc = (defer_sigma && h->Rx == 1) ? exchange_halos_async(h, arrs, 3, g.Hy, s) : exchange_slab_halos(h, arrs, 3, g.Hy, s);
         if (rc) return rc;
     }
     CSI_CUDA(h, cudaGetLastError());
@@ -454,10 +493,11 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
     const int nsub = h->cfg.substeps;
     if (h->cfg.timestepper == CSI_FE) {  // fe.jl:13-34
         launch_tracer_tendencies(c, g, p, f);
-        if ((rc = momentum_impl(h, f, dt, nsub, s))) return rc;
+        if ((rc = momentum_impl(h, f, dt, nsub, s, true))) return rc;
         launch_dynamic_step(c, g, f, f.h, f.a, f.hs, dt);
         if (h->thermo_on) launch_thermodynamics(c, g, h->thermo_cfg, h->thermo_f, h->cfg.ice_density, dt);  // fe.jl:30
-        return update_state_impl(h, f, s);
+        if ((rc = update_state_impl(h, f, s))) return rc;
+        return wait_halos(h, s);  // the caller sees exchanged stress halos
     }
     // cache_current_fields!  rk.jl:29-42
     if ((rc = copy_parent(h, f.hm, f.h, s))) return rc;
@@ -468,12 +508,12 @@ int time_step_impl(csi_handle *h, const DFields &f, double dt, int first, cudaSt
     for (int beta = 3; beta >= 1; beta--) {  // SplitRungeKutta3: dtau = dt / beta
         const double dtau = dt / beta;
         launch_tracer_tendencies(c, g, p, f);                      // rk.jl:84
-        if ((rc = momentum_impl(h, f, dtau, nsub, s))) return rc;  // rk.jl:87
+        if ((rc = momentum_impl(h, f, dtau, nsub, s, true))) return rc;  // rk.jl:87 (stress halos exchanged asynchronously, evp:275-280)
         launch_dynamic_step(c, g, f, f.hm, f.am, f.hsm, dtau);     // rk.jl:89
         if (h->thermo_on) launch_thermodynamics(c, g, h->thermo_cfg, h->thermo_f, h->cfg.ice_density, dtau);  // rk.jl:91
         if ((rc = update_state_impl(h, f, s))) return rc;
     }
-    return CSI_OK;
+    return wait_halos(h, s);  // the caller sees exchanged stress halos
 }
 
 // Packed west/east strips of a 2-D partition: `width` columns x every parent row of each array, array after array.
@@ -769,6 +809,8 @@ int csi_destroy(csi_handle *h)
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+    if (h->ev_async_in) cudaEventDestroy(h->ev_async_in);
+    if (h->ev_async_done) cudaEventDestroy(h->ev_async_done);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->scratch) cudaFree(h->scratch);
     if (h->out_dev) cudaFree(h->out_dev);
@@ -1054,6 +1096,22 @@ int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, 
     DArr d[16];
     for (int k = 0; k < narrays; k++) d[k] = to_darr(arrays[k]);
     return exchange_slab_halos(h, d, narrays, width, (cudaStream_t)stream);
+}
+
+int csi_exchange_halos_async(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    if (!arrays || narrays < 1 || narrays > 16) return fail(h, CSI_ERR_ARG, "csi_exchange_halos_async: bad arguments");
+    if (h->halo_pending) return fail(h, CSI_ERR_ARG, "csi_exchange_halos_async: an asynchronous exchange is already in flight (csi_wait_halos first)");
+    DArr d[16];
+    for (int k = 0; k < narrays; k++) d[k] = to_darr(arrays[k]);
+    return exchange_halos_async(h, d, narrays, width, (cudaStream_t)stream);
+}
+
+int csi_wait_halos(csi_handle *h, csi_stream stream)
+{
+    if (!h) return CSI_ERR_ARG;
+    return wait_halos(h, (cudaStream_t)stream);
 }
 
 int64_t csi_launch_count(const csi_handle *h) { return h ? h->launches : 0; }

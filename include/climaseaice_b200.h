@@ -201,6 +201,15 @@ int csi_comm_init(csi_handle *h, const uint8_t id128[128], int32_t rank, int32_t
 /* distributed fill_halo_regions! of one field across slab neighbours (Oceananigans
  * DistributedComputations, used at src/sea_ice_model.jl:381-384, evp.jl:275-280) */
 int csi_exchange_halos(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream);
+/* fill_halo_regions!(fields; async = true) and synchronize_communication!(field)
+ * (src/Rheologies/elasto_visco_plastic_rheology.jl:275-280 and :204-206): csi_exchange_halos_async orders the exchange behind
+ * the work already queued on `stream` and runs it on the handle's communication stream -- `stream` itself does not wait;
+ * csi_wait_halos makes `stream` wait for the exchange in flight (stream-ordered, the host does not block).  One exchange
+ * may be in flight per handle.  csi_time_step uses this pair itself for the stress halos of finalize_rheology!: the exchange
+ * overlaps the stage's h / aice update, thermodynamics and update_state!, and is synchronised where the reference does it,
+ * at the next initialize_rheology! (and before csi_time_step returns control of the arrays to the caller's stream). */
+int csi_exchange_halos_async(csi_handle *h, const csi_array *arrays, int32_t narrays, int32_t width, csi_stream stream);
+int csi_wait_halos(csi_handle *h, csi_stream stream);
 
 /* ---- slab thermodynamics -----------------------------------------------
  * thermodynamic_time_step!(model, ice_thermodynamics, snow_thermodynamics, dt)
