@@ -74,7 +74,11 @@ enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, 
        // optional stage constants (compile-time switches CSI_PRE_*): reciprocals of the face-mass sums at u / v nodes (with the
        // marginal-ice decision folded in), of the centre mass and of the corner mass sum, the corner sum of P, and the
        // 4-point sums of the ocean velocity at u / v nodes
-       F_RM2U, F_RM2V, F_RMC, F_RMF, F_PF4, F_SVE, F_SUE, NF };
+       F_RM2U, F_RM2V, F_RMC, F_RMF, F_PF4, F_SVE, F_SUE,
+       // stage constants of the less common configurations (k_prep): the value of nodes that are not dynamically active
+       // (marginal ice ? free-drift velocity : 0), the bottom term tau_bot / m_i * aice_i of a prescribed bottom stress, the
+       // 4-point sums of the atmosphere velocity of a top SemiImplicitStress, and the packed free-drift arrays
+       F_UFD, F_VFD, F_TB1X, F_TB1Y, F_SVA, F_SUA, F_FDU, F_FDV, NF };
 #ifndef CSI_PRE_RM2
 #define CSI_PRE_RM2 0
 #endif
@@ -92,6 +96,15 @@ enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E2
 
 constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64 + ((SXD * SYD + 63) / 64) * 64;  // + two mbarriers + node flags
 
+// planes of the pointwise inputs of one velocity phase (the component it updates)
+struct PhasePtrs {
+    const double *n;          // previous-stage velocity (u^n / v^n)
+    const double *t1, *tt;    // top stress: FAST precomputed term (or the atmosphere velocity of a top SemiImplicitStress) / IEEE raw array
+    const double *sa, *oth;   // top SemiImplicitStress: 4-point sum of the other atmosphere component (FAST) / its raw plane (IEEE)
+    const double *tb1, *tbr;  // prescribed bottom stress: FAST precomputed term / IEEE raw array
+    const double *fd;         // value of nodes that are not dynamically active
+    const double *rm, *ue, *sv;  // experiments CSI_PRE_RM2 / CSI_PRE_SVE
+};
 struct Params {
     int Nx, Ny;          // interior size
     int pitch, rows;     // internal layout
@@ -122,12 +135,15 @@ struct Params {
     int ty0;              // first tile row of this launch (a substep may be launched in row bands, see fused_steps)
     // planes of this launch (set per substep by fused_steps): the pointwise inputs of the first (c) / second (d) velocity
     // phase -- previous-stage velocity, precomputed top-stress term (FAST pass), raw top stress (IEEE pass) -- and the outputs
-    const double *g_cn, *g_ct1, *g_ctt, *g_dn, *g_dt1, *g_dtt;
+    PhasePtrs pc, pd;
     const double *g_rmc, *g_rmf, *g_pf4;  // reciprocal centre mass / corner mass sum, corner sum of P (CSI_PRE_RMC, CSI_PRE_PF4)
-    const double *g_crm, *g_drm;          // reciprocal face-mass sums of the first / second velocity component (CSI_PRE_RM2)
-    const double *g_cue, *g_csv, *g_due, *g_dsv;  // ocean velocity at the node and the 4-point sum of the other component (CSI_PRE_SVE)
     double *o_c, *o_d, *o_s11, *o_s22, *o_s12;  // first / second velocity component, stresses
     int use_t1;           // a top stress exists (field or constant): the FAST pass reads its precomputed term
+    // less common configurations (GEN instantiation only)
+    int fd_on, fd_kind;   // free drift: marginal-ice nodes take a stage-constant velocity (k_prep) instead of 0
+    int top_sis, top_arr; // SemiImplicitStress on top; its u_a, v_a are arrays (else the constants ta_x, ta_y)
+    int bot_expl, bot_arr, bot_kind, top_kind;  // prescribed bottom stress (numbers or arrays; constants tb_x, tb_y)
+    double top_rhoCd, ta_x, ta_y, tb_x, tb_y;
     // tile columns / rows (inclusive) whose cells all lie inside every store window, have no periodic image and no wall
     // neighbour, and whose velocity nodes are all evolved: the vast majority; they skip the per-node edge tests
     int it_x0, it_x1, it_y0, it_y1;
@@ -374,61 +390,52 @@ struct MathSlow {
     template <bool CHK = true, bool SGN = true> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
-// u at (i, r): se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395.  *0 = column i-1.
-template <bool GEN, class M>
-__device__ __forceinline__ double u_node(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
-                                         double uold, double vbar, double xcross, double ue, double vebar, double ttop, double un, double sD1, double sD0,
-                                         double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
+// External-stress inputs of one velocity node (ext:8-40,84-146,176-210; stress_balance_free_drift.jl:61-129).  "own" is the
+// component being updated, "other" the transverse one.  FAST pass: 4-point SUMS and precomputed stage-constant terms (k_prep);
+// IEEE pass: the reference's means and the raw stresses.
+struct Ext {
+    double ue, oe;   // bottom SemiImplicitStress: u_e at the node; 4 x mean (FAST) / mean (IEEE) of the other component of u_e
+    double ua, oa;   // top SemiImplicitStress likewise (atmosphere velocity)
+    double t1;       // top stress that is nothing / numbers / arrays: FAST tau_top / m_i * aice_i (k_prep); IEEE raw tau_top
+    double tb;       // bottom stress that is numbers / arrays:        FAST tau_bot / m_i * aice_i (k_prep); IEEE raw tau_bot
+    double fd;       // value of a node that is not dynamically active: marginal ice ? free-drift velocity : 0 (k_prep)
+};
+
+// One velocity node, reference tree: u at (i, r) se:197-229, mt:11-41, ext:176-196, isd:39-44, evp:384,391-395 (*0 = column
+// i-1), or v at (i, r) se:231-264, mt:44-74, ext:183-202, isd:46-51, evp:385,397-401 (*0 = row r-1; NEG_TT: the sign of the
+// tension term).  old / obar: the node's own component and the 4-point mean of the other one.
+template <bool GEN, bool NEG_TT, class M>
+__device__ __forceinline__ double vel_node(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
+                                           double old, double obar, double cross, const Ext &x, double vn, double sD1, double sD0,
+                                           double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
 {
     const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
     const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
     const double dtau = mm.divn(p.dt, Ra);
-    double coef = 0.0, tbot = 0.0;
-    if (GEN ? p.sis != 0 : true) {
-        const double du = ue - uold, dv = vebar - vbar;
-        coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
-        tbot = coef * ue;
+    double cbot = 0.0, tbot = 0.0, ctop = 0.0, ttop = x.t1;
+    if (GEN ? p.sis != 0 : true) {   // implicit_tau_coefficient / explicit_tau of a SemiImplicitStress (ext:176-202)
+        const double d_own = x.ue - old, d_oth = x.oe - obar;
+        cbot = p.rhoCd * mm.sqrt_(d_own * d_own + d_oth * d_oth);
+        tbot = cbot * x.ue;
+    } else if (GEN && p.bot_expl) tbot = x.tb;
+    if (GEN && p.top_sis) {
+        const double d_own = x.ua - old, d_oth = x.oa - obar;
+        ctop = p.top_rhoCd * mm.sqrt_(d_own * d_own + d_oth * d_oth);
+        ttop = ctop * x.ua;
     }
-    const double rheo = mm.divn(mm.div(un - uold, dtau), Ra);
+    const double rheo = mm.divn(mm.div(vn - old, dtau), Ra);
     const double d = nm.a * (sD1 - sD0) / 2;
-    const double tt = mm.divc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd) / 2;
+    const double tn = nm.t2hi * sT1 - nm.t2lo * sT0;
+    const double tt = mm.divc(NEG_TT ? -tn : tn, nm.td, nm.rtd) / 2;
     const double SS = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig = mm.divc(d + tt + SS, nm.az, nm.raz);
-    double G = -xcross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
+    double G = -cross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
     G = mi <= 0 ? 0.0 : G;
-    double tau = mm.divn(coef - 0.0, Rm) * ai;
+    double tau = mm.divn(cbot - ctop, Rm) * ai;
     tau = mi <= 0 ? 0.0 : tau;
-    const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
+    const double D = mm.div(old + dtau * G, 1 + dtau * tau);
     const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
-    return jl_mul_bool(active_ice ? uD : 0.0, active);  // free_drift = nothing: marginal ice -> 0
-}
-// v at (i, r): se:231-264, mt:44-74, ext:183-202, isd:46-51, evp:385,397-401.  *0 = row r-1.
-template <bool GEN, class M>
-__device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1, double al0,
-                                         double vold, double ubar, double ycross, double ve, double uebar, double ttop, double vn, double sD1, double sD0,
-                                         double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm)
-{
-    const double mi = (m1 + m0) / 2, ai = (a1 + a0_) / 2, abar = (al1 + al0) / 2;
-    const NodeRecip Ra = mm.recip(abar), Rm = mm.recip(mi);
-    const double dtau = mm.divn(p.dt, Ra);
-    double coef = 0.0, tbot = 0.0;
-    if (GEN ? p.sis != 0 : true) {
-        const double dv = ve - vold, du = uebar - ubar;
-        coef = p.rhoCd * mm.sqrt_(du * du + dv * dv);
-        tbot = coef * ve;
-    }
-    const double rheo = mm.divn(mm.div(vn - vold, dtau), Ra);
-    const double d = nm.a * (sD1 - sD0) / 2;
-    const double tt = mm.divc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd) / 2;
-    const double SS = mm.divc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
-    const double dsig = mm.divc(d + tt + SS, nm.az, nm.raz);
-    double G = -ycross - mm.divn(ttop, Rm) * ai + mm.divn(tbot, Rm) * ai + mm.divn(dsig, Rm) + (has_imm ? mm.divn(imm, Rm) : 0.0) + (0.0 + rheo);
-    G = mi <= 0 ? 0.0 : G;
-    double tau = mm.divn(coef - 0.0, Rm) * ai;
-    tau = mi <= 0 ? 0.0 : tau;
-    const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
-    const bool active_ice = (mi >= p.min_mass) & (ai >= p.min_conc);
-    return jl_mul_bool(active_ice ? vD : 0.0, active);
+    return jl_mul_bool(active_ice ? D : ((GEN && p.fd_on) ? x.fd : 0.0), active);  // free_drift = nothing: marginal ice -> 0
 }
 
 // ---- the scaled expression tree (FAST pass) -----------------------------------------------------
@@ -449,15 +456,15 @@ __device__ __forceinline__ double v_node(M &mm, const Params &p, const NodeMetri
 // cannot leave the normal range and is not tested again; products that could underflow (squares of strain rates) only
 // feed tested radicands, where an addend below 2^-1022 cannot move a sum of at least 2^-300.  A tile that leaves the
 // windows is redone with the reference tree (MathSlow).
-template <bool GEN, class M>
-__device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
-                                           double al0, double uold, double sv, double xcross, double ue, double sve, double t1, double un, double sD1,
-                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2, double rm)
+template <bool GEN, bool NEG_TT, class M>
+__device__ __forceinline__ double vel_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
+                                             double al0, double old, double osum, double cross, const Ext &x, double vn, double sD1,
+                                             double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2, double rm)
 {
-    // nm.s2hi, nm.s2lo hold 2 x the squared metrics; sv, sve = 4 vbar, 4 ve_bar; imm2 = 2 x the immersed term
+    // nm.s2hi, nm.s2lo hold 2 x the squared metrics; osum, x.oe, x.oa = 4 x the means of the other component; imm2 = 2 x the immersed term
     const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
-    // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
+    // marginal ice and open water (face mass or concentration under the thresholds) get their stage-constant value (0, or the
+    // free-drift velocity) whatever G is: a harmless mass keeps those nodes from failing the tile's divisor test
 #if CSI_PRE_RM2
     // rm: the reciprocal of the face-mass sum from k_prep -- -1 for marginal ice / open water, +inf where the divisor
     // would have failed the range test (the poisoned quotients then fail the window test of the velocity quotient)
@@ -471,64 +478,36 @@ __device__ __forceinline__ double u_node_s(M &mm, const Params &p, const NodeMet
     const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
 #endif
     const double dtau = mm.divn_nc(p.dt2, Ra);  // dt / alpha_bar; alpha in [alpha-, alpha+]: nothing to check
-    double coef = 0.0, tbot = 0.0;
+    // d_own, d_oth4: differences of validated inputs and checked quotients (zero or >= 2^-352, < 2^303): the squares stay normal
+    double cbot = 0.0, ctop = 0.0;
+    // the top term tau_top / m_i * aice_i and, for a prescribed bottom stress, the bottom term: stage constants computed once
+    // per stage by k_prep with these very operations; a SemiImplicitStress side is evaluated here (ext:176-202)
+    double topT = x.t1, botT = 0.0;
     if (GEN ? p.sis != 0 : true) {
-        const double du = ue - uold, dv4 = sve - sv;
-        // du, dv4: differences of validated inputs and checked quotients (zero or >= 2^-352, < 2^303): the squares stay normal
-        coef = p.rhoCd * mm.template sqrt_<false, false>(__fma_rn(dv4 * dv4, 0.0625, du * du));
-        tbot = coef * ue;
+        const double d_own = x.ue - old, d_oth4 = x.oe - osum;
+        cbot = p.rhoCd * mm.template sqrt_<false, false>(__fma_rn(d_oth4 * d_oth4, 0.0625, d_own * d_own));
+        // quotients over the face mass (its range is tested): tau_bottom and coef are a checked square root times a validated
+        // input and a constant -- they cannot leave the normal range
+        botT = mm.divn_nc(cbot * x.ue, Rm) * a2;
+    } else if (GEN && p.bot_expl) botT = x.tb;
+    else botT = mm.divn_nc(0.0, Rm) * a2;   // (bottom stress nothing: the reference's 0 / m_i * aice_i)
+    if (GEN && p.top_sis) {
+        const double d_own = x.ua - old, d_oth4 = x.oa - osum;
+        ctop = p.top_rhoCd * mm.template sqrt_<false, false>(__fma_rn(d_oth4 * d_oth4, 0.0625, d_own * d_own));
+        topT = mm.divn_nc(ctop * x.ua, Rm) * a2;
     }
-    const double rheo2 = mm.divn_nc(mm.template div_nc<true>(un - uold, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
+    const double rheo2 = mm.divn_nc(mm.template div_nc<true>(vn - old, dtau), Ra);  // rheo / 2 (a checked quotient over alpha)
     const double d2 = nm.a * (sD1 - sD0);
     // sigma = validated input + checked increments (zero or >= 2^-352, < 2^310): the stress divergence needs no test;
     // whatever it adds up to, the velocity quotient below is tested
-    const double tt2 = mm.divc_nc(nm.t2hi * sT1 - nm.t2lo * sT0, nm.td, nm.rtd);
+    const double tn = nm.t2hi * sT1 - nm.t2lo * sT0;
+    const double tt2 = mm.divc_nc(NEG_TT ? -tn : tn, nm.td, nm.rtd);
     const double SS2 = mm.divc_nc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
     const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
-    // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
-    // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
-    // t1 = tau_top / m_i * aice_i: a stage constant, computed once per stage by k_prep with these very operations
-    const double G = -xcross - t1 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
-    const double uD = mm.div(uold + dtau * G, 1 + dtau * tau);
-    return jl_mul_bool(active_ice ? uD : 0.0, active);
-}
-template <bool GEN, class M>
-__device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMetric &nm, bool active, double m1, double m0, double a1, double a0_, double al1,
-                                           double al0, double vold, double su, double ycross, double ve, double sue, double t1, double vn, double sD1,
-                                           double sD0, double sT1, double sT0, double s12hi, double s12lo, bool has_imm, double imm2, double rm)
-{
-    const double m2 = m1 + m0, a2 = a1 + a0_, ab2 = al1 + al0;
-    // marginal ice and open water (face mass or concentration under the thresholds) get velocity 0 whatever G is
-    // (free_drift = nothing): a harmless mass keeps those nodes from failing the tile's divisor test
-#if CSI_PRE_RM2
-    const bool active_ice = rm > 0.0;
-    NodeRecip Rm;
-    Rm.d = active_ice ? m2 : 1.0;
-    Rm.r = active_ice ? rm : 1.0;
-    const NodeRecip Ra = mm.template recip<true>(ab2);
-#else
-    const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
-    const NodeRecip Ra = mm.template recip<true>(ab2), Rm = mm.recip(active_ice ? m2 : 1.0);
-#endif
-    const double dtau = mm.divn_nc(p.dt2, Ra);
-    double coef = 0.0, tbot = 0.0;
-    if (GEN ? p.sis != 0 : true) {
-        const double dv = ve - vold, du4 = sue - su;
-        coef = p.rhoCd * mm.template sqrt_<false, false>(__fma_rn(du4 * du4, 0.0625, dv * dv));
-        tbot = coef * ve;
-    }
-    const double rheo2 = mm.divn_nc(mm.template div_nc<true>(vn - vold, dtau), Ra);
-    const double d2 = nm.a * (sD1 - sD0);
-    const double tt2 = mm.divc_nc(-(nm.t2hi * sT1 - nm.t2lo * sT0), nm.td, nm.rtd);
-    const double SS2 = mm.divc_nc(nm.s2hi * s12hi - nm.s2lo * s12lo, nm.sd, nm.rsd);
-    const double dsig2 = mm.divc_nc(d2 + tt2 + SS2, nm.az, nm.raz);
-    // quotients over the face mass (its range is tested): tau_top is a validated input, tau_bottom and coef a checked square root
-    // times a validated input and a constant, dsig2 a checked quotient -- none of them can leave the normal range
-    const double G = -ycross - t1 + mm.divn_nc(tbot, Rm) * a2 + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
-    const double tau = mm.divn_nc(coef - 0.0, Rm) * a2;
-    const double vD = mm.div(vold + dtau * G, 1 + dtau * tau);
-    return jl_mul_bool(active_ice ? vD : 0.0, active);
+    const double G = -cross - topT + botT + mm.divn_nc(dsig2, Rm) + (has_imm ? mm.divn(imm2, Rm) : 0.0) + __fma_rn(rheo2, 2.0, 0.0);
+    const double tau = mm.divn_nc(cbot - ctop, Rm) * a2;  // (m2 <= 0 cannot pass the divisor window: no selects)
+    const double D = mm.div(old + dtau * G, 1 + dtau * tau);
+    return jl_mul_bool(active_ice ? D : ((GEN && p.fd_on) ? x.fd : 0.0), active);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
@@ -541,7 +520,8 @@ __device__ __forceinline__ double v_node_s(M &mm, const Params &p, const NodeMet
 
 // pointwise inputs of one velocity node: previous-stage velocity, top-stress term, and the optional stage constants
 struct Pt {
-    double n, t, rm, ue, sv;
+    double n, t, sa, tb, fd, rm, ue, sv;
+    const double *oth;   // IEEE pass, top SemiImplicitStress: the node in the raw plane of the other atmosphere component
 };
 struct TileCtx {
     int I0, J0;  // reference index of the first velocity cell of the tile
@@ -624,8 +604,6 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     };
     // previous-stage velocity and top-stress input of the two velocity phases: the FAST pass reads the precomputed term
     // tau_top / m_i * aice_i (k_prep), the IEEE pass the raw stress
-    const double *gC1 = p.g_cn, *gC2 = M::SCALED ? p.g_ct1 : p.g_ctt;
-    const double *gD1 = p.g_dn, *gD2 = M::SCALED ? p.g_dt1 : p.g_dtt;
     const bool use_t = M::SCALED ? (GEN ? p.use_t1 != 0 : true) : use_top;
     uint32_t c_g[2], d_g[2];
     if (INTERIOR) {
@@ -834,18 +812,26 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     }
     // the pointwise inputs of phase C are requested before the barrier, so their L2 latency overlaps the wait
     constexpr bool PRE_SVE = M::SCALED && CSI_PRE_SVE, PRE_RM2 = M::SCALED && CSI_PRE_RM2;
-    auto load_pt = [&](bool on, uint32_t g, const double *gn, const double *gt, const double *grm, const double *gue, const double *gsv, double tconst) {
+    auto load_pt = [&](bool on, uint32_t g, const PhasePtrs &pp, double tconst, double bconst) {
         Pt pt;  // (members a configuration does not use stay unset and cost nothing)
-        pt.n = on ? __ldg(gn + g) : 0.0;
-        pt.t = (on && use_t) ? __ldg(gt + g) : (M::SCALED ? 0.0 : tconst);
-        if (PRE_RM2) pt.rm = on ? __ldg(grm + g) : 1.0;
-        if (PRE_SVE) pt.ue = (on && use_ue) ? __ldg(gue + g) : 0.0;
-        if (PRE_SVE) pt.sv = (on && use_ue) ? __ldg(gsv + g) : 0.0;
+        pt.n = on ? __ldg(pp.n + g) : 0.0;
+        const double *gt = M::SCALED ? pp.t1 : pp.tt;
+        const bool top_sis = GEN && p.top_sis;
+        pt.t = (on && (top_sis ? p.top_arr != 0 : use_t)) ? __ldg(gt + g) : (M::SCALED ? 0.0 : tconst);
+        if (GEN && p.top_sis) {
+            if (M::SCALED) pt.sa = (on && p.top_arr) ? __ldg(pp.sa + g) : 0.0;
+            else pt.oth = pp.oth + g;
+        }
+        if (GEN && p.bot_expl) pt.tb = M::SCALED ? (on ? __ldg(pp.tb1 + g) : 0.0) : ((on && p.bot_arr) ? __ldg(pp.tbr + g) : bconst);
+        if (GEN && p.fd_on) pt.fd = on ? __ldg(pp.fd + g) : 0.0;
+        if (PRE_RM2) pt.rm = on ? __ldg(pp.rm + g) : 1.0;
+        if (PRE_SVE) pt.ue = (on && use_ue) ? __ldg(pp.ue + g) : 0.0;
+        if (PRE_SVE) pt.sv = (on && use_ue) ? __ldg(pp.sv + g) : 0.0;
         return pt;
     };
     Pt cpt[2];
 #pragma unroll
-    for (int q = 0; q < 2; q++) cpt[q] = load_pt(c_on[q], c_g[q], gC1, gC2, p.g_crm, p.g_cue, p.g_csv, VFIRST ? p.tty : p.ttx);
+    for (int q = 0; q < 2; q++) cpt[q] = load_pt(c_on[q], c_g[q], p.pc, VFIRST ? p.tty : p.ttx, VFIRST ? p.tb_y : p.tb_x);
     __syncthreads();
 
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
@@ -899,18 +885,29 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (mt.dxff(r + 1) * 1.0);
             imm = mm.divc(qE - qW + qN - qS, mt.azfc(r) * 1.0, mt.razfc(r));
         }
+        Ext x;
+        x.ue = ue; x.oe = vebar; x.t1 = ttop;
+        if (GEN && p.top_sis) {  // (u_a, v_a): arrays read pointwise, the 4-point sum of v_a from k_prep / its mean from the raw plane
+            x.t1 = 0.0;
+            x.ua = p.top_arr ? pt.t : p.ta_x;
+            if (M::SCALED) x.oa = p.top_arr ? pt.sa : (p.ta_y + p.ta_y) + (p.ta_y + p.ta_y);
+            else if (p.top_arr) x.oa = ((__ldg(pt.oth - 1) + __ldg(pt.oth)) / 2 + (__ldg(pt.oth + p.pitch - 1) + __ldg(pt.oth + p.pitch)) / 2) / 2;
+            else x.oa = ((p.ta_y + p.ta_y) / 2 + (p.ta_y + p.ta_y) / 2) / 2;
+        }
+        if (GEN && p.bot_expl) x.tb = pt.tb;
+        if (GEN && p.fd_on) x.fd = pt.fd;
         const double dyc2 = mt.dycc2(r), dyf = mt.dyfc(r);
         double val;
         if (M::SCALED) {
             const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2d(r + 1), mt.dxff2d(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
             // (a node that is not evolved returns its old value whatever is computed: harmless masses keep it from failing the tile)
             const double m1 = upd ? SB(b, A_H, 0, 0) : 1.0, m0 = upd ? SB(b, A_H, -1, 0) : 1.0;
-            val = u_node_s<GEN>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
-                                uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5);
+            val = vel_node_s<GEN, false>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+                                         uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5);
         } else {
             const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
-            val = u_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
-                              uold, vbar, xcross, ue, vebar, ttop, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+            val = vel_node<GEN, false>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+                                       uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         }
         return upd ? val : uold;
     };
@@ -961,12 +958,23 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const double qS = 0.0 * (mt.dxcc(r - 1) * 1.0), qN = 0.0 * (mt.dxcc(r) * 1.0);
             imm = mm.divc(qE - qW + qN - qS, mt.azcf(r) * 1.0, mt.razcf(r));
         }
+        Ext x;
+        x.ue = ve; x.oe = uebar; x.t1 = ttop;
+        if (GEN && p.top_sis) {
+            x.t1 = 0.0;
+            x.ua = p.top_arr ? pt.t : p.ta_y;
+            if (M::SCALED) x.oa = p.top_arr ? pt.sa : (p.ta_x + p.ta_x) + (p.ta_x + p.ta_x);
+            else if (p.top_arr) x.oa = ((__ldg(pt.oth - p.pitch) + __ldg(pt.oth - p.pitch + 1)) / 2 + (__ldg(pt.oth) + __ldg(pt.oth + 1)) / 2) / 2;
+            else x.oa = ((p.ta_x + p.ta_x) / 2 + (p.ta_x + p.ta_x) / 2) / 2;
+        }
+        if (GEN && p.bot_expl) x.tb = pt.tb;
+        if (GEN && p.fd_on) x.fd = pt.fd;
         const double dyf2 = M::SCALED ? mt.dyff2d(r) : mt.dyff2(r), dxf = mt.dxcf(r);
         const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
-        const double val = M::SCALED ? v_node_s<GEN>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                                     SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
-                                     : v_node<GEN>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                                   SB(b, A_AL, 0, -1), vold, ubar, ycross, ve, uebar, ttop, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        const double val = M::SCALED ? vel_node_s<GEN, true>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                                             SB(b, A_AL, 0, -1), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
+                                     : vel_node<GEN, true>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
+                                                           SB(b, A_AL, 0, -1), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
     };
 
@@ -979,7 +987,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
     Pt dpt[2];  // likewise for phase D
 #pragma unroll
-    for (int q = 0; q < 2; q++) dpt[q] = load_pt(d_on[q], d_g[q], gD1, gD2, p.g_drm, p.g_due, p.g_dsv, VFIRST ? p.ttx : p.tty);
+    for (int q = 0; q < 2; q++) dpt[q] = load_pt(d_on[q], d_g[q], p.pd, VFIRST ? p.ttx : p.tty, VFIRST ? p.tb_x : p.tb_y);
     __syncthreads();
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
@@ -1268,6 +1276,79 @@ __global__ void k_prep(Params p, int top_const)
         p.base[(size_t)F_T1X * plane + o] = t1x;
         p.base[(size_t)F_T1Y * plane + o] = t1y;
     }
+    // ---- less common configurations (GEN instantiation of the kernel) ----
+    if (p.bot_expl) {  // prescribed bottom stress: + tau_bot / m_i * aice_i (mt:33,66), same form as the top term
+        double tbx = 0.0, tby = 0.0;
+        if (west) {
+            const double m2 = m11 + m01, a2 = a11 + A[o - 1];
+            const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+            tbx = ((p.bot_arr ? p.base[(size_t)F_UE * plane + o] : p.tb_x) / (active_ice ? m2 : 1.0)) * a2;
+        }
+        if (south) {
+            const double m2 = m11 + m10, a2 = a11 + A[o - p.pitch];
+            const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
+            tby = ((p.bot_arr ? p.base[(size_t)F_VE * plane + o] : p.tb_y) / (active_ice ? m2 : 1.0)) * a2;
+        }
+        p.base[(size_t)F_TB1X * plane + o] = tbx;
+        p.base[(size_t)F_TB1Y * plane + o] = tby;
+    }
+    const bool north = r + 1 < p.rows, east = c + 1 < p.pitch;
+    if (p.top_sis && p.top_arr) {  // 4-point sums of the atmosphere velocity: 4 v_a-bar at u nodes, 4 u_a-bar at v nodes (ext:176-202)
+        const double *UA = p.base + (size_t)F_TX * plane, *VA = p.base + (size_t)F_TY * plane;
+        p.base[(size_t)F_SVA * plane + o] = (west && north) ? (VA[o - 1] + VA[o]) + (VA[o + p.pitch - 1] + VA[o + p.pitch]) : 0.0;
+        p.base[(size_t)F_SUA * plane + o] = (south && east) ? (UA[o - p.pitch] + UA[o - p.pitch + 1]) + (UA[o] + UA[o + 1]) : 0.0;
+    }
+    if (p.fd_on) {
+        // The value of a node that is not dynamically active: marginal ice (face mass and concentration above eps) takes the
+        // free-drift velocity, anything else 0 (se:224-228, 259-263).  Free drift depends on the external stresses and velocities
+        // only (stress_balance_free_drift.jl:61-129), so it is a constant of the stage; reference expression trees throughout.
+        const double eps = 2.220446049250313e-16;
+        const double *U0 = p.base + (size_t)F_U0 * plane, *V0 = p.base + (size_t)F_V0 * plane;
+        const bool d_bot = p.sis != 0;                      // the SemiImplicitStress side; o = the other side
+        const int o_kind = d_bot ? p.top_kind : p.bot_kind;
+        const bool o_arr = d_bot ? p.top_arr != 0 : p.bot_arr != 0, d_arr = d_bot ? p.use_ue != 0 : p.top_arr != 0;
+        const double *OX_ = p.base + (size_t)(d_bot ? F_TX : F_UE) * plane, *OY_ = p.base + (size_t)(d_bot ? F_TY : F_VE) * plane;
+        const double *DX_ = p.base + (size_t)(d_bot ? F_UE : F_TX) * plane, *DY_ = p.base + (size_t)(d_bot ? F_VE : F_TY) * plane;
+        const double ocx = d_bot ? p.ta_x : p.tb_x, ocy = d_bot ? p.ta_y : p.tb_y, dcx = d_bot ? p.ue_c : p.ta_x, dcy = d_bot ? p.ve_c : p.ta_y;
+        const double Cdrag = d_bot ? p.rhoCd : p.top_rhoCd;
+        // x/y_momentum_stress of the side that is not a SemiImplicitStress: explicit stress - zero * velocity (ext:34-38)
+        auto xms = [&](size_t q) { return (o_kind == CSI_STRESS_NONE ? 0.0 : (o_arr ? OX_[q] : ocx)) - 0.0 * U0[q]; };
+        auto yms = [&](size_t q) { return (o_kind == CSI_STRESS_NONE ? 0.0 : (o_arr ? OY_[q] : ocy)) - 0.0 * V0[q]; };
+        double ufd = 0.0, vfd = 0.0;
+        if (west) {
+            const double mi = (m11 + m01) / 2, ai = (a11 + A[o - 1]) / 2;
+            double uF = 0.0;
+            if (p.fd_kind == CSI_FD_FIELDS) uF = p.base[(size_t)F_FDU * plane + o];
+            else if (north) {
+                const double tx = xms(o);
+                const double ty = ((yms(o - 1) + yms(o)) / 2 + (yms(o + p.pitch - 1) + yms(o + p.pitch)) / 2) / 2;
+                const double t = sqrt(tx * tx + ty * ty);
+                const double Ud = d_arr ? DX_[o] : dcx;
+                uF = Ud - (t == 0 ? t : tx / sqrt(Cdrag * t));
+            }
+            ufd = ((mi > eps) & (ai > eps)) ? uF : 0.0;
+        }
+        if (south) {
+            const double mi = (m11 + m10) / 2, ai = (a11 + A[o - p.pitch]) / 2;
+            double vF = 0.0;
+            if (p.fd_kind == CSI_FD_FIELDS) vF = p.base[(size_t)F_FDV * plane + o];
+            else if (east) {
+                const double tx = ((xms(o - p.pitch) + xms(o - p.pitch + 1)) / 2 + (xms(o) + xms(o + 1)) / 2) / 2;
+                const double ty = yms(o);
+                const double t = sqrt(tx * tx + ty * ty);
+                const double Ud = d_arr ? DY_[o] : dcy;
+                vF = Ud - (t == 0 ? t : ty / sqrt(Cdrag * t));
+            }
+            vfd = ((mi > eps) & (ai > eps)) ? vF : 0.0;
+        }
+        p.base[(size_t)F_UFD * plane + o] = ufd;
+        p.base[(size_t)F_VFD * plane + o] = vfd;
+        // these values become velocities: the FAST pass's induction needs them zero or in [2^-300, 2^300) like every input
+        for (double val : {ufd, vfd}) {
+            const uint32_t hi = (uint32_t)__double2hiint(val) & 0x7fffffffu, e = hi >> 20;
+            if ((hi | (uint32_t)__double2loint(val)) != 0u && (e < 1023u - 300u || e >= 1023u + 300u)) atomicOr(p.invalid, 1);
+        }
+    }
 #if CSI_PRE_RM2
     p.base[(size_t)F_RM2U * plane + o] = rmu;
     p.base[(size_t)F_RM2V * plane + o] = rmv;
@@ -1291,7 +1372,6 @@ __global__ void k_prep(Params p, int top_const)
 #if CSI_PRE_SVE
     if (p.use_ue) {
         const double *UE = p.base + (size_t)F_UE * plane, *VE = p.base + (size_t)F_VE * plane;
-        const bool north = r + 1 < p.rows, east = c + 1 < p.pitch;
         // 4 v_e-bar at the u node (i, j): (i-1, j) + (i, j) + (i-1, j+1) + (i, j+1); 4 u_e-bar at the v node: (i, j-1) + (i+1, j-1) + (i, j) + (i+1, j)
         p.base[(size_t)F_SVE * plane + o] = (west && north) ? (VE[o - 1] + VE[o]) + (VE[o + p.pitch - 1] + VE[o + p.pitch]) : 0.0;
         p.base[(size_t)F_SUE * plane + o] = (south && east) ? (UE[o - p.pitch] + UE[o - p.pitch + 1]) + (UE[o] + UE[o + 1]) : 0.0;
@@ -1351,15 +1431,15 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
             for (int q = 0; q < g.metL; q++)
                 if (!recip_is_safe(g.met_host[(size_t)k * g.metL + q])) { snprintf(why, nwhy, "a grid metric is not eligible for the constant-division shortcut"); return 0; }
     } else if (p.cor == CSI_CORIOLIS_SPHERICAL) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
-    if (p.fd_kind != CSI_FD_NONE) { snprintf(why, nwhy, "free-drift velocities (general kernels only)"); return 0; }
-    if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT) { snprintf(why, nwhy, "SemiImplicitStress on top (general kernels only)"); return 0; }
-    if (p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD) { snprintf(why, nwhy, "prescribed bottom stress (general kernels only)"); return 0; }
+    if (p.fd_kind == CSI_FD_FIELDS && (!f.fd_u.p || !f.fd_v.p)) { snprintf(why, nwhy, "free-drift arrays missing"); return 0; }
+    if ((f.top_x.p == nullptr) != (f.top_y.p == nullptr)) { snprintf(why, nwhy, "top_x/top_y kinds differ"); return 0; }
     if (!g.met && (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az))) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
     if (g.Nx < 8 || g.Ny < 8) { snprintf(why, nwhy, "grid too small"); return 0; }
     // premises of the scaled expression tree (exact power-of-two scalings): thresholds and constants far inside the normal range
     // (and the quotients left unchecked in the kernel -- by cell areas, by alpha -- stay far from over/underflow)
     auto sane = [](double x) { return x == 0.0 || (fabs(x) >= 1e-30 && fabs(x) <= 1e30); };
     auto sane_len = [](double x) { return x >= 1e-6 && x <= 1e12; };  // grid spacings in metres (areas: the square)
+    if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT && !sane(p.top_rho * p.top_Cd)) { snprintf(why, nwhy, "top drag coefficient outside the range the exact scalings assume"); return 0; }
     bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && p.Dmin >= 1e-30 && p.Dmin <= 1e30 && sane(p.em2) &&
               sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i) && p.rho_i > 0;
     if (!g.met) ok = ok && sane_len(g.dx) && sane_len(g.dy);
@@ -1523,6 +1603,13 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.use_top = p.top_kind == CSI_STRESS_FIELD;
     P.use_t1 = p.top_kind == CSI_STRESS_FIELD || p.top_kind == CSI_STRESS_CONST;
     P.use_ue = f.ue.p != nullptr && p.bot_kind == CSI_STRESS_SEMI_IMPLICIT;
+    P.fd_on = p.fd_kind != CSI_FD_NONE; P.fd_kind = p.fd_kind;
+    P.top_sis = p.top_kind == CSI_STRESS_SEMI_IMPLICIT; P.top_arr = f.top_x.p != nullptr;
+    P.bot_expl = p.bot_kind == CSI_STRESS_CONST || p.bot_kind == CSI_STRESS_FIELD; P.bot_arr = f.ue.p != nullptr; P.bot_kind = p.bot_kind;
+    P.top_kind = p.top_kind;
+    P.top_rhoCd = p.top_rho * p.top_Cd;
+    P.ta_x = p.ttx; P.ta_y = p.tty;   // constants of a top SemiImplicitStress without arrays
+    P.tb_x = p.ue_c; P.tb_y = p.ve_c; // constants of a prescribed bottom stress
     P.u_sn_bc = p.u_sn_bc; P.v_we_bc = p.v_we_bc; P.u_sn_val = p.u_sn_val; P.v_we_val = p.v_we_val;
     P.dt = dt;
     P.dx = g.dx; P.dy = g.dy; P.az = g.az; P.dx2 = g.dx * g.dx; P.dy2 = g.dy * g.dy;
@@ -1564,8 +1651,9 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     pack(f.s11, F_S11_0, 1, 0, 0); pack(f.s22, F_S22_0, 1, 0, 0); pack(f.s12, F_S12_0, 1, 1, 1);
     pack(f.h, F_H, 0, 0, 0); pack(f.a, F_A, 0, 0, 0); pack(f.P, F_P, 0, 0, 0);
     pack(f.un, F_UN, 0, 1, 0); pack(f.vn, F_VN, 0, 0, 1);
-    if (P.use_top) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
-    if (P.use_ue) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
+    if (P.use_top || (P.top_sis && P.top_arr)) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
+    if (P.use_ue || (P.bot_expl && P.bot_arr)) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
+    if (p.fd_kind == CSI_FD_FIELDS) { pack(f.fd_u, F_FDU, 0, 1, 0); pack(f.fd_v, F_FDV, 0, 0, 1); }
     // stage constants of the substep loop (ice mass, top-stress terms)
     k_prep<<<dim3((pl->pitch + 127) / 128, pl->rows), 128, 0, c.stream>>>(P, p.top_kind == CSI_STRESS_CONST);
     ++*c.launches;
@@ -1619,19 +1707,25 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
             const size_t plane = (size_t)P.pitch * P.rows;
             auto at = [&](int f) { return P.base + (size_t)f * plane; };
             const int fo = P.out_set ? F_U1 : F_U0;
-            P.g_cn = at(vfirst ? F_VN : F_UN); P.g_ct1 = at(vfirst ? F_T1Y : F_T1X); P.g_ctt = at(vfirst ? F_TY : F_TX);
-            P.g_dn = at(vfirst ? F_UN : F_VN); P.g_dt1 = at(vfirst ? F_T1X : F_T1Y); P.g_dtt = at(vfirst ? F_TX : F_TY);
+            // x: the planes of a u phase, y: of a v phase
+            PhasePtrs X, Y;
+            X.n = at(F_UN); Y.n = at(F_VN);
+            X.tt = at(F_TX); Y.tt = at(F_TY);
+            X.t1 = P.top_sis ? X.tt : at(F_T1X); Y.t1 = P.top_sis ? Y.tt : at(F_T1Y);   // (a top SemiImplicitStress reads u_a, v_a themselves)
+            X.sa = at(F_SVA); Y.sa = at(F_SUA); X.oth = Y.tt; Y.oth = X.tt;
+            X.tb1 = at(F_TB1X); Y.tb1 = at(F_TB1Y); X.tbr = at(F_UE); Y.tbr = at(F_VE);
+            X.fd = at(F_UFD); Y.fd = at(F_VFD);
+            X.rm = at(F_RM2U); Y.rm = at(F_RM2V); X.ue = at(F_UE); Y.ue = at(F_VE); X.sv = at(F_SVE); Y.sv = at(F_SUE);
+            P.pc = vfirst ? Y : X;
+            P.pd = vfirst ? X : Y;
             P.o_c = at(fo + (vfirst ? 1 : 0)); P.o_d = at(fo + (vfirst ? 0 : 1));
             P.o_s11 = at(fo + 2); P.o_s22 = at(fo + 3); P.o_s12 = at(fo + 4);
-            P.g_crm = at(vfirst ? F_RM2V : F_RM2U); P.g_drm = at(vfirst ? F_RM2U : F_RM2V);
-            P.g_cue = at(vfirst ? F_VE : F_UE); P.g_csv = at(vfirst ? F_SUE : F_SVE);
-            P.g_due = at(vfirst ? F_UE : F_VE); P.g_dsv = at(vfirst ? F_SVE : F_SUE);
             P.g_rmc = at(F_RMC); P.g_rmf = at(F_RMF); P.g_pf4 = at(F_PF4);
         }
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
-        const bool common = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
-        const bool common_met = P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
+        const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
+        const bool common_met = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
         auto band = [&](int t0, int t1) -> cudaError_t {
             if (t1 <= t0) return cudaSuccess;
             P.ty0 = t0;

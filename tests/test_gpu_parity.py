@@ -414,21 +414,25 @@ def test_latitude_longitude_grid_rejects_bad_metrics():
         model_from_case(bad)
 
 
+@pytest.mark.parametrize("impl", ["unfused", "fused"])
 @pytest.mark.parametrize("variant", ["bottom_drag", "top_drag", "fields", "both_drag", "const_top_drag"])
 @pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
-def test_free_drift_top_drag_and_snow(variant, timestepper):
+def test_free_drift_top_drag_and_snow(variant, timestepper, impl):
     """free-drift velocities of marginal ice (StressBalanceFreeDrift closed forms for either side, and
     (u=, v=) arrays: stress_balance_free_drift.jl:61-129), SemiImplicitStress as the top stress and prescribed
     bottom stresses (ext.jl:8-40,176-210), and snow-thickness advection (tracer_tendency:47-52, fe.jl:84-94)."""
     from climaseaice_b200.synthetic import marginal_ice_case
     case = marginal_ice_case(48, substeps=12, variant=variant, timestepper=timestepper)
-    m = model_from_case(case, solver_impl="auto")
+    m = model_from_case(case, solver_impl=impl)
     o = oracle_from_case(case)
     for _ in range(2):
         m.time_step(case.dt); o.time_step(case.dt)
     _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "hs", "s11", "s22", "s12", "Ghs")))
     u = interior_of(m.all_fields()["u"].numpy(), case)
     assert np.isfinite(u).all() and np.abs(u).max() > 1e-3
+    if impl == "fused":   # the tile kernel ran, and on its FAST pass: free drift, top drag and prescribed bottom stress are
+        inv, redone, tiles = m.fused_stats()   # stage constants / GEN branches of it, not a reason to fall back
+        assert tiles > 0 and inv == 0 and redone <= 0.05 * case.substeps * tiles, (inv, redone, tiles)
     m.close()
 
 
@@ -466,11 +470,11 @@ def test_stress_balance_free_drift_argument_errors():
     h = C.c_void_p()
     assert L.lib().csi_create(C.byref(cfg), C.byref(h)) == -1 and b"not both" in L.lib().csi_last_error(None)
     m.close()
-    # "fused" refuses what only the general kernels implement
-    from climaseaice_b200.synthetic import marginal_ice_case
-    mc = marginal_ice_case(32, substeps=2, variant="fields")
+    # "fused" refuses what only the general kernels implement: two-dimensional metrics
+    from climaseaice_b200.synthetic import curvilinear_case
+    mc = curvilinear_case(40, 32, substeps=2)
     mf = model_from_case(mc, solver_impl="fused")
-    with pytest.raises(RuntimeError, match="free-drift"):
+    with pytest.raises(RuntimeError, match="two-dimensional metrics"):
         mf.time_step(mc.dt)
     mf.close()
 
@@ -527,6 +531,24 @@ def test_extreme_magnitudes_stay_bitwise(impl, nsub):
     _assert_parity(compare_model(m, o, case, names=("u", "v", "s11", "s22", "s12", "alpha", "P")))
     if impl == "auto":
         assert m.fused_stats()[0] == 1   # subnormal inputs fail the validation: the whole stage takes the IEEE pass
+    m.close()
+
+
+@pytest.mark.parametrize("variant", ["bottom_drag", "top_drag", "fields", "both_drag", "const_top_drag"])
+def test_ieee_pass_of_the_less_common_configurations(variant):
+    """Free drift, a SemiImplicitStress on top and prescribed bottom stresses inside the fused kernel's IEEE re-pass (the
+    reference's expression tree with plain operators): a subnormal thickness fails the stage's input validation, every
+    tile takes that pass, and the result is still the oracle's bit for bit."""
+    from climaseaice_b200.synthetic import marginal_ice_case
+    case = marginal_ice_case(48, substeps=6, variant=variant, timestepper="ForwardEuler", snow=False)
+    case.fields["h"][case.Hy + 3, case.Hx + 3] = 1e-310
+    m = model_from_case(case, solver_impl="fused")
+    o = oracle_from_case(case)
+    m.update_state(); o.update_state()
+    m.time_step_momentum(case.dt); o.time_step_momentum(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "s11", "s22", "s12", "alpha")))
+    inv, redone, tiles = m.fused_stats()
+    assert inv == 1 and redone >= tiles
     m.close()
 
 
