@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1214,8 +1215,23 @@ struct PackItem {
     int dup;     // also write field + 5 (second copy of an evolving field)
     int lx, ly;  // location, for the extent of the copy window on Bounded axes
 };
-__global__ void k_pack(PackItem it, Params p, int w)
+// every field of a stage in ONE launch (blockIdx.z selects the item): on small grids the per-field launches cost more than
+// the copies
+struct PackList {
+    PackItem it[16];
+    int n;
+};
+struct UnpackItem {
+    DArr a;
+    int field, i0, i1, j0, j1;
+};
+struct UnpackList {
+    UnpackItem it[9];
+    int n;
+};
+__global__ void k_pack(const __grid_constant__ PackList L, const __grid_constant__ Params p, int w)
 {
+    const PackItem &it = L.it[blockIdx.z];
     // window: i in [1-w, Nx+w(+1)] (w = Hx on a partitioned x axis), j in [1-w', Ny+w'(+1)], clipped to the parent
     const int i = 1 - w + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 - p.oy + blockIdx.y;
@@ -1378,11 +1394,12 @@ __global__ void k_prep(Params p, int top_const)
     }
 #endif
 }
-__global__ void k_unpack(PackItem it, Params p, int i0, int i1, int j0, int j1)
+__global__ void k_unpack(const __grid_constant__ UnpackList L, const __grid_constant__ Params p)
 {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = j0 + blockIdx.y;
-    if (i > i1 || j > j1) return;
+    const UnpackItem &it = L.it[blockIdx.z];
+    const int i = it.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = it.j0 + blockIdx.y;
+    if (i > it.i1 || j > it.j1) return;
     const size_t plane = (size_t)p.pitch * p.rows;
     at(it.a, i, j) = p.base[(size_t)it.field * plane + (size_t)(j - 1 + p.oy) * p.pitch + (size_t)(i - 1 + OX)];
 }
@@ -1401,7 +1418,6 @@ struct FusedPlan {
     int pitch = 0, rows = 0, oy = 0;
     CUtensorMap tmap;
     int Nx = 0, Ny = 0;
-    bool attr_set = false;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1641,12 +1657,9 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
 
     // pack: caller parents -> internal layout (window includes W halo cells; evolving fields into both copies)
     const int w = (g.conn_w || g.conn_e) ? g.Hx : W;
-    auto pack = [&](const DArr &a, int field, int dup, int lx, int ly) {
-        PackItem it{a, field, dup, lx, ly};
-        dim3 pg((g.Nx + 2 * w + 2 + 127) / 128, g.Ny + 2 * pl->oy);
-        k_pack<<<pg, 128, 0, c.stream>>>(it, P, w);
-        ++*c.launches;
-    };
+    PackList PL;
+    PL.n = 0;
+    auto pack = [&](const DArr &a, int field, int dup, int lx, int ly) { PL.it[PL.n++] = PackItem{a, field, dup, lx, ly}; };
     pack(f.u, F_U0, 1, 1, 0); pack(f.v, F_V0, 1, 0, 1);
     pack(f.s11, F_S11_0, 1, 0, 0); pack(f.s22, F_S22_0, 1, 0, 0); pack(f.s12, F_S12_0, 1, 1, 1);
     pack(f.h, F_H, 0, 0, 0); pack(f.a, F_A, 0, 0, 0); pack(f.P, F_P, 0, 0, 0);
@@ -1654,6 +1667,8 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     if (P.use_top || (P.top_sis && P.top_arr)) { pack(f.top_x, F_TX, 0, 1, 0); pack(f.top_y, F_TY, 0, 0, 1); }
     if (P.use_ue || (P.bot_expl && P.bot_arr)) { pack(f.ue, F_UE, 0, 1, 0); pack(f.ve, F_VE, 0, 0, 1); }
     if (p.fd_kind == CSI_FD_FIELDS) { pack(f.fd_u, F_FDU, 0, 1, 0); pack(f.fd_v, F_FDV, 0, 0, 1); }
+    k_pack<<<dim3((g.Nx + 2 * w + 2 + 127) / 128, g.Ny + 2 * pl->oy, PL.n), 128, 0, c.stream>>>(PL, P, w);
+    ++*c.launches;
     // stage constants of the substep loop (ice mass, top-stress terms)
     k_prep<<<dim3((pl->pitch + 127) / 128, pl->rows), 128, 0, c.stream>>>(P, p.top_kind == CSI_STRESS_CONST);
     ++*c.launches;
@@ -1688,6 +1703,9 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
 // `halo_ready` (slabs): an event recorded on another stream after the halo rows of the current copy have been received.
 // The first substep is then launched in row bands: the tile rows whose boxes stay inside rows 1..Ny go first and overlap
 // the exchange, the tile rows that read halo rows wait for the event.
+// (Replaying a block of substeps as a CUDA graph was measured on BASELINE config 1 as shipped -- 128 x 128, 50 tiles -- and
+// changed nothing: 5.029 vs 5.030 ms per time_step!.  Such grids are bound by the latency of one tile pass, about 10 us with
+// two warps per scheduler, not by the gaps between launches; the graph path was removed again.)
 int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool aux_last, char *err, int nerr, cudaEvent_t halo_ready)
 {
     using namespace fz;
@@ -1784,12 +1802,14 @@ int fused_end(FusedPlan *pl, const LaunchCtx &c, const DFields &f, char *err, in
     const int in_set = pl->cur_set;
     const int nsub = 1;
     // unpack the final copy into the caller's arrays (interior / stress window); halos are refilled by the caller
+    UnpackList UL;
+    UL.n = 0;
+    int wmax = 0, hmax = 0;
     auto unpack = [&](const DArr &a, int field, int i0, int i1, int j0, int j1) {
         if (!a.p) return;
-        PackItem it{a, field, 0, 0, 0};
-        dim3 ug((i1 - i0 + 1 + 127) / 128, j1 - j0 + 1);
-        k_unpack<<<ug, 128, 0, c.stream>>>(it, P, i0, i1, j0, j1);
-        ++*c.launches;
+        UL.it[UL.n++] = UnpackItem{a, field, i0, i1, j0, j1};
+        wmax = std::max(wmax, i1 - i0 + 1);
+        hmax = std::max(hmax, j1 - j0 + 1);
     };
     const int fo = in_set ? F_U1 : F_U0;
     if (nsub > 0) {
@@ -1802,6 +1822,8 @@ int fused_end(FusedPlan *pl, const LaunchCtx &c, const DFields &f, char *err, in
         unpack(f.zc, F_ZC, P.sx0, P.sx1, P.sy0, P.sy1);
         unpack(f.zf, F_ZF, P.sx0, P.sx1, P.sy0, P.sy1);
         unpack(f.delta, F_DELTA, P.sx0, P.sx1, P.sy0, P.sy1);
+        k_unpack<<<dim3((wmax + 127) / 128, hmax, UL.n), 128, 0, c.stream>>>(UL, P);
+        ++*c.launches;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, nerr, "%s", cudaGetErrorString(e)); return (int)e; }
