@@ -654,9 +654,13 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         const int L = cfg->Ny + 2 * cfg->Hy + 1;
         for (int k = 0; k < 12; k++) {
             if (!cfg->metrics[k]) return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_METRIC_J needs all 12 metric arrays");
-            // rows the stencils touch: j = 0 .. Ny+2 (stress ring + the j+1 metrics it reads)
-            for (int j = 0; j <= cfg->Ny + 2; j++)
-                if (j - 1 + cfg->Hy < L && !(cfg->metrics[k][j - 1 + cfg->Hy] > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive");
+            // rows the stencils touch: j = 0 .. Ny+2 (stress ring + the j+1 metrics it reads); on a partition the kernels run
+            // over the widened range of se:40-46 and divide by the metrics of every halo row of a connected side
+            const int Ry_ = cfg->nranks > 1 ? cfg->nranks / (cfg->partition_x > 1 ? cfg->partition_x : 1) : 1;
+            const int ry_ = cfg->nranks > 1 ? cfg->rank / (cfg->partition_x > 1 ? cfg->partition_x : 1) : 0;
+            const bool cs = Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ > 0), cn = Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ < Ry_ - 1);
+            for (int j = cs ? 1 - cfg->Hy : 0; j <= (cn ? cfg->Ny + cfg->Hy + 1 : cfg->Ny + 2); j++)
+                if (j - 1 + cfg->Hy >= 0 && j - 1 + cfg->Hy < L && !(cfg->metrics[k][j - 1 + cfg->Hy] > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive on every row the kernels touch (halo rows of connected sides included)");
         }
     }
     if (cfg->substeps < 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: substeps must be >= 1");
