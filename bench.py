@@ -433,6 +433,36 @@ def run_gpu(args):
         del hs
         torch.cuda.empty_cache()
 
+    # BASELINE config 5 on the N GPUs of this run: coupled thermodynamics + dynamics + advection on the 1/12-degree lat-lon cap,
+    # y-slabs of 4320 x (336 / N) with NCCL halo exchange (beside the headline, never instead of it)
+    config5 = None
+    if world > 1 and not args.no_configs and 336 % world == 0:
+        from climaseaice_b200.synthetic import arctic_cap_case
+        c5 = arctic_cap_case(4320, 336, H=7, substeps=SUBSTEPS, dt=600.0)
+        s5 = slab_of(c5, rank, world, 2 * K + 3)
+        m5 = model_from_case(s5, solver_impl=args.solver, partition=(rank, world, K), device=dev)
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        m5.comm_init(ids[0])
+        m5.time_step(c5.dt)   # warm-up; the first step also runs update_state!
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(2):
+            m5.time_step(c5.dt)
+        ev1.record()
+        barrier()
+        t5 = torch.tensor([ev0.elapsed_time(ev1) / 2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        st5 = m5.fused_stats()
+        config5 = {"ms_per_time_step": float(t5.item()), "cell_updates_per_s": c5.Nx * c5.Ny * 3 * SUBSTEPS / (float(t5.item()) * 1e-3),
+                   "per_gpu": [s5.Nx, s5.Ny], "fused_stats": list(st5),
+                   "note": "one time_step! = 3 RK stages x (WENO7 tendencies + 150 substeps + h/aice update + slab thermodynamics); lat-lon metrics, "
+                           "HydrostaticSphericalCoriolis; slabs this thin are bound by the latency of a tile pass and the exchange, not by throughput"}
+        m5.close()
+        del m5
+        torch.cuda.empty_cache()
+
     # weak-scaling baseline: the same per-GPU block (16384 x 2048, doubly periodic) on ONE GPU of this box in this run
     weak1 = None
     if world > 1 and rank == 0 and not args.no_weak_baseline:
@@ -477,6 +507,8 @@ def run_gpu(args):
             line["weak_baseline_1gpu"] = weak1
         if configs:
             line["configs"] = configs
+        if config5:
+            line["configs"] = {f"config5_arctic_cap_4320x336_on_{ngpus}_gpus": config5}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -131,11 +131,16 @@ template <bool XDIR> __device__ __forceinline__ int buffer_immersed(const DGrid 
     return 1;
 }
 
-static constexpr int ATX = 32, ATY = 8, AH = 4;  // tile and the widest stencil halo (WENO7)
+// A CTA of 32 x 8 threads owns 31 x 7 cells: its 32 x 7 x-faces and 31 x 8 y-faces are then ONE sweep of the threads each.  (With a
+// 32 x 8 cell tile the 33 x 8 and 32 x 9 faces took a second, almost empty sweep, and the block barrier behind it was the kernel's
+// largest stall: profiles/r02_tracer_tendencies_kernel_ncu.md.)
+static constexpr int BTX = 32, BTY = 8;          // threads
+static constexpr int ATX = 31, ATY = 7, AH = 4;  // cells per tile and the widest stencil halo (WENO7)
+static_assert((ATX + 1) * ATY <= BTX * BTY && ATX * (ATY + 1) <= BTX * BTY, "one sweep per face direction");
 
 // G^n.h = -div(U h), G^n.aice = -div(U aice) and, with snow (NQ = 3), G^n.hs = -div(U hs)  (tracer_tendency:27-52)
 template <int B, int NQ>
-__global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_constant__ DGrid g, const __grid_constant__ DParams p,
+__global__ void __launch_bounds__(BTX *BTY) k_tracer_tendencies(const __grid_constant__ DGrid g, const __grid_constant__ DParams p,
                                                                  const __grid_constant__ DFields f)
 {
     constexpr int SX = ATX + 2 * AH, SY = ATY + 2 * AH;
@@ -143,8 +148,8 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
     __shared__ double fx[NQ][ATY][ATX + 1];    // x-face fluxes
     __shared__ double fy[NQ][ATY + 1][ATX];    // y-face fluxes
     const int i0 = blockIdx.x * ATX + 1, j0 = blockIdx.y * ATY + 1;
-    const int tid = threadIdx.y * ATX + threadIdx.x;
-    for (int t = tid; t < SX * SY; t += ATX * ATY) {
+    const int tid = threadIdx.y * BTX + threadIdx.x;
+    for (int t = tid; t < SX * SY; t += BTX * BTY) {
         const int li = t % SX, lj = t / SX;
         int gi = i0 - AH + li, gj = j0 - AH + lj;
         // stay inside the parent array (cells beyond the halo are never used by a valid stencil)
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
     __syncthreads();
     const bool bx_lo = g.topo_x == CSI_BOUNDED && !g.conn_w, bx_hi = g.topo_x == CSI_BOUNDED && !g.conn_e, by_lo = g.topo_y == CSI_BOUNDED && !g.conn_s, by_hi = g.topo_y == CSI_BOUNDED && !g.conn_n;
     // x faces: (ATX+1) x ATY
-    for (int t = tid; t < (ATX + 1) * ATY; t += ATX * ATY) {
+    for (int t = tid; t < (ATX + 1) * ATY; t += BTX * BTY) {
         const int li = t % (ATX + 1), lj = t / (ATX + 1);
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx + 1 && j <= g.Ny) {
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
         }
     }
     // y faces: ATX x (ATY+1)
-    for (int t = tid; t < ATX * (ATY + 1); t += ATX * ATY) {
+    for (int t = tid; t < ATX * (ATY + 1); t += BTX * BTY) {
         const int li = t % ATX, lj = t / ATX;
         const int i = i0 + li, j = j0 + lj;
         if (i <= g.Nx && j <= g.Ny + 1) {
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(ATX *ATY) k_tracer_tendencies(const __grid_con
     }
     __syncthreads();
     const int li = threadIdx.x, lj = threadIdx.y, i = i0 + li, j = j0 + lj;
-    if (i <= g.Nx && j <= g.Ny) {
+    if (li < ATX && lj < ATY && i <= g.Nx && j <= g.Ny) {
         const double V = azcc(g, i, j) * 1.0;
         at(f.Gh, i, j) = -(1 / V * ((fx[0][lj][li + 1] - fx[0][lj][li]) + (fy[0][lj + 1][li] - fy[0][lj][li])));
         at(f.Ga, i, j) = -(1 / V * ((fx[1][lj][li + 1] - fx[1][lj][li]) + (fy[1][lj + 1][li] - fy[1][lj][li])));
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(256) k_zero_tendencies(const __grid_constant__
 
 void launch_tracer_tendencies(const LaunchCtx &c, const DGrid &g, const DParams &p, const DFields &f)
 {
-    dim3 grid((g.Nx + ATX - 1) / ATX, (g.Ny + ATY - 1) / ATY), block(ATX, ATY);
+    dim3 grid((g.Nx + ATX - 1) / ATX, (g.Ny + ATY - 1) / ATY), block(BTX, BTY);
     switch (p.adv_order) {
     case 0: k_zero_tendencies<<<dim3((g.Nx + 255) / 256, g.Ny), 256, 0, c.stream>>>(g, f); break;
 #define CSI_TT(B_)                                                                     \

@@ -639,11 +639,11 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     if (cfg->metric_kind == CSI_METRIC_IJ) {
         const int L = cfg->Ny + 2 * cfg->Hy + 1, Wd = cfg->Nx + 2 * cfg->Hx + 1;
         if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: HydrostaticSphericalCoriolis with two-dimensional metrics");
-        if (cfg->nranks > 1) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: partitions with two-dimensional metrics");
+        if (cfg->nranks > 1 && cfg->partition_x > 1) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: partitions along x with two-dimensional metrics");
         for (int k = 0; k < 12; k++) {
             if (!cfg->metrics[k]) return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_METRIC_IJ needs all 12 metric arrays");
-            // cells the stencils touch: i = 0 .. Nx+2, j = 0 .. Ny+2
-            for (int j = 0; j <= cfg->Ny + 2; j++)
+            // cells the stencils touch: i = 0 .. Nx+2, j = 0 .. Ny+2 (every halo row on a partition: widened windows, se:40-46)
+            for (int j = (cfg->nranks > 1 ? 1 - cfg->Hy : 0); j <= (cfg->nranks > 1 ? cfg->Ny + cfg->Hy + 1 : cfg->Ny + 2); j++)
                 for (int i = 0; i <= cfg->Nx + 2; i++)
                     if (j - 1 + cfg->Hy < L && i - 1 + cfg->Hx < Wd && !(cfg->metrics[k][(size_t)(j - 1 + cfg->Hy) * Wd + (i - 1 + cfg->Hx)] > 0))
                         return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive");
@@ -681,7 +681,6 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         if (cfg->nranks % Rx != 0) return fail(nullptr, CSI_ERR_ARG, "csi_create: nranks must be a multiple of partition_x");
         if (cfg->nranks / Rx > 1 && cfg->Hy < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: partitions along y need Hy >= 2*exchange_every + 3 (se.jl:55-56)");
         if (Rx > 1 && cfg->Hx < 2 * K + 3) return fail(nullptr, CSI_ERR_ARG, "csi_create: partitions along x need Hx >= 2*exchange_every + 3 (se.jl:55-56)");
-        if (Rx > 1 && cfg->immersed_mask) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: immersed masks with a partition along x");
     } else if (Rx > 1) return fail(nullptr, CSI_ERR_ARG, "csi_create: partition_x > 1 needs nranks > 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

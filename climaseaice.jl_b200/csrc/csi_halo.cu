@@ -34,10 +34,12 @@ __global__ void k_fill_y_periodic(DArr a, int Ny, int Hy)
     at(a, i, Ny + k) = at(a, i, k);
 }
 
-__global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val, int do_west, int do_east)
+// j0..j1 / i0..i1: 1..N of the other axis, widened over the halo of its connected sides on a partition -- the substep loop
+// computes there too (se:40-46), and a wall's boundary condition belongs to every column / row that is computed
+__global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int j0, int j1, int mode, double val, int do_west, int do_east)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (j > Ny) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + j0;
+    if (j > j1) return;
     const double Dw = dxff(g, 1, j), De = dxff(g, Nx + 1, j);  // Delta x at (Face, Face) on the walls, as Oceananigans' left/right_gradient uses
     if (mode == FILL_NOFLUX) {
         if (do_west) at(a, 0, j) = at(a, 1, j);
@@ -52,10 +54,10 @@ __global__ void k_fill_x_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, doub
     }
 }
 
-__global__ void k_fill_y_bounded(DGrid g, DArr a, int Nx, int Ny, int mode, double val, int do_south, int do_north)
+__global__ void k_fill_y_bounded(DGrid g, DArr a, int i0, int i1, int Ny, int mode, double val, int do_south, int do_north)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > Nx) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + i0;
+    if (i > i1) return;
     const double Ds = dyff(g, i, 1), Dn = dyff(g, i, Ny + 1);
     if (mode == FILL_NOFLUX) {
         if (do_south) at(a, i, 0) = at(a, i, 1);
@@ -84,7 +86,8 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             mode = FILL_IMPENETRABLE;
         }
         if (mode != FILL_NONE) {
-            k_fill_x_bounded<<<(g.Ny + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val, !g.conn_w, !g.conn_e);
+            const int j0 = g.conn_s ? 1 - g.Hy : 1, j1 = g.conn_n ? g.Ny + g.Hy : g.Ny;
+            k_fill_x_bounded<<<(j1 - j0 + T) / T, T, 0, c.stream>>>(g, a, g.Nx, j0, j1, mode, val, !g.conn_w, !g.conn_e);
             ++*c.launches;
         }
     }
@@ -98,7 +101,8 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
             mode = FILL_IMPENETRABLE;
         }
         if (mode != FILL_NONE) {
-            k_fill_y_bounded<<<(g.Nx + T - 1) / T, T, 0, c.stream>>>(g, a, g.Nx, g.Ny, mode, val, !g.conn_s, !g.conn_n);
+            const int i0 = g.conn_w ? 1 - g.Hx : 1, i1 = g.conn_e ? g.Nx + g.Hx : g.Nx;
+            k_fill_y_bounded<<<(i1 - i0 + T) / T, T, 0, c.stream>>>(g, a, i0, i1, g.Ny, mode, val, !g.conn_s, !g.conn_n);
             ++*c.launches;
         }
     }

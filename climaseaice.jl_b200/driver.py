@@ -18,7 +18,7 @@ def grid_from_case(case: Case, device=None, partitioned_y=False, partitioned_x=F
     if case.metric_arrays is not None and next(iter(case.metric_arrays.values())).ndim == 2:   # orthogonal curvilinear grid
         from .model import OrthogonalSphericalShellGrid
         return OrthogonalSphericalShellGrid(size=(case.Nx, case.Ny), metrics=case.metric_arrays, halo=(case.Hx, case.Hy),
-                                            topology=(case.topology[0], case.topology[1], "Flat"), device=device)
+                                            topology=(case.topology[0], case.topology[1], "Flat"), device=device, partitioned_y=partitioned_y)
     if case.latlon is not None:
         return LatitudeLongitudeGrid(size=(case.Nx, case.Ny), longitude=case.latlon[0], latitude=case.latlon[1],
                                      halo=(case.Hx, case.Hy), topology=(case.topology[0], case.topology[1], "Flat"),
@@ -88,9 +88,14 @@ class HostStepper:
         if partition is not None:   # one rank of a partition: host blocks with halos, NCCL exchange inside the call
             self.model.comm_init(unique_id)
         self.host = {}
+        # arrays the host entry points copy in either direction are pinned; the others (P, u^n, zeta, Delta, G^n ...: written and
+        # read on the device only) just need a host address and a shape
+        copied = {"u", "v", "h", "a", "s11", "s22", "s12", "alpha", "top_x", "top_y", "ue", "ve", "hs", "fd_u", "fd_v", "um", "vm"}
         for n, fld in self.model.all_fields().items():
-            t = torch.empty(fld.parent.shape, dtype=torch.float64).pin_memory()
-            t.copy_(fld.parent)
+            t = torch.empty(fld.parent.shape, dtype=torch.float64)
+            if n in copied:
+                t = t.pin_memory()
+                t.copy_(fld.parent)
             self.host[n] = t
         self.fields = L.csi_fields()
         for n, t in self.host.items():

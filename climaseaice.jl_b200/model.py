@@ -98,8 +98,9 @@ class OrthogonalSphericalShellGrid(RectilinearGrid):
     (dx, dy, Az at the four horizontal locations), i.e. what Oceananigans' `Δxᶜᶜᵃ` ... `Azᶠᶠᵃ` return.  `nodes()` are index
     coordinates.  Runs on the general (per-kernel) solver formulation."""
 
-    def __init__(self, size, metrics, halo=(3, 3), topology=(Bounded, Bounded, Flat), device=None):
-        super().__init__(size, (0.0, float(size[0])), (0.0, float(size[1])), halo=halo, topology=topology, device=device)
+    def __init__(self, size, metrics, halo=(3, 3), topology=(Bounded, Bounded, Flat), device=None, partitioned_y=False):
+        super().__init__(size, (0.0, float(size[0])), (0.0, float(size[1])), halo=halo, topology=topology, device=device,
+                         partitioned_y=partitioned_y)
         self.metrics = {}
         shp = (self.Ny + 2 * self.Hy + 1, self.Nx + 2 * self.Hx + 1)
         for n in METRIC_NAMES:

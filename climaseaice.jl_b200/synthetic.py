@@ -227,6 +227,15 @@ def curvilinear_case(N=72, Ny=56, H=4, seed=SEED, substeps=20, dt=600.0, advecti
         M["dx" + name] = spacing(x, y, 4000.0, 0.3) + 0 * (x + y)
         M["dy" + name] = spacing(x, y, 3000.0, 1.1) + 0 * (x + y)
         M["az" + name] = M["dx" + name] * M["dy" + name]
+    # along a Periodic axis the halo metrics are exact images of the interior ones (as Oceananigans fills them): index j maps
+    # to ((j - 1) mod N) + 1, so face N + 1 is face 1.  A partition relies on it: a rank recomputes its neighbour's rows.
+    ii = np.arange(1 - H, N + H + 2)
+    jj = np.arange(1 - H, Ny + H + 2)
+    for k in list(M):
+        if topology[0] == "Periodic":
+            M[k] = M[k][:, ((ii - 1) % N) + H]
+        if topology[1] == "Periodic":
+            M[k] = M[k][((jj - 1) % Ny) + H, :]
     c.metric_arrays = {k: np.ascontiguousarray(v) for k, v in M.items()}
     rng = np.random.default_rng(seed)
     X, Y = c.nodes(LOC["h"])
@@ -333,9 +342,8 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
     """Rank-local y-slab (halo Hy) of a case whose x axis is anything and whose y axis is Periodic (halo rows =
     periodic images) or Bounded (halo rows = the global parent's rows where it has them, zeros beyond)."""
     assert case.Ny % nranks == 0
-    assert case.mask is None, "slabs of masked cases are not built here"
     ny = case.Ny // nranks
-    c = dataclasses.replace(case, name=case.name + f"-slab{rank}", Ny=ny, Hy=Hy, Ly=case.Ly / nranks, fields={}, metric_arrays=None)
+    c = dataclasses.replace(case, name=case.name + f"-slab{rank}", Ny=ny, Hy=Hy, Ly=case.Ly / nranks, fields={}, metric_arrays=None, mask=None)
     if case.latlon is not None:
         # the slab's rows of the GLOBAL grid's metrics (same expressions per global row index => same bits as on one rank);
         # local row jl = 1-Hy .. ny+Hy+1 is global row rank*ny + jl
@@ -354,6 +362,20 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
             ok = (pj >= 0) & (pj < arr.shape[0])
             out[ok, :] = arr[pj[ok], :]
             c.fields[k] = out
+    if case.latlon is None and case.metric_arrays is not None:
+        # two-dimensional metrics: the slab's rows of the global arrays (local row j is global row rank * ny + j; wrapped
+        # along a Periodic axis, clamped into the global parent beyond a wall, where nothing reads them)
+        jl = np.arange(1 - Hy, ny + Hy + 2) + rank * ny
+        rows = ((jl - 1) % case.Ny) + case.Hy if case.topology[1] == "Periodic" else np.clip(jl - 1 + case.Hy, 0, case.Ny + 2 * case.Hy)
+        c.metric_arrays = {k: np.ascontiguousarray(v[rows, :]) for k, v in case.metric_arrays.items()}
+    if case.mask is not None:   # the immersed mask (centres) travels with the rows; beyond a Bounded parent nothing is immersed
+        if case.topology[1] == "Periodic":
+            c.mask = np.ascontiguousarray(case.mask[case.Hy:case.Hy + case.Ny, :][j % case.Ny, :])
+        else:
+            c.mask = np.zeros((ny + 2 * Hy, case.mask.shape[1]), dtype=np.uint8)
+            pj = j + case.Hy
+            ok = (pj >= 0) & (pj < case.mask.shape[0])
+            c.mask[ok, :] = case.mask[pj[ok], :]
     return c
 
 
@@ -366,8 +388,16 @@ def block_of(case: Case, rank: int, Rx: int, Ry: int, Hx: int, Hy: int) -> Case:
     if Rx == 1:
         return sl
     nx = case.Nx // Rx
-    c = dataclasses.replace(sl, name=case.name + f"-block{rx}.{ry}", Nx=nx, Hx=Hx, Lx=case.Lx / Rx, fields={})
+    c = dataclasses.replace(sl, name=case.name + f"-block{rx}.{ry}", Nx=nx, Hx=Hx, Lx=case.Lx / Rx, fields={}, mask=None)
     i = np.arange(rx * nx - Hx, (rx + 1) * nx + Hx)               # 0-based global interior column of every block column
+    if sl.mask is not None:
+        if case.topology[0] == "Periodic":
+            c.mask = np.ascontiguousarray(sl.mask[:, case.Hx:case.Hx + case.Nx][:, i % case.Nx])
+        else:
+            c.mask = np.zeros((sl.mask.shape[0], nx + 2 * Hx), dtype=np.uint8)
+            pi = i + case.Hx
+            ok = (pi >= 0) & (pi < sl.mask.shape[1])
+            c.mask[:, ok] = sl.mask[:, pi[ok]]
     for k, arr in sl.fields.items():
         if case.topology[0] == "Periodic":
             interior = arr[:, case.Hx:case.Hx + case.Nx]

@@ -13,7 +13,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 entry.load_package()
 from climaseaice_b200 import lib  # noqa: E402
-from climaseaice_b200.synthetic import block_of, periodic_case, slab_of  # noqa: E402
+from climaseaice_b200.synthetic import block_of, coastline_case, curvilinear_case, periodic_case, slab_of  # noqa: E402
 
 
 def main():
@@ -51,6 +51,32 @@ def main():
         recv = [torch.empty_like(first) for _ in range(world)]
         dist.all_gather(recv, first)
         ok &= np.array_equal(east, recv[(rank + 1) % world].numpy())
+    # immersed mask of a partitioned case (BASELINE config 4 in miniature): the slabs' interior rows tile the global mask, and a
+    # slab's halo rows are its neighbours' rows (Bounded y: nothing immersed beyond the global parent)
+    cc = coastline_case(Ny=16 * world, H=7, substeps=K)
+    cs = slab_of(cc, rank, world, Hy)
+    mine = torch.from_numpy(np.ascontiguousarray(cs.mask[Hy:Hy + cs.Ny]))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    ok &= np.array_equal(torch.cat(parts, 0).numpy(), cc.mask[cc.Hy:cc.Hy + cc.Ny])
+    if rank + 1 < world:
+        ok &= np.array_equal(cs.mask[Hy + cs.Ny:], parts[rank + 1].numpy()[:Hy])
+    cb = block_of(cc, rank, world, 1, Hy, Hy)          # the same case cut along its periodic x axis
+    mine = torch.from_numpy(np.ascontiguousarray(cb.mask[Hy:Hy + cb.Ny, Hy:Hy + cb.Nx]))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    ok &= np.array_equal(torch.cat(parts, 1).numpy(), cc.mask[cc.Hy:cc.Hy + cc.Ny, cc.Hx:cc.Hx + cc.Nx])
+    ok &= np.array_equal(cb.mask[Hy:Hy + cb.Ny, Hy + cb.Nx:], parts[(rank + 1) % world].numpy()[:, :Hy])
+    # two-dimensional metrics on y-slabs: local row j of a slab is global row rank * ny + j of the (exactly periodic) global arrays
+    mc = curvilinear_case(24, 16 * world, H=7, substeps=K, topology=("Periodic", "Periodic"))
+    ms = slab_of(mc, rank, world, Hy)
+    for name, G in mc.metric_arrays.items():
+        loc = ms.metric_arrays[name]
+        ok &= loc.shape == (ms.Ny + 2 * Hy + 1, mc.Nx + 2 * mc.Hx + 1)
+        for jl in range(1 - Hy, ms.Ny + Hy + 2):
+            jg = (rank * ms.Ny + jl - 1) % mc.Ny + 1
+            ok &= np.array_equal(loc[jl - 1 + Hy], G[jg - 1 + mc.Hy])
+        ok &= np.array_equal(G[mc.Hy], G[mc.Hy + mc.Ny]) and bool((loc > 0).all())      # face Ny + 1 is face 1
     flag = torch.tensor([0 if ok else 1])
     dist.all_reduce(flag)
     if rank == 0:

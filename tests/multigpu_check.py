@@ -41,6 +41,13 @@ def main():
         case.u_bc_value = 0.0
         for k in ("v", "top_y", "ve"):
             case.fields[k] = np.ascontiguousarray(np.vstack([case.fields[k], case.fields[k][-1:]]))
+    if topo == "coastline":   # BASELINE config 4 in miniature: Periodic x Bounded, immersed coast, linear immersed drag, uniform wind
+        from climaseaice_b200.synthetic import coastline_case
+        case = coastline_case(Ny=24 * Ry, H=7, substeps=10)
+        assert case.Nx % Rx == 0
+    if topo == "curvilinear":  # two-dimensional metrics (orthogonal curvilinear mesh), doubly periodic, general kernels
+        from climaseaice_b200.synthetic import curvilinear_case
+        case = curvilinear_case(64, 32 * Ry, H=7, substeps=10, topology=("Periodic", "Periodic"))
     if topo == "arctic":      # BASELINE config 5 in miniature: lat-lon cap, coupled thermodynamics, zonally periodic, walls in y
         case = arctic_cap_case(96, 24 * world, H=7, substeps=10)
     Hy = max(2 * K + 3, 7)

@@ -29,7 +29,8 @@ def test_slab_partition_logic_gloo_world2():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 10, "periodic"),
-                                            ("unfused", 3, "bounded_y"), ("auto", 4, "bounded_y"), ("auto", 3, "arctic"), ("unfused", 3, "arctic")])
+                                            ("unfused", 3, "bounded_y"), ("auto", 4, "bounded_y"), ("auto", 3, "arctic"), ("unfused", 3, "arctic"),
+                                            ("fused", 3, "coastline"), ("unfused", 3, "coastline"), ("auto", 3, "curvilinear")])
 def test_two_gpus_equal_one_gpu(solver, K, topo):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -39,7 +40,8 @@ def test_two_gpus_equal_one_gpu(solver, K, topo):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 4, "bounded_x"), ("unfused", 3, "bounded_x")])
+@pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 4, "bounded_x"), ("unfused", 3, "bounded_x"),
+                                            ("fused", 3, "coastline"), ("unfused", 3, "coastline")])
 def test_two_gpus_split_along_x_equal_one_gpu(solver, K, topo):
     """Partition(2, 1): packed west/east strips instead of zero-copy rows (test/distributed_tests_utils.jl:60-62 runs (4,1))."""
     if torch.cuda.device_count() < 2:
@@ -50,7 +52,8 @@ def test_two_gpus_split_along_x_equal_one_gpu(solver, K, topo):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("solver,K,topo", [("auto", 3, "periodic"), ("unfused", 3, "periodic"), ("auto", 3, "bounded_x")])
+@pytest.mark.parametrize("solver,K,topo", [("auto", 3, "periodic"), ("unfused", 3, "periodic"), ("auto", 3, "bounded_x"), ("unfused", 3, "bounded_x"),
+                                            ("fused", 3, "coastline"), ("unfused", 3, "coastline")])
 def test_four_gpus_2x2_equal_one_gpu(solver, K, topo):
     """Partition(2, 2): strips, rows and the corners the rows carry (test/distributed_tests_utils.jl:60-62 runs (2,2))."""
     if torch.cuda.device_count() < 4:
