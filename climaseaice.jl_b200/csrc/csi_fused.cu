@@ -1072,6 +1072,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             return false;
         }
     }
+    if (!INTERIOR)
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         // stresses (and aux) of the node this thread updated in phase B
@@ -1266,27 +1267,36 @@ __global__ void k_prep(Params p, int top_const)
     const double a11 = A[o];
     const double m11 = H[o] * p.rho_i * a11;
     p.base[(size_t)F_M * plane + o] = m11;
+#if CSI_PRE_RM2 || CSI_PRE_RMC
     // a divisor the FAST pass may use with a stored reciprocal: inside the range window of MathFast::chkd, low word not all ones
     auto safe = [](double d) {
         return (uint32_t)__double2hiint(d) - MathFast::DLO <= MathFast::DSPAN && (uint32_t)__double2loint(d) != 0xffffffffu;
     };
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
+#endif
     const bool west = c >= 1, south = r >= 1;
     const double m01 = west ? H[o - 1] * p.rho_i * A[o - 1] : 0.0, m10 = south ? H[o - p.pitch] * p.rho_i * A[o - p.pitch] : 0.0;
-    double t1x = 0.0, t1y = 0.0, rmu = -1.0, rmv = -1.0;
+    double t1x = 0.0, t1y = 0.0;
+#if CSI_PRE_RM2
+    double rmu = -1.0, rmv = -1.0;
+#endif
     if (west) {
         const double m2 = m11 + m01, a2 = a11 + A[o - 1];
         const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
         const double tt = !p.use_t1 ? 0.0 : (top_const ? p.ttx : p.base[(size_t)F_TX * plane + o]);
         t1x = (tt / (active_ice ? m2 : 1.0)) * a2;
+#if CSI_PRE_RM2
         rmu = active_ice ? (safe(m2) ? 1.0 / m2 : inf) : -1.0;
+#endif
     }
     if (south) {
         const double m2 = m11 + m10, a2 = a11 + A[o - p.pitch];
         const bool active_ice = (m2 >= p.min_mass2) & (a2 >= p.min_conc2);
         const double tt = !p.use_t1 ? 0.0 : (top_const ? p.tty : p.base[(size_t)F_TY * plane + o]);
         t1y = (tt / (active_ice ? m2 : 1.0)) * a2;
+#if CSI_PRE_RM2
         rmv = active_ice ? (safe(m2) ? 1.0 / m2 : inf) : -1.0;
+#endif
     }
     if (p.use_t1) {
         p.base[(size_t)F_T1X * plane + o] = t1x;
