@@ -155,6 +155,8 @@ def lib():
     L.csi_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.csi_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
     L.csi_exchange_halos.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_void_p]
+    L.csi_exchange_halos_async.argtypes = [H, C.POINTER(csi_array), C.c_int32, C.c_int32, C.c_void_p]
+    L.csi_wait_halos.argtypes = [H, C.c_void_p]
     L.csi_launch_count.restype = C.c_int64
     L.csi_launch_count.argtypes = [H]
     L.csi_fused_stats.argtypes = [H, C.POINTER(C.c_int64)]

@@ -90,6 +90,37 @@ def test_anticyclone_bounded_domain(impl):
     m.close()
 
 
+@pytest.mark.parametrize("impl", ("unfused", "fused"))
+def test_five_time_steps_stay_bitwise(impl):
+    """Round-off does not creep in over several steps: five full time_step! calls (2250 substeps, 15 advection stages) of the
+    Bounded anticyclone case, every prognostic and stress field bit for bit equal to the oracle's after each step."""
+    case = anticyclone_case(56, substeps=150)
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    for step in range(5):
+        m.time_step(case.dt); o.time_step(case.dt)
+        res = compare_model(m, o, case)
+        assert all(same for _, same in res.values()), (step, res)
+    m.close()
+
+
+def test_async_halo_entry_points_on_one_rank():
+    """csi_exchange_halos_async / csi_wait_halos (fill_halo_regions!(...; async = true) / synchronize_communication!, evp:204-206,
+    275-280) are no-ops without a partition; the partitioned behaviour is what the multi-GPU tests compare with one GPU."""
+    import ctypes as C
+    from climaseaice_b200 import _lib as L
+    case = periodic_case(24, substeps=2)
+    m = model_from_case(case)
+    arr = (L.csi_array * 1)(m.all_fields()["s11"].as_csi())
+    lib = L.lib()
+    lib.csi_exchange_halos_async.argtypes = [C.c_void_p, C.POINTER(L.csi_array), C.c_int32, C.c_int32, C.c_void_p]
+    lib.csi_wait_halos.argtypes = [C.c_void_p, C.c_void_p]
+    assert lib.csi_exchange_halos_async(m._handle, arr, 1, 3, m._stream()) == 0
+    assert lib.csi_wait_halos(m._handle, m._stream()) == 0
+    assert lib.csi_exchange_halos_async(m._handle, None, 1, 3, m._stream()) == -1   # CSI_ERR_ARG
+    m.close()
+
+
 def test_anticyclone_config1_as_shipped():
     """examples/ice_advected_by_anticyclone.jl as shipped: 128^2, H = 7, substeps = 150, RK3, WENO7."""
     case = anticyclone_case(128, noise=0.0)

@@ -46,6 +46,38 @@ def test_struct_layout_matches_header(tmp_path):
     assert C.sizeof(L.csi_array) == 24 and C.sizeof(L.csi_fields) == 24 * len(L.FIELD_NAMES) == 24 * 29
 
 
+def test_julia_shim_structs_match_the_ctypes_mirror():
+    """Julia cannot run in this image, so the shim's C-struct mirrors are desk-checked mechanically: `CsiConfig` in
+    julia/ClimaSeaIceB200.jl must list the members of csi_config in the header's order with the matching Julia type, and
+    FIELD_ORDER the 29 members of csi_fields (the ctypes mirror is itself checked against the C compiler above)."""
+    import re
+    from pathlib import Path
+    src = (Path(__file__).resolve().parents[1] / "julia" / "ClimaSeaIceB200.jl").read_text()
+    body = src[src.index("Base.@kwdef struct CsiConfig"):]
+    body = body[:body.index("\nend")]
+    jl = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*::\s*([A-Za-z0-9{}, ]+?)(?=\s*(?:=|;|\n|$))", body)
+    jl = [(n, t.strip()) for n, t in jl]
+    want = []
+    for n, ct in L.csi_config._fields_:
+        if ct is C.c_int32:
+            t = "Int32"
+        elif ct is C.c_double:
+            t = "Float64"
+        elif n == "immersed_mask":
+            t = "Ptr{UInt8}"
+        elif n == "metrics":
+            t = "NTuple{12, Ptr{Float64}}"
+        else:
+            t = "Ptr{Float64}"
+        want.append((n, t))
+    assert jl == want, [(a, b) for a, b in zip(jl, want) if a != b][:3]
+    order = re.search(r"const FIELD_ORDER = \((.*?)\)", src, re.S).group(1)
+    assert tuple(re.findall(r":([A-Za-z0-9_]+)", order)) == tuple(L.FIELD_NAMES)
+    # the drop-in methods have the reference's arities (3-argument time_step_momentum!, no extra handle argument)
+    assert re.search(r"function time_step_momentum!\(model, dynamics::B200Dynamics, Δt\)", src)
+    assert "h::Handle)" not in src
+
+
 def test_correctly_rounded_exp_matches_binary128():
     rng = np.random.default_rng(3)
     xs = np.concatenate([-20 * rng.uniform(0, 1, 20000), rng.uniform(-700, 700, 5000), [0.0, -0.0, 1.0, -1.0, -20.0, 709.0, -744.0]])
