@@ -1011,6 +1011,19 @@ static int download(csi_handle *h, const csi_fields *hf, const int *which, int n
     }
     return CSI_OK;
 }
+// An array the call rewrites only on the interior and its first ring (alpha: a diagnostic without halo fill): that window is
+// copied back and the rest of the host array is left as it is, so the array need not be uploaded to preserve its halo.
+static int download_window(csi_handle *h, const csi_fields *hf, int k, cudaStream_t s)
+{
+    const csi_array &a = field_at(*hf, k);
+    if (!a.ptr) return CSI_OK;
+    const int i0 = std::max(a.off_x - 1, 0), i1 = std::min(a.off_x + h->cfg.Nx + 1, a.nx_tot);  // columns [i0, i1)
+    const int j0 = std::max(a.off_y - 1, 0), j1 = std::min(a.off_y + h->cfg.Ny + 1, a.ny_tot);
+    const size_t pitch = (size_t)a.nx_tot * sizeof(double), off = (size_t)j0 * a.nx_tot + i0;
+    CSI_CUDA(h, cudaMemcpy2DAsync(a.ptr + off, pitch, h->mirror[k] + off, pitch, (size_t)(i1 - i0) * sizeof(double), (size_t)(j1 - j0), cudaMemcpyDeviceToHost, s));
+    h->last_d2h += (size_t)(i1 - i0) * (j1 - j0) * sizeof(double);
+    return CSI_OK;
+}
 
 int csi_time_step_host(csi_handle *h, const csi_fields *hf, double dt, int32_t nsteps, int32_t first)
 {
@@ -1047,8 +1060,11 @@ int csi_evp_substeps_host(csi_handle *h, const csi_fields *hf, double dt_stage, 
     if (!h->own_stream) CSI_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     cudaStream_t s = h->own_stream;
     csi_fields dev;
-    // inputs of time_step_momentum!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17), and Psi^-.u, .v (22, 23) under RK3
-    const uint32_t in_mask = 0x7fu | (1u << 10) | (0xfu << 14) | (3u << K_FDU) | (h->cfg.timestepper == CSI_RK3 ? (0x3u << 22) : 0u);
+    // inputs of time_step_momentum!: u v h a s11 s22 s12 (0-6), top_x top_y ue ve (14-17), the free-drift arrays, and Psi^-.u, .v
+    // (22, 23) under RK3 -- where reset_velocities! (se:87-93) overwrites u, v with them before anything reads u, v, so those two
+    // are not uploaded.  alpha is written, not read: only the window the call rewrites comes back (download_window).
+    const bool reset = h->cfg.timestepper == CSI_RK3 && field_at(*hf, 22).ptr && field_at(*hf, 23).ptr;
+    const uint32_t in_mask = (reset ? 0x7cu : 0x7fu) | (0xfu << 14) | (3u << K_FDU) | (reset ? (0x3u << 22) : 0u);
     h->last_h2d = h->last_d2h = 0;
     int rc = upload_all(h, hf, &dev, s, in_mask, &h->last_h2d);
     if (rc) return rc;
@@ -1058,8 +1074,9 @@ int csi_evp_substeps_host(csi_handle *h, const csi_fields *hf, double dt_stage, 
         Timed t(h, s);
         if ((rc = momentum_impl(h, df, dt_stage, nsubsteps, s))) return rc;
     }
-    const int outs[] = {0, 1, 4, 5, 6, 10};  // u v s11 s22 s12 alpha
-    if ((rc = download(h, hf, outs, 6, s))) return rc;
+    const int outs[] = {0, 1, 4, 5, 6};  // u v s11 s22 s12; alpha: the window the call rewrites
+    if ((rc = download(h, hf, outs, 5, s))) return rc;
+    if ((rc = download_window(h, hf, 10, s))) return rc;
     CSI_CUDA(h, cudaStreamSynchronize(s));
     return CSI_OK;
 }

@@ -144,6 +144,35 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     m.close(); hs.model.close()
 
 
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_host_buffer_momentum_entry_point_matches_device_entry_point(timestepper):
+    """csi_evp_substeps_host == csi_evp_substeps.  Under RK3 the host call does not upload u, v (reset_velocities! overwrites
+    them with Psi^-.u, .v, se:87-93) nor alpha (written, never read; only the rewritten window comes back): poison those host
+    arrays to prove they are not read."""
+    case = anticyclone_case(40, substeps=12, timestepper=timestepper)
+    m = model_from_case(case)
+    hs = HostStepper(case)
+    m.update_state(); hs.model.update_state()
+    if timestepper == "SplitRungeKutta3":
+        m.cache_current_fields()
+        for n in ("u", "v"):
+            hs.host[n + "m"].copy_(hs.model.all_fields()[n].parent)    # Psi^- = the state update_state! left on the device
+    for n in ("u", "v", "h", "a"):                                      # the halos update_state! filled, as a host caller holds them
+        hs.host[n].copy_(hs.model.all_fields()[n].parent)
+    if timestepper == "SplitRungeKutta3":
+        hs.host["u"].fill_(float("nan")); hs.host["v"].fill_(float("nan"))
+    hs.host["alpha"].fill_(float("nan"))
+    m.time_step_momentum(case.dt)
+    hs.evp_substeps(case.dt, case.substeps)
+    torch.cuda.synchronize()
+    for n in ("u", "v", "s11", "s22", "s12", "alpha"):
+        g, w = interior_of(m.all_fields()[n].numpy(), case), interior_of(hs.host[n].numpy(), case)
+        assert np.isfinite(w).all() and np.array_equal(g, w), n
+    h2d, d2h = hs.last_transfer_bytes()
+    assert h2d == sum(hs.host[k].numel() * 8 for k in (("h", "a", "s11", "s22", "s12", "top_x", "top_y", "ue", "ve") + (("um", "vm") if timestepper == "SplitRungeKutta3" else ("u", "v")))), h2d
+    m.close(); hs.model.close()
+
+
 def test_diagnostics_and_cfl():
     case = periodic_case(64, substeps=10, aice="mixed")
     m = model_from_case(case)
