@@ -24,7 +24,7 @@
 //     which replaces the two halo-fill launches per substep.
 //   * Arithmetic is bit-exact (compiled with -fmad=false).  The FAST pass uses branch-free, correctly rounded
 //     division / reciprocal / square root built from FMAs and a power-of-two-scaled form of the reference's expression
-//     trees (see MathFast and the comment above u_node_s); its premises are enforced by range validation of all inputs
+//     trees (see MathFast and the comment above vel_node_s); its premises are enforced by range validation of all inputs
 //     once per stage (k_pack) and by window tests on the quotients and radicands that carry the state forward.  A tile
 //     whose operands leave the windows is recomputed with plain IEEE operators and the reference's own trees (MathSlow);
 //     csi_fused_stats reports how often that happened.
@@ -71,15 +71,15 @@ enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, 
        F_H, F_A, F_P, F_UN, F_VN, F_TX, F_TY, F_UE, F_VE, F_ALPHA, F_ZC, F_ZF, F_DELTA,
        // stage constants written once per stage by k_prep (see there): ice mass, and the top-stress term of the velocity
        // tendencies (tau_top / m_i * aice_i at u and v nodes)
-       F_M, F_T1X, F_T1Y,
-       // optional stage constants (compile-time switches CSI_PRE_*): reciprocals of the face-mass sums at u / v nodes (with the
-       // marginal-ice decision folded in), of the centre mass and of the corner mass sum, the corner sum of P, and the
-       // 4-point sums of the ocean velocity at u / v nodes
-       F_RM2U, F_RM2V, F_RMC, F_RMF, F_PF4, F_SVE, F_SUE,
+       F_M, F_T1X, F_T1Y, NF_COMMON,
        // stage constants of the less common configurations (k_prep): the value of nodes that are not dynamically active
        // (marginal ice ? free-drift velocity : 0), the bottom term tau_bot / m_i * aice_i of a prescribed bottom stress, the
        // 4-point sums of the atmosphere velocity of a top SemiImplicitStress, and the packed free-drift arrays
-       F_UFD, F_VFD, F_TB1X, F_TB1Y, F_SVA, F_SUA, F_FDU, F_FDV, NF };
+       F_UFD = NF_COMMON, F_VFD, F_TB1X, F_TB1Y, F_SVA, F_SUA, F_FDU, F_FDV, NF_GEN,
+       // optional stage constants (compile-time switches CSI_PRE_*, measured and rejected: DESIGN.md section 5.1): reciprocals of
+       // the face-mass sums at u / v nodes (with the marginal-ice decision folded in), of the centre mass and of the corner mass
+       // sum, the corner sum of P, and the 4-point sums of the ocean velocity at u / v nodes
+       F_RM2U = NF_GEN, F_RM2V, F_RMC, F_RMF, F_PF4, F_SVE, F_SUE, NF };
 #ifndef CSI_PRE_RM2
 #define CSI_PRE_RM2 0
 #endif
@@ -1255,7 +1255,7 @@ __global__ void k_pack(const __grid_constant__ PackList L, const __grid_constant
 // Stage constants of the substep loop, written once per time_step_momentum! (h, aice, tau_top do not change inside it):
 //   F_M    m = h rho aice at every node (ClimaSeaIce.jl:42; the reference recomputes it at every use)
 //   F_T1X  the top-stress term of the u tendency, tau_x / m_i * aice_i (mt:33, ext:176-181) in the FAST pass's scaled form
-//          (tau_x / 2 m_i') * 2 aice_i with m_i' the harmless mass of marginal nodes -- the very operations u_node_s used to
+//          (tau_x / 2 m_i') * 2 aice_i with m_i' the harmless mass of marginal nodes -- the very operations the node function used to
 //          repeat every substep, so the bits are the same; F_T1Y likewise for v.
 // The IEEE pass keeps reading the raw stress.
 __global__ void k_prep(Params p, int top_const)
@@ -1337,7 +1337,9 @@ __global__ void k_prep(Params p, int top_const)
         const double *DX_ = p.base + (size_t)(d_bot ? F_UE : F_TX) * plane, *DY_ = p.base + (size_t)(d_bot ? F_VE : F_TY) * plane;
         const double ocx = d_bot ? p.ta_x : p.tb_x, ocy = d_bot ? p.ta_y : p.tb_y, dcx = d_bot ? p.ue_c : p.ta_x, dcy = d_bot ? p.ve_c : p.ta_y;
         const double Cdrag = d_bot ? p.rhoCd : p.top_rhoCd;
-        // x/y_momentum_stress of the side that is not a SemiImplicitStress: explicit stress - zero * velocity (ext:34-38)
+        // x/y_momentum_stress of the side that is not a SemiImplicitStress: explicit stress - zero * velocity (ext:34-38).  The
+        // velocity is the stage's first; the product is +-0 and only decides the sign of a stress that is exactly -0 where the
+        // drag side's velocity is exactly 0 too -- the one place where the reference's per-substep evaluation could differ
         auto xms = [&](size_t q) { return (o_kind == CSI_STRESS_NONE ? 0.0 : (o_arr ? OX_[q] : ocx)) - 0.0 * U0[q]; };
         auto yms = [&](size_t q) { return (o_kind == CSI_STRESS_NONE ? 0.0 : (o_arr ? OY_[q] : ocy)) - 0.0 * V0[q]; };
         double ufd = 0.0, vfd = 0.0;
@@ -1427,6 +1429,7 @@ struct FusedPlan {
     double *base = nullptr;
     int pitch = 0, rows = 0, oy = 0;
     CUtensorMap tmap;
+    int nf = 0;             // planes allocated: the common set, + those of the less common configurations, + the experiments'
     int Nx = 0, Ny = 0;
 };
 
@@ -1480,10 +1483,12 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     return 1;
 }
 
-FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
+FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
 {
     using namespace fz;
     FusedPlan *pl = new FusedPlan();
+    const bool gen_planes = prm.fd_kind != CSI_FD_NONE || prm.top_kind == CSI_STRESS_SEMI_IMPLICIT || prm.bot_kind == CSI_STRESS_CONST || prm.bot_kind == CSI_STRESS_FIELD;
+    pl->nf = (CSI_PRE_RM2 || CSI_PRE_RMC || CSI_PRE_PF4 || CSI_PRE_SVE) ? (int)NF : (gen_planes ? (int)NF_GEN : (int)NF_COMMON);
     pl->Nx = g.Nx;
     pl->Ny = g.Ny;
     pl->oy = (g.conn_s || g.conn_n) ? g.Hy : W + 1;
@@ -1492,7 +1497,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     pl->pitch = ((OX + g.Nx + 1 + wx + 1 + 15) / 16) * 16;
     pl->rows = g.Ny + 2 * pl->oy + 1;
     if ((double)pl->pitch * (double)pl->rows >= 2147483647.0) { snprintf(err, nerr, "fused solver: block too large for 32-bit in-plane offsets"); delete pl; return nullptr; }
-    const size_t bytes = (size_t)NF * pl->pitch * pl->rows * sizeof(double);
+    const size_t bytes = (size_t)pl->nf * pl->pitch * pl->rows * sizeof(double);
     cudaError_t e = cudaMalloc(&pl->base, bytes);
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
     cudaMemset(pl->base, 0, bytes);
@@ -1556,7 +1561,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &, char *err, int nerr)
     }
     EncodeTiledFn enc = get_encode();
     if (!enc) { snprintf(err, nerr, "cuTensorMapEncodeTiled unavailable"); cudaFree(pl->base); delete pl; return nullptr; }
-    cuuint64_t dims[3] = {(cuuint64_t)pl->pitch, (cuuint64_t)pl->rows, (cuuint64_t)NF};
+    cuuint64_t dims[3] = {(cuuint64_t)pl->pitch, (cuuint64_t)pl->rows, (cuuint64_t)pl->nf};
     cuuint64_t strides[2] = {(cuuint64_t)pl->pitch * 8, (cuuint64_t)pl->pitch * pl->rows * 8};
     cuuint32_t box[3] = {(cuuint32_t)SXD, (cuuint32_t)SYD, 1};
     cuuint32_t estr[3] = {1, 1, 1};
