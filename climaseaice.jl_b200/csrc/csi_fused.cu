@@ -554,7 +554,17 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // ---- TMA: tile + halo of every stencil field; u, v first (phase A starts on them) ----
     if (tid == 0) {
         const int x = tc.I0 - 2 - 1 + OX, y = tc.J0 - 2 - 1 + p.oy;
-        auto ld = [&](int arr, int field, uint64_t *b) { tma_load_row(sm + arr * ASTRIDE, tmap, b, x, y, field); };
+#ifdef CSI_EXPERIMENT_CONST_L2
+        // timing experiment only (wrong results): every tile reads its stage constants from a 4 x 4-tile patch that stays in L2,
+        // i.e. the kernel as it would run if those 72 B per cell-update never came from HBM
+        const int xk = OX - 2 + OUTX * (blockIdx.x % 4), yk = p.oy - 3 + OUTY * (blockIdx.y % 4);   // (even column: 16-byte aligned box)
+#else
+        const int xk = x, yk = y;
+#endif
+        auto ld = [&](int arr, int field, uint64_t *b) {
+            const bool cst = field == F_M || field == F_A || field == F_P || field == F_UE || field == F_VE;
+            tma_load_row(sm + arr * ASTRIDE, tmap, b, cst ? xk : x, cst ? yk : y, field);
+        };
         ld(A_U, tc.fin + 0, &bar[0]);
         ld(A_V, tc.fin + 1, &bar[0]);
         mbar_expect_tx(&bar[0], 2u * SXD * SYD * sizeof(double));
@@ -573,11 +583,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         mbar_expect_tx(&bar[1], (uint32_t)n * SXD * SYD * sizeof(double));
 #ifndef CSI_EXPERIMENT_NO_PREFETCH
         // pull the pointwise inputs of phases C / D towards L2 while the tile lands and A, B run
-        tma_prefetch_box(tmap, x, y, F_UN);
-        tma_prefetch_box(tmap, x, y, F_VN);
+        tma_prefetch_box(tmap, xk, yk, F_UN);
+        tma_prefetch_box(tmap, xk, yk, F_VN);
         if (M::SCALED ? (GEN ? p.use_t1 != 0 : true) : use_top) {
-            tma_prefetch_box(tmap, x, y, M::SCALED ? F_T1X : F_TX);
-            tma_prefetch_box(tmap, x, y, M::SCALED ? F_T1Y : F_TY);
+            tma_prefetch_box(tmap, xk, yk, M::SCALED ? F_T1X : F_TX);
+            tma_prefetch_box(tmap, xk, yk, M::SCALED ? F_T1Y : F_TY);
         }
         if (M::SCALED && CSI_PRE_RMC) { tma_prefetch_box(tmap, x, y, F_RMC); tma_prefetch_box(tmap, x, y, F_RMF); }
         if (M::SCALED && CSI_PRE_PF4) tma_prefetch_box(tmap, x, y, F_PF4);
@@ -598,6 +608,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     const bool d_on[2] = {lane < OUTX && d_sy0 <= OUTY, lane < OUTX && d_sy0 + 1 <= OUTY};
     // offsets inside one plane fit 32 bits (pitch x rows < 2^31 doubles is checked when the plan is built)
     const int o00 = (tc.J0 - 2 + p.oy) * p.pitch + (tc.I0 - 2 + OX);  // node (sx, sy) = (0, 0)
+#ifdef CSI_EXPERIMENT_CONST_L2
+    const int o00k = (p.oy - 2 + OUTY * (int)(blockIdx.y % 4)) * p.pitch + (OX - 1 + OUTX * (int)(blockIdx.x % 4));
+#else
+    const int o00k = o00;
+#endif
     auto goff = [&](int sx, int sy) -> int {
         // clamped into the plane: edge tiles reach past the allocation (those nodes are never stored)
         const int row = min(max(tc.J0 - 1 + sy - 1 + p.oy, 0), p.rows - 1), col = min(max(tc.I0 - 1 + sx - 1 + OX, 0), p.pitch - 1);
@@ -608,8 +623,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     const bool use_t = M::SCALED ? (GEN ? p.use_t1 != 0 : true) : use_top;
     uint32_t c_g[2], d_g[2];
     if (INTERIOR) {
-        c_g[0] = o00 + c_sy0 * p.pitch + c_sx;
-        d_g[0] = o00 + d_sy0 * p.pitch + d_sx;
+        c_g[0] = o00k + c_sy0 * p.pitch + c_sx;
+        d_g[0] = o00k + d_sy0 * p.pitch + d_sx;
         c_g[1] = c_g[0] + p.pitch;
         d_g[1] = d_g[0] + p.pitch;
     } else {
@@ -1065,8 +1080,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                     }
                 }
                 if (d_on[q]) {  // node (lane + 1, 2 wrp + 1 + q): the offset the pointwise inputs of phase D were read at
-                    p.o_d[d_g[q]] = w2[q];
-                    p.o_c[d_g[q]] = S(AW, d_sx, d_sy0 + q);
+                    const uint32_t dg = d_g[q] + (uint32_t)(o00 - o00k);   // (o00k == o00 outside the timing experiment)
+                    p.o_d[dg] = w2[q];
+                    p.o_c[dg] = S(AW, d_sx, d_sy0 + q);
                 }
             }
             return false;
