@@ -20,8 +20,8 @@ using Oceananigans.Architectures: architecture
 using Oceananigans.BoundaryConditions: BoundaryCondition, Value
 using Oceananigans.Coriolis: FPlane, HydrostaticSphericalCoriolis, fᶠᶠᵃ
 using Oceananigans.DistributedComputations: Distributed
-using Oceananigans.Grids: halo_size, topology, Periodic, Bounded, LeftConnected, RightConnected, FullyConnected
-using Oceananigans.ImmersedBoundaries: ImmersedBoundaryGrid, inactive_cell
+using Oceananigans.Grids: halo_size, topology, inactive_cell, Periodic, Bounded, LeftConnected, RightConnected, FullyConnected
+using Oceananigans.ImmersedBoundaries: ImmersedBoundaryGrid
 using Oceananigans.Models: update_model_field_time_series!
 using Oceananigans.Operators
 using Oceananigans.TimeSteppers: SplitRungeKuttaTimeStepper
