@@ -93,7 +93,10 @@ enum { F_U0 = 0, F_V0, F_S11_0, F_S22_0, F_S12_0, F_U1, F_V1, F_S11_1, F_S22_1, 
 #define CSI_PRE_SVE 0
 #endif
 // shared-memory arrays (each SXD x SYD doubles)
-enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_E11, A_E22, A_E12, A_AL, A_W, NARR };
+// (order matters in one place: the branch-free strain-rate sweep of phase A reads one row above / one column left of the tile in
+// the u / dx and v / dx arrays, which live in the slots of A_AL and A_W -- i.e. the tail of whatever array precedes them; A_AL
+// therefore follows an array nothing writes during that sweep, and A_W only ever reaches the unused padding of its predecessor)
+enum { A_U = 0, A_V, A_H, A_A, A_P, A_S11, A_S22, A_S12, A_UE, A_VE, A_AL, A_E11, A_E22, A_E12, A_W, NARR };
 
 constexpr size_t SMEM_BYTES = (size_t)NARR * ASTRIDE * sizeof(double) + 64 + ((SXD * SYD + 63) / 64) * 64;  // + two mbarriers + node flags
 
