@@ -5,7 +5,7 @@ modules here are the host-side mirror of the reference's user interface for that
 """
 from . import _lib
 from ._lib import CsiError, lib
-from .model import (Bounded, Center, ConductiveFlux, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, HydrostaticSphericalCoriolis,
+from .model import (Bounded, Folded, Center, ConductiveFlux, ElastoViscoPlasticRheology, FPlane, Face, Field, Flat, HydrostaticSphericalCoriolis,
                     IceWaterThermalEquilibrium, LatitudeLongitudeGrid, LinearHeatFlux, OrthogonalSphericalShellGrid, MeltingConstrainedFluxBalance, Periodic,
                     PhaseTransitions, PrescribedTemperature, RadiativeEmission, RectilinearGrid, SeaIceModel,
                     SeaIceMomentumEquation, SemiImplicitStress, SlabThermodynamics, SplitExplicitSolver,

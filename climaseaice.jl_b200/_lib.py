@@ -14,7 +14,7 @@ import os
 LIB_PATH = Path(os.environ.get("CSI_B200_LIB", str(_HERE / "libclimaseaice_b200.so")))  # override only for kernel-variant experiments
 
 ABI_VERSION = 1
-PERIODIC, BOUNDED = 0, 1
+PERIODIC, BOUNDED, FOLDED = 0, 1, 2
 STRESS_NONE, STRESS_CONST, STRESS_FIELD, STRESS_SEMI_IMPLICIT = 0, 1, 2, 3
 REPLACEMENT_PRESSURE, ICE_STRENGTH = 0, 1
 CORIOLIS_NONE, CORIOLIS_FPLANE, CORIOLIS_SPHERICAL = 0, 1, 2
@@ -64,6 +64,8 @@ class csi_config(C.Structure):
         ("metric_kind", C.c_int32), ("serial_exchange", C.c_int32), ("metrics", C.POINTER(C.c_double) * 12),
         ("free_drift_kind", C.c_int32), ("reserved3_", C.c_int32), ("top_rho_e", C.c_double), ("top_Cd", C.c_double),
         ("coriolis_f_ff", C.POINTER(C.c_double)),
+        ("fold_target", C.POINTER(C.c_int32) * 4), ("fold_source", C.POINTER(C.c_int32) * 4), ("fold_count", C.c_int32 * 4),
+        ("fold_sign_velocity", C.c_double), ("fold_sign_external", C.c_double),
     ]
 
 

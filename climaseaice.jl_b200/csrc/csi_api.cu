@@ -84,6 +84,7 @@ struct csi_handle {
     uint8_t *mask_dev = nullptr;
     double *met_dev = nullptr;
     double *fff_dev = nullptr;
+    std::vector<int32_t *> fold_dev;
     std::vector<uint8_t> mask_host;
     std::vector<double> met_host, fff_host;
     FusedPlan *fused = nullptr;
@@ -153,7 +154,7 @@ int check_array(csi_handle *h, const csi_array &a, const FieldInfo &fi, bool req
     const csi_config &c = h->cfg;
     // Face fields carry N+1 points along a Bounded axis, except along a partitioned axis (the wall point lives in the halo)
     const int ex = c.Nx + 2 * c.Hx + ((fi.lx && c.topo_x == CSI_BOUNDED && h->Rx == 1) ? 1 : 0);
-    const int ey = c.Ny + 2 * c.Hy + ((fi.ly && c.topo_y == CSI_BOUNDED && h->nranks == 1) ? 1 : 0);
+    const int ey = c.Ny + 2 * c.Hy + ((fi.ly && (c.topo_y == CSI_BOUNDED || c.topo_y == CSI_FOLDED) && h->nranks == 1) ? 1 : 0);
     if (a.nx_tot != ex || a.ny_tot != ey || a.off_x != c.Hx || a.off_y != c.Hy) {
         char buf[256];
         snprintf(buf, sizeof buf, "field '%s': parent %dx%d offsets (%d,%d), expected %dx%d offsets (%d,%d)", fi.name, a.nx_tot,
@@ -322,12 +323,12 @@ int momentum_impl(csi_handle *h, const DFields &f, double dt, int nsub, cudaStre
     launch_initialize_rheology(c, g, p, f);  // evp.jl:192-216
     // update_external_stress!  ext.jl:72-78,148-152
     if (p.top_kind == CSI_STRESS_FIELD || p.top_kind == CSI_STRESS_SEMI_IMPLICIT) {
-        launch_fill_halo(c, g, p, f.top_x, 1, 0, 0);
-        launch_fill_halo(c, g, p, f.top_y, 0, 1, 0);
+        launch_fill_halo(c, g, p, f.top_x, 1, 0, 3);
+        launch_fill_halo(c, g, p, f.top_y, 0, 1, 3);
     }
     if (p.bot_kind == CSI_STRESS_FIELD || p.bot_kind == CSI_STRESS_SEMI_IMPLICIT) {
-        launch_fill_halo(c, g, p, f.ue, 1, 0, 0);
-        launch_fill_halo(c, g, p, f.ve, 0, 1, 0);
+        launch_fill_halo(c, g, p, f.ue, 1, 0, 3);
+        launch_fill_halo(c, g, p, f.ve, 0, 1, 3);
     }
     launch_fill_halo(c, g, p, f.u, 1, 0, 1);  // se.jl:170-171
     launch_fill_halo(c, g, p, f.v, 0, 1, 2);
@@ -548,7 +549,7 @@ int exchange_slab_halos(csi_handle *h, const DArr *arrs, int n, int width, cudaS
     const DGrid &g = h->g;
     // conn_* already encode the topology: a Bounded axis has no wrap-around neighbour
     const int south = g.conn_s ? ((h->ry + h->Ry - 1) % h->Ry) * h->Rx + h->rx : -1;
-    const int north = g.conn_n ? ((h->ry + 1) % h->Ry) * h->Rx + h->rx : -1;
+    const int north = (g.conn_n && !g.fold) ? ((h->ry + 1) % h->Ry) * h->Rx + h->rx : -1;  // (a fold is filled locally)
     const int west = g.conn_w ? h->ry * h->Rx + (h->rx + h->Rx - 1) % h->Rx : -1;
     const int east = g.conn_e ? h->ry * h->Rx + (h->rx + 1) % h->Rx : -1;
     if (west >= 0 || east >= 0) {
@@ -632,8 +633,35 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     if (cfg->advection_order != 0 && cfg->advection_order != 1 && cfg->advection_order != 3 && cfg->advection_order != 5 && cfg->advection_order != 7)
         return fail(nullptr, CSI_ERR_ARG, "csi_create: advection_order must be 0, 1, 3, 5 or 7");
     if (cfg->Hx < B || cfg->Hy < B) return fail(nullptr, CSI_ERR_ARG, "csi_create: halo smaller than the advection stencil");
-    if ((cfg->topo_x != CSI_PERIODIC && cfg->topo_x != CSI_BOUNDED) || (cfg->topo_y != CSI_PERIODIC && cfg->topo_y != CSI_BOUNDED))
-        return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED");
+    if ((cfg->topo_x != CSI_PERIODIC && cfg->topo_x != CSI_BOUNDED) || (cfg->topo_y != CSI_PERIODIC && cfg->topo_y != CSI_BOUNDED && cfg->topo_y != CSI_FOLDED))
+        return fail(nullptr, CSI_ERR_ARG, "csi_create: topology must be CSI_PERIODIC or CSI_BOUNDED (topo_y: or CSI_FOLDED)");
+    if (cfg->topo_y == CSI_FOLDED) {
+        // the north fold of a tripolar grid: copy lists for the four locations, indices inside a parent of that location
+        if (cfg->partition_x > 1) return fail(nullptr, CSI_ERR_UNSUPPORTED, "csi_create: a folded grid with a partition along x (the fold mirrors columns across ranks)");
+        const int part = cfg->nranks > 1;
+        const bool holder = !part || cfg->rank == cfg->nranks - 1;   // y-slabs: the last one holds the fold, the others ignore the lists
+        for (int loc = 0; holder && loc < 4; loc++) {
+            const int lx = loc & 1, ly = loc >> 1;
+            const long ex = cfg->Nx + 2 * cfg->Hx + ((lx && cfg->topo_x == CSI_BOUNDED) ? 1 : 0), ey = cfg->Ny + 2 * cfg->Hy + ((ly && !part) ? 1 : 0);
+            if (cfg->fold_count[loc] < 0 || (cfg->fold_count[loc] > 0 && (!cfg->fold_target[loc] || !cfg->fold_source[loc])))
+                return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_FOLDED needs fold_target / fold_source for every location with fold_count > 0");
+            for (int k = 0; k < cfg->fold_count[loc]; k++)
+                if (cfg->fold_target[loc][k] < 0 || cfg->fold_target[loc][k] >= ex * ey || cfg->fold_source[loc][k] < 0 || cfg->fold_source[loc][k] >= ex * ey)
+                    return fail(nullptr, CSI_ERR_ARG, "csi_create: a fold index lies outside the parent array of its location");
+            // the copies of one list run concurrently: every target is written once, and nothing that is read is also written
+            std::vector<char> role((size_t)(ex * ey), 0);
+            for (int k = 0; k < cfg->fold_count[loc]; k++) {
+                if (role[cfg->fold_target[loc][k]]) return fail(nullptr, CSI_ERR_ARG, "csi_create: a fold copy list names the same target twice");
+                role[cfg->fold_target[loc][k]] = 1;
+            }
+            for (int k = 0; k < cfg->fold_count[loc]; k++)
+                if (role[cfg->fold_source[loc][k]]) return fail(nullptr, CSI_ERR_ARG, "csi_create: a fold copy list reads an element that it also writes (order-dependent)");
+        }
+        if (holder && (cfg->fold_count[0] == 0 || cfg->fold_count[1] == 0 || cfg->fold_count[2] == 0 || cfg->fold_count[3] == 0))
+            return fail(nullptr, CSI_ERR_ARG, "csi_create: CSI_FOLDED needs a copy list for each of the four locations");
+        if (holder && (!(cfg->fold_sign_velocity == 1.0 || cfg->fold_sign_velocity == -1.0) || !(cfg->fold_sign_external == 1.0 || cfg->fold_sign_external == -1.0)))
+            return fail(nullptr, CSI_ERR_ARG, "csi_create: fold signs must be +1 or -1");
+    }
     if (cfg->metric_kind != CSI_METRIC_REGULAR && cfg->metric_kind != CSI_METRIC_J && cfg->metric_kind != CSI_METRIC_IJ)
         return fail(nullptr, CSI_ERR_ARG, "csi_create: metric_kind must be CSI_METRIC_REGULAR, CSI_METRIC_J or CSI_METRIC_IJ");
     if (cfg->metric_kind == CSI_METRIC_IJ) {
@@ -658,7 +686,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
             // over the widened range of se:40-46 and divide by the metrics of every halo row of a connected side
             const int Ry_ = cfg->nranks > 1 ? cfg->nranks / (cfg->partition_x > 1 ? cfg->partition_x : 1) : 1;
             const int ry_ = cfg->nranks > 1 ? cfg->rank / (cfg->partition_x > 1 ? cfg->partition_x : 1) : 0;
-            const bool cs = Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ > 0), cn = Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ < Ry_ - 1);
+            const bool cs = Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ > 0), cn = (Ry_ > 1 && (cfg->topo_y == CSI_PERIODIC || ry_ < Ry_ - 1)) || cfg->topo_y == CSI_FOLDED;
             for (int j = cs ? 1 - cfg->Hy : 0; j <= (cn ? cfg->Ny + cfg->Hy + 1 : cfg->Ny + 2); j++)
                 if (j - 1 + cfg->Hy >= 0 && j - 1 + cfg->Hy < L && !(cfg->metrics[k][j - 1 + cfg->Hy] > 0)) return fail(nullptr, CSI_ERR_ARG, "csi_create: grid metrics must be positive on every row the kernels touch (halo rows of connected sides included)");
         }
@@ -699,7 +727,8 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     cudaSetDevice(cfg->device);
     DGrid &g = h->g;
     g.Nx = cfg->Nx; g.Ny = cfg->Ny; g.Hx = cfg->Hx; g.Hy = cfg->Hy;
-    g.topo_x = cfg->topo_x; g.topo_y = cfg->topo_y;
+    g.topo_x = cfg->topo_x;
+    g.topo_y = cfg->topo_y == CSI_FOLDED ? CSI_BOUNDED : cfg->topo_y;  // a folded axis: a wall in the south, no wall in the north
     // partition Rx x Ry, rank = ry * Rx + rx: a side is "connected" when another rank owns the cells beyond it
     h->Rx = h->nranks > 1 ? Rx : 1;
     h->Ry = h->nranks / h->Rx;
@@ -707,6 +736,18 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     h->ry = h->rank / h->Rx;
     g.conn_s = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry > 0);
     g.conn_n = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry < h->Ry - 1);
+    g.fold = 0;
+    for (int loc = 0; loc < 4; loc++) { g.fold_t[loc] = g.fold_s[loc] = nullptr; g.fold_n[loc] = 0; }
+    g.fold_sv = g.fold_se = 1.0;
+    if (cfg->topo_y == CSI_FOLDED && !g.conn_n) {
+        // the rank that holds the fold: its north side is connected -- to itself, through the copy lists -- not a wall.  The general
+        // kernels then run over the widened window of a connected side (se:40-46); what they compute in the north halo rows
+        // is overwritten by the fold fill that follows every velocity update, exactly as a distributed fill would overwrite it
+        g.conn_n = 1;
+        g.fold = 1;
+        g.fold_sv = cfg->fold_sign_velocity;
+        g.fold_se = cfg->fold_sign_external;
+    }
     g.conn_w = h->Rx > 1 && (cfg->topo_x == CSI_PERIODIC || h->rx > 0);
     g.conn_e = h->Rx > 1 && (cfg->topo_x == CSI_PERIODIC || h->rx < h->Rx - 1);
     g.dx = cfg->dx; g.dy = cfg->dy; g.az = cfg->dx * cfg->dy;
@@ -794,6 +835,21 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         g.fff_host = h->fff_host.data();
         h->cfg.coriolis_f_ff = nullptr;
     }
+    if (g.fold) {
+        for (int loc = 0; loc < 4; loc++) {
+            const size_t nb = sizeof(int32_t) * (size_t)cfg->fold_count[loc];
+            int32_t *t = nullptr, *s = nullptr;
+            if ((e = cudaMalloc(&t, nb)) != cudaSuccess || (e = cudaMalloc(&s, nb)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(fold lists)"); }
+            cudaMemcpy(t, cfg->fold_target[loc], nb, cudaMemcpyDefault);
+            cudaMemcpy(s, cfg->fold_source[loc], nb, cudaMemcpyDefault);
+            h->fold_dev.push_back(t);
+            h->fold_dev.push_back(s);
+            g.fold_t[loc] = t;
+            g.fold_s[loc] = s;
+            g.fold_n[loc] = cfg->fold_count[loc];
+        }
+    }
+    for (int loc = 0; loc < 4; loc++) h->cfg.fold_target[loc] = h->cfg.fold_source[loc] = nullptr;  // the caller's arrays are not retained
     h->mirror.assign(NFIELDS, nullptr);
     h->mirror_n.assign(NFIELDS, 0);
     *out = h;
@@ -807,6 +863,7 @@ int csi_destroy(csi_handle *h)
     if (h->fused) fused_destroy(h->fused);
     if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
     for (double *m : h->mirror) if (m) cudaFree(m);
+    for (int32_t *q : h->fold_dev) if (q) cudaFree(q);
     if (h->xbuf) cudaFree(h->xbuf);
     if (h->agree_dev) cudaFree(h->agree_dev);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);

@@ -1470,6 +1470,7 @@ static EncodeTiledFn get_encode()
 
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
+    if (g.fold) { snprintf(why, nwhy, "a folded (tripolar) north boundary (general kernels only)"); return 0; }
     if (g.met && g.metW) { snprintf(why, nwhy, "two-dimensional metrics (general kernels only)"); return 0; }
     if (g.met) {
         // every metric that appears as a divisor must qualify for the constant-division shortcut, on every row a tile can touch

@@ -72,6 +72,15 @@ __global__ void k_fill_y_bounded(DGrid g, DArr a, int i0, int i1, int Ny, int mo
     }
 }
 
+// the north fold (CSI_FOLDED): parent[target] = sign * parent[source] for every entry of the location's copy list
+__global__ void k_fill_fold(DArr a, const int32_t *target, const int32_t *source, int n, double sign)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) a.p[target[k]] = sign * a.p[source[k]];
+}
+
+// which: 0 default boundary conditions, 1 = u, 2 = v (their own wall conditions, fold sign of velocities), 3 = an external stress /
+// velocity array (default conditions, fold sign of external fields)
 void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, const DArr &a, int lx, int ly, int which)
 {
     if (!a.p) return;
@@ -113,6 +122,14 @@ void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, cons
     if (g.topo_y == CSI_PERIODIC && !g.conn_s && !g.conn_n) {
         k_fill_y_periodic<<<dim3((a.sx + T - 1) / T, g.Hy), T, 0, c.stream>>>(a, g.Ny, g.Hy);
         ++*c.launches;
+    }
+    if (g.fold) {  // last: its sources are interior cells, its targets include the corners the periodic fill has just written
+        const int loc = (lx ? 1 : 0) + (ly ? 2 : 0);
+        if (g.fold_n[loc] > 0) {
+            const double sign = (which == 1 || which == 2) ? g.fold_sv : (which == 3 ? g.fold_se : 1.0);
+            k_fill_fold<<<(g.fold_n[loc] + T - 1) / T, T, 0, c.stream>>>(a, g.fold_t[loc], g.fold_s[loc], g.fold_n[loc], sign);
+            ++*c.launches;
+        }
     }
 }
 

@@ -33,6 +33,12 @@ struct DGrid {
     int metL, metW;         // rows of the metric arrays; columns per row (0: the metrics depend on j only)
     const double *met_host;  // host copies (plan construction only): the 12 x metL metrics, and f at (Face, Face) or NULL
     const double *fff_host;
+    // north fold of a tripolar grid (CSI_FOLDED; topo_y is then CSI_BOUNDED with conn_n = 1: the north side is no wall): copy lists
+    // per location lx + 2 ly, applied by the halo fill after the fills of the other sides
+    int fold;
+    const int32_t *fold_t[4], *fold_s[4];
+    int fold_n[4];
+    double fold_sv, fold_se;
 };
 
 // grid metrics at (i, j): constants on a RectilinearGrid, functions of j on a LatitudeLongitudeGrid (metW == 0), full 2-D

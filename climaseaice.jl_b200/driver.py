@@ -71,7 +71,7 @@ def model_from_case(case: Case, solver_impl="auto", partition=None, device=None)
                       bottom_heat_flux=case.thermo.get("bottom_heat_flux", 0.0), ice_salinity=case.thermo.get("ice_salinity", 0.0))
     m = SeaIceModel(grid, dynamics=dyn, advection=adv, timestepper=case.timestepper, boundary_conditions=bcs,
                     solver_impl=solver_impl, partition=partition, immersed_mask=case.mask, immersed_drag=case.immersed_drag,
-                    snow_thickness="hs" in F, **thermo)
+                    snow_thickness="hs" in F, fold=case.fold, **thermo)
     m.set(h=F["h"], a=F["a"], u=F["u"], v=F["v"])
     if "hs" in F:
         m.set(hs=F["hs"])

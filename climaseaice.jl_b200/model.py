@@ -26,6 +26,7 @@ from . import _lib as L
 from .metrics import METRIC_NAMES, latitude_longitude_metrics, spherical_coriolis_f_ff
 
 Periodic, Bounded, Flat = "Periodic", "Bounded", "Flat"
+Folded = "Folded"   # y axis of a tripolar grid: a wall in the south, the fold (Zipper boundary condition) in the north
 Center, Face = 0, 1
 
 
@@ -41,8 +42,8 @@ class RectilinearGrid:
         self.Hx, self.Hy = int(halo[0]), int(halo[1])
         self.x, self.y = (float(x[0]), float(x[1])), (float(y[0]), float(y[1]))
         self.topology = tuple(topology[:2])
-        for t in self.topology:
-            if t not in (Periodic, Bounded):
+        for k, t in enumerate(self.topology):
+            if t not in (Periodic, Bounded) and not (k == 1 and t == Folded):
                 raise ValueError(f"unsupported topology {t!r}")
         self.dx = (self.x[1] - self.x[0]) / self.Nx
         self.dy = (self.y[1] - self.y[0]) / self.Ny
@@ -50,12 +51,12 @@ class RectilinearGrid:
 
     @property
     def topo_codes(self):
-        return tuple(L.PERIODIC if t == Periodic else L.BOUNDED for t in self.topology)
+        return tuple(L.PERIODIC if t == Periodic else (L.FOLDED if t == Folded else L.BOUNDED) for t in self.topology)
 
     def parent_shape(self, loc):
         """(sy, sx) of a field's parent: Face fields carry N+1 points along Bounded axes."""
         sx = self.Nx + 2 * self.Hx + (1 if (loc[0] == Face and self.topology[0] == Bounded and not self.partitioned_x) else 0)
-        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] == Bounded and not self.partitioned_y) else 0)
+        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] == Face and self.topology[1] in (Bounded, Folded) and not self.partitioned_y) else 0)
         return sy, sx
 
     def nodes(self, loc, with_halos=True):
@@ -343,7 +344,7 @@ class SeaIceModel:
                  ice_density=900.0, ice_thermodynamics=None, solver_impl="auto", immersed_mask=None,
                  partition=None, immersed_drag=(0.0, 0.0), snow_thickness=False, snow_thermodynamics=None,
                  top_heat_flux=None, bottom_heat_flux=0.0, snowfall=0.0, snow_density=330.0,
-                 ice_consolidation_thickness=0.05, ice_salinity=0.0, phase_transitions=None):
+                 ice_consolidation_thickness=0.05, ice_salinity=0.0, phase_transitions=None, fold=None):
         if dynamics is None and ice_thermodynamics is None:
             raise ValueError("pass a SeaIceMomentumEquation as `dynamics` and/or SlabThermodynamics as `ice_thermodynamics`")
         if snow_thermodynamics is not None and ice_thermodynamics is None:
@@ -385,6 +386,14 @@ class SeaIceModel:
         # examples/ice_advected_on_coastline.jl:91-98
         self.immersed_drag = (float(immersed_drag[0]), float(immersed_drag[1]))
         self._mask = None if immersed_mask is None else np.ascontiguousarray(immersed_mask, dtype=np.uint8)
+        # Folded y axis (tripolar grid): fold = dict(maps={(lx, ly): (target, source)}, sign_velocity=-1.0, sign_external=1.0), the
+        # copy lists of the north fold in linear parent indices -- what the host's fill_halo_regions! does on its grid
+        self._fold = fold
+        holds_fold = partition is None or partition[0] == partition[1] - 1 or (len(partition) > 3 and partition[3] > 1)   # y-slabs: the last one
+        if fold is not None and grid.topology[1] != Folded:
+            raise ValueError("only a Folded y axis takes `fold`")
+        if grid.topology[1] == Folded and holds_fold and fold is None:
+            raise ValueError("a Folded y axis needs `fold` (on a partition: on the last y-slab)")
         self._handle = C.c_void_p()
         self._solver_impl = dict(auto=L.SOLVER_AUTO, unfused=L.SOLVER_UNFUSED, fused=L.SOLVER_FUSED)[solver_impl]
         cfg = self._config()
@@ -541,6 +550,17 @@ class SeaIceModel:
         cfg.timestepper = L.RK3 if self.timestepper == "SplitRungeKutta3" else L.FE
         cfg.solver_impl = self._solver_impl
         cfg.immersed_drag_u, cfg.immersed_drag_v = self.immersed_drag
+        if self._fold is not None:
+            self._fold_keep = []
+            for (lx, ly), (tg, sr) in self._fold["maps"].items():
+                k = lx + 2 * ly
+                tg = np.ascontiguousarray(tg, dtype=np.int32); sr = np.ascontiguousarray(sr, dtype=np.int32)
+                self._fold_keep += [tg, sr]
+                cfg.fold_target[k] = tg.ctypes.data_as(C.POINTER(C.c_int32))
+                cfg.fold_source[k] = sr.ctypes.data_as(C.POINTER(C.c_int32))
+                cfg.fold_count[k] = tg.size
+            cfg.fold_sign_velocity = float(self._fold.get("sign_velocity", -1.0))
+            cfg.fold_sign_external = float(self._fold.get("sign_external", 1.0))
         if self.partition:
             cfg.rank, cfg.nranks, cfg.exchange_every = self.partition[:3]
             cfg.partition_x = int(self.partition[3]) if len(self.partition) > 3 else 0

@@ -53,6 +53,7 @@ class Case:
     latlon: tuple | None = None          # ((lon0, lon1), (lat0, lat1)) in degrees: LatitudeLongitudeGrid; Lx, Ly = extents in degrees
     rotation_rate: float | None = None   # lat-lon only: HydrostaticSphericalCoriolis(rotation_rate) instead of FPlane(coriolis_f)
     metric_arrays: dict | None = None    # explicit j-indexed metric arrays (a slab's rows of the global grid's metrics)
+    fold: dict | None = None             # Folded y axis: dict(maps={(lx, ly): (target, source)}, sign_velocity, sign_external)
     thermo: dict | None = None           # slab thermodynamics on top of the dynamics: scalars bottom_heat_flux, ice_salinity;
                                          # arrays Tu (initial top temperature) and Qtop (external top heat flux) live in `fields`
 
@@ -80,9 +81,12 @@ class Case:
     def dy(self):
         return self.Ly / self.Ny
 
+    def bounded_like(self, axis):
+        return self.topology[axis] in ("Bounded", "Folded")
+
     def parent_shape(self, loc):
         sx = self.Nx + 2 * self.Hx + (1 if (loc[0] and self.topology[0] == "Bounded") else 0)
-        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] and self.topology[1] == "Bounded") else 0)
+        sy = self.Ny + 2 * self.Hy + (1 if (loc[1] and self.topology[1] in ("Bounded", "Folded")) else 0)
         return sy, sx
 
     def nodes(self, loc):
@@ -250,6 +254,57 @@ def curvilinear_case(N=72, Ny=56, H=4, seed=SEED, substeps=20, dt=600.0, advecti
     return c
 
 
+def example_fold_maps(Nx, Ny, Hx, Hy, topo_x="Periodic", part_y=False):
+    """Copy lists of a north fold through the centre row j = Ny (a U-point pivot, the older of the two fold variants of Oceananigans'
+    TripolarGrid, written down from memory): an EXAMPLE for the tests of the mechanism -- a real host derives its lists from its own
+    fill_halo_regions! (julia/ClimaSeaIceB200.jl: fold_maps), and the library takes whatever lists it is given.
+        centres in x:  i' = Nx - i + 1        faces in x:  i' = Nx - i + 2   (wrapped periodically into 1..Nx)
+        centres in y:  (i, Ny + k) <- (i', Ny - k), k = 1..Hy, and the pivot row itself, (i, Ny) <- (i', Ny) for i > Nx / 2 (and its periodic images)
+        faces in y:    (i, Ny + k) <- (i', Ny - k + 1), k = 1..Hy + 1
+    Every parent column is filled, x halos included."""
+    maps = {}
+    for lx in (0, 1):
+        for ly in (0, 1):
+            sx = Nx + 2 * Hx + (1 if (lx and topo_x == "Bounded") else 0)
+            tg, sr = [], []
+            idx = lambda i, j: (j - 1 + Hy) * sx + (i - 1 + Hx)
+            for pi in range(sx):
+                i = pi + 1 - Hx
+                ip = (Nx - i + (2 if lx else 1) - 1) % Nx + 1
+                for k in range(1, Hy + (2 if (ly and not part_y) else 1)):   # (a y-slab's Face-y parent has no extra row)
+                    tg.append(idx(i, Ny + k)); sr.append(idx(ip, Ny - k + (1 if ly else 0)))
+                iw = (i - 1) % Nx + 1   # the periodic image of a halo column
+                if not ly and iw > Nx // 2 and ip != iw:
+                    tg.append(idx(i, Ny)); sr.append(idx(ip, Ny))
+            maps[(lx, ly)] = (np.asarray(tg, dtype=np.int32), np.asarray(sr, dtype=np.int32))
+    return maps
+
+
+def folded_case(Nx=48, Ny=40, H=5, seed=SEED, substeps=12, dt=600.0, timestepper="SplitRungeKutta3", mask=True) -> Case:
+    """A tripolar-like case: two-dimensional metrics, zonally periodic, a wall in the south and a fold in the north (example copy
+    lists, velocities with sign -1), optionally an immersed island touching the fold.  Exercises the mechanism the library offers
+    for Oceananigans' TripolarGrid; not a statement about that grid's index convention."""
+    c = curvilinear_case(Nx, Ny, H=H, seed=seed, substeps=substeps, dt=dt, timestepper=timestepper, topology=("Periodic", "Bounded"))
+    c.name = "folded"
+    c.topology = ("Periodic", "Folded")
+    c.u_bc_value = 0.0
+    c.fold = dict(maps=example_fold_maps(Nx, Ny, H, H), sign_velocity=-1.0, sign_external=1.0)
+    rng = np.random.default_rng(seed + 11)
+    c.fields["u"] = _wrap_periodic(c, 0.05 * rng.uniform(-1, 1, c.fields["u"].shape), LOC["u"])
+    c.fields["v"] = _wrap_periodic(c, 0.05 * rng.uniform(-1, 1, c.fields["v"].shape), LOC["v"])
+    if mask:
+        X, Y = c.nodes(LOC["h"])
+        land = ((X / c.Lx - 0.3) ** 2 + (Y / c.Ly - 0.95) ** 2) < 0.01
+        m = land.astype(np.uint8)
+        # the mask obeys the fold like any centre field (sign +1), and periodicity in x
+        tg, sr = c.fold["maps"][(0, 0)]
+        m = _wrap_periodic(c, m.astype(np.float64), LOC["h"])
+        flat = m.reshape(-1)
+        flat[tg] = flat[sr]
+        c.mask = np.ascontiguousarray(m.astype(np.uint8))
+    return c
+
+
 def arctic_cap_case(Nx=192, Ny=48, H=7, seed=SEED, substeps=20, dt=600.0, timestepper="SplitRungeKutta3") -> Case:
     """BASELINE config 5 in miniature: a zonally periodic lat-lon cap (lambda in (0, 360), phi in (60, 88); the metrics
     shrink 14x towards the pole), HydrostaticSphericalCoriolis, EVP dynamics + WENO advection coupled to bare-ice slab thermodynamics with a
@@ -344,6 +399,9 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
     assert case.Ny % nranks == 0
     ny = case.Ny // nranks
     c = dataclasses.replace(case, name=case.name + f"-slab{rank}", Ny=ny, Hy=Hy, Ly=case.Ly / nranks, fields={}, metric_arrays=None, mask=None)
+    if case.fold is not None:
+        # only the last slab holds the fold; its lists are the example's, over the slab's own rows and (deeper) halo
+        c.fold = dict(case.fold, maps=example_fold_maps(case.Nx, ny, case.Hx, Hy, topo_x=case.topology[0], part_y=True)) if rank == nranks - 1 else None
     if case.latlon is not None:
         # the slab's rows of the GLOBAL grid's metrics (same expressions per global row index => same bits as on one rank);
         # local row jl = 1-Hy .. ny+Hy+1 is global row rank*ny + jl
@@ -376,6 +434,9 @@ def slab_of(case: Case, rank: int, nranks: int, Hy: int) -> Case:
             pj = j + case.Hy
             ok = (pj >= 0) & (pj < case.mask.shape[0])
             c.mask[ok, :] = case.mask[pj[ok], :]
+            if c.fold is not None:   # the slab's halo is deeper than the global one: the mask beyond the fold is its image
+                tg, sr = c.fold["maps"][(0, 0)]
+                c.mask.reshape(-1)[tg] = c.mask.reshape(-1)[sr]
     return c
 
 

@@ -39,7 +39,9 @@ typedef struct {
     int32_t off_x, off_y;   /* halo offsets (Hx, Hy of the grid the field lives on) */
 } csi_array;
 
-enum { CSI_PERIODIC = 0, CSI_BOUNDED = 1 };
+/* CSI_FOLDED (topo_y only): a wall in the south, a fold in the north -- the Zipper boundary condition of Oceananigans' TripolarGrid
+ * (src/sea_ice_model.jl:56-64 gives u and v the sign -1).  The fold itself is passed as a copy list, see csi_config.fold_target */
+enum { CSI_PERIODIC = 0, CSI_BOUNDED = 1, CSI_FOLDED = 2 };
 enum { CSI_STRESS_NONE = 0, CSI_STRESS_CONST = 1, CSI_STRESS_FIELD = 2, CSI_STRESS_SEMI_IMPLICIT = 3 };
 enum { CSI_REPLACEMENT_PRESSURE = 0, CSI_ICE_STRENGTH = 1 };
 /* SPHERICAL: Oceananigans' HydrostaticSphericalCoriolis (EnstrophyConserving scheme) on a LatitudeLongitudeGrid;
@@ -117,7 +119,7 @@ typedef struct {
      * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above.
      * CSI_METRIC_IJ (orthogonal curvilinear grids: OrthogonalSphericalShellGrid, rotated or stretched meshes): the same
      * twelve metrics as two-dimensional host arrays of (Ny + 2*Hy + 1) rows x (Nx + 2*Hx + 1) columns, i fastest, the value
-     * at (i, j) stored at [(j - 1 + Hy) * (Nx + 2*Hx + 1) + (i - 1 + Hx)]; general kernels only, one rank, no fold. */
+     * at (i, j) stored at [(j - 1 + Hy) * (Nx + 2*Hx + 1) + (i - 1 + Hx)]; general kernels only; one rank or y-slabs. */
     int32_t metric_kind;
     int32_t serial_exchange;    /* slabs + fused solver: 0 = the halo exchange between blocks of K substeps runs on its own stream
                                    while the next substep's interior tiles compute (boundary tiles wait for it); 1 = on the compute stream */
@@ -132,6 +134,20 @@ typedef struct {
     /* CSI_CORIOLIS_SPHERICAL: f^ffa = 2 Omega sin(phi^f) per row, Ny + 2*Hy + 1 doubles, row j at [j - 1 + Hy] (host
      * array, copied at csi_create); evaluated by the host with Oceananigans' own f^ffa */
     const double *coriolis_f_ff;
+    /* topo_y = CSI_FOLDED: what fill_halo_regions! does at the north boundary of the host's grid, as one copy list per location
+     * (c,c), (f,c), (c,f), (f,f): after the local fills of the other sides, parent[target[k]] = sign * parent[source[k]], with
+     * linear parent indices (i fastest) into an array of that location.  The host derives the lists from its own grid -- a
+     * Julia host by filling a scratch field with its linear indices and calling fill_halo_regions! once per location
+     * (julia/ClimaSeaIceB200.jl: fold_maps) -- so no index convention of the fold is built into the library.  Targets may be
+     * halo cells of any side and interior cells (the duplicated row of a centre-pivot fold).  sign: fold_sign_velocity for u, v
+     * (-1 in the reference), fold_sign_external for the external stress / velocity arrays top_x, top_y, ue, ve, +1 for every
+     * other field.  Checked at csi_create: indices inside the parent, every target once, nothing both read and written (the
+     * copies of one list run concurrently).  Host arrays, copied at csi_create.  General kernels, one rank or y-slabs (the
+     * last slab holds the fold; the other ranks ignore these members). */
+    const int32_t *fold_target[4];
+    const int32_t *fold_source[4];
+    int32_t fold_count[4];
+    double fold_sign_velocity, fold_sign_external;
 } csi_config;
 
 /* The arrays the hot path touches.  Unused ones may have ptr == NULL. */

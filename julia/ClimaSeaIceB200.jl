@@ -17,7 +17,8 @@ module ClimaSeaIceB200
 using CUDA
 using Oceananigans
 using Oceananigans.Architectures: architecture
-using Oceananigans.BoundaryConditions: BoundaryCondition, Value
+using Oceananigans.BoundaryConditions: BoundaryCondition, Value, fill_halo_regions!
+using Oceananigans.Fields: instantiated_location
 using Oceananigans.Coriolis: FPlane, HydrostaticSphericalCoriolis, fᶠᶠᵃ
 using Oceananigans.DistributedComputations: Distributed
 using Oceananigans.Grids: halo_size, topology, inactive_cell, Periodic, Bounded, LeftConnected, RightConnected, FullyConnected
@@ -78,6 +79,10 @@ Base.@kwdef struct CsiConfig
     free_drift_kind :: Int32 = 0; reserved3_ :: Int32 = 0
     top_rho_e :: Float64 = 1.3; top_Cd :: Float64 = 1.2e-3
     coriolis_f_ff :: Ptr{Float64} = C_NULL
+    fold_target :: NTuple{4, Ptr{Int32}} = ntuple(_ -> Ptr{Int32}(C_NULL), 4)
+    fold_source :: NTuple{4, Ptr{Int32}} = ntuple(_ -> Ptr{Int32}(C_NULL), 4)
+    fold_count :: NTuple{4, Int32} = ntuple(_ -> Int32(0), 4)
+    fold_sign_velocity :: Float64 = -1.0; fold_sign_external :: Float64 = 1.0
 end
 
 # csi_fields: 29 csi_array in header order
@@ -133,6 +138,45 @@ topo_code(::Type{Bounded})  = Int32(1)
 # (its rank index tells it which sides are rank boundaries): FullyConnected everywhere <=> Periodic, else Bounded
 global_topo_code(T, periodic_globally) = T in (LeftConnected, RightConnected, FullyConnected) ? Int32(periodic_globally ? 0 : 1) : topo_code(T)
 
+# ---- the north fold of a TripolarGrid (topo_y = CSI_FOLDED = 2) -------------------------------------------------
+# The library builds in NO index convention of the fold: it applies, after its own periodic / wall fills, a list of copies
+# parent[target] = sign * parent[source] per location.  The lists are read off Oceananigans' own fill_halo_regions!: a scratch
+# field with the boundary conditions of the real one is filled with (its own 0-based linear parent index + 1), its halos are
+# filled, and every element at or beyond row Ny whose value changed names its source (|value| - 1) and its sign.
+is_folded(ugrid) = ugrid isa OrthogonalSphericalShellGrid && nameof(typeof(ugrid.conformal_mapping)) === :Tripolar
+
+function fold_probe(field)
+    cpu = on_architecture(CPU(), field.grid)
+    loc = instantiated_location(field)
+    f = Field(loc, cpu; boundary_conditions = field.boundary_conditions)
+    p = parent(f)
+    sx, sy = size(p, 1), size(p, 2)
+    p[:, :, 1] .= reshape(Float64.(1:sx*sy), sx, sy)
+    fill_halo_regions!(f)
+    _, Ny, _ = size(cpu); _, Hy, _ = halo_size(cpu)
+    target, source, signs = Int32[], Int32[], Float64[]
+    for pj in Ny+Hy:sy, pi in 1:sx              # the pivot row (parent row Ny + Hy, 1-based) and everything north of it
+        own, val = (pj - 1) * sx + pi, p[pi, pj, 1]
+        abs(val) == own && val > 0 && continue
+        push!(target, own - 1); push!(source, Int32(abs(val)) - 1); push!(signs, sign(val))
+    end
+    allequal(signs) || unsupported("a fold whose sign varies within one field")
+    return target, source, isempty(signs) ? 1.0 : first(signs)
+end
+
+function fold_maps(model)
+    u, v, hh = model.velocities.u, model.velocities.v, model.ice_thickness
+    grid = u.grid
+    ff = Field((Face(), Face(), Center()), grid)      # the stress nodes: default boundary conditions of the location
+    tu, su, gu = fold_probe(u); tv, sv, gv = fold_probe(v); tc, sc, gc = fold_probe(hh); tf, sf, _ = fold_probe(ff)
+    gu == gv || unsupported("different fold signs for u and v")
+    gc == 1.0 || unsupported("a sign-reversing fold for thickness")
+    bot = model.dynamics.external_momentum_stresses.bottom
+    ge = (bot isa SemiImplicitStress && bot.uₑ isa Field) ? fold_probe(bot.uₑ)[3] : 1.0
+    # order of csi_config.fold_*: (Center, Center), (Face, Center), (Center, Face), (Face, Face)
+    return (targets = (tc, tu, tv, tf), sources = (sc, su, sv, sf), sign_velocity = gu, sign_external = ge)
+end
+
 const METRIC_OPS = (Δxᶜᶜᶜ, Δxᶠᶜᶜ, Δxᶜᶠᶜ, Δxᶠᶠᶜ, Δyᶜᶜᶜ, Δyᶠᶜᶜ, Δyᶜᶠᶜ, Δyᶠᶠᶜ, Azᶜᶜᶜ, Azᶠᶜᶜ, Azᶜᶠᶜ, Azᶠᶠᶜ)
 # LatitudeLongitudeGrid: twelve j-indexed vectors (metric_kind = 1), index j at [j + Hy] (1-based), evaluated with
 # Oceananigans' own operators so the library divides by exactly the numbers the reference kernels would
@@ -182,6 +226,14 @@ function create(model::SeaIceModel; solver_impl = 0, exchange_every = 4, immerse
         arrs = latlon ? metric_vectors(ugrid) : metric_arrays(ugrid)
         push!(keep, arrs)
         metric_kind, metrics = Int32(latlon ? 1 : 2), ntuple(k -> pointer(arrs[k]), 12)
+    end
+
+    # a tripolar grid: copy lists of the fold, taken from Oceananigans' own halo fill (see fold_probe)
+    folded = is_folded(ugrid)
+    fold = nothing
+    if folded
+        fold = fold_maps(model)
+        push!(keep, fold)
     end
 
     # partition: Distributed(arch; partition = Partition(Rx, Ry)), rank = ry * Rx + rx (test/distributed_tests_utils.jl:60-62)
@@ -249,7 +301,11 @@ function create(model::SeaIceModel; solver_impl = 0, exchange_every = 4, immerse
     timestepper = ts isa SplitRungeKuttaTimeStepper ? Int32(0) : ts isa ForwardEulerTimeStepper ? Int32(1) : unsupported("timestepper $(typeof(ts))")
 
     cfg = CsiConfig(; Nx, Ny, Hx, Hy, device = CUDA.deviceid(),
-                    topo_x = global_topo_code(TX, xper), topo_y = global_topo_code(TY, yper),
+                    topo_x = global_topo_code(TX, xper), topo_y = folded ? Int32(2) : global_topo_code(TY, yper),
+                    fold_target = folded ? ntuple(k -> pointer(fold.targets[k]), 4) : ntuple(_ -> Ptr{Int32}(C_NULL), 4),
+                    fold_source = folded ? ntuple(k -> pointer(fold.sources[k]), 4) : ntuple(_ -> Ptr{Int32}(C_NULL), 4),
+                    fold_count = folded ? ntuple(k -> Int32(length(fold.targets[k])), 4) : ntuple(_ -> Int32(0), 4),
+                    fold_sign_velocity = folded ? fold.sign_velocity : -1.0, fold_sign_external = folded ? fold.sign_external : 1.0,
                     dx = regular ? Float64(ugrid.Δxᶜᵃᵃ) : 0.0, dy = regular ? Float64(ugrid.Δyᵃᶜᵃ) : 0.0,
                     immersed_mask = mask, metric_kind, metrics,
                     ice_compressive_strength = r.ice_compressive_strength, ice_compaction_hardening = r.ice_compaction_hardening,

@@ -81,7 +81,8 @@ static inline double vccc(G g, int i, int j) { return azcc(g, i, j) * 1.0; }
  * ------------------------------------------------------------------------------------------- */
 static inline int outside_domain(G g, int i, int j)
 {
-    return (g->topo_x == CSIO_BOUNDED && (i < 1 || i > g->Nx)) || (g->topo_y == CSIO_BOUNDED && (j < 1 || j > g->Ny));
+    return (g->topo_x == CSIO_BOUNDED && (i < 1 || i > g->Nx)) || (g->topo_y == CSIO_BOUNDED && (j < 1 || j > g->Ny)) ||
+           (g->topo_y == CSIO_FOLDED && j < 1); /* nothing is outside beyond a fold */
 }
 static inline int immersed_cell(G g, int i, int j)
 {
@@ -541,7 +542,7 @@ static void fill_x_bounded(G g, P p, csio_field *f, int lx, int ly, int which)
         }
     }
 }
-static void fill_y_bounded(G g, P p, csio_field *f, int lx, int ly, int which)
+static void fill_y_bounded(G g, P p, csio_field *f, int lx, int ly, int which, int north)
 {
     (void)lx;
     int Ny = g->Ny;
@@ -551,16 +552,23 @@ static void fill_y_bounded(G g, P p, csio_field *f, int lx, int ly, int which)
                 double val = p->u_sn_val;
                 double Ds = dyff(g, i, 1), Dn = dyff(g, i, Ny + 1);
                 F(*f, i, 0) = F(*f, i, 1) + ((F(*f, i, 1) - val) / (Ds / 2)) * (-Ds);
-                F(*f, i, Ny + 1) = F(*f, i, Ny) + ((val - F(*f, i, Ny)) / (Dn / 2)) * Dn;
+                if (north) F(*f, i, Ny + 1) = F(*f, i, Ny) + ((val - F(*f, i, Ny)) / (Dn / 2)) * Dn;
             } else {
                 F(*f, i, 0) = F(*f, i, 1);
-                F(*f, i, Ny + 1) = F(*f, i, Ny);
+                if (north) F(*f, i, Ny + 1) = F(*f, i, Ny);
             }
         } else if (which == 2) {
             F(*f, i, 1) = 0.0;
-            F(*f, i, Ny + 1) = 0.0;
+            if (north) F(*f, i, Ny + 1) = 0.0;
         }
     }
+}
+/* the north fold: a copy list with a sign (see csio_grid); `ext`: the field is an external stress / velocity array */
+static void fill_fold(G g, csio_field *f, int lx, int ly, int which, int ext)
+{
+    const int loc = (lx ? 1 : 0) + (ly ? 2 : 0);
+    const double sign = (which == 1 || which == 2) ? g->fold_sign_velocity : (ext ? g->fold_sign_external : 1.0);
+    for (int k = 0; k < g->fold_count[loc]; k++) f->p[g->fold_target[loc][k]] = sign * f->p[g->fold_source[loc][k]];
 }
 static void fill_x_periodic(G g, csio_field *f)
 {
@@ -587,9 +595,10 @@ int csio_fill_halo(G g, P p, csio_field *f, int lx, int ly, int which)
 {
     if (!f->p) return 0;
     if (g->topo_x == CSIO_BOUNDED) fill_x_bounded(g, p, f, lx, ly, which);
-    if (g->topo_y == CSIO_BOUNDED) fill_y_bounded(g, p, f, lx, ly, which);
+    if (g->topo_y == CSIO_BOUNDED || g->topo_y == CSIO_FOLDED) fill_y_bounded(g, p, f, lx, ly, which, g->topo_y == CSIO_BOUNDED);
     if (g->topo_x == CSIO_PERIODIC) fill_x_periodic(g, f);
     if (g->topo_y == CSIO_PERIODIC) fill_y_periodic(g, f);
+    if (g->topo_y == CSIO_FOLDED) fill_fold(g, f, lx, ly, which, which == 3);
     return 0;
 }
 
@@ -612,12 +621,12 @@ int csio_time_step_momentum(G g, P p, csio_state *s, double dt, int nsub)
     csio_initialize_rheology(g, p, s); /* se.jl:130 */
     /* update_external_stress! (ext.jl:72-78,148-152): halo refresh of the stress inputs */
     if (p->top_kind == CSIO_STRESS_FIELD || p->top_kind == CSIO_STRESS_SEMI_IMPLICIT) {
-        if (pm->top_x.p) csio_fill_halo(g, p, &pm->top_x, 1, 0, 0);
-        if (pm->top_y.p) csio_fill_halo(g, p, &pm->top_y, 0, 1, 0);
+        if (pm->top_x.p) csio_fill_halo(g, p, &pm->top_x, 1, 0, 3);
+        if (pm->top_y.p) csio_fill_halo(g, p, &pm->top_y, 0, 1, 3);
     }
     if (p->bot_kind == CSIO_STRESS_FIELD || p->bot_kind == CSIO_STRESS_SEMI_IMPLICIT) {
-        if (pm->ue.p) csio_fill_halo(g, p, &pm->ue, 1, 0, 0);
-        if (pm->ve.p) csio_fill_halo(g, p, &pm->ve, 0, 1, 0);
+        if (pm->ue.p) csio_fill_halo(g, p, &pm->ue, 1, 0, 3);
+        if (pm->ve.p) csio_fill_halo(g, p, &pm->ve, 0, 1, 3);
     }
     csio_fill_halo(g, p, &s->u, 1, 0, 1); /* se.jl:170-171 */
     csio_fill_halo(g, p, &s->v, 0, 1, 2);

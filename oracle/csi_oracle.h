@@ -36,7 +36,8 @@ typedef struct {
     int32_t ox, oy; /* halo offsets: element (i,j) lives at p[(i-1+ox) + (j-1+oy)*sx] */
 } csio_field;
 
-enum { CSIO_PERIODIC = 0, CSIO_BOUNDED = 1 };
+/* CSIO_FOLDED (y axis only): a wall in the south, a fold (Oceananigans' Zipper boundary condition of the tripolar grid) in the north */
+enum { CSIO_PERIODIC = 0, CSIO_BOUNDED = 1, CSIO_FOLDED = 2 };
 enum { CSIO_REGULAR = 0, CSIO_JMETRIC = 1, CSIO_IJMETRIC = 2 };
 
 typedef struct {
@@ -51,6 +52,13 @@ typedef struct {
     const double *azcc, *azfc, *azcf, *azff;
     /* optional immersed mask at cell centres, shape (Nx+2Hx) x (Ny+2Hy), 1 = immersed (inactive) */
     const uint8_t *mask;
+    /* CSIO_FOLDED: the north fold as a copy list per location (c,c), (f,c), (c,f), (f,f): after the local fills of the other
+     * sides, parent[target[k]] = sign * parent[source[k]] (linear parent indices, i fastest).  The list is whatever the host's
+     * fill_halo_regions! does on that grid (src/sea_ice_model.jl:56-64 only sets the sign of u and v to -1); sign: u, v take
+     * fold_sign_velocity, external stress / velocity arrays fold_sign_external, everything else +1 */
+    const int32_t *fold_target[4], *fold_source[4];
+    int32_t fold_count[4];
+    double fold_sign_velocity, fold_sign_external;
 } csio_grid;
 
 /* external stress kinds: sea_ice_external_stress.jl:8-27,176-202 */

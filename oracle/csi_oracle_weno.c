@@ -102,7 +102,7 @@ static double weno_from_cells(int B, const double *q)
  * /root/reference/examples/ice_advected_on_coastline.jl:54-55). */
 static int cell_inactive(const csio_grid *g, int i, int j)
 {
-    if ((g->topo_x == CSIO_BOUNDED && (i < 1 || i > g->Nx)) || (g->topo_y == CSIO_BOUNDED && (j < 1 || j > g->Ny))) return 1;
+    if ((g->topo_x == CSIO_BOUNDED && (i < 1 || i > g->Nx)) || (g->topo_y == CSIO_BOUNDED && (j < 1 || j > g->Ny)) || (g->topo_y == CSIO_FOLDED && j < 1)) return 1;
     if (!g->mask) return 0;
     int sx = g->Nx + 2 * g->Hx, sy = g->Ny + 2 * g->Hy;
     int pi = i - 1 + g->Hx, pj = j - 1 + g->Hy;
@@ -114,10 +114,10 @@ static int cell_inactive(const csio_grid *g, int i, int j)
 }
 static int buffer_at(int B, int topo, int N, int i)
 {
-    if (topo != CSIO_BOUNDED) return B;
+    if (topo != CSIO_BOUNDED && topo != CSIO_FOLDED) return B;
     int b = B;
     if (i - 1 < b) b = i - 1;
-    if (N + 1 - i < b) b = N + 1 - i;
+    if (topo == CSIO_BOUNDED && N + 1 - i < b) b = N + 1 - i;   /* (a fold is not a wall: full order next to it) */
     return b < 1 ? 1 : b;
 }
 /* dir = 0: x face (i, j), stencil along i; dir = 1: y face, stencil along j */

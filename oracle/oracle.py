@@ -20,7 +20,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "libcsi_oracle.so"
 
-PERIODIC, BOUNDED = 0, 1
+PERIODIC, BOUNDED, FOLDED = 0, 1, 2
 STRESS_NONE, STRESS_CONST, STRESS_FIELD, STRESS_SEMI_IMPLICIT = 0, 1, 2, 3
 RK3, FE = 0, 1
 
@@ -44,7 +44,9 @@ class Grid(C.Structure):
         ("dx", C.c_double), ("dy", C.c_double),
     ] + [(n, C.POINTER(C.c_double)) for n in
          ("dxcc", "dxfc", "dxcf", "dxff", "dycc", "dyfc", "dycf", "dyff", "azcc", "azfc", "azcf", "azff")] + [
-        ("mask", C.POINTER(C.c_uint8))]
+        ("mask", C.POINTER(C.c_uint8)),
+        ("fold_target", C.POINTER(C.c_int32) * 4), ("fold_source", C.POINTER(C.c_int32) * 4), ("fold_count", C.c_int32 * 4),
+        ("fold_sign_velocity", C.c_double), ("fold_sign_external", C.c_double)]
 
 
 class Params(C.Structure):
@@ -118,7 +120,7 @@ def _as_field(arr, ox, oy):
 def parent_shape(Nx, Ny, Hx, Hy, topo, loc):
     """Oceananigans parent extents: Face fields carry N+1 points along Bounded axes."""
     sx = Nx + 2 * Hx + (1 if (loc[0] and topo[0] == BOUNDED) else 0)
-    sy = Ny + 2 * Hy + (1 if (loc[1] and topo[1] == BOUNDED) else 0)
+    sy = Ny + 2 * Hy + (1 if (loc[1] and topo[1] in (BOUNDED, FOLDED)) else 0)
     return sy, sx
 
 
@@ -136,7 +138,7 @@ class OracleModel:
     """Owns numpy copies of every field and drives the C oracle on them."""
 
     def __init__(self, Nx, Ny, Hx, Hy, topo=(PERIODIC, PERIODIC), dx=1.0, dy=1.0, params=None, fields=None,
-                 metrics=None, mask=None):
+                 metrics=None, mask=None, fold=None):
         self.Nx, self.Ny, self.Hx, self.Hy, self.topo = Nx, Ny, Hx, Hy, tuple(topo)
         prm = dict(DEFAULT_PARAMS)
         prm.update(params or {})
@@ -173,6 +175,19 @@ class OracleModel:
             assert m.shape == (Ny + 2 * Hy, Nx + 2 * Hx)
             self._keep.append(m)
             self.g.mask = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        if self.topo[1] == FOLDED:
+            # fold = dict(maps={loc: (target, source)}, sign_velocity=-1.0, sign_external=1.0), loc in ((0,0),(1,0),(0,1),(1,1))
+            assert fold is not None, "a FOLDED y axis needs its copy lists"
+            for loc, (tg, sr) in fold["maps"].items():
+                k = loc[0] + 2 * loc[1]
+                tg = np.ascontiguousarray(tg, dtype=np.int32); sr = np.ascontiguousarray(sr, dtype=np.int32)
+                assert tg.shape == sr.shape
+                self._keep += [tg, sr]
+                self.g.fold_target[k] = tg.ctypes.data_as(C.POINTER(C.c_int32))
+                self.g.fold_source[k] = sr.ctypes.data_as(C.POINTER(C.c_int32))
+                self.g.fold_count[k] = tg.size
+            self.g.fold_sign_velocity = fold.get("sign_velocity", -1.0)
+            self.g.fold_sign_external = fold.get("sign_external", 1.0)
         self.p = Params()
         for k, v in prm.items():
             if k == "f_ff":   # HydrostaticSphericalCoriolis: j-indexed f at (Face, Face)
@@ -193,7 +208,7 @@ class OracleModel:
     def interior(self, name):
         lx, ly = LOC[name]
         nx = self.Nx + (1 if (lx and self.topo[0] == BOUNDED) else 0)
-        ny = self.Ny + (1 if (ly and self.topo[1] == BOUNDED) else 0)
+        ny = self.Ny + (1 if (ly and self.topo[1] in (BOUNDED, FOLDED)) else 0)
         return self.arr[name][self.Hy:self.Hy + ny, self.Hx:self.Hx + nx]
 
     def _refs(self):

@@ -41,11 +41,11 @@ def oracle_params(case) -> dict:
 
 
 def oracle_from_case(case, **overrides) -> O.OracleModel:
-    topo = tuple(O.PERIODIC if t == "Periodic" else O.BOUNDED for t in case.topology)
+    topo = tuple(dict(Periodic=O.PERIODIC, Bounded=O.BOUNDED, Folded=O.FOLDED)[t] for t in case.topology)
     p = oracle_params(case)
     p.update(overrides)
     return O.OracleModel(case.Nx, case.Ny, case.Hx, case.Hy, topo=topo, dx=case.dx, dy=case.dy, params=p,
-                         fields={k: v.copy() for k, v in case.fields.items()}, mask=case.mask, metrics=case.metrics())
+                         fields={k: v.copy() for k, v in case.fields.items()}, mask=case.mask, metrics=case.metrics(), fold=case.fold)
 
 
 # GPU field name -> oracle field name

@@ -48,6 +48,9 @@ def main():
     if topo == "curvilinear":  # two-dimensional metrics (orthogonal curvilinear mesh), doubly periodic, general kernels
         from climaseaice_b200.synthetic import curvilinear_case
         case = curvilinear_case(64, 32 * Ry, H=7, substeps=10, topology=("Periodic", "Periodic"))
+    if topo == "folded":       # a tripolar-like mesh: two-dimensional metrics, a fold in the north (held by the last slab), an island at the fold
+        from climaseaice_b200.synthetic import folded_case
+        case = folded_case(64, 32 * Ry, H=7, substeps=10)
     if topo == "arctic":      # BASELINE config 5 in miniature: lat-lon cap, coupled thermodynamics, zonally periodic, walls in y
         case = arctic_cap_case(96, 24 * world, H=7, substeps=10)
     Hy = max(2 * K + 3, 7)

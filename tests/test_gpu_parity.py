@@ -9,7 +9,7 @@ import torch
 
 from climaseaice_b200.driver import HostStepper, model_from_case
 from climaseaice_b200.synthetic import anticyclone_case, periodic_case
-from tests.helpers import compare_model, interior_of, oracle_from_case, rel_err
+from tests.helpers import NAME_MAP, compare_model, interior_of, oracle_from_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -635,4 +635,37 @@ def test_out_of_window_intermediates_fall_back_per_tile(impl):
     if impl == "auto":
         invalid, redone, tiles = m.fused_stats()
         assert invalid == 0 and 0 < redone < 3 * tiles, (invalid, redone, tiles)   # the tiles concerned, not the whole stage
+    m.close()
+
+
+@pytest.mark.parametrize("impl", ("unfused", "auto"))
+@pytest.mark.parametrize("mask", (False, True))
+@pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
+def test_folded_north_boundary(impl, mask, timestepper):
+    """topo_y = CSI_FOLDED (the north fold of Oceananigans' TripolarGrid, handed over as copy lists the host reads off its own
+    fill_halo_regions!): velocities change sign across the fold, thickness and concentration do not, the south is a wall.
+    Parity with the oracle on the whole interior AND on the folded halo elements; runs on the general kernels."""
+    from climaseaice_b200.synthetic import folded_case
+    case = folded_case(substeps=12, mask=mask, timestepper=timestepper)
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    F = m.all_fields()
+    for n, loc, sign in (("u", (1, 0), -1.0), ("v", (0, 1), -1.0), ("h", (0, 0), 1.0), ("a", (0, 0), 1.0)):
+        tg, sr = case.fold["maps"][loc]
+        g = F[n].numpy().reshape(-1)
+        assert np.array_equal(g[tg], sign * g[sr]), n
+        assert np.array_equal(g[tg], o.arr[NAME_MAP[n]].reshape(-1)[tg]), n
+    assert m.fused_stats()[2] == 0     # the tile kernel refuses a fold: the general kernels ran
+    m.close()
+
+
+def test_fused_solver_refuses_a_fold():
+    from climaseaice_b200.synthetic import folded_case
+    case = folded_case(substeps=4)
+    m = model_from_case(case, solver_impl="fused")
+    with pytest.raises(RuntimeError, match="folded"):
+        m.time_step(case.dt)
     m.close()

@@ -55,7 +55,7 @@ def test_julia_shim_structs_match_the_ctypes_mirror():
     src = (Path(__file__).resolve().parents[1] / "julia" / "ClimaSeaIceB200.jl").read_text()
     body = src[src.index("Base.@kwdef struct CsiConfig"):]
     body = body[:body.index("\nend")]
-    jl = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*::\s*([A-Za-z0-9{}, ]+?)(?=\s*(?:=|;|\n|$))", body)
+    jl = re.findall(r"^\s*([A-Za-z_][A-Za-z0-9_]*)\s*::\s*([A-Za-z0-9{}, ]+?)(?=\s*(?:=|;|\n|$))", body.replace(";", "\n"), re.M)
     jl = [(n, t.strip()) for n, t in jl]
     want = []
     for n, ct in L.csi_config._fields_:
@@ -67,6 +67,10 @@ def test_julia_shim_structs_match_the_ctypes_mirror():
             t = "Ptr{UInt8}"
         elif n == "metrics":
             t = "NTuple{12, Ptr{Float64}}"
+        elif n in ("fold_target", "fold_source"):
+            t = "NTuple{4, Ptr{Int32}}"
+        elif n == "fold_count":
+            t = "NTuple{4, Int32}"
         else:
             t = "Ptr{Float64}"
         want.append((n, t))
@@ -130,6 +134,54 @@ def test_create_rejects_bad_arguments():
     cfg.nranks, cfg.exchange_every = 2, 4
     assert lib.csi_create(C.byref(cfg), C.byref(h)) == -1 and b"2*exchange_every" in lib.csi_last_error(None)
     assert lib.csi_evp_substeps(None, None, 1.0, 1, None) == -1
+
+
+def test_create_validates_fold_copy_lists():
+    """CSI_FOLDED: the copy lists are checked before anything touches the device -- all four locations present, indices inside the
+    parent of their location, signs +-1, every target written once and nothing both read and written (the copies run concurrently)."""
+    from climaseaice_b200.synthetic import example_fold_maps
+    lib = csi.lib()
+    h = C.c_void_p()
+    Nx = Ny = 16
+    H = 4
+
+    def attempt(maps, sv=-1.0, se=1.0, partition_x=1):
+        cfg = L.csi_config()
+        cfg.abi_version, cfg.Nx, cfg.Ny, cfg.Hx, cfg.Hy, cfg.dx, cfg.dy, cfg.substeps = 1, Nx, Ny, H, H, 1.0, 1.0, 1
+        cfg.advection_order, cfg.topo_x, cfg.topo_y = 3, L.PERIODIC, L.FOLDED
+        cfg.fold_sign_velocity, cfg.fold_sign_external = sv, se
+        if partition_x > 1:
+            cfg.nranks, cfg.partition_x, cfg.exchange_every = partition_x, partition_x, 1
+        keep = []
+        for (lx, ly), (tg, sr) in maps.items():
+            k = lx + 2 * ly
+            tg, sr = np.ascontiguousarray(tg, dtype=np.int32), np.ascontiguousarray(sr, dtype=np.int32)
+            keep += [tg, sr]
+            cfg.fold_target[k] = tg.ctypes.data_as(C.POINTER(C.c_int32))
+            cfg.fold_source[k] = sr.ctypes.data_as(C.POINTER(C.c_int32))
+            cfg.fold_count[k] = tg.size
+        rc = lib.csi_create(C.byref(cfg), C.byref(h))
+        return rc, lib.csi_last_error(None)
+
+    good = example_fold_maps(Nx, Ny, H, H)
+    rc, msg = attempt({k: v for k, v in good.items() if k != (1, 1)})
+    assert rc == -1 and b"each of the four locations" in msg
+    bad = dict(good); bad[(0, 0)] = (good[(0, 0)][0], good[(0, 0)][1] + 10 ** 6)
+    rc, msg = attempt(bad)
+    assert rc == -1 and b"outside the parent" in msg
+    rc, msg = attempt(good, sv=0.5)
+    assert rc == -1 and b"signs" in msg
+    bad = dict(good); bad[(1, 0)] = (np.r_[good[(1, 0)][0], good[(1, 0)][0][:1]], np.r_[good[(1, 0)][1], good[(1, 0)][1][:1]])
+    rc, msg = attempt(bad)
+    assert rc == -1 and b"same target twice" in msg
+    bad = dict(good); bad[(0, 1)] = (good[(0, 1)][0], np.r_[good[(0, 1)][0][1:2], good[(0, 1)][1][1:]])
+    rc, msg = attempt(bad)
+    assert rc == -1 and b"also writes" in msg
+    rc, msg = attempt(good, partition_x=2)
+    assert rc != 0 and b"partition along x" in msg
+    if not torch.cuda.is_available():   # a valid description gets as far as the device
+        rc, msg = attempt(good)
+        assert rc == -4 and b"no CUDA device" in msg
 
 
 def test_synthetic_cases_are_deterministic_and_periodic():

@@ -23,6 +23,7 @@ def latlon_metrics(N, H, lam=(0, 60), phi=(20, 70)):
 
 
 @pytest.mark.parametrize("N", [40, 80])
+
 def test_energy_budget_adjoint_identity(N):
     """test/test_rheology_energy_budget.jl:50-124 on the same lat-lon grid and trig fields."""
     H = 4
@@ -356,3 +357,24 @@ def test_constant_state_is_preserved_along_a_coast():
     # (a stencil reading the island's zeros would give O(0.1))
     assert np.abs(G[~near]).max() < 1e-14
     assert np.isfinite(G).all()
+
+def test_fold_fill_applies_the_copy_lists_with_their_signs():
+    """CSI_FOLDED (the north fold of a tripolar grid, given as copy lists): after every step the velocities obey their lists with
+    sign -1, thickness and concentration with sign +1; the south stays a wall; the lists of the example never read what they write."""
+    from climaseaice_b200.synthetic import folded_case
+    case = folded_case(substeps=8)
+    for (tg, sr) in case.fold["maps"].values():
+        assert np.unique(tg).size == tg.size and not np.intersect1d(tg, sr).size
+    o = oracle_from_case(case)
+    for _ in range(2):
+        o.time_step(case.dt)
+    flat = lambda n: o.arr[n].reshape(-1)
+    for n, loc, sign in (("u", (1, 0), -1.0), ("v", (0, 1), -1.0), ("h", (0, 0), 1.0), ("a", (0, 0), 1.0)):
+        tg, sr = case.fold["maps"][loc]
+        assert np.array_equal(flat(n)[tg], sign * flat(n)[sr]), n
+        assert np.isfinite(o.arr[n]).all()
+    assert np.abs(o.arr["u"]).max() > 1e-3 and np.abs(o.arr["v"][-case.Hy - 3:-case.Hy]).max() > 1e-4   # ice moves at the fold
+    assert np.all(o.arr["v"][case.Hy, case.Hx:-case.Hx] == 0)   # the southern wall
+    # the fold is not a wall: the flow carries ice across it (thickness changes in the last row)
+    h0 = case.fields["h"][case.Hy + case.Ny - 1, case.Hx:-case.Hx]
+    assert np.abs(o.arr["h"][case.Hy + case.Ny - 1, case.Hx:-case.Hx] - h0).max() > 1e-6

@@ -1,2 +1,7 @@
-cd /root/repo 2>/dev/null || cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_parity.py tests/test_c_abi.py -m gpu -q -k "free_drift or c_caller or configuration_switches or bench_configuration or immersed or coastline" 2>&1 | tail -30
+#!/bin/bash
+# A subset of the GPU tests by keyword.  usage: tools/run_subset.sh "KEYWORDS" [TAG]
+cd "$(dirname "$0")/.."
+K=${1:-fold}
+TAG=${2:-subset}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -k "$K" > gpurun_out/subset_$TAG.log 2>&1; echo "pytest rc=$?"; tail -40 gpurun_out/subset_$TAG.log
