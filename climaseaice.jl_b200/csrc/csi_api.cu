@@ -824,6 +824,9 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         g.met = h->met_dev;
         g.metL = L;
         g.metW = Wd;
+        h->met_host.resize((size_t)12 * n);
+        for (int k = 0; k < 12; k++) std::copy(cfg->metrics[k], cfg->metrics[k] + n, h->met_host.begin() + (size_t)k * n);
+        g.met_host = h->met_host.data();
         for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;
     }
     if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) {

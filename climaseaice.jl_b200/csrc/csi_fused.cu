@@ -156,6 +156,10 @@ struct Params {
     const double *met;    // j-dependent metrics (lat-lon grids), or NULL on a regular grid: one record of MC_N doubles per row,
                           // the pointer pre-offset so that the record of reference row j starts at met[j * MC_N]; MET_PAD padding
                           // records on either side, so that no tile needs a clamp
+    const double *met2;   // two-dimensional metrics (orthogonal curvilinear grids), or NULL: MC2_N planes in the internal layout
+                          // (entry of node (i, j) at the node's in-plane offset), MET2_PAD padding rows on either side of each
+                          // plane so that the neighbours an edge tile names need no clamp (they hold valid metrics of other nodes)
+    long long met2_stride; // doubles between two planes
     int *invalid;         // device flag raised by k_pack when an input is neither zero nor in [2^-300, 2^300): the whole
                           // stage then runs the IEEE pass (the FAST pass relies on validated inputs, see MathFast)
 };
@@ -167,31 +171,46 @@ enum { MC_DXCC = 0, MC_DXFC, MC_DXCF, MC_DXFF, MC_DYCC, MC_DYFC, MC_DYCF, MC_DYF
        MC_FFF, MC_N };
 constexpr int MET_PAD = 40;  // padding records of the metric table (>= tile height + halos beyond either end)
 
-// Metric<false>: the regular grid's constants (kernel parameters); Metric<true>: the row's own values, read from the
-// records of the tile's rows staged in shared memory (warp-uniform, conflict-free broadcasts).  r is the reference row index j.
+// Metric<0>: the regular grid's constants (kernel parameters); Metric<1>: the row's own values, read from the records of the
+// tile's rows staged in shared memory (warp-uniform, conflict-free broadcasts); Metric<2>: the node's own values, read through
+// the read-only path from planes in the internal layout (coalesced along a row, neighbours from L1 / L2).
+// r is the reference row index j, o the node's in-plane offset (only Metric<2> looks at it).
 constexpr int MET_ROWS = BY + 5;  // rows J0 - 3 .. J0 + BY + 1: every row a tile's stencils and wall cells name
 static_assert(MET_ROWS * MC_N <= SXD * SYD, "the staged metric records must fit the shared-memory array they borrow");
-template <bool MET>
+constexpr int MET2_PAD = BY + 8;  // padding rows of the two-dimensional metric planes (a tile's halo and its neighbours beyond either end)
+constexpr int MC2_N = 20;         // planes: the twelve metrics and the eight reciprocals
+__host__ __device__ constexpr int met2_plane_of(int col) { return col < 12 ? col : col - (MC_RDXFC - 12); }
+template <int MET>
 struct Metric {
     const Params &p;
-    const double *smt;  // staged records (MET only): row r at smt[(r - rbase) * MC_N]
+    const double *smt;  // staged records (MET == 1): row r at smt[(r - rbase) * MC_N]
     int rbase;
-    __device__ __forceinline__ double ld(int col, int r) const
+    __device__ __forceinline__ double ld(int col, int o, int r) const
     {
+        if (MET == 2) return __ldg(p.met2 + met2_plane_of(col) * p.met2_stride + o);
         return smt[(r - rbase) * MC_N + col];
     }
 #define CSI_MET(name, col, regular) \
-    __device__ __forceinline__ double name(int r) const { return MET ? ld(col, r) : (regular); }
+    __device__ __forceinline__ double name(int o, int r) const { return MET ? ld(col, o, r) : (regular); }
     CSI_MET(dxcc, MC_DXCC, p.dx) CSI_MET(dxfc, MC_DXFC, p.dx) CSI_MET(dxcf, MC_DXCF, p.dx) CSI_MET(dxff, MC_DXFF, p.dx)
     CSI_MET(dycc, MC_DYCC, p.dy) CSI_MET(dyfc, MC_DYFC, p.dy) CSI_MET(dycf, MC_DYCF, p.dy) CSI_MET(dyff, MC_DYFF, p.dy)
     CSI_MET(azcc, MC_AZCC, p.az) CSI_MET(azfc, MC_AZFC, p.az) CSI_MET(azcf, MC_AZCF, p.az) CSI_MET(azff, MC_AZFF, p.az)
-    CSI_MET(dxcc2, MC_DXCC2, p.dx2) CSI_MET(dycc2, MC_DYCC2, p.dy2) CSI_MET(dxff2, MC_DXFF2, p.dx2) CSI_MET(dyff2, MC_DYFF2, p.dy2)
     CSI_MET(rdxfc, MC_RDXFC, p.rdx) CSI_MET(rdxcf, MC_RDXCF, p.rdx) CSI_MET(rdyfc, MC_RDYFC, p.rdy) CSI_MET(rdycf, MC_RDYCF, p.rdy)
     CSI_MET(razcc, MC_RAZCC, p.raz) CSI_MET(razfc, MC_RAZFC, p.raz) CSI_MET(razcf, MC_RAZCF, p.raz) CSI_MET(razff, MC_RAZFF, p.raz)
-    CSI_MET(fff, MC_FFF, p.f)
 #undef CSI_MET
-    __device__ __forceinline__ double dxff2d(int r) const { return MET ? 2 * ld(MC_DXFF2, r) : p.dx2d; }  // 2 dx^2 (exact)
-    __device__ __forceinline__ double dyff2d(int r) const { return MET ? 2 * ld(MC_DYFF2, r) : p.dy2d; }
+    // the squares the SBP operators use (the reference writes dx^2 = dx * dx): staged per row, or formed from the node's metric
+#define CSI_MET_SQ(name, col, base, regular)                                                           \
+    __device__ __forceinline__ double name(int o, int r) const                                         \
+    {                                                                                                   \
+        if (MET == 2) { const double v = ld(base, o, r); return v * v; }                               \
+        return MET ? ld(col, o, r) : (regular);                                                        \
+    }
+    CSI_MET_SQ(dxcc2, MC_DXCC2, MC_DXCC, p.dx2) CSI_MET_SQ(dycc2, MC_DYCC2, MC_DYCC, p.dy2)
+    CSI_MET_SQ(dxff2, MC_DXFF2, MC_DXFF, p.dx2) CSI_MET_SQ(dyff2, MC_DYFF2, MC_DYFF, p.dy2)
+#undef CSI_MET_SQ
+    __device__ __forceinline__ double fff(int r) const { return MET == 1 ? smt[(r - rbase) * MC_N + MC_FFF] : p.f; }
+    __device__ __forceinline__ double dxff2d(int o, int r) const { return MET ? 2 * dxff2(o, r) : p.dx2d; }  // 2 dx^2 (exact)
+    __device__ __forceinline__ double dyff2d(int o, int r) const { return MET ? 2 * dyff2(o, r) : p.dy2d; }
 };
 
 // the metric factors of one velocity node's stress divergence (isd:39-51): d = a (sD1 - sD0) / 2,
@@ -539,15 +558,15 @@ struct TileCtx {
 // MET: j-dependent metrics (lat-lon grid) read from the per-row table instead of the regular grid's constants.
 // INTERIOR: the tile lies inside every store window, has no periodic image, wall neighbour or unevolved node (Params::it_x0):
 // its instantiation carries none of the per-node edge logic.
-template <bool VFIRST, bool AUX, bool GEN, bool MET, class M, bool INTERIOR>
+template <bool VFIRST, bool AUX, bool GEN, int MET, class M, bool INTERIOR>
 __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc, int inv)
 {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     // lat-lon variant: the first-velocity array W shares the slot of e11 (dead after phase B) and W's own slot holds the
     // metric records of the tile's rows, copied once per pass from the per-row table
-    constexpr int AW = MET ? A_E11 : A_W;
+    constexpr int AW = MET == 1 ? A_E11 : A_W;
     const Metric<MET> mt{p, sm + A_W * ASTRIDE, tc.J0 - 3};
-    if (MET) {
+    if (MET == 1) {
         const double *src = p.met + (tc.J0 - 3) * MC_N;
         for (int n = tid; n < MET_ROWS * MC_N; n += NT) sm[A_W * ASTRIDE + n] = __ldg(src + n);
         __syncthreads();
@@ -690,25 +709,28 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if ((k + 1) * NT > SXD * SYD && n >= SXD * SYD) break;
         if (sx >= SXD - 1) { sx -= SXD; sy++; }
         const int r = tc.J0 - 1 + sy;  // reference row of the node
+        const int o = o00 + sy * p.pitch + sx, op = o + p.pitch, om = o - p.pitch;  // in-plane offsets: the node, its north / south neighbour
         double *b = sm + n;  // = &S(0, sx, sy)
         const double u00 = SB(b, A_U, 0, 0), v00 = SB(b, A_V, 0, 0);
         if (sx < BX && sy < BY) {
             const double u10 = SB(b, A_U, 1, 0), v01 = SB(b, A_V, 0, 1);
-            const double dyf = mt.dyfc(r), rdyf = mt.rdyfc(r), dxf0 = mt.dxcf(r), dxf1 = mt.dxcf(r + 1), az = mt.azcc(r), raz = mt.razcc(r);
-            const double D = mm.divc_nc((dyf * u10 - dyf * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
+            // (on a lat-lon grid the two dy^fc are the same number)
+            const double dyf0 = mt.dyfc(o, r), rdyf0 = mt.rdyfc(o, r), dyf1 = mt.dyfc(o + 1, r), rdyf1 = mt.rdyfc(o + 1, r);
+            const double dxf0 = mt.dxcf(o, r), dxf1 = mt.dxcf(op, r + 1), az = mt.azcc(o, r), raz = mt.razcc(o, r);
+            const double D = mm.divc_nc((dyf1 * u10 - dyf0 * u00) + (dxf1 * v01 - dxf0 * v00), az, raz);
             // (u, v are validated inputs or tested quotients of the previous substep: no window test on u / metric)
-            const double T = mm.divc_nc(mt.dycc2(r) * (mm.divc_nc(u10, dyf, rdyf) - mm.divc_nc(u00, dyf, rdyf)) -
-                                         mt.dxcc2(r) * (mm.divc_nc(v01, dxf1, mt.rdxcf(r + 1)) - mm.divc_nc(v00, dxf0, mt.rdxcf(r))),
+            const double T = mm.divc_nc(mt.dycc2(o, r) * (mm.divc_nc(u10, dyf1, rdyf1) - mm.divc_nc(u00, dyf0, rdyf0)) -
+                                         mt.dxcc2(o, r) * (mm.divc_nc(v01, dxf1, mt.rdxcf(op, r + 1)) - mm.divc_nc(v00, dxf0, mt.rdxcf(o, r))),
                                      az, raz);
             SB(b, A_E11, 0, 0) = M::SCALED ? D + T : (D + T) / 2;
             SB(b, A_E22, 0, 0) = M::SCALED ? D - T : (D - T) / 2;
         }
         if (sx >= 0 && sy >= 0) {
             const double u0m = SB(b, A_U, 0, -1), vm0 = SB(b, A_V, -1, 0);
-            const double dyc = mt.dycf(r), rdyc = mt.rdycf(r);
-            const double Sh = mm.divc_nc(mt.dxff2(r) * (mm.divc_nc(u00, mt.dxfc(r), mt.rdxfc(r)) - mm.divc_nc(u0m, mt.dxfc(r - 1), mt.rdxfc(r - 1))) +
-                                          mt.dyff2(r) * (mm.divc_nc(v00, dyc, rdyc) - mm.divc_nc(vm0, dyc, rdyc)),
-                                      mt.azff(r), mt.razff(r));
+            const double dyc0 = mt.dycf(o, r), rdyc0 = mt.rdycf(o, r), dycm = mt.dycf(o - 1, r), rdycm = mt.rdycf(o - 1, r);
+            const double Sh = mm.divc_nc(mt.dxff2(o, r) * (mm.divc_nc(u00, mt.dxfc(o, r), mt.rdxfc(o, r)) - mm.divc_nc(u0m, mt.dxfc(om, r - 1), mt.rdxfc(om, r - 1))) +
+                                          mt.dyff2(o, r) * (mm.divc_nc(v00, dyc0, rdyc0) - mm.divc_nc(vm0, dycm, rdycm)),
+                                      mt.azff(o, r), mt.razff(o, r));
             SB(b, A_E12, 0, 0) = M::SCALED ? Sh : Sh / 2;
         }
     }
@@ -731,7 +753,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll UNROLL_B
     for (int q = 0; q < 2; q++) {
         const int sx = lane, sy = 2 * wrp + q;
-        const int rB = tc.J0 - 1 + sy;
+        const int rB = tc.J0 - 1 + sy, oB = o00 + sy * p.pitch + sx;
         double *b = &S(0, sx, sy);
         double zc, zf, Dc, s11n, s22n, s12n, mc, mf, g2c, g2f;
         bool mc0 = false, mf0 = false;
@@ -777,11 +799,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             if (PRE_RMC) {
                 // reciprocals from k_prep: 1 resp. 1/4 in open water, +inf where the divisor would have failed its range test
                 // (the quotient then fails its window test)
-                g2c = mm.divc_nc(mm.divc(zc * p.ca * p.dt, mc0 ? 1.0 : mc, b_rmc[q]), mt.azcc(rB), mt.razcc(rB));
-                g2f = mm.divc_nc(mm.divc(zf * p.ca * p.dt4, mf0 ? 4.0 : mf, b_rmf[q]), mt.azff(rB), mt.razff(rB));
+                g2c = mm.divc_nc(mm.divc(zc * p.ca * p.dt, mc0 ? 1.0 : mc, b_rmc[q]), mt.azcc(oB, rB), mt.razcc(oB, rB));
+                g2f = mm.divc_nc(mm.divc(zf * p.ca * p.dt4, mf0 ? 4.0 : mf, b_rmf[q]), mt.azff(oB, rB), mt.razff(oB, rB));
             } else {
-                g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc0 ? 1.0 : mc), mt.azcc(rB), mt.razcc(rB));
-                g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf0 ? 4.0 : mf), mt.azff(rB), mt.razff(rB));
+                g2c = mm.divc_nc(mm.div(zc * p.ca * p.dt, mc0 ? 1.0 : mc), mt.azcc(oB, rB), mt.razcc(oB, rB));
+                g2f = mm.divc_nc(mm.div(zf * p.ca * p.dt4, mf0 ? 4.0 : mf), mt.azff(oB, rB), mt.razff(oB, rB));
             }
             Dc = AUX ? Dc2 * 0.5 : 0.0;
         } else {
@@ -805,8 +827,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         s12n = 2 * ef * e12f;
         mc = SB(b, A_H, 0, 0);
         mf = ((SB(b, A_H, -1, -1) + SB(b, A_H, 0, -1)) / 2 + (SB(b, A_H, -1, 0) + mc) / 2) / 2;
-        g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(rB), mt.razcc(rB));
-        g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(rB), mt.razff(rB));
+        g2c = mm.divc(mm.div(zc * p.ca * p.dt, mc), mt.azcc(oB, rB), mt.razcc(oB, rB));
+        g2f = mm.divc(mm.div(zf * p.ca * p.dt, mf), mt.azff(oB, rB), mt.razff(oB, rB));
         }
         // (a clean FAST pass has no NaN quotient and no mass <= 0: both would have left the windows)
         if (!M::SCALED) g2c = (g2c != g2c) ? p.amax2 : g2c;
@@ -857,6 +879,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     auto u_at = [&](int sx, int sy, int VS, const Pt &pt) -> double {
         const double un = pt.n, ttop = pt.t;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
+        const int o = o00 + sy * p.pitch + sx, op = o + p.pitch;
         bool upd = true, wall_active = true;
         if (!INTERIOR) {
             upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
@@ -868,11 +891,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double vbar = M::SCALED ? vsum : ((SB(b, VS, -1, 0) + SB(b, VS, 0, 0)) / 2 + (SB(b, VS, -1, 1) + SB(b, VS, 0, 1)) / 2) / 2;
         // (the switch-free variants: FPlane on regular grids, HydrostaticSphericalCoriolis on lat-lon grids)
         double xcross = ((GEN && p.cor == CSI_CORIOLIS_NONE) || (MET && !GEN)) ? 0.0 : (M::SCALED ? -p.f4 * vsum : -p.f * vbar);
-        if (MET && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc
-            const double dx0 = mt.dxcf(r), dx1 = mt.dxcf(r + 1);
+        if (MET == 1 && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // -Iy(f^ff) * Ix(Iy(dx^cf v)) / dx^fc (lat-lon grids only)
+            const double dx0 = mt.dxcf(o, r), dx1 = mt.dxcf(op, r + 1);
             const double gm = (dx0 * SB(b, VS, -1, 0) + dx1 * SB(b, VS, -1, 1)) / 2, g0 = (dx0 * SB(b, VS, 0, 0) + dx1 * SB(b, VS, 0, 1)) / 2;
             const double fbar = (mt.fff(r) + mt.fff(r + 1)) / 2;
-            xcross = mm.divc(-fbar * ((gm + g0) / 2), mt.dxfc(r), mt.rdxfc(r));
+            xcross = mm.divc(-fbar * ((gm + g0) / 2), mt.dxfc(o, r), mt.rdxfc(o, r));
         }
         double ue = p.ue_c, vebar = M::SCALED ? (p.ve_c + p.ve_c) + (p.ve_c + p.ve_c) : ((p.ve_c + p.ve_c) / 2 + (p.ve_c + p.ve_c) / 2) / 2;
         if (PRE_SVE && use_ue) {
@@ -899,10 +922,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         double imm = 0.0;
         if (has_imm) {
             const double bc = (-p.imm_u) * uold;
-            const double qW = 0.0 * (mt.dycc(r) * 1.0), qE = 0.0 * (mt.dycc(r) * 1.0);
-            const double qS = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dxff(r) * 1.0);
-            const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (mt.dxff(r + 1) * 1.0);
-            imm = mm.divc(qE - qW + qN - qS, mt.azfc(r) * 1.0, mt.razfc(r));
+            const double qW = 0.0 * (mt.dycc(o - 1, r) * 1.0), qE = 0.0 * (mt.dycc(o, r) * 1.0);
+            const double qS = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dxff(o, r) * 1.0);
+            const double qN = ((FLG(sx, sy + 1) & 2) ? bc : 0.0) * (mt.dxff(op, r + 1) * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, mt.azfc(o, r) * 1.0, mt.razfc(o, r));
         }
         Ext x;
         x.ue = ue; x.oe = vebar; x.t1 = ttop;
@@ -915,16 +938,16 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         if (GEN && p.bot_expl) x.tb = pt.tb;
         if (GEN && p.fd_on) x.fd = pt.fd;
-        const double dyc2 = mt.dycc2(r), dyf = mt.dyfc(r);
+        const double dyc2 = mt.dycc2(o, r), dyc2w = mt.dycc2(o - 1, r), dyf = mt.dyfc(o, r);  // (dyc2w == dyc2 unless the metrics depend on i)
         double val;
         if (M::SCALED) {
-            const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2d(r + 1), mt.dxff2d(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
+            const NodeMetric nm{dyf, dyc2, dyc2w, dyf, mt.rdyfc(o, r), mt.dxff2d(op, r + 1), mt.dxff2d(o, r), mt.dxfc(o, r), mt.rdxfc(o, r), mt.azfc(o, r), mt.razfc(o, r)};
             // (a node that is not evolved returns its old value whatever is computed: harmless masses keep it from failing the tile)
             const double m1 = upd ? SB(b, A_H, 0, 0) : 1.0, m0 = upd ? SB(b, A_H, -1, 0) : 1.0;
             val = vel_node_s<GEN, false>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
                                          uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5);
         } else {
-            const NodeMetric nm{dyf, dyc2, dyc2, dyf, mt.rdyfc(r), mt.dxff2(r + 1), mt.dxff2(r), mt.dxfc(r), mt.rdxfc(r), mt.azfc(r), mt.razfc(r)};
+            const NodeMetric nm{dyf, dyc2, dyc2w, dyf, mt.rdyfc(o, r), mt.dxff2(op, r + 1), mt.dxff2(o, r), mt.dxfc(o, r), mt.rdxfc(o, r), mt.azfc(o, r), mt.razfc(o, r)};
             val = vel_node<GEN, false>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
                                        uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         }
@@ -933,6 +956,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     auto v_at = [&](int sx, int sy, int US, const Pt &pt) -> double {
         const double vn = pt.n, ttop = pt.t;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
+        const int o = o00 + sy * p.pitch + sx, om = o - p.pitch;
         bool upd = true, wall_active = true;
         if (!INTERIOR) {
             upd = r >= p.cy0 && r <= p.cy1 && i >= p.cx0 && i <= p.cx1;
@@ -942,11 +966,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double usum = (SB(b, US, 0, -1) + SB(b, US, 1, -1)) + (SB(b, US, 0, 0) + SB(b, US, 1, 0));
         const double ubar = M::SCALED ? usum : ((SB(b, US, 0, -1) + SB(b, US, 1, -1)) / 2 + (SB(b, US, 0, 0) + SB(b, US, 1, 0)) / 2) / 2;
         double ycross = ((GEN && p.cor == CSI_CORIOLIS_NONE) || (MET && !GEN)) ? 0.0 : (M::SCALED ? p.f4 * usum : p.f * ubar);
-        if (MET && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf
-            const double dy0 = mt.dyfc(r - 1), dy1 = mt.dyfc(r);
+        if (MET == 1 && (!GEN || p.cor == CSI_CORIOLIS_SPHERICAL)) {  // +Ix(f^ff) * Iy(Ix(dy^fc u)) / dy^cf (lat-lon grids only)
+            const double dy0 = mt.dyfc(om, r - 1), dy1 = mt.dyfc(o, r);
             const double gm = (dy0 * SB(b, US, 0, -1) + dy0 * SB(b, US, 1, -1)) / 2, g0 = (dy1 * SB(b, US, 0, 0) + dy1 * SB(b, US, 1, 0)) / 2;
             const double fj = mt.fff(r), fbar = (fj + fj) / 2;
-            ycross = mm.divc(fbar * ((gm + g0) / 2), mt.dycf(r), mt.rdycf(r));
+            ycross = mm.divc(fbar * ((gm + g0) / 2), mt.dycf(o, r), mt.rdycf(o, r));
         }
         double ve = p.ve_c, uebar = M::SCALED ? (p.ue_c + p.ue_c) + (p.ue_c + p.ue_c) : ((p.ue_c + p.ue_c) / 2 + (p.ue_c + p.ue_c) / 2) / 2;
         if (PRE_SVE && use_ue) {
@@ -972,10 +996,10 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         double imm = 0.0;
         if (has_imm) {  // isd:84-101, -C*v on west/east immersed faces
             const double bc = (-p.imm_v) * vold;
-            const double qW = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dyff(r) * 1.0);
-            const double qE = ((FLG(sx + 1, sy) & 2) ? bc : 0.0) * (mt.dyff(r) * 1.0);
-            const double qS = 0.0 * (mt.dxcc(r - 1) * 1.0), qN = 0.0 * (mt.dxcc(r) * 1.0);
-            imm = mm.divc(qE - qW + qN - qS, mt.azcf(r) * 1.0, mt.razcf(r));
+            const double qW = ((FLG(sx, sy) & 2) ? -bc : 0.0) * (mt.dyff(o, r) * 1.0);
+            const double qE = ((FLG(sx + 1, sy) & 2) ? bc : 0.0) * (mt.dyff(o + 1, r) * 1.0);
+            const double qS = 0.0 * (mt.dxcc(om, r - 1) * 1.0), qN = 0.0 * (mt.dxcc(o, r) * 1.0);
+            imm = mm.divc(qE - qW + qN - qS, mt.azcf(o, r) * 1.0, mt.razcf(o, r));
         }
         Ext x;
         x.ue = ve; x.oe = uebar; x.t1 = ttop;
@@ -988,8 +1012,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         if (GEN && p.bot_expl) x.tb = pt.tb;
         if (GEN && p.fd_on) x.fd = pt.fd;
-        const double dyf2 = M::SCALED ? mt.dyff2d(r) : mt.dyff2(r), dxf = mt.dxcf(r);
-        const NodeMetric nm{dxf, mt.dxcc2(r), mt.dxcc2(r - 1), dxf, mt.rdxcf(r), dyf2, dyf2, mt.dycf(r), mt.rdycf(r), mt.azcf(r), mt.razcf(r)};
+        const double dyf2 = M::SCALED ? mt.dyff2d(o, r) : mt.dyff2(o, r), dyf2e = M::SCALED ? mt.dyff2d(o + 1, r) : mt.dyff2(o + 1, r), dxf = mt.dxcf(o, r);
+        const NodeMetric nm{dxf, mt.dxcc2(o, r), mt.dxcc2(om, r - 1), dxf, mt.rdxcf(o, r), dyf2e, dyf2, mt.dycf(o, r), mt.rdycf(o, r), mt.azcf(o, r), mt.razcf(o, r)};
         const double val = M::SCALED ? vel_node_s<GEN, true>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
                                                              SB(b, A_AL, 0, -1), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
                                      : vel_node<GEN, true>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
@@ -1043,7 +1067,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // over the full parent extent, so corners hold images of the wall cells)
         if (is_u && ((p.wall_s && r == 1) || (p.wall_n && r == p.Ny))) {
             const int ix = p.px ? (i <= W ? p.Nx : (i > p.Nx - W ? -p.Nx : 0)) : 0;
-            const double Dw = r == 1 ? mt.dyff(1) : mt.dyff(p.Ny + 1);  // Delta y at (Face, Face) on the wall
+            const int ow = (p.oy + (r == 1 ? 0 : p.Ny)) * p.pitch + (i - 1 + OX);
+            const double Dw = r == 1 ? mt.dyff(ow, 1) : mt.dyff(ow, p.Ny + 1);  // Delta y at (Face, Face) on the wall
             const double wv = r == 1 ? (p.u_sn_bc == CSI_BC_VALUE ? val + ((val - p.u_sn_val) / (Dw / 2)) * (-Dw) : val)
                                      : (p.u_sn_bc == CSI_BC_VALUE ? val + ((p.u_sn_val - val) / (Dw / 2)) * Dw : val);
             double *w = r == 1 ? q - p.pitch : q + p.pitch;
@@ -1052,7 +1077,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         }
         if (!is_u && ((p.wall_w && i == 1) || (p.wall_e && i == p.Nx))) {
             const int iy = p.py ? (r <= W ? p.Ny : (r > p.Ny - W ? -p.Ny : 0)) : 0;
-            const double Dw = mt.dxff(r);
+            const double Dw = mt.dxff((r - 1 + p.oy) * p.pitch + (i == 1 ? 0 : p.Nx) + OX, r);  // Delta x at (Face, Face) on the wall
             const double wv = i == 1 ? (p.v_we_bc == CSI_BC_VALUE ? val + ((val - p.v_we_val) / (Dw / 2)) * (-Dw) : val)
                                      : (p.v_we_bc == CSI_BC_VALUE ? val + ((p.v_we_val - val) / (Dw / 2)) * Dw : val);
             double *w = i == 1 ? q - 1 : q + 1;
@@ -1126,7 +1151,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
 // alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
-template <bool VFIRST, bool AUX, bool GEN, bool MET>
+template <bool VFIRST, bool AUX, bool GEN, int MET>
 __global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1441,6 +1466,8 @@ __global__ void k_unpack(const __grid_constant__ UnpackList L, const __grid_cons
 struct FusedPlan {
     uint8_t *flags = nullptr;
     double *met = nullptr;  // per-row metric table (lat-lon grids)
+    double *met2 = nullptr; // two-dimensional metric planes (orthogonal curvilinear grids), MC2_N x (rows + 2 MET2_PAD) x pitch
+    long long met2_stride = 0;
     int *invalid = nullptr; // device flag: an input of the current stage is outside the validated range
     fz::Params P;
     dim3 grid;
@@ -1471,15 +1498,17 @@ static EncodeTiledFn get_encode()
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
     if (g.fold) { snprintf(why, nwhy, "a folded (tripolar) north boundary (general kernels only)"); return 0; }
-    if (g.met && g.metW) { snprintf(why, nwhy, "two-dimensional metrics (general kernels only)"); return 0; }
+    if (g.met && g.metW && (g.conn_w || g.conn_e)) { snprintf(why, nwhy, "two-dimensional metrics with a partition along x"); return 0; }
+    const size_t metn = (size_t)g.metL * (g.metW ? g.metW : 1);  // entries per metric array
     if (g.met) {
-        // every metric that appears as a divisor must qualify for the constant-division shortcut, on every row a tile can touch
+        // every metric that appears as a divisor must qualify for the constant-division shortcut, on every node a tile can touch
         if (!g.met_host) { snprintf(why, nwhy, "host copy of the grid metrics missing"); return 0; }
         const int divisors[8] = {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF};
         for (int k : divisors)
-            for (int q = 0; q < g.metL; q++)
-                if (!recip_is_safe(g.met_host[(size_t)k * g.metL + q])) { snprintf(why, nwhy, "a grid metric is not eligible for the constant-division shortcut"); return 0; }
-    } else if (p.cor == CSI_CORIOLIS_SPHERICAL) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
+            for (size_t q = 0; q < metn; q++)
+                if (!recip_is_safe(g.met_host[(size_t)k * metn + q])) { snprintf(why, nwhy, "a grid metric is not eligible for the constant-division shortcut"); return 0; }
+    }
+    if (p.cor == CSI_CORIOLIS_SPHERICAL && (!g.met || g.metW)) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
     if (p.fd_kind == CSI_FD_FIELDS && (!f.fd_u.p || !f.fd_v.p)) { snprintf(why, nwhy, "free-drift arrays missing"); return 0; }
     if ((f.top_x.p == nullptr) != (f.top_y.p == nullptr)) { snprintf(why, nwhy, "top_x/top_y kinds differ"); return 0; }
     if (!g.met && (!recip_is_safe(g.dx) || !recip_is_safe(g.dy) || !recip_is_safe(g.az))) { snprintf(why, nwhy, "grid metric not eligible for the constant-division shortcut"); return 0; }
@@ -1496,7 +1525,10 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
         for (int k : {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF})
             // rows whose results are kept: the interior and the wall ring; a slab's connected side uses its whole halo
             for (int q = (g.conn_s ? 0 : g.Hy - 1); q < (g.conn_n ? g.metL : std::min(g.metL, g.Hy + g.Ny + 2)) && ok; q++)
-                ok = k >= M_AZCC ? (g.met_host[(size_t)k * g.metL + q] >= 1e-12 && g.met_host[(size_t)k * g.metL + q] <= 1e24) : sane_len(g.met_host[(size_t)k * g.metL + q]);
+                for (int c = 0; c < (g.metW ? g.metW : 1) && ok; c++) {
+                    const double v = g.met_host[(size_t)k * metn + (size_t)q * (g.metW ? g.metW : 1) + c];
+                    ok = k >= M_AZCC ? (v >= 1e-12 && v <= 1e24) : sane_len(v);
+                }
     if (!ok) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;
@@ -1551,7 +1583,25 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
         if (cudaMalloc(&pl->flags, fl.size()) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flags)"); cudaFree(pl->base); delete pl; return nullptr; }
         cudaMemcpy(pl->flags, fl.data(), fl.size(), cudaMemcpyHostToDevice);
     }
-    if (g.met_host) {
+    if (g.met_host && g.metW) {
+        // two-dimensional metrics: MC2_N planes in the internal layout, node (i, j) at its in-plane offset; beyond the host arrays
+        // (padding rows, slack columns) the nearest host value, so that whatever an edge tile names is a valid metric
+        const size_t prow = (size_t)pl->rows + 2 * MET2_PAD, pn = prow * pl->pitch;
+        const size_t hn = (size_t)g.metL * g.metW;
+        std::vector<double> tb((size_t)MC2_N * pn);
+        const int rcol[8] = {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF};  // order of MC_RDXFC .. MC_RAZFF
+        for (size_t rr = 0; rr < prow; rr++)
+            for (int c = 0; c < pl->pitch; c++) {
+                const int i = c + 1 - OX, j = (int)rr - MET2_PAD + 1 - pl->oy;
+                const size_t pi = (size_t)std::min(std::max(i - 1 + g.Hx, 0), g.metW - 1), pj = (size_t)std::min(std::max(j - 1 + g.Hy, 0), g.metL - 1);
+                const size_t src = pj * g.metW + pi, dst = rr * pl->pitch + c;
+                for (int k = 0; k < 12; k++) tb[(size_t)k * pn + dst] = g.met_host[(size_t)k * hn + src];
+                for (int k = 0; k < 8; k++) tb[(size_t)(12 + k) * pn + dst] = 1.0 / g.met_host[(size_t)rcol[k] * hn + src];
+            }
+        if (cudaMalloc(&pl->met2, tb.size() * sizeof(double)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(metric planes)"); cudaFree(pl->base); delete pl; return nullptr; }
+        cudaMemcpy(pl->met2, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice);
+        pl->met2_stride = (long long)pn;
+    } else if (g.met_host) {
         // per-row metric table in internal row coordinates: row rho holds reference row j = rho + 1 - oy
         std::vector<double> tb((size_t)MC_N * (pl->rows + 2 * MET_PAD), 1.0);
         auto src = [&](int which, int rho) {
@@ -1597,11 +1647,12 @@ void fused_destroy(FusedPlan *pl)
     if (pl->base) cudaFree(pl->base);
     if (pl->flags) cudaFree(pl->flags);
     if (pl->met) cudaFree(pl->met);
+    if (pl->met2) cudaFree(pl->met2);
     if (pl->invalid) cudaFree(pl->invalid);
     delete pl;
 }
 
-template <bool VFIRST, bool AUX, bool GEN, bool MET> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
+template <bool VFIRST, bool AUX, bool GEN, int MET> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
     // the attribute is per device (a process may hold handles on several devices through csi_config.device)
@@ -1617,7 +1668,7 @@ template <bool VFIRST, bool AUX, bool GEN, bool MET> static cudaError_t launch_o
     return cudaGetLastError();
 }
 // GEN x MET: the regular grid has a switch-free variant; lat-lon grids (MET) always keep the run-time switches
-template <bool GEN, bool MET> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
+template <bool GEN, int MET> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
 {
     if (vfirst) return aux ? launch_one<true, true, GEN, MET>(pl, P, grid, s) : launch_one<true, false, GEN, MET>(pl, P, grid, s);
     return aux ? launch_one<false, true, GEN, MET>(pl, P, grid, s) : launch_one<false, false, GEN, MET>(pl, P, grid, s);
@@ -1675,13 +1726,15 @@ int fused_begin(FusedPlan *pl, const LaunchCtx &c, const DGrid &g, const DParams
     P.dt2 = 2 * dt; P.dt4 = 4 * dt; P.f4 = p.f * 0.25; P.Dmin2 = 2 * p.Dmin; P.Dmin8 = 8 * p.Dmin;
     P.min_mass2 = 2 * p.min_mass; P.min_conc2 = 2 * p.min_conc; P.dx2d = 2 * P.dx2; P.dy2d = 2 * P.dy2;
     P.gnan = jl_clamp(sqrt(P.amax2), p.amin, p.amax);
-    P.sq = !pl->met && g.dx == g.dy;
+    P.sq = !pl->met && !pl->met2 && g.dx == g.dy;
     P.base = pl->base;
     P.flags = pl->flags;
     P.met = pl->met ? pl->met + (size_t)(MET_PAD - 1 + pl->oy) * MC_N : nullptr;  // record of row j at met[j * MC_N]
+    P.met2 = pl->met2 ? pl->met2 + (size_t)MET2_PAD * pl->pitch : nullptr;  // entry of the node at in-plane offset o at met2[o]
+    P.met2_stride = pl->met2_stride;
     P.invalid = pl->invalid;
     cudaMemsetAsync(pl->invalid, 0, 2 * sizeof(int), c.stream);  // re-validated by the pack kernels below; tile counter reset
-    if (pl->met) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }
+    if (pl->met || pl->met2) { P.dx = P.dy = P.az = P.dx2 = P.dy2 = P.rdx = P.rdy = P.raz = 1.0; }
 
     // the TMA box of tile column k starts at internal column a0 - 3 + OX + OUTX k: keep it even (16-byte aligned)
     P.a0 = P.sx0 < P.vx0 ? P.sx0 : P.vx0;
@@ -1777,15 +1830,16 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         }
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
-        const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met;
+        const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met && !P.met2;
         const bool common_met = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
         auto band = [&](int t0, int t1) -> cudaError_t {
             if (t1 <= t0) return cudaSuccess;
             P.ty0 = t0;
             const dim3 gb(grid.x, t1 - t0);
             ++*c.launches;
-            if (P.met) return common_met ? launch_sub<false, true>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, true>(pl, P, gb, c.stream, vfirst, aux);
-            return common ? launch_sub<false, false>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, false>(pl, P, gb, c.stream, vfirst, aux);
+            if (P.met2) return launch_sub<true, 2>(pl, P, gb, c.stream, vfirst, aux);   // (orthogonal curvilinear grids keep the run-time switches)
+            if (P.met) return common_met ? launch_sub<false, 1>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, 1>(pl, P, gb, c.stream, vfirst, aux);
+            return common ? launch_sub<false, 0>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, 0>(pl, P, gb, c.stream, vfirst, aux);
         };
         cudaError_t e;
         if (k == 0 && halo_ready && t_hi > t_lo) {

@@ -437,30 +437,54 @@ def test_latitude_longitude_grid(impl, topology, timestepper):
     m.close()
 
 
+@pytest.mark.parametrize("impl", ("unfused", "fused", "auto"))
 @pytest.mark.parametrize("topology", [("Bounded", "Bounded"), ("Periodic", "Bounded"), ("Periodic", "Periodic")])
 @pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
-def test_two_dimensional_metrics(topology, timestepper):
+def test_two_dimensional_metrics(impl, topology, timestepper):
     """Metrics that depend on i and j (CSI_METRIC_IJ: orthogonal curvilinear grids, the metric layout of Oceananigans'
     OrthogonalSphericalShellGrid family): every dx/dy/Az of the strain rates, the stress divergence, the relaxation
     factors, the flux divergence, the value BCs and the reductions is taken at the
-    (i, j) the reference's operators name.  General kernels; the fused kernel declines such grids."""
+    (i, j) the reference's operators name -- in the general kernels and in the fused tile kernel, which reads each node's
+    metrics and their correctly rounded reciprocals from planes in its own layout."""
     from climaseaice_b200.synthetic import curvilinear_case
     case = curvilinear_case(72, 56, substeps=20, topology=topology, timestepper=timestepper)
     met = case.metrics()
     assert met["dxcc"].max() / met["dxcc"].min() > 1.5 and np.ptp(met["dxcc"], axis=1).max() > 100.0   # they vary along i too
-    m = model_from_case(case, solver_impl="auto")
+    m = model_from_case(case, solver_impl=impl)
     o = oracle_from_case(case)
     for _ in range(2):
         m.time_step(case.dt); o.time_step(case.dt)
     _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "delta")))
     assert np.abs(interior_of(m.all_fields()["u"].numpy(), case)).max() > 1e-4
-    assert m.fused_stats() == (0, 0, 0)                      # the general kernels ran
+    st = m.fused_stats()
+    assert (st[2] > 0) == (impl != "unfused") and st[0] == 0   # the tile kernel ran (tiles per substep) on validated inputs
+    assert st[1] <= st[2] // 4                                  # ... and its FAST pass carried the tiles, not the IEEE re-pass
     assert m.cell_advection_timescale() == pytest.approx(o.cell_advection_timescale(), rel=1e-15)
     d = m.diagnostics()
     az = met["azcc"][case.Hy:case.Hy + case.Ny, case.Hx:case.Hx + case.Nx]
     assert d["sum_h_Az"] == pytest.approx((o.interior("h") * az).sum(), rel=1e-13)
-    with pytest.raises(RuntimeError, match="two-dimensional metrics"):
-        model_from_case(case, solver_impl="fused").time_step(case.dt)
+    m.close()
+
+
+@pytest.mark.parametrize("impl", ("unfused", "fused"))
+def test_two_dimensional_metrics_with_a_coast(impl):
+    """An island and the linear immersed drag on a curvilinear mesh (Periodic x Bounded): the immersed stress divergence takes its
+    face lengths and areas at the node's own (i, j) too."""
+    from climaseaice_b200.synthetic import LOC, curvilinear_case
+    case = curvilinear_case(64, 48, H=5, substeps=16, topology=("Periodic", "Bounded"))
+    X, Y = case.nodes(LOC["h"])
+    land = (((X / case.Lx - 0.4) ** 2 + (Y / case.Ly - 0.55) ** 2) < 0.012) | ((X / case.Lx > 0.8) & (Y / case.Ly > 0.85))
+    mask = land.astype(np.uint8)
+    mask[:, :case.Hx] = mask[:, case.Nx:case.Nx + case.Hx]
+    mask[:, case.Nx + case.Hx:] = mask[:, case.Hx:2 * case.Hx]
+    case.mask = np.ascontiguousarray(mask)
+    case.immersed_drag = (2e-3, 1e-3)
+    m = model_from_case(case, solver_impl=impl)
+    o = oracle_from_case(case)
+    for _ in range(2):
+        m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case, names=("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "delta")))
+    assert (m.fused_stats()[2] > 0) == (impl == "fused")
     m.close()
 
 
@@ -530,11 +554,11 @@ def test_stress_balance_free_drift_argument_errors():
     h = C.c_void_p()
     assert L.lib().csi_create(C.byref(cfg), C.byref(h)) == -1 and b"not both" in L.lib().csi_last_error(None)
     m.close()
-    # "fused" refuses what only the general kernels implement: two-dimensional metrics
-    from climaseaice_b200.synthetic import curvilinear_case
-    mc = curvilinear_case(40, 32, substeps=2)
+    # "fused" refuses what only the general kernels implement: a folded north boundary
+    from climaseaice_b200.synthetic import folded_case
+    mc = folded_case(substeps=2)
     mf = model_from_case(mc, solver_impl="fused")
-    with pytest.raises(RuntimeError, match="two-dimensional metrics"):
+    with pytest.raises(RuntimeError, match="folded"):
         mf.time_step(mc.dt)
     mf.close()
 

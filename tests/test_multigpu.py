@@ -30,7 +30,7 @@ def test_slab_partition_logic_gloo_world2():
 @pytest.mark.gpu
 @pytest.mark.parametrize("solver,K,topo", [("unfused", 3, "periodic"), ("auto", 3, "periodic"), ("auto", 10, "periodic"),
                                             ("unfused", 3, "bounded_y"), ("auto", 4, "bounded_y"), ("auto", 3, "arctic"), ("unfused", 3, "arctic"),
-                                            ("fused", 3, "coastline"), ("unfused", 3, "coastline"), ("auto", 3, "curvilinear"),
+                                            ("fused", 3, "coastline"), ("unfused", 3, "coastline"), ("auto", 3, "curvilinear"), ("unfused", 3, "curvilinear"),
                                             ("auto", 3, "folded"), ("unfused", 1, "folded")])
 def test_two_gpus_equal_one_gpu(solver, K, topo):
     if torch.cuda.device_count() < 2:
