@@ -283,6 +283,42 @@ def extra_configuration_legs(dev, local, steps=2):
         "ms_per_time_step": ms, "cell_updates_per_s": c5.Nx * c5.Ny * 3 * SUBSTEPS / (ms * 1e-3), "launches_per_time_step": nl,
         "fused_stats": list(st),
         "note": "lat-lon metrics, HydrostaticSphericalCoriolis, slab thermodynamics, RK3; the 8-GPU slabs of this case are 4320 x 42 per rank"}
+    torch.cuda.empty_cache()
+    # beyond BASELINE's list: the grids of the "next" row (f2) -- two-dimensional metrics (fused tile kernel reading per-node metric
+    # planes, beside the general kernels) and a tripolar-like mesh with a north fold (general kernels), momentum only
+    from climaseaice_b200.synthetic import curvilinear_case, folded_case
+
+    def time_momentum(case, solver, n):
+        m = model_from_case(case, solver_impl=solver, device=dev)
+        m.update_state()
+        m.time_step_momentum(DT_STAGE, SUBSTEPS)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n):
+            m.time_step_momentum(DT_STAGE, SUBSTEPS)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms, st = ev0.elapsed_time(ev1) / n, m.fused_stats()
+        m.close()
+        del m
+        torch.cuda.empty_cache()
+        return ms, st
+
+    cc = curvilinear_case(2048, 2048, H=7, substeps=SUBSTEPS, topology=("Periodic", "Bounded"))
+    msf, stf = time_momentum(cc, "fused", steps)
+    msu, _ = time_momentum(cc, "unfused", 1)
+    out["extra_curvilinear_2048_two_dimensional_metrics"] = {
+        "fused_ms_per_step": msf, "fused_cell_updates_per_s": cc.Nx * cc.Ny * SUBSTEPS / (msf * 1e-3), "fused_stats": list(stf),
+        "general_kernels_ms_per_step": msu, "general_kernels_cell_updates_per_s": cc.Nx * cc.Ny * SUBSTEPS / (msu * 1e-3),
+        "note": "orthogonal curvilinear mesh (spacings vary +-25 % along both axes), Periodic x Bounded; one time_step_momentum! of 150 substeps"}
+    del cc
+    cf = folded_case(2048, 1024, H=7, substeps=SUBSTEPS)
+    msu, _ = time_momentum(cf, "auto", 1)
+    out["extra_tripolar_like_2048x1024_north_fold"] = {
+        "general_kernels_ms_per_step": msu, "general_kernels_cell_updates_per_s": cf.Nx * cf.Ny * SUBSTEPS / (msu * 1e-3),
+        "note": "two-dimensional metrics, zonally periodic, north fold (copy lists), an island at the fold; the fold couples the two velocity "
+                "phases of a substep across mirrored columns, so the one-launch tile kernel does not apply (DESIGN.md section 7)"}
     return out
 
 

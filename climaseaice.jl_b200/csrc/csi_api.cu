@@ -757,6 +757,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.metL = 0;
     g.metW = 0;
     g.met_host = nullptr;
+    g.met_fused_why = nullptr;
     g.fff_host = nullptr;
     DParams &p = h->p;
     p.Pstar = cfg->ice_compressive_strength;
@@ -829,6 +830,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
         g.met_host = h->met_host.data();
         for (int k = 0; k < 12; k++) h->cfg.metrics[k] = nullptr;
     }
+    g.met_fused_why = fused_metrics_check(g);
     if (cfg->coriolis_kind == CSI_CORIOLIS_SPHERICAL) {
         const int L = cfg->Ny + 2 * cfg->Hy + 1;
         if ((e = cudaMalloc(&h->fff_dev, sizeof(double) * L)) != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(coriolis)"); }

@@ -47,6 +47,15 @@ namespace csi {
 
 namespace fz {
 
+#ifndef CSI_FUSED_MINB_MET2
+#define CSI_FUSED_MINB_MET2 2   // CTAs per SM of the two-dimensional-metric instantiation (more registers: its per-node loads in flight)
+#endif
+#ifndef CSI_FUSED_MINB_MET1
+#define CSI_FUSED_MINB_MET1 2   // per-row metrics (lat-lon grids): 80 registers spill 0.6-0.8 KB per thread; measured +16 % at 128
+#endif
+#ifndef CSI_FUSED_MINB_GEN
+#define CSI_FUSED_MINB_GEN CSI_FUSED_MINB
+#endif
 #ifndef CSI_TILE_BY
 #define CSI_TILE_BY 16
 #endif
@@ -256,6 +265,11 @@ __device__ __forceinline__ void tma_load_row(double *dst, const CUtensorMap *map
 __device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *map, int x, int y, int z)
 {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+// pulls a contiguous run of global memory (16-byte aligned, a multiple of 16 bytes) towards L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void *g, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -570,6 +584,15 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         const double *src = p.met + (tc.J0 - 3) * MC_N;
         for (int n = tid; n < MET_ROWS * MC_N; n += NT) sm[A_W * ASTRIDE + n] = __ldg(src + n);
         __syncthreads();
+    }
+    if (MET == 2 && M::SCALED) {
+        // two-dimensional metrics are read node by node through the read-only path in every phase: start the tile's rows of all
+        // planes on their way from HBM to L2 now, behind the TMA loads below, so that those reads find them there
+        const int xb = tc.I0 - 3 + OX, yb = tc.J0 - 3 + p.oy;   // the TMA box of the tile (even column: 16-byte aligned rows)
+        for (int n = tid; n < MC2_N * SYD; n += NT) {
+            const int k = n / SYD, row = n - k * SYD;
+            bulk_prefetch_l2(p.met2 + k * p.met2_stride + (long long)(yb + row) * p.pitch + xb, SXD * (uint32_t)sizeof(double));
+        }
     }
     const size_t plane = (size_t)p.pitch * p.rows;
     const bool use_ue = GEN ? p.use_ue != 0 : true, use_top = GEN ? p.use_top != 0 : true;
@@ -1152,7 +1175,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
 // alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
 template <bool VFIRST, bool AUX, bool GEN, int MET>
-__global__ void __launch_bounds__(NT, CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
+__global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : MET == 1 ? CSI_FUSED_MINB_MET1 : GEN ? CSI_FUSED_MINB_GEN : CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
@@ -1495,19 +1518,35 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
+// The grid's metric arrays against the premises of the fused kernel: checked once, when the handle is created (the arrays
+// never change afterwards, and a sweep over twelve two-dimensional arrays per momentum solve would cost more than the solve).
+const char *fused_metrics_check(const DGrid &g)
+{
+    if (!g.met) return nullptr;
+    const int cols = g.metW ? g.metW : 1;
+    const size_t metn = (size_t)g.metL * cols;  // entries per metric array
+    // every metric that appears as a divisor must qualify for the constant-division shortcut, on every node a tile can touch
+    if (!g.met_host) return "host copy of the grid metrics missing";
+    const int divisors[8] = {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF};
+    for (int k : divisors)
+        for (size_t q = 0; q < metn; q++)
+            if (!recip_is_safe(g.met_host[(size_t)k * metn + q])) return "a grid metric is not eligible for the constant-division shortcut";
+    // premises of the scaled expression tree: grid spacings in metres (areas: the square) far inside the normal range, on the rows
+    // whose results are kept: the interior and the wall ring; a slab's connected side uses its whole halo
+    for (int k : divisors)
+        for (int q = (g.conn_s ? 0 : g.Hy - 1); q < (g.conn_n ? g.metL : std::min(g.metL, g.Hy + g.Ny + 2)); q++)
+            for (int c = 0; c < cols; c++) {
+                const double v = g.met_host[(size_t)k * metn + (size_t)q * cols + c];
+                if (!(k >= M_AZCC ? (v >= 1e-12 && v <= 1e24) : (v >= 1e-6 && v <= 1e12))) return "a grid metric is outside the range the fused kernel's exact scalings assume";
+            }
+    return nullptr;
+}
+
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
     if (g.fold) { snprintf(why, nwhy, "a folded (tripolar) north boundary (general kernels only)"); return 0; }
     if (g.met && g.metW && (g.conn_w || g.conn_e)) { snprintf(why, nwhy, "two-dimensional metrics with a partition along x"); return 0; }
-    const size_t metn = (size_t)g.metL * (g.metW ? g.metW : 1);  // entries per metric array
-    if (g.met) {
-        // every metric that appears as a divisor must qualify for the constant-division shortcut, on every node a tile can touch
-        if (!g.met_host) { snprintf(why, nwhy, "host copy of the grid metrics missing"); return 0; }
-        const int divisors[8] = {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF};
-        for (int k : divisors)
-            for (size_t q = 0; q < metn; q++)
-                if (!recip_is_safe(g.met_host[(size_t)k * metn + q])) { snprintf(why, nwhy, "a grid metric is not eligible for the constant-division shortcut"); return 0; }
-    }
+    if (g.met && g.met_fused_why) { snprintf(why, nwhy, "%s", g.met_fused_why); return 0; }
     if (p.cor == CSI_CORIOLIS_SPHERICAL && (!g.met || g.metW)) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
     if (p.fd_kind == CSI_FD_FIELDS && (!f.fd_u.p || !f.fd_v.p)) { snprintf(why, nwhy, "free-drift arrays missing"); return 0; }
     if ((f.top_x.p == nullptr) != (f.top_y.p == nullptr)) { snprintf(why, nwhy, "top_x/top_y kinds differ"); return 0; }
@@ -1520,15 +1559,7 @@ int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *wh
     if (p.top_kind == CSI_STRESS_SEMI_IMPLICIT && !sane(p.top_rho * p.top_Cd)) { snprintf(why, nwhy, "top drag coefficient outside the range the exact scalings assume"); return 0; }
     bool ok = p.min_conc >= 1e-30 && p.min_mass >= 1e-30 && p.amin >= 1e-30 && p.amax <= 1e30 && p.amin <= p.amax && sane(p.f) && p.Dmin >= 1e-30 && p.Dmin <= 1e30 && sane(p.em2) &&
               sane(p.ca) && sane(p.rho_e * p.Cd) && sane(p.rho_i) && p.rho_i > 0;
-    if (!g.met) ok = ok && sane_len(g.dx) && sane_len(g.dy);
-    else
-        for (int k : {M_DXFC, M_DXCF, M_DYFC, M_DYCF, M_AZCC, M_AZFC, M_AZCF, M_AZFF})
-            // rows whose results are kept: the interior and the wall ring; a slab's connected side uses its whole halo
-            for (int q = (g.conn_s ? 0 : g.Hy - 1); q < (g.conn_n ? g.metL : std::min(g.metL, g.Hy + g.Ny + 2)) && ok; q++)
-                for (int c = 0; c < (g.metW ? g.metW : 1) && ok; c++) {
-                    const double v = g.met_host[(size_t)k * metn + (size_t)q * (g.metW ? g.metW : 1) + c];
-                    ok = k >= M_AZCC ? (v >= 1e-12 && v <= 1e24) : sane_len(v);
-                }
+    if (!g.met) ok = ok && sane_len(g.dx) && sane_len(g.dy);   // (metric arrays: fused_metrics_check, once per handle)
     if (!ok) { snprintf(why, nwhy, "a threshold or constant is outside the range the fused kernel's exact scalings assume"); return 0; }
     if ((f.ue.p == nullptr) != (f.ve.p == nullptr)) { snprintf(why, nwhy, "ue/ve kinds differ"); return 0; }
     (void)p;

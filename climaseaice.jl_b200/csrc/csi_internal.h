@@ -35,6 +35,7 @@ void launch_diagnostics(const LaunchCtx &c, const DGrid &g, const DFields &f, do
 // ---- fused path (csi_fused.cu) ---------------------------------------------------------------
 struct FusedPlan;  // opaque; owns ping-pong buffers and tensor maps
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy);
+const char *fused_metrics_check(const DGrid &g);   // NULL, or why the grid's metric arrays rule the fused kernel out (csi_create)
 FusedPlan *fused_create(const DGrid &g, const DParams &p, char *err, int nerr);
 void fused_destroy(FusedPlan *);
 // runs `nsub` substeps starting at substep index `first_sub` (1-based parity as in se.jl:173-189)

@@ -31,6 +31,7 @@ struct DGrid {
     // order dxcc dxfc dxcf dxff dycc dyfc dycf dyff azcc azfc azcf azff.  NULL on a regular RectilinearGrid.
     const double *met;
     int metL, metW;         // rows of the metric arrays; columns per row (0: the metrics depend on j only)
+    const char *met_fused_why;  // NULL, or why the metric arrays rule the fused kernel out (checked once at csi_create)
     const double *met_host;  // host copies (plan construction only): the 12 x metL metrics, and f at (Face, Face) or NULL
     const double *fff_host;
     // north fold of a tripolar grid (CSI_FOLDED; topo_y is then CSI_BOUNDED with conn_n = 1: the north side is no wall): copy lists

@@ -1,4 +1,4 @@
-"""Run a few momentum solves on one GPU (for ncu / quick timing): python tools/profile_case.py N nsub [solver] [bounded]"""
+"""Run a few momentum solves on one GPU (for ncu / quick timing): python tools/profile_case.py N nsub [solver] [bounded|coastline|curvilinear|latlon]"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -13,6 +13,12 @@ if kind == "bounded":
 elif kind == "coastline":
     from climaseaice_b200.synthetic import coastline_case
     case = coastline_case(Ny=N, substeps=nsub)
+elif kind == "curvilinear":
+    from climaseaice_b200.synthetic import curvilinear_case
+    case = curvilinear_case(N, N, H=7, substeps=nsub, topology=("Periodic", "Bounded"))
+elif kind == "latlon":
+    from climaseaice_b200.synthetic import latlon_case
+    case = latlon_case(N, H=7, substeps=nsub, topology=("Periodic", "Bounded"))
 else:
     case = periodic_case(N, substeps=nsub, aice="mixed")
 m = model_from_case(case, solver_impl=solver)
