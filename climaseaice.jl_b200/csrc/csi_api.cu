@@ -85,6 +85,7 @@ struct csi_handle {
     double *met_dev = nullptr;
     double *fff_dev = nullptr;
     std::vector<int32_t *> fold_dev;
+    std::vector<int32_t> fold_host[8];   // host copies of the fold lists: target / source of the four locations
     std::vector<uint8_t> mask_host;
     std::vector<double> met_host, fff_host;
     FusedPlan *fused = nullptr;
@@ -737,7 +738,7 @@ int csi_create(const csi_config *cfg, csi_handle **out)
     g.conn_s = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry > 0);
     g.conn_n = h->Ry > 1 && (cfg->topo_y == CSI_PERIODIC || h->ry < h->Ry - 1);
     g.fold = 0;
-    for (int loc = 0; loc < 4; loc++) { g.fold_t[loc] = g.fold_s[loc] = nullptr; g.fold_n[loc] = 0; }
+    for (int loc = 0; loc < 4; loc++) { g.fold_t[loc] = g.fold_s[loc] = g.fold_t_host[loc] = g.fold_s_host[loc] = nullptr; g.fold_n[loc] = 0; }
     g.fold_sv = g.fold_se = 1.0;
     if (cfg->topo_y == CSI_FOLDED && !g.conn_n) {
         // the rank that holds the fold: its north side is connected -- to itself, through the copy lists -- not a wall.  The general
@@ -849,6 +850,10 @@ int csi_create(const csi_config *cfg, csi_handle **out)
             cudaMemcpy(s, cfg->fold_source[loc], nb, cudaMemcpyDefault);
             h->fold_dev.push_back(t);
             h->fold_dev.push_back(s);
+            h->fold_host[2 * loc].assign(cfg->fold_target[loc], cfg->fold_target[loc] + cfg->fold_count[loc]);
+            h->fold_host[2 * loc + 1].assign(cfg->fold_source[loc], cfg->fold_source[loc] + cfg->fold_count[loc]);
+            g.fold_t_host[loc] = h->fold_host[2 * loc].data();
+            g.fold_s_host[loc] = h->fold_host[2 * loc + 1].data();
             g.fold_t[loc] = t;
             g.fold_s[loc] = s;
             g.fold_n[loc] = cfg->fold_count[loc];

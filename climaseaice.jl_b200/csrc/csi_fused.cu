@@ -572,7 +572,9 @@ struct TileCtx {
 // MET: j-dependent metrics (lat-lon grid) read from the per-row table instead of the regular grid's constants.
 // INTERIOR: the tile lies inside every store window, has no periodic image, wall neighbour or unevolved node (Params::it_x0):
 // its instantiation carries none of the per-node edge logic.
-template <bool VFIRST, bool AUX, bool GEN, int MET, class M, bool INTERIOR>
+// PH: 0 = the whole substep; 1 = phases A-C alone (stores the stresses, alpha and the first velocity), 2 = phase D alone (reads
+// them back).  Meshes with a fold run their northernmost tile rows as 1, fold fill of the first velocity, 2: see fused_steps.
+template <bool VFIRST, bool AUX, bool GEN, int MET, int PH, class M, bool INTERIOR>
 __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t parity, const CUtensorMap *tmap, const Params &p, const TileCtx &tc, int inv)
 {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -610,16 +612,24 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const bool cst = field == F_M || field == F_A || field == F_P || field == F_UE || field == F_VE;
             tma_load_row(sm + arr * ASTRIDE, tmap, b, cst ? xk : x, cst ? yk : y, field);
         };
-        ld(A_U, tc.fin + 0, &bar[0]);
-        ld(A_V, tc.fin + 1, &bar[0]);
+        if (PH == 2) {
+            // the second velocity phase alone: its own component of the previous substep, and what the A-C launch stored -- the
+            // first velocity (with the fold applied since), the new stresses and alpha
+            ld(VFIRST ? A_U : A_V, tc.fin + (VFIRST ? 0 : 1), &bar[0]);
+            ld(AW, tc.fout + (VFIRST ? 1 : 0), &bar[0]);
+        } else {
+            ld(A_U, tc.fin + 0, &bar[0]);
+            ld(A_V, tc.fin + 1, &bar[0]);
+        }
         mbar_expect_tx(&bar[0], 2u * SXD * SYD * sizeof(double));
         int n = 6;
         ld(A_H, F_M, &bar[1]);  // ice mass (k_prep): the array is called A_H for historical reasons
         ld(A_A, F_A, &bar[1]);
-        ld(A_P, F_P, &bar[1]);
-        ld(A_S11, tc.fin + 2, &bar[1]);
-        ld(A_S22, tc.fin + 3, &bar[1]);
-        ld(A_S12, tc.fin + 4, &bar[1]);
+        if (PH == 2) ld(A_AL, F_ALPHA, &bar[1]);
+        else ld(A_P, F_P, &bar[1]);
+        ld(A_S11, (PH == 2 ? tc.fout : tc.fin) + 2, &bar[1]);
+        ld(A_S22, (PH == 2 ? tc.fout : tc.fin) + 3, &bar[1]);
+        ld(A_S12, (PH == 2 ? tc.fout : tc.fin) + 4, &bar[1]);
         if (use_ue && !(M::SCALED && CSI_PRE_SVE)) {
             ld(A_UE, F_UE, &bar[1]);
             ld(A_VE, F_VE, &bar[1]);
@@ -694,6 +704,9 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     // ---------------- phase A: strain rates (evp:360-375), ice mass (ClimaSeaIce.jl:42) ----------------
     // e11, e22 on [-1, BX-1] x [-1, BY-1]; e12 on [0, BX] x [0, BY]; m everywhere (in place over h)
     mbar_wait(&bar[0], parity);
+    if (PH == 2) mbar_wait(&bar[1], parity);
+    double aux_zc[2], aux_zf[2], aux_Dc[2];
+    if (PH != 2) {
     if (M::SCALED && !MET && p.sq) {
         // regular grid with dx == dy: u / dx and v / dx serve both the tension and the shear operator; divide every
         // u, v of the tile once (into the arrays phases B and C fill later) instead of eight times per node
@@ -762,7 +775,6 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
     mbar_wait(&bar[1], parity);  // (the ice mass m = h rho aice arrives precomputed: k_prep)
 
     // ---------------- phase B: viscosities + stress update (evp:236-354), nodes [0,BX) x [0,BY) --------
-    double aux_zc[2], aux_zf[2], aux_Dc[2];
     constexpr bool PRE_RMC = M::SCALED && CSI_PRE_RMC, PRE_PF4 = M::SCALED && CSI_PRE_PF4;
     double b_rmc[2] = {0.0, 0.0}, b_rmf[2] = {0.0, 0.0}, b_pf4[2] = {0.0, 0.0};
     if (PRE_RMC || PRE_PF4) {
@@ -874,6 +886,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         aux_zf[q] = zf;
         aux_Dc[q] = Dc;
     }
+    }  // (PH != 2)
     // the pointwise inputs of phase C are requested before the barrier, so their L2 latency overlaps the wait
     constexpr bool PRE_SVE = M::SCALED && CSI_PRE_SVE, PRE_RM2 = M::SCALED && CSI_PRE_RM2;
     auto load_pt = [&](bool on, uint32_t g, const PhasePtrs &pp, double tconst, double bconst) {
@@ -894,10 +907,19 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         return pt;
     };
     Pt cpt[2];
+    if (PH != 2) {
 #pragma unroll
-    for (int q = 0; q < 2; q++) cpt[q] = load_pt(c_on[q], c_g[q], p.pc, VFIRST ? p.tty : p.ttx, VFIRST ? p.tb_y : p.tb_x);
+        for (int q = 0; q < 2; q++) cpt[q] = load_pt(c_on[q], c_g[q], p.pc, VFIRST ? p.tty : p.ttx, VFIRST ? p.tb_y : p.tb_x);
+    }
     __syncthreads();
 
+    // alpha at a neighbour of a velocity node.  Phase D alone reads it back from its plane: nodes of the box beyond the plane
+    // arrive as zeros (TMA), where the whole substep would hold a computed alpha -- none of them feeds a stored cell, but a zero
+    // divisor must not send the tile to the IEEE pass
+    auto AL = [&](const double *b, int off) -> double {
+        const double v = b[A_AL * ASTRIDE + off];
+        return (PH == 2 && v == 0.0) ? p.amin : v;
+    };
     // u at node (sx, sy); VS = array holding the v it reads (old v, or the first-velocity array)
     auto u_at = [&](int sx, int sy, int VS, const Pt &pt) -> double {
         const double un = pt.n, ttop = pt.t;
@@ -967,11 +989,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const NodeMetric nm{dyf, dyc2, dyc2w, dyf, mt.rdyfc(o, r), mt.dxff2d(op, r + 1), mt.dxff2d(o, r), mt.dxfc(o, r), mt.rdxfc(o, r), mt.azfc(o, r), mt.razfc(o, r)};
             // (a node that is not evolved returns its old value whatever is computed: harmless masses keep it from failing the tile)
             const double m1 = upd ? SB(b, A_H, 0, 0) : 1.0, m0 = upd ? SB(b, A_H, -1, 0) : 1.0;
-            val = vel_node_s<GEN, false>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+            val = vel_node_s<GEN, false>(mm, p, nm, active, m1, m0, SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), AL(b, 0), AL(b, -1),
                                          uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5);
         } else {
             const NodeMetric nm{dyf, dyc2, dyc2w, dyf, mt.rdyfc(o, r), mt.dxff2(op, r + 1), mt.dxff2(o, r), mt.dxfc(o, r), mt.rdxfc(o, r), mt.azfc(o, r), mt.razfc(o, r)};
-            val = vel_node<GEN, false>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), SB(b, A_AL, 0, 0), SB(b, A_AL, -1, 0),
+            val = vel_node<GEN, false>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, -1, 0), SB(b, A_A, 0, 0), SB(b, A_A, -1, 0), AL(b, 0), AL(b, -1),
                                        uold, vbar, xcross, x, un, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         }
         return upd ? val : uold;
@@ -1037,33 +1059,39 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         if (GEN && p.fd_on) x.fd = pt.fd;
         const double dyf2 = M::SCALED ? mt.dyff2d(o, r) : mt.dyff2(o, r), dyf2e = M::SCALED ? mt.dyff2d(o + 1, r) : mt.dyff2(o + 1, r), dxf = mt.dxcf(o, r);
         const NodeMetric nm{dxf, mt.dxcc2(o, r), mt.dxcc2(om, r - 1), dxf, mt.rdxcf(o, r), dyf2e, dyf2, mt.dycf(o, r), mt.rdycf(o, r), mt.azcf(o, r), mt.razcf(o, r)};
-        const double val = M::SCALED ? vel_node_s<GEN, true>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                                             SB(b, A_AL, 0, -1), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
-                                     : vel_node<GEN, true>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), SB(b, A_AL, 0, 0),
-                                                           SB(b, A_AL, 0, -1), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
+        const double val = M::SCALED ? vel_node_s<GEN, true>(mm, p, nm, active, upd ? SB(b, A_H, 0, 0) : 1.0, upd ? SB(b, A_H, 0, -1) : 1.0, SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), AL(b, 0),
+                                                             AL(b, -SXD), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, 2 * imm, upd ? pt.rm : 0.5)
+                                     : vel_node<GEN, true>(mm, p, nm, active, SB(b, A_H, 0, 0), SB(b, A_H, 0, -1), SB(b, A_A, 0, 0), SB(b, A_A, 0, -1), AL(b, 0),
+                                                           AL(b, -SXD), vold, ubar, ycross, x, vn, a1 + b1, a0 + b0, a1 - b1, a0 - b0, s12hi, s12lo, has_imm, imm);
         return upd ? val : vold;
     };
 
     // ---------------- phase C: first velocity on the cells the second one reads -------------------------
+    if (PH != 2) {
 #pragma unroll UNROLL_CD
-    for (int q = 0; q < 2; q++)
-        if (c_on[q]) {
-            const int sy = c_sy0 + q;
-            S(AW, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, cpt[q]) : u_at(c_sx, sy, A_V, cpt[q]);
-        }
+        for (int q = 0; q < 2; q++)
+            if (c_on[q]) {
+                const int sy = c_sy0 + q;
+                S(AW, c_sx, sy) = VFIRST ? v_at(c_sx, sy, A_U, cpt[q]) : u_at(c_sx, sy, A_V, cpt[q]);
+            }
+    }
     Pt dpt[2];  // likewise for phase D
+    if (PH != 1) {
 #pragma unroll
-    for (int q = 0; q < 2; q++) dpt[q] = load_pt(d_on[q], d_g[q], p.pd, VFIRST ? p.ttx : p.tty, VFIRST ? p.tb_x : p.tb_y);
+        for (int q = 0; q < 2; q++) dpt[q] = load_pt(d_on[q], d_g[q], p.pd, VFIRST ? p.ttx : p.tty, VFIRST ? p.tb_x : p.tb_y);
+    }
     __syncthreads();
 
     // ---------------- phase D: second velocity on the output cells [1,30] x [1,14] ----------------------
     double w2[2] = {0.0, 0.0};
+    if (PH != 1) {
 #pragma unroll UNROLL_CD
-    for (int q = 0; q < 2; q++)
-        if (d_on[q]) {
-            const int sy = d_sy0 + q;
-            w2[q] = VFIRST ? u_at(d_sx, sy, AW, dpt[q]) : v_at(d_sx, sy, AW, dpt[q]);
-        }
+        for (int q = 0; q < 2; q++)
+            if (d_on[q]) {
+                const int sy = d_sy0 + q;
+                w2[q] = VFIRST ? u_at(d_sx, sy, AW, dpt[q]) : v_at(d_sx, sy, AW, dpt[q]);
+            }
+    }
 
     const bool bad = __syncthreads_or(mm.bad() | (inv != 0));
     if (bad) return true;
@@ -1118,13 +1146,13 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 #pragma unroll
             for (int q = 0; q < 2; q++, so += (uint32_t)p.pitch) {
                 const int sx = lane, sy = 2 * wrp + q;
-                if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
+                if (PH != 2 && sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY) {
                     p.o_s11[so] = S(A_S11, sx, sy);
                     p.o_s22[so] = S(A_S22, sx, sy);
                     p.o_s12[so] = S(A_S12, sx, sy);
+                    if (AUX || PH == 1) (p.base + so)[(size_t)F_ALPHA * plane] = S(A_AL, sx, sy);   // (phase D alone reads alpha back)
                     if (AUX) {
                         double *g = p.base + so;
-                        g[(size_t)F_ALPHA * plane] = S(A_AL, sx, sy);
                         g[(size_t)F_ZC * plane] = aux_zc[q];
                         g[(size_t)F_ZF * plane] = aux_zf[q];
                         g[(size_t)F_DELTA * plane] = aux_Dc[q];
@@ -1132,8 +1160,8 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
                 }
                 if (d_on[q]) {  // node (lane + 1, 2 wrp + 1 + q): the offset the pointwise inputs of phase D were read at
                     const uint32_t dg = d_g[q] + (uint32_t)(o00 - o00k);   // (o00k == o00 outside the timing experiment)
-                    p.o_d[dg] = w2[q];
-                    p.o_c[dg] = S(AW, d_sx, d_sy0 + q);
+                    if (PH != 1) p.o_d[dg] = w2[q];
+                    if (PH != 2) p.o_c[dg] = S(AW, d_sx, d_sy0 + q);
                 }
             }
             return false;
@@ -1145,12 +1173,12 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
         // stresses (and aux) of the node this thread updated in phase B
         const int sx = lane, sy = 2 * wrp + q;
         const int i = tc.I0 - 1 + sx, r = tc.J0 - 1 + sy;
-        if (sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY && i >= p.sx0 && i <= p.sx1 && r >= p.sy0 && r <= p.sy1) {
+        if (PH != 2 && sx >= 1 && sx <= OUTX && sy >= 1 && sy <= OUTY && i >= p.sx0 && i <= p.sx1 && r >= p.sy0 && r <= p.sy1) {
             put(tc.fout + 2, i, r, S(A_S11, sx, sy));
             put(tc.fout + 3, i, r, S(A_S22, sx, sy));
             put(tc.fout + 4, i, r, S(A_S12, sx, sy));
+            if (AUX || PH == 1) put(F_ALPHA, i, r, S(A_AL, sx, sy));
             if (AUX) {
-                put(F_ALPHA, i, r, S(A_AL, sx, sy));
                 put(F_ZC, i, r, aux_zc[q]);
                 put(F_ZF, i, r, aux_zf[q]);
                 put(F_DELTA, i, r, aux_Dc[q]);
@@ -1161,11 +1189,11 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
             const int dsy = d_sy0 + q;
             const int ui = tc.I0 - 1 + d_sx, ur = tc.J0 - 1 + dsy;
             if (VFIRST) {
-                put_vel(tc.fout + 0, ui, ur, w2[q], true);
-                put_vel(tc.fout + 1, ui, ur, S(AW, d_sx, dsy), false);
+                if (PH != 1) put_vel(tc.fout + 0, ui, ur, w2[q], true);
+                if (PH != 2) put_vel(tc.fout + 1, ui, ur, S(AW, d_sx, dsy), false);
             } else {
-                put_vel(tc.fout + 1, ui, ur, w2[q], false);
-                put_vel(tc.fout + 0, ui, ur, S(AW, d_sx, dsy), true);
+                if (PH != 1) put_vel(tc.fout + 1, ui, ur, w2[q], false);
+                if (PH != 2) put_vel(tc.fout + 0, ui, ur, S(AW, d_sx, dsy), true);
             }
         }
     }
@@ -1174,7 +1202,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
 // alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
-template <bool VFIRST, bool AUX, bool GEN, int MET>
+template <bool VFIRST, bool AUX, bool GEN, int MET, int PH = 0>
 __global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : MET == 1 ? CSI_FUSED_MINB_MET1 : GEN ? CSI_FUSED_MINB_GEN : CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1198,14 +1226,17 @@ __global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : MET == 1 
     // The flag is requested here and consumed where the FAST pass decides whether it may store (no stall on its latency;
     // a pass over unvalidated inputs computes garbage and stores nothing)
     const int inv = *p.invalid;
-    const bool redo = interior ? tile_pass<VFIRST, AUX, GEN, MET, MathFast, true>(sm, bar, 0, &tmap, p, tc, inv)
-                               : tile_pass<VFIRST, AUX, GEN, MET, MathFast, false>(sm, bar, 0, &tmap, p, tc, inv);
+    const bool redo = interior ? tile_pass<VFIRST, AUX, GEN, MET, PH, MathFast, true>(sm, bar, 0, &tmap, p, tc, inv)
+                               : tile_pass<VFIRST, AUX, GEN, MET, PH, MathFast, false>(sm, bar, 0, &tmap, p, tc, inv);
     // an operand left the windows of the shortcut arithmetic (zero ice mass, NaN, a quotient out of range ...):
     // reload the tile and redo it with plain IEEE operators and the reference's expression tree
     if (redo) {
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(p.invalid + 1, 1);  // diagnostics: tiles that took the IEEE pass
-        tile_pass<VFIRST, AUX, GEN, MET, MathSlow, false>(sm, bar, 1, &tmap, p, tc, 0);
+#ifdef CSI_DEBUG_REDO
+        if (threadIdx.x == 0) printf("IEEE re-pass: tile (%d, %d) of (%d, %d), I0 = %d, J0 = %d, phases %d, vfirst %d\n", (int)blockIdx.x, by, (int)gridDim.x, (int)gridDim.y + p.ty0, tc.I0, tc.J0, PH, (int)VFIRST);
+#endif
+        tile_pass<VFIRST, AUX, GEN, MET, PH, MathSlow, false>(sm, bar, 1, &tmap, p, tc, 0);
     }
 }
 #undef S
@@ -1489,6 +1520,12 @@ __global__ void k_unpack(const __grid_constant__ UnpackList L, const __grid_cons
 struct FusedPlan {
     uint8_t *flags = nullptr;
     double *met = nullptr;  // per-row metric table (lat-lon grids)
+    // a folded north boundary: the copy lists of u and v in the internal layout (in-plane offsets), their sign, and the first
+    // tile row whose second velocity phase can read a first-velocity value the fold replaces (fused_steps)
+    int32_t *fold_t[2] = {nullptr, nullptr}, *fold_s[2] = {nullptr, nullptr};
+    int fold_n[2] = {0, 0};
+    double fold_sign = 1.0;
+    int fold_jmin = 0;      // southernmost reference row a list writes
     double *met2 = nullptr; // two-dimensional metric planes (orthogonal curvilinear grids), MC2_N x (rows + 2 MET2_PAD) x pitch
     long long met2_stride = 0;
     int *invalid = nullptr; // device flag: an input of the current stage is outside the validated range
@@ -1544,7 +1581,8 @@ const char *fused_metrics_check(const DGrid &g)
 
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy)
 {
-    if (g.fold) { snprintf(why, nwhy, "a folded (tripolar) north boundary (general kernels only)"); return 0; }
+    if (g.fold && !(g.met && g.metW)) { snprintf(why, nwhy, "a folded (tripolar) north boundary on a grid without two-dimensional metrics (general kernels only)"); return 0; }
+    if (g.fold && (!g.fold_t_host[1] || !g.fold_t_host[2])) { snprintf(why, nwhy, "host copies of the fold lists missing"); return 0; }
     if (g.met && g.metW && (g.conn_w || g.conn_e)) { snprintf(why, nwhy, "two-dimensional metrics with a partition along x"); return 0; }
     if (g.met && g.met_fused_why) { snprintf(why, nwhy, "%s", g.met_fused_why); return 0; }
     if (p.cor == CSI_CORIOLIS_SPHERICAL && (!g.met || g.metW)) { snprintf(why, nwhy, "HydrostaticSphericalCoriolis needs a lat-lon grid"); return 0; }
@@ -1614,6 +1652,38 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
         if (cudaMalloc(&pl->flags, fl.size()) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flags)"); cudaFree(pl->base); delete pl; return nullptr; }
         cudaMemcpy(pl->flags, fl.data(), fl.size(), cudaMemcpyHostToDevice);
     }
+    if (g.fold) {
+        // the copy lists of u (Face, Center) and v (Center, Face), re-indexed from the caller's parents to the internal layout;
+        // targets in halo columns the internal layout does not keep are dropped (nothing reads them), sources must exist
+        for (int w = 0; w < 2; w++) {
+            const int loc = w + 1, lx = loc & 1;
+            const int sxp = g.Nx + 2 * g.Hx + ((lx && g.topo_x == CSI_BOUNDED && !g.conn_w && !g.conn_e) ? 1 : 0);
+            std::vector<int32_t> tg, sr;
+            int jmin = 1 << 30;
+            for (int k = 0; k < g.fold_n[loc]; k++) {
+                const int t = g.fold_t_host[loc][k], q = g.fold_s_host[loc][k];
+                const int ti = t % sxp + 1 - g.Hx, tj = t / sxp + 1 - g.Hy, qi = q % sxp + 1 - g.Hx, qj = q / sxp + 1 - g.Hy;
+                const int tc = ti - 1 + OX, tr = tj - 1 + pl->oy, qc = qi - 1 + OX, qr = qj - 1 + pl->oy;
+                if (tc < 0 || tc >= pl->pitch || tr < 0 || tr >= pl->rows) continue;
+                if (qc < 0 || qc >= pl->pitch || qr < 0 || qr >= pl->rows) { snprintf(err, nerr, "fused solver: a fold source lies outside the internal layout"); cudaFree(pl->base); delete pl; return nullptr; }
+                tg.push_back(tr * pl->pitch + tc);
+                sr.push_back(qr * pl->pitch + qc);
+                jmin = std::min(jmin, tj);
+            }
+            pl->fold_n[w] = (int)tg.size();
+            if (w == 0 || jmin < pl->fold_jmin) pl->fold_jmin = jmin;
+            if (tg.empty()) continue;
+            if (cudaMalloc(&pl->fold_t[w], tg.size() * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&pl->fold_s[w], sr.size() * sizeof(int32_t)) != cudaSuccess) {
+                snprintf(err, nerr, "cudaMalloc(fold lists)"); cudaFree(pl->base); delete pl; return nullptr;
+            }
+            cudaMemcpy(pl->fold_t[w], tg.data(), tg.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+            cudaMemcpy(pl->fold_s[w], sr.data(), sr.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+        }
+        pl->fold_sign = g.fold_sv;
+        // phase D alone reads alpha back from its plane, also at nodes no launch stores: a value of alpha's range there
+        std::vector<double> ones((size_t)pl->pitch * pl->rows, prm.amin);
+        cudaMemcpy(pl->base + (size_t)F_ALPHA * pl->pitch * pl->rows, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (g.met_host && g.metW) {
         // two-dimensional metrics: MC2_N planes in the internal layout, node (i, j) at its in-plane offset; beyond the host arrays
         // (padding rows, slack columns) the nearest host value, so that whatever an edge tile names is a valid metric
@@ -1679,11 +1749,12 @@ void fused_destroy(FusedPlan *pl)
     if (pl->flags) cudaFree(pl->flags);
     if (pl->met) cudaFree(pl->met);
     if (pl->met2) cudaFree(pl->met2);
+    for (int w = 0; w < 2; w++) { if (pl->fold_t[w]) cudaFree(pl->fold_t[w]); if (pl->fold_s[w]) cudaFree(pl->fold_s[w]); }
     if (pl->invalid) cudaFree(pl->invalid);
     delete pl;
 }
 
-template <bool VFIRST, bool AUX, bool GEN, int MET> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
+template <bool VFIRST, bool AUX, bool GEN, int MET, int PH = 0> static cudaError_t launch_one(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s)
 {
     using namespace fz;
     // the attribute is per device (a process may hold handles on several devices through csi_config.device)
@@ -1691,12 +1762,19 @@ template <bool VFIRST, bool AUX, bool GEN, int MET> static cudaError_t launch_on
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN, MET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_evp_substep_fused<VFIRST, AUX, GEN, MET, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    k_evp_substep_fused<VFIRST, AUX, GEN, MET><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
+    k_evp_substep_fused<VFIRST, AUX, GEN, MET, PH><<<grid, NT, SMEM_BYTES, s>>>(pl->tmap, P);
     return cudaGetLastError();
+}
+// the split substep of a mesh with a fold (two-dimensional metrics): phases A-C / phase D alone
+template <int PH> static cudaError_t launch_split(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
+{
+    if (PH == 2) return vfirst ? launch_one<true, false, true, 2, 2>(pl, P, grid, s) : launch_one<false, false, true, 2, 2>(pl, P, grid, s);
+    if (vfirst) return aux ? launch_one<true, true, true, 2, PH>(pl, P, grid, s) : launch_one<true, false, true, 2, PH>(pl, P, grid, s);
+    return aux ? launch_one<false, true, true, 2, PH>(pl, P, grid, s) : launch_one<false, false, true, 2, PH>(pl, P, grid, s);
 }
 // GEN x MET: the regular grid has a switch-free variant; lat-lon grids (MET) always keep the run-time switches
 template <bool GEN, int MET> static cudaError_t launch_sub(const FusedPlan *pl, const fz::Params &P, dim3 grid, cudaStream_t s, bool vfirst, bool aux)
@@ -1863,7 +1941,7 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         // the common configuration runs the variant compiled without run-time switches
         const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met && !P.met2;
         const bool common_met = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
-        auto band = [&](int t0, int t1) -> cudaError_t {
+        auto band = [&](int t0, int t1, bool aux) -> cudaError_t {
             if (t1 <= t0) return cudaSuccess;
             P.ty0 = t0;
             const dim3 gb(grid.x, t1 - t0);
@@ -1873,14 +1951,47 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
             return common ? launch_sub<false, 0>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, 0>(pl, P, gb, c.stream, vfirst, aux);
         };
         cudaError_t e;
-        if (k == 0 && halo_ready && t_hi > t_lo) {
-            e = band(t_lo, t_hi);
+        if (pl->fold_n[0] > 0 || pl->fold_n[1] > 0) {
+            // A mesh with a fold.  The reference fills halos -- the fold included -- between the two velocity updates of a substep
+            // (se:178-187), and the second one reads, next to the fold, first-velocity values the fold has just replaced by those of
+            // mirrored columns: another tile's.  Tile rows that can see such a value run the substep in two launches with the
+            // fold fill between them; the rows below them (the bulk) run the one-launch substep, the last of them also storing
+            // alpha, which phase D alone reads back one row below its own tiles.
+            if (k == 0 && halo_ready && (e = cudaStreamWaitEvent(c.stream, halo_ready, 0)) != cudaSuccess) { snprintf(err, nerr, "wait: %s", cudaGetErrorString(e)); return (int)e; }
+            int tf = 0;   // first tile row of the split band: its tile, halo ring included, reaches row fold_jmin - 1 or beyond
+            while (tf < (int)grid.y && y0 + OUTY * tf + OUTY + 1 < pl->fold_jmin - 1) tf++;
+            const int wf = vfirst ? 1 : 0, ws = vfirst ? 0 : 1;   // list (0: u, 1: v) of the first / second velocity of this substep
+            const size_t plane = (size_t)P.pitch * P.rows;
+            auto fold_fill = [&](int w) {
+                if (pl->fold_n[w] <= 0) return;
+                DArr a;
+                a.p = P.base + (size_t)((P.out_set ? F_U1 : F_U0) + w) * plane;
+                a.sx = P.pitch; a.sy = P.rows; a.ox = OX; a.oy = P.oy;
+                launch_fold_list(c, a, pl->fold_t[w], pl->fold_s[w], pl->fold_n[w], pl->fold_sign);
+            };
+            e = band(0, tf - 1, aux);
+            if (e == cudaSuccess) e = band(std::max(tf - 1, 0), tf, true);
+            if (e == cudaSuccess && tf < (int)grid.y) {
+                P.ty0 = tf;
+                const dim3 gb(grid.x, grid.y - tf);
+                ++*c.launches;
+                e = launch_split<1>(pl, P, gb, c.stream, vfirst, aux);
+                fold_fill(wf);
+                ++*c.launches;
+                if (e == cudaSuccess) e = launch_split<2>(pl, P, gb, c.stream, vfirst, aux);
+                fold_fill(ws);
+            } else if (e == cudaSuccess) {
+                fold_fill(wf);
+                fold_fill(ws);
+            }
+        } else if (k == 0 && halo_ready && t_hi > t_lo) {
+            e = band(t_lo, t_hi, aux);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, halo_ready, 0);
-            if (e == cudaSuccess) e = band(0, t_lo);
-            if (e == cudaSuccess) e = band(t_hi, (int)grid.y);
+            if (e == cudaSuccess) e = band(0, t_lo, aux);
+            if (e == cudaSuccess) e = band(t_hi, (int)grid.y, aux);
         } else {
             if (k == 0 && halo_ready && (e = cudaStreamWaitEvent(c.stream, halo_ready, 0)) != cudaSuccess) { snprintf(err, nerr, "wait: %s", cudaGetErrorString(e)); return (int)e; }
-            e = band(0, (int)grid.y);
+            e = band(0, (int)grid.y, aux);
         }
         if (e != cudaSuccess) { snprintf(err, nerr, "launch: %s", cudaGetErrorString(e)); return (int)e; }
         pl->cur_set ^= 1;

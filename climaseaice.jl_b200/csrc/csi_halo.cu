@@ -79,6 +79,13 @@ __global__ void k_fill_fold(DArr a, const int32_t *target, const int32_t *source
     if (k < n) a.p[target[k]] = sign * a.p[source[k]];
 }
 
+void launch_fold_list(const LaunchCtx &c, const DArr &a, const int32_t *target, const int32_t *source, int n, double sign)
+{
+    if (n <= 0) return;
+    k_fill_fold<<<(n + 127) / 128, 128, 0, c.stream>>>(a, target, source, n, sign);
+    ++*c.launches;
+}
+
 // which: 0 default boundary conditions, 1 = u, 2 = v (their own wall conditions, fold sign of velocities), 3 = an external stress /
 // velocity array (default conditions, fold sign of external fields)
 void launch_fill_halo(const LaunchCtx &c, const DGrid &g, const DParams &p, const DArr &a, int lx, int ly, int which)

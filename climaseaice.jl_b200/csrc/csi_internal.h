@@ -35,6 +35,7 @@ void launch_diagnostics(const LaunchCtx &c, const DGrid &g, const DFields &f, do
 // ---- fused path (csi_fused.cu) ---------------------------------------------------------------
 struct FusedPlan;  // opaque; owns ping-pong buffers and tensor maps
 int fused_supported(const DGrid &g, const DParams &p, const DFields &f, char *why, int nwhy);
+void launch_fold_list(const LaunchCtx &c, const DArr &a, const int32_t *target, const int32_t *source, int n, double sign);
 const char *fused_metrics_check(const DGrid &g);   // NULL, or why the grid's metric arrays rule the fused kernel out (csi_create)
 FusedPlan *fused_create(const DGrid &g, const DParams &p, char *err, int nerr);
 void fused_destroy(FusedPlan *);

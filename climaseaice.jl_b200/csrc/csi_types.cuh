@@ -38,6 +38,7 @@ struct DGrid {
     // per location lx + 2 ly, applied by the halo fill after the fills of the other sides
     int fold;
     const int32_t *fold_t[4], *fold_s[4];
+    const int32_t *fold_t_host[4], *fold_s_host[4];  // host copies of the lists (plan construction of the fused solver)
     int fold_n[4];
     double fold_sv, fold_se;
 };

@@ -119,7 +119,7 @@ typedef struct {
      * horizontal locations).  The arrays are copied at csi_create.  CSI_METRIC_REGULAR uses dx, dy above.
      * CSI_METRIC_IJ (orthogonal curvilinear grids: OrthogonalSphericalShellGrid, rotated or stretched meshes): the same
      * twelve metrics as two-dimensional host arrays of (Ny + 2*Hy + 1) rows x (Nx + 2*Hx + 1) columns, i fastest, the value
-     * at (i, j) stored at [(j - 1 + Hy) * (Nx + 2*Hx + 1) + (i - 1 + Hx)]; general kernels only; one rank or y-slabs. */
+     * at (i, j) stored at [(j - 1 + Hy) * (Nx + 2*Hx + 1) + (i - 1 + Hx)]; one rank or y-slabs (a partition along x: general kernels refuse it). */
     int32_t metric_kind;
     int32_t serial_exchange;    /* slabs + fused solver: 0 = the halo exchange between blocks of K substeps runs on its own stream
                                    while the next substep's interior tiles compute (boundary tiles wait for it); 1 = on the compute stream */
@@ -142,8 +142,9 @@ typedef struct {
      * halo cells of any side and interior cells (the duplicated row of a centre-pivot fold).  sign: fold_sign_velocity for u, v
      * (-1 in the reference), fold_sign_external for the external stress / velocity arrays top_x, top_y, ue, ve, +1 for every
      * other field.  Checked at csi_create: indices inside the parent, every target once, nothing both read and written (the
-     * copies of one list run concurrently).  Host arrays, copied at csi_create.  General kernels, one rank or y-slabs (the
-     * last slab holds the fold; the other ranks ignore these members). */
+     * copies of one list run concurrently).  The lists should cover the x halo columns of the rows they write (the fold is
+     * applied after the periodic fill in x).  Host arrays, copied at csi_create.  One rank or y-slabs (the last slab holds the
+     * fold; the other ranks ignore these members); the fused solver takes a fold on grids with two-dimensional metrics. */
     const int32_t *fold_target[4];
     const int32_t *fold_source[4];
     int32_t fold_count[4];

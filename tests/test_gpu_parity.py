@@ -554,9 +554,8 @@ def test_stress_balance_free_drift_argument_errors():
     h = C.c_void_p()
     assert L.lib().csi_create(C.byref(cfg), C.byref(h)) == -1 and b"not both" in L.lib().csi_last_error(None)
     m.close()
-    # "fused" refuses what only the general kernels implement: a folded north boundary
-    from climaseaice_b200.synthetic import folded_case
-    mc = folded_case(substeps=2)
+    # "fused" refuses what only the general kernels implement: a folded north boundary without two-dimensional metrics
+    mc = _regular_fold_case()
     mf = model_from_case(mc, solver_impl="fused")
     with pytest.raises(RuntimeError, match="folded"):
         mf.time_step(mc.dt)
@@ -662,13 +661,14 @@ def test_out_of_window_intermediates_fall_back_per_tile(impl):
     m.close()
 
 
-@pytest.mark.parametrize("impl", ("unfused", "auto"))
+@pytest.mark.parametrize("impl", ("unfused", "auto", "fused"))
 @pytest.mark.parametrize("mask", (False, True))
 @pytest.mark.parametrize("timestepper", ["SplitRungeKutta3", "ForwardEuler"])
 def test_folded_north_boundary(impl, mask, timestepper):
     """topo_y = CSI_FOLDED (the north fold of Oceananigans' TripolarGrid, handed over as copy lists the host reads off its own
     fill_halo_regions!): velocities change sign across the fold, thickness and concentration do not, the south is a wall.
-    Parity with the oracle on the whole interior AND on the folded halo elements; runs on the general kernels."""
+    Parity with the oracle on the whole interior AND on the folded halo elements -- on the general kernels, and on the fused tile
+    kernel, whose tile rows next to the fold run the substep as two launches with the fold fill of the first velocity between."""
     from climaseaice_b200.synthetic import folded_case
     case = folded_case(substeps=12, mask=mask, timestepper=timestepper)
     m = model_from_case(case, solver_impl=impl)
@@ -682,14 +682,50 @@ def test_folded_north_boundary(impl, mask, timestepper):
         g = F[n].numpy().reshape(-1)
         assert np.array_equal(g[tg], sign * g[sr]), n
         assert np.array_equal(g[tg], o.arr[NAME_MAP[n]].reshape(-1)[tg]), n
-    assert m.fused_stats()[2] == 0     # the tile kernel refuses a fold: the general kernels ran
+    st = m.fused_stats()
+    assert (st[2] > 0) == (impl != "unfused") and st[0] == 0
     m.close()
 
 
-def test_fused_solver_refuses_a_fold():
+def test_folded_north_boundary_larger_than_one_tile_row():
+    """Several tile rows: the bulk runs the one-launch substep, the rows next to the fold the split one; fused == general kernels
+    bit for bit on every evolving field (interior and the fold's targets), and the FAST pass carries the tiles."""
     from climaseaice_b200.synthetic import folded_case
-    case = folded_case(substeps=4)
+    case = folded_case(96, 80, H=7, substeps=20)
+    a, b = model_from_case(case, solver_impl="fused"), model_from_case(case, solver_impl="unfused")
+    for _ in range(2):
+        a.time_step(case.dt); b.time_step(case.dt)
+    Fa, Fb = a.all_fields(), b.all_fields()
+    for n in ("u", "v", "h", "a", "s11", "s22", "s12"):
+        assert np.array_equal(interior_of(Fa[n].numpy(), case), interior_of(Fb[n].numpy(), case)), n
+    for n, loc in (("u", (1, 0)), ("v", (0, 1))):
+        tg, _ = case.fold["maps"][loc]
+        assert np.array_equal(Fa[n].numpy().reshape(-1)[tg], Fb[n].numpy().reshape(-1)[tg]), n
+    st = a.fused_stats()
+    assert st[2] > 0 and st[0] == 0 and st[1] <= st[2] // 2
+    a.close(); b.close()
+
+
+def _regular_fold_case():
+    """A fold on a regular grid (no metric arrays): only the general kernels take it."""
+    from climaseaice_b200.synthetic import example_fold_maps
+    case = periodic_case(48, Ny=40, substeps=4, aice="mixed")
+    case.topology = ("Periodic", "Folded")
+    case.u_bc_value = 0.0
+    for k in ("v", "top_y", "ve"):
+        case.fields[k] = np.ascontiguousarray(np.vstack([case.fields[k], case.fields[k][-1:]]))
+    case.fold = dict(maps=example_fold_maps(case.Nx, case.Ny, case.Hx, case.Hy), sign_velocity=-1.0, sign_external=1.0)
+    return case
+
+
+def test_fused_solver_refuses_a_fold_without_two_dimensional_metrics():
+    case = _regular_fold_case()
     m = model_from_case(case, solver_impl="fused")
     with pytest.raises(RuntimeError, match="folded"):
         m.time_step(case.dt)
+    m.close()
+    m, o = model_from_case(case, solver_impl="auto"), oracle_from_case(case)   # auto: the general kernels, equal to the oracle
+    m.time_step(case.dt); o.time_step(case.dt)
+    _assert_parity(compare_model(m, o, case))
+    assert m.fused_stats()[2] == 0
     m.close()
