@@ -51,7 +51,9 @@ namespace fz {
 #define CSI_FUSED_MINB_MET2 2   // CTAs per SM of the two-dimensional-metric instantiation (more registers: its per-node loads in flight)
 #endif
 #ifndef CSI_FUSED_MINB_MET1
-#define CSI_FUSED_MINB_MET1 2   // per-row metrics (lat-lon grids): 80 registers spill 0.6-0.8 KB per thread; measured +16 % at 128
+#define CSI_FUSED_MINB_MET1 2   // per-row metrics (lat-lon grids) with the run-time switches: 80 registers spill 0.6-0.8 KB per thread,
+                                // measured +16 % at 128.  (The switch-free lat-lon variant -- BASELINE config 5 -- spills under 0.1 KB
+                                // and loses 15 % at two CTAs per SM: it stays at CSI_FUSED_MINB.)
 #endif
 #ifndef CSI_FUSED_MINB_GEN
 #define CSI_FUSED_MINB_GEN CSI_FUSED_MINB
@@ -1203,7 +1205,7 @@ __device__ __forceinline__ bool tile_pass(double *sm, uint64_t *bar, uint32_t pa
 // VFIRST: odd substep (v then u, se.jl:183-187) or even (u then v, :178-182).  AUX: also write
 // alpha, zeta_c, zeta_f, Delta (last substep of a stage).  GEN: keep the run-time configuration switches.
 template <bool VFIRST, bool AUX, bool GEN, int MET, int PH = 0>
-__global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : MET == 1 ? CSI_FUSED_MINB_MET1 : GEN ? CSI_FUSED_MINB_GEN : CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
+__global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : (MET == 1 && GEN) ? CSI_FUSED_MINB_MET1 : GEN ? CSI_FUSED_MINB_GEN : CSI_FUSED_MINB) k_evp_substep_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
