@@ -1241,6 +1241,78 @@ __global__ void __launch_bounds__(NT, MET == 2 ? CSI_FUSED_MINB_MET2 : (MET == 1
         tile_pass<VFIRST, AUX, GEN, MET, PH, MathSlow, false>(sm, bar, 1, &tmap, p, tc, 0);
     }
 }
+// ---- small grids: a block of substeps in ONE cooperative launch ------------------------------------
+// When every tile of the grid is resident at once (tiles <= SMs x CTAs per SM), a substep costs one tile pass plus the gap
+// between two launches, and the gap is the larger part (BASELINE config 1 as shipped: 50 tiles, 11 us per substep).  This
+// kernel keeps its CTAs over `nsub` substeps: tile pass, grid-wide barrier, tile pass ... -- the same tile_pass
+// instantiations, the same stores, with a barrier where the stream order between two launches was.  Two parameter blocks:
+// the planes read / written and the order of the velocity phases alternate with the parity of the substep.
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int target)
+{
+    // this CTA's global stores (generic proxy) must be visible to the other CTAs' TMA loads (async proxy) of the next substep
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target);
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(NT, GEN ? CSI_FUSED_MINB_GEN : CSI_FUSED_MINB)
+    k_evp_substeps_persistent(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params p_even, const __grid_constant__ Params p_odd, int first_sub, int nsub,
+                              unsigned int *sync)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + NARR * ASTRIDE);
+    const int y0 = p_even.sy0 < p_even.vy0 ? p_even.sy0 : p_even.vy0;
+    TileCtx tc;
+    tc.I0 = p_even.a0 + blockIdx.x * OUTX;
+    tc.J0 = y0 + blockIdx.y * OUTY;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int inv = *p_even.invalid;
+    const unsigned int nblocks = gridDim.x * gridDim.y;
+    uint32_t parity = 0;   // both mbarriers complete one phase per tile pass
+    for (int k = 0; k < nsub; k++) {
+        bool redo;
+        if ((first_sub + k) & 1) {   // odd substep: v first (se.jl:183-187)
+            tc.fin = p_odd.in_set ? F_U1 : F_U0;
+            tc.fout = p_odd.out_set ? F_U1 : F_U0;
+            redo = tile_pass<true, false, GEN, 0, 0, MathFast, false>(sm, bar, parity, &tmap, p_odd, tc, inv);
+            parity ^= 1u;
+            if (redo) {
+                __syncthreads();
+                if (threadIdx.x == 0) atomicAdd(p_odd.invalid + 1, 1);
+                tile_pass<true, false, GEN, 0, 0, MathSlow, false>(sm, bar, parity, &tmap, p_odd, tc, 0);
+                parity ^= 1u;
+            }
+        } else {
+            tc.fin = p_even.in_set ? F_U1 : F_U0;
+            tc.fout = p_even.out_set ? F_U1 : F_U0;
+            redo = tile_pass<false, false, GEN, 0, 0, MathFast, false>(sm, bar, parity, &tmap, p_even, tc, inv);
+            parity ^= 1u;
+            if (redo) {
+                __syncthreads();
+                if (threadIdx.x == 0) atomicAdd(p_even.invalid + 1, 1);
+                tile_pass<false, false, GEN, 0, 0, MathSlow, false>(sm, bar, parity, &tmap, p_even, tc, 0);
+                parity ^= 1u;
+            }
+        }
+        grid_barrier(sync, nblocks * (unsigned int)(k + 1));
+    }
+}
 #undef S
 #undef SB
 #undef FLG
@@ -1528,9 +1600,12 @@ struct FusedPlan {
     int fold_n[2] = {0, 0};
     double fold_sign = 1.0;
     int fold_jmin = 0;      // southernmost reference row a list writes
+    bool partitioned = false;  // a side of the block is connected to another rank (halo exchanges between blocks of substeps)
     double *met2 = nullptr; // two-dimensional metric planes (orthogonal curvilinear grids), MC2_N x (rows + 2 MET2_PAD) x pitch
     long long met2_stride = 0;
     int *invalid = nullptr; // device flag: an input of the current stage is outside the validated range
+    int persistent = -1;    // small grids: -1 not decided, 0 no, 1 the block of substeps runs as one cooperative launch (GEN = false), 2 (GEN = true)
+    long long persistent_launches = 0;
     fz::Params P;
     dim3 grid;
     int cur_set = 0;
@@ -1614,6 +1689,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
     pl->nf = (CSI_PRE_RM2 || CSI_PRE_RMC || CSI_PRE_PF4 || CSI_PRE_SVE) ? (int)NF : (gen_planes ? (int)NF_GEN : (int)NF_COMMON);
     pl->Nx = g.Nx;
     pl->Ny = g.Ny;
+    pl->partitioned = g.conn_s || g.conn_n || g.conn_w || g.conn_e;
     pl->oy = (g.conn_s || g.conn_n) ? g.Hy : W + 1;
     const int wx = (g.conn_w || g.conn_e) ? g.Hx : W;  // halo columns kept in the internal layout
     if (wx > OX - 3) { snprintf(err, nerr, "fused solver: Hx = %d exceeds the internal x halo (%d)", g.Hx, OX - 3); delete pl; return nullptr; }
@@ -1624,8 +1700,8 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
     cudaError_t e = cudaMalloc(&pl->base, bytes);
     if (e != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); delete pl; return nullptr; }
     cudaMemset(pl->base, 0, bytes);
-    if (cudaMalloc(&pl->invalid, 2 * sizeof(int)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flag)"); cudaFree(pl->base); delete pl; return nullptr; }
-    cudaMemset(pl->invalid, 0, 2 * sizeof(int));
+    if (cudaMalloc(&pl->invalid, 4 * sizeof(int)) != cudaSuccess) { snprintf(err, nerr, "cudaMalloc(flag)"); cudaFree(pl->base); delete pl; return nullptr; }
+    cudaMemset(pl->invalid, 0, 4 * sizeof(int));   // [0] inputs failed validation, [1] tile passes redone, [2] grid barrier of the persistent kernel
     cudaDeviceSynchronize();  // the plan may be used next from a non-blocking stream
     if (g.mask_host) {
         // node flags from the centre mask, with the reference's inactive_cell / immersed_peripheral_node logic
@@ -1915,10 +1991,10 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
     int t_lo = 0, t_hi = (int)grid.y;  // interior band [t_lo, t_hi)
     while (t_lo < (int)grid.y && y0 + OUTY * t_lo - 2 < 1) t_lo++;
     while (t_hi > t_lo && y0 + OUTY * (t_hi - 1) + OUTY + 1 > P.Ny) t_hi--;
-    for (int k = 0; k < nsub; k++) {
-        const int sub = first_sub + k;
-        P.in_set = pl->cur_set;
-        P.out_set = pl->cur_set ^ 1;
+    // the planes one substep reads and writes: they alternate with the parity of the substep
+    auto point = [&](Params &P, int sub, int cur_set) {
+        P.in_set = cur_set;
+        P.out_set = cur_set ^ 1;
         const bool vfirst = (sub % 2) != 0;
         {
             const size_t plane = (size_t)P.pitch * P.rows;
@@ -1939,6 +2015,56 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
             P.o_s11 = at(fo + 2); P.o_s22 = at(fo + 3); P.o_s12 = at(fo + 4);
             P.g_rmc = at(F_RMC); P.g_rmf = at(F_RMF); P.g_pf4 = at(F_PF4);
         }
+    };
+    // Small grids on one rank: all substeps but the last (which also writes alpha, zeta, Delta) in one cooperative launch
+    int k0 = 0;
+    {
+        const bool common0 = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags;
+        const int npers = aux_last ? nsub - 1 : nsub;
+        if (pl->persistent < 0) {
+            pl->persistent = 0;
+            const char *env = getenv("CSI_PERSISTENT");   // 0 disables (A/B measurements)
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            const bool eligible = coop && !P.met && !P.met2 && !(env && env[0] == '0') && pl->fold_n[0] == 0 && pl->fold_n[1] == 0 &&
+                                  !pl->partitioned;
+            if (eligible) {
+                cudaError_t e1 = common0 ? cudaFuncSetAttribute(k_evp_substeps_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)
+                                         : cudaFuncSetAttribute(k_evp_substeps_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+                if (e1 == cudaSuccess)
+                    e1 = common0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_evp_substeps_persistent<false>, NT, SMEM_BYTES)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_evp_substeps_persistent<true>, NT, SMEM_BYTES);
+                if (e1 == cudaSuccess && (long long)grid.x * grid.y <= (long long)sms * per_sm) pl->persistent = common0 ? 1 : 2;
+                cudaGetLastError();
+            }
+        }
+        if (pl->persistent > 0 && (pl->persistent == 1) == common0 && npers >= 2 && !halo_ready) {
+            Params Pe = P, Po = P;
+            Pe.ty0 = Po.ty0 = 0;
+            // substep `first_sub + k` reads copy (cur_set + k) & 1
+            const int par0 = first_sub & 1;
+            point(par0 ? Po : Pe, first_sub, pl->cur_set);
+            point(par0 ? Pe : Po, first_sub + 1, pl->cur_set ^ 1);
+            unsigned int *sync = reinterpret_cast<unsigned int *>(pl->invalid + 2);
+            cudaMemsetAsync(sync, 0, sizeof(unsigned int), c.stream);
+            int fs = first_sub, ns = npers;
+            void *args[] = {(void *)&pl->tmap, (void *)&Pe, (void *)&Po, (void *)&fs, (void *)&ns, (void *)&sync};
+            cudaError_t e = pl->persistent == 1 ? cudaLaunchCooperativeKernel((void *)k_evp_substeps_persistent<false>, grid, dim3(NT), args, SMEM_BYTES, c.stream)
+                                                : cudaLaunchCooperativeKernel((void *)k_evp_substeps_persistent<true>, grid, dim3(NT), args, SMEM_BYTES, c.stream);
+            if (e != cudaSuccess) { snprintf(err, nerr, "cooperative launch: %s", cudaGetErrorString(e)); return (int)e; }
+            ++*c.launches;
+            ++pl->persistent_launches;
+            pl->cur_set ^= (npers & 1);
+            k0 = npers;
+        }
+    }
+    for (int k = k0; k < nsub; k++) {
+        const int sub = first_sub + k;
+        point(P, sub, pl->cur_set);
+        const bool vfirst = (sub % 2) != 0;
         const bool aux = aux_last && k == nsub - 1;
         // the common configuration runs the variant compiled without run-time switches
         const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met && !P.met2;

@@ -729,3 +729,37 @@ def test_fused_solver_refuses_a_fold_without_two_dimensional_metrics():
     _assert_parity(compare_model(m, o, case))
     assert m.fused_stats()[2] == 0
     m.close()
+
+
+@pytest.mark.parametrize("kind", ("anticyclone", "periodic_mixed", "coastline"))
+def test_small_grid_cooperative_launch_equals_launch_per_substep(kind, monkeypatch):
+    """Grids whose tiles are all resident at once run the substeps of a stage, but the last, as ONE cooperative launch with a
+    grid-wide barrier between substeps (k_evp_substeps_persistent); CSI_PERSISTENT=0 keeps the launch per substep.  Same tile
+    passes, same stores: every field equal bit for bit, and both equal to the oracle; the launch count shows which path ran."""
+    from climaseaice_b200.synthetic import coastline_case
+    if kind == "anticyclone":
+        case = anticyclone_case(128, noise=0.0, substeps=40)      # BASELINE config 1 as shipped, fewer substeps
+    elif kind == "periodic_mixed":
+        case = periodic_case(96, Ny=64, substeps=25, aice="mixed")
+    else:
+        case = coastline_case(Ny=48, substeps=30)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CSI_PERSISTENT", mode)
+        m = model_from_case(case, solver_impl="fused")
+        m.time_step(case.dt)
+        l0 = m.launch_count
+        m.time_step(case.dt)
+        F = m.all_fields()
+        runs[mode] = ({n: F[n].numpy().copy() for n in ("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "zeta_f", "delta")}, m.launch_count - l0, m.fused_stats())
+        if mode == "1":
+            o = oracle_from_case(case)
+            for _ in range(2):
+                o.time_step(case.dt)
+            _assert_parity(compare_model(m, o, case))
+        m.close()
+    for n, a in runs["0"][0].items():
+        assert np.array_equal(interior_of(a, case), interior_of(runs["1"][0][n], case)), n
+    stages = 3 if case.timestepper == "SplitRungeKutta3" else 1
+    assert runs["0"][1] - runs["1"][1] == stages * (case.substeps - 2)     # substeps 1 .. n - 1 became one launch per stage
+    assert runs["0"][2] == runs["1"][2]
