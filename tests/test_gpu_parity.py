@@ -488,6 +488,23 @@ def test_two_dimensional_metrics_with_a_coast(impl):
     m.close()
 
 
+@pytest.mark.parametrize("topology", [("Periodic", "Bounded"), ("Periodic", "Periodic")])
+def test_two_dimensional_metrics_many_tiles_fused_equals_general(topology):
+    """11 x 18 tiles, most of them interior tiles (the instantiation without edge logic): the fused kernel on per-node metric
+    planes equals the general kernels bit for bit on every evolving field and on the auxiliaries of the last substep."""
+    from climaseaice_b200.synthetic import curvilinear_case
+    case = curvilinear_case(320, 240, H=5, substeps=12, topology=topology)
+    a, b = model_from_case(case, solver_impl="fused"), model_from_case(case, solver_impl="unfused")
+    for _ in range(2):
+        a.time_step(case.dt); b.time_step(case.dt)
+    Fa, Fb = a.all_fields(), b.all_fields()
+    for n in ("u", "v", "h", "a", "s11", "s22", "s12", "alpha", "zeta_c", "zeta_f", "delta"):
+        assert np.array_equal(interior_of(Fa[n].numpy(), case), interior_of(Fb[n].numpy(), case)), n
+    st = a.fused_stats()
+    assert st[2] >= 11 * 18 and st[0] == 0 and st[1] <= st[2] // 10
+    a.close(); b.close()
+
+
 def test_latitude_longitude_grid_rejects_bad_metrics():
     from climaseaice_b200.synthetic import latlon_case
     bad = latlon_case(32, substeps=4)
