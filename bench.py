@@ -518,7 +518,10 @@ def run_gpu(args):
 
     configs = None
     if ngpus == 1 and rank == 0 and not args.no_configs and not (args.nx or args.periodic):
-        configs = extra_configuration_legs(dev, local)
+        try:
+            configs = extra_configuration_legs(dev, local)
+        except Exception as exc:   # the legs stand beside the headline: a failure there is reported, it never costs the line
+            configs = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         cpu = None
