@@ -13,7 +13,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 entry.load_package()
 from climaseaice_b200 import lib  # noqa: E402
-from climaseaice_b200.synthetic import block_of, coastline_case, curvilinear_case, periodic_case, slab_of  # noqa: E402
+from climaseaice_b200.synthetic import block_of, coastline_case, curvilinear_case, folded_case, periodic_case, slab_of  # noqa: E402
 
 
 def main():
@@ -77,6 +77,27 @@ def main():
             jg = (rank * ms.Ny + jl - 1) % mc.Ny + 1
             ok &= np.array_equal(loc[jl - 1 + Hy], G[jg - 1 + mc.Hy])
         ok &= np.array_equal(G[mc.Hy], G[mc.Hy + mc.Ny]) and bool((loc > 0).all())      # face Ny + 1 is face 1
+    # a north fold on y-slabs: only the last slab carries copy lists; in (i, j) relative to the slab's north edge they are the
+    # global case's lists (rows within the global halo), plus the deeper rows of the slab's own halo; sources stay inside the slab
+    fc = folded_case(24, 16 * world, H=7, substeps=K)
+    fs = slab_of(fc, rank, world, Hy)
+    ok &= (fs.fold is not None) == (rank == world - 1)
+    if fs.fold is not None:
+        for loc, (tg, sr) in fs.fold["maps"].items():
+            sxp = fs.Nx + 2 * fs.Hx
+
+            def rel(idx, H, Ny):   # (column, row above the north edge) of a linear parent index
+                return idx % sxp, idx // sxp - (Ny - 1 + H)
+
+            mine = {rel(t, Hy, fs.Ny): rel(q, Hy, fs.Ny) for t, q in zip(tg, sr)}
+            gt, gs = fc.fold["maps"][loc]
+            for t, q in zip(gt, gs):
+                ok &= mine.get(rel(t, fc.Hy, fc.Ny)) == rel(q, fc.Hy, fc.Ny)
+            ok &= all(-fs.Ny < r <= 0 for _, r in mine.values())          # every source is an interior row of this slab
+            ok &= np.unique(tg).size == tg.size and not np.intersect1d(tg, sr).size
+        m = fs.mask.reshape(-1)
+        tg, sr = fs.fold["maps"][(0, 0)]
+        ok &= np.array_equal(m[tg], m[sr])                                  # the slab's mask obeys the fold in its deeper halo too
     flag = torch.tensor([0 if ok else 1])
     dist.all_reduce(flag)
     if rank == 0:
