@@ -255,7 +255,8 @@ def extra_configuration_legs(dev, local, steps=2):
     out["config1_anticyclone_128_as_shipped"] = {
         "ms_per_time_step": ms, "us_per_substep": ms * 1e3 / (3 * SUBSTEPS), "launches_per_time_step": nl,
         "cell_updates_per_s": 128 * 128 * 3 * SUBSTEPS / (ms * 1e-3), "fused_stats": list(st),
-        "note": "one time_step! = 3 RK stages x (WENO7 tendencies + 150 substeps + h/aice update); 16 k cells do not fill 148 SMs"}
+        "note": "one time_step! = 3 RK stages x (WENO7 tendencies + 150 substeps + h/aice update); 16 k cells do not fill 148 SMs; "
+                "the substeps of a stage but the last run as one cooperative launch with a grid-wide barrier (CSI_PERSISTENT=0: one launch per substep)"}
     # config 4: ice_advected_on_coastline with the immersed land mask, 8192 x 4096 (2 Ny x Ny as the example), momentum only
     c4 = coastline_case(Ny=4096, substeps=SUBSTEPS)
     m = model_from_case(c4, solver_impl="auto", device=dev)

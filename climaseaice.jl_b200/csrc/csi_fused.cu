@@ -1615,6 +1615,10 @@ struct FusedPlan {
     int fold_n[2] = {0, 0};
     double fold_sign = 1.0;
     int fold_jmin = 0;      // southernmost reference row a list writes
+    int fold_jsrc_min = 0;  // southernmost reference row a list reads
+    // the split band of a substep runs on a stream of its own, beside the bulk of the mesh (fused_steps)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool partitioned = false;  // a side of the block is connected to another rank (halo exchanges between blocks of substeps)
     double *met2 = nullptr; // two-dimensional metric planes (orthogonal curvilinear grids), MC2_N x (rows + 2 MET2_PAD) x pitch
     long long met2_stride = 0;
@@ -1752,7 +1756,7 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
             const int loc = w + 1, lx = loc & 1;
             const int sxp = g.Nx + 2 * g.Hx + ((lx && g.topo_x == CSI_BOUNDED && !g.conn_w && !g.conn_e) ? 1 : 0);
             std::vector<int32_t> tg, sr;
-            int jmin = 1 << 30;
+            int jmin = 1 << 30, jsrc = 1 << 30;
             for (int k = 0; k < g.fold_n[loc]; k++) {
                 const int t = g.fold_t_host[loc][k], q = g.fold_s_host[loc][k];
                 const int ti = t % sxp + 1 - g.Hx, tj = t / sxp + 1 - g.Hy, qi = q % sxp + 1 - g.Hx, qj = q / sxp + 1 - g.Hy;
@@ -1762,9 +1766,11 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
                 tg.push_back(tr * pl->pitch + tc);
                 sr.push_back(qr * pl->pitch + qc);
                 jmin = std::min(jmin, tj);
+                jsrc = std::min(jsrc, qj);
             }
             pl->fold_n[w] = (int)tg.size();
             if (w == 0 || jmin < pl->fold_jmin) pl->fold_jmin = jmin;
+            if (w == 0 || jsrc < pl->fold_jsrc_min) pl->fold_jsrc_min = jsrc;
             if (tg.empty()) continue;
             if (cudaMalloc(&pl->fold_t[w], tg.size() * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&pl->fold_s[w], sr.size() * sizeof(int32_t)) != cudaSuccess) {
                 snprintf(err, nerr, "cudaMalloc(fold lists)"); cudaFree(pl->base); delete pl; return nullptr;
@@ -1773,6 +1779,13 @@ FusedPlan *fused_create(const DGrid &g, const DParams &prm, char *err, int nerr)
             cudaMemcpy(pl->fold_s[w], sr.data(), sr.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
         }
         pl->fold_sign = g.fold_sv;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // (hi is the greatest priority: the band's small launches go first when slots free up)
+        if (cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi) != cudaSuccess || cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            pl->side = nullptr;   // (the band then runs on the caller's stream, after the bulk)
+        }
         // phase D alone reads alpha back from its plane, also at nodes no launch stores: a value of alpha's range there
         std::vector<double> ones((size_t)pl->pitch * pl->rows, prm.amin);
         cudaMemcpy(pl->base + (size_t)F_ALPHA * pl->pitch * pl->rows, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -1843,6 +1856,9 @@ void fused_destroy(FusedPlan *pl)
     if (pl->met) cudaFree(pl->met);
     if (pl->met2) cudaFree(pl->met2);
     for (int w = 0; w < 2; w++) { if (pl->fold_t[w]) cudaFree(pl->fold_t[w]); if (pl->fold_s[w]) cudaFree(pl->fold_s[w]); }
+    if (pl->side) cudaStreamDestroy(pl->side);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     if (pl->invalid) cudaFree(pl->invalid);
     delete pl;
 }
@@ -2084,15 +2100,16 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
         // the common configuration runs the variant compiled without run-time switches
         const bool common = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_FPLANE && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && !P.met && !P.met2;
         const bool common_met = !P.fd_on && P.sis && P.use_ue && P.use_top && P.cor == CSI_CORIOLIS_SPHERICAL && P.pform == CSI_REPLACEMENT_PRESSURE && !P.flags && P.met;
-        auto band = [&](int t0, int t1, bool aux) -> cudaError_t {
+        auto band_on = [&](cudaStream_t st, int t0, int t1, bool aux) -> cudaError_t {
             if (t1 <= t0) return cudaSuccess;
             P.ty0 = t0;
             const dim3 gb(grid.x, t1 - t0);
             ++*c.launches;
-            if (P.met2) return launch_sub<true, 2>(pl, P, gb, c.stream, vfirst, aux);   // (orthogonal curvilinear grids keep the run-time switches)
-            if (P.met) return common_met ? launch_sub<false, 1>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, 1>(pl, P, gb, c.stream, vfirst, aux);
-            return common ? launch_sub<false, 0>(pl, P, gb, c.stream, vfirst, aux) : launch_sub<true, 0>(pl, P, gb, c.stream, vfirst, aux);
+            if (P.met2) return launch_sub<true, 2>(pl, P, gb, st, vfirst, aux);   // (orthogonal curvilinear grids keep the run-time switches)
+            if (P.met) return common_met ? launch_sub<false, 1>(pl, P, gb, st, vfirst, aux) : launch_sub<true, 1>(pl, P, gb, st, vfirst, aux);
+            return common ? launch_sub<false, 0>(pl, P, gb, st, vfirst, aux) : launch_sub<true, 0>(pl, P, gb, st, vfirst, aux);
         };
+        auto band = [&](int t0, int t1, bool aux) -> cudaError_t { return band_on(c.stream, t0, t1, aux); };
         cudaError_t e;
         if (pl->fold_n[0] > 0 || pl->fold_n[1] > 0) {
             // A mesh with a fold.  The reference fills halos -- the fold included -- between the two velocity updates of a substep
@@ -2105,27 +2122,42 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
             while (tf < (int)grid.y && y0 + OUTY * tf + OUTY + 1 < pl->fold_jmin - 1) tf++;
             const int wf = vfirst ? 1 : 0, ws = vfirst ? 0 : 1;   // list (0: u, 1: v) of the first / second velocity of this substep
             const size_t plane = (size_t)P.pitch * P.rows;
-            auto fold_fill = [&](int w) {
+            auto fold_fill = [&](const LaunchCtx &cc, int w) {
                 if (pl->fold_n[w] <= 0) return;
                 DArr a;
                 a.p = P.base + (size_t)((P.out_set ? F_U1 : F_U0) + w) * plane;
                 a.sx = P.pitch; a.sy = P.rows; a.ox = OX; a.oy = P.oy;
-                launch_fold_list(c, a, pl->fold_t[w], pl->fold_s[w], pl->fold_n[w], pl->fold_sign);
+                launch_fold_list(cc, a, pl->fold_t[w], pl->fold_s[w], pl->fold_n[w], pl->fold_sign);
             };
-            e = band(0, tf - 1, aux);
-            if (e == cudaSuccess) e = band(std::max(tf - 1, 0), tf, true);
+            // Everything the band reads that this substep writes -- the sources of the fold fills, and alpha / sigma / the first
+            // velocity one row below its tiles -- comes from the band's own launches or from the tile row right below it (the one
+            // that also stores alpha); both read the previous substep's planes only, like the bulk.  So tile row tf - 1 and the
+            // band run as a chain on a stream of their own, beside the bulk launch, and join it before the next substep.
+            const bool beside = pl->side && tf >= 2 && tf < (int)grid.y && y0 + OUTY * (tf - 1) <= pl->fold_jsrc_min;
+            const cudaStream_t bs = beside ? pl->side : c.stream;
+            const LaunchCtx cb{bs, c.launches};
+            if (beside) {
+                e = cudaEventRecord(pl->ev_fork, c.stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(pl->side, pl->ev_fork, 0);
+            } else e = band(0, tf - 1, aux);
+            if (e == cudaSuccess) e = band_on(bs, std::max(tf - 1, 0), tf, true);
             if (e == cudaSuccess && tf < (int)grid.y) {
                 P.ty0 = tf;
                 const dim3 gb(grid.x, grid.y - tf);
                 ++*c.launches;
-                e = launch_split<1>(pl, P, gb, c.stream, vfirst, aux);
-                fold_fill(wf);
+                e = launch_split<1>(pl, P, gb, bs, vfirst, aux);
+                fold_fill(cb, wf);
                 ++*c.launches;
-                if (e == cudaSuccess) e = launch_split<2>(pl, P, gb, c.stream, vfirst, aux);
-                fold_fill(ws);
+                if (e == cudaSuccess) e = launch_split<2>(pl, P, gb, bs, vfirst, aux);
+                fold_fill(cb, ws);
             } else if (e == cudaSuccess) {
-                fold_fill(wf);
-                fold_fill(ws);
+                fold_fill(cb, wf);
+                fold_fill(cb, ws);
+            }
+            if (beside) {
+                if (e == cudaSuccess) e = cudaEventRecord(pl->ev_join, pl->side);
+                if (e == cudaSuccess) e = band(0, tf - 1, aux);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, pl->ev_join, 0);
             }
         } else if (k == 0 && halo_ready && t_hi > t_lo) {
             e = band(t_lo, t_hi, aux);

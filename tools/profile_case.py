@@ -1,4 +1,4 @@
-"""Run a few momentum solves on one GPU (for ncu / quick timing): python tools/profile_case.py N nsub [solver] [bounded|coastline|curvilinear|latlon]"""
+"""Run a few momentum solves on one GPU (for ncu / quick timing): python tools/profile_case.py N nsub [solver] [bounded|coastline|curvilinear|folded|latlon]"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -16,6 +16,9 @@ elif kind == "coastline":
 elif kind == "curvilinear":
     from climaseaice_b200.synthetic import curvilinear_case
     case = curvilinear_case(N, N, H=7, substeps=nsub, topology=("Periodic", "Bounded"))
+elif kind == "folded":
+    from climaseaice_b200.synthetic import folded_case
+    case = folded_case(N, N // 2, H=7, substeps=nsub)
 elif kind == "latlon":
     from climaseaice_b200.synthetic import latlon_case
     case = latlon_case(N, H=7, substeps=nsub, topology=("Periodic", "Bounded"))
