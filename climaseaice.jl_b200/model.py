@@ -94,10 +94,11 @@ class LatitudeLongitudeGrid(RectilinearGrid):
 
 class OrthogonalSphericalShellGrid(RectilinearGrid):
     """Orthogonal curvilinear grid given by its metrics (Oceananigans' OrthogonalSphericalShellGrid family: rotated,
-    stretched or conformally mapped meshes; no fold): `metrics[name]` is a (Ny + 2Hy + 1) x (Nx + 2Hx + 1) array with the
+    stretched or conformally mapped meshes; with topology (Periodic, Folded) and `SeaIceModel(..., fold=...)` a tripolar mesh): `metrics[name]` is a (Ny + 2Hy + 1) x (Nx + 2Hx + 1) array with the
     value at index (i, j) -- halos included -- stored at [j - 1 + Hy, i - 1 + Hx], for the twelve names of METRIC_NAMES
     (dx, dy, Az at the four horizontal locations), i.e. what Oceananigans' `Δxᶜᶜᵃ` ... `Azᶠᶠᵃ` return.  `nodes()` are index
-    coordinates.  Runs on the general (per-kernel) solver formulation."""
+    coordinates.  The fused tile kernel reads the metrics per node from planes in its own layout; a partition along x runs on
+    the general (per-kernel) solver formulation."""
 
     def __init__(self, size, metrics, halo=(3, 3), topology=(Bounded, Bounded, Flat), device=None, partitioned_y=False):
         super().__init__(size, (0.0, float(size[0])), (0.0, float(size[1])), halo=halo, topology=topology, device=device,
