@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT))
 import __graft_entry__ as entry  # noqa: E402
 
 entry.load_package()
-from climaseaice_b200.synthetic import anticyclone_case, curvilinear_case, latlon_case, periodic_case  # noqa: E402
+from climaseaice_b200.synthetic import anticyclone_case, coastline_case, curvilinear_case, folded_case, latlon_case, periodic_case  # noqa: E402
 from tests.helpers import oracle_from_case  # noqa: E402
 
 CASES = {
@@ -23,6 +23,8 @@ CASES = {
     "periodic_18x22_fe_weno5": lambda: periodic_case(18, Ny=22, substeps=9, aice="mixed", advection_order=5, timestepper="ForwardEuler"),
     "latlon_48_rk3_weno7": lambda: latlon_case(48, substeps=20, topology=("Periodic", "Bounded")),          # j-dependent metrics
     "curvilinear_72x56_rk3_weno7": lambda: curvilinear_case(72, 56, substeps=20),                            # (i, j)-dependent metrics
+    "coastline_96x48_rk3_weno7": lambda: coastline_case(Ny=48, substeps=16),                                 # immersed coast, drag BC, reduced WENO
+    "folded_48x40_rk3_weno7": lambda: folded_case(48, 40, substeps=12),                                      # north fold (copy lists), island
 }
 FIELDS = ("u", "v", "h", "a", "s11", "s22", "s12", "alpha")
 
