@@ -478,7 +478,9 @@ def run_gpu(args):
     if world > 1 and not args.no_configs and 336 % world == 0:
         from climaseaice_b200.synthetic import arctic_cap_case
         c5 = arctic_cap_case(4320, 336, H=7, substeps=SUBSTEPS, dt=600.0)
-        K5 = K if 336 // world > 100 else 8   # thin slabs: fewer, deeper exchanges (measured on 4 GPUs: 25.96 ms at K = 4, 23.85 at K = 8)
+        # thin slabs: fewer, deeper exchanges (measured on 4 GPUs, 84 rows per rank: 25.96 ms at K = 4, 23.85 at K = 8; the 42-row slabs of
+        # 8 GPUs were measured at K = 4 only and keep it)
+        K5 = 8 if 336 // world == 84 else K
         s5 = slab_of(c5, rank, world, 2 * K5 + 3)
         m5 = model_from_case(s5, solver_impl=args.solver, partition=(rank, world, K5), device=dev)
         ids = [nccl_unique_id() if rank == 0 else None]
