@@ -2085,11 +2085,17 @@ int fused_steps(FusedPlan *pl, const LaunchCtx &c, int first_sub, int nsub, bool
             void *args[] = {(void *)&pl->tmap, (void *)&Pe, (void *)&Po, (void *)&fs, (void *)&ns, (void *)&sync};
             cudaError_t e = pl->persistent == 1 ? cudaLaunchCooperativeKernel((void *)k_evp_substeps_persistent<false>, grid, dim3(NT), args, SMEM_BYTES, c.stream)
                                                 : cudaLaunchCooperativeKernel((void *)k_evp_substeps_persistent<true>, grid, dim3(NT), args, SMEM_BYTES, c.stream);
-            if (e != cudaSuccess) { snprintf(err, nerr, "cooperative launch: %s", cudaGetErrorString(e)); return (int)e; }
-            ++*c.launches;
-            ++pl->persistent_launches;
-            pl->cur_set ^= (npers & 1);
-            k0 = npers;
+            if (e == cudaSuccess) {
+                ++*c.launches;
+                ++pl->persistent_launches;
+                pl->cur_set ^= (npers & 1);
+                k0 = npers;
+            } else {
+                // (e.g. fewer SMs available to this context than the occupancy query assumed: nothing was launched; the
+                // substeps below run one launch each, now and from here on)
+                cudaGetLastError();
+                pl->persistent = 0;
+            }
         }
     }
     for (int k = k0; k < nsub; k++) {
